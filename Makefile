@@ -1,0 +1,59 @@
+# Builds everything in-tree (the .so files travel to the GPU box with the
+# snapshot; they are git-ignored).
+#   liblighthugger_b200.so  the product: sm_100a CUDA kernels + C ABI
+#   liblh_host.so           host-side scene preparation (C++20)
+#   oracle/liblh_oracle.so  CPU restatement of the reference (test infrastructure)
+#   oracle/_ref/...         the reference's own scene-prep code compiled in place (only where /root/reference exists)
+NVCC ?= /usr/local/cuda/bin/nvcc
+CXX ?= g++
+REF ?= /root/reference
+
+LIBDIR := lighthugger_b200/lib
+CUDA_SRCS := $(wildcard lighthugger_b200/csrc/*.cu)
+CUDA_HDRS := $(wildcard lighthugger_b200/csrc/*.cuh lighthugger_b200/csrc/*.h include/*.h)
+HOST_SRCS := $(wildcard lighthugger_b200/host/*.cpp)
+HOST_HDRS := $(wildcard lighthugger_b200/host/*.hpp include/*.h)
+ORACLE_SRCS := $(wildcard oracle/*.cpp)
+ORACLE_HDRS := $(wildcard oracle/*.h oracle/*.hpp include/*.h)
+
+# -fmad=false: the pinned arithmetic model has no FMA contraction
+NVCCFLAGS := -gencode arch=compute_100a,code=sm_100a -O3 -std=c++20 -lineinfo -fmad=false \
+             -Xcompiler -fPIC,-fvisibility=hidden -Iinclude -Ilighthugger_b200/csrc
+LDFLAGS_SO := -Wl,--exclude-libs,ALL
+CXXFLAGS := -O2 -std=c++20 -fPIC -fvisibility=hidden -ffp-contract=off -Iinclude -Wall -Wextra -Wno-unused-parameter
+
+all: cuda host oracle ref
+
+cuda: $(LIBDIR)/liblighthugger_b200.so
+host: $(LIBDIR)/liblh_host.so
+oracle: oracle/liblh_oracle.so
+
+$(LIBDIR)/liblighthugger_b200.so: $(CUDA_SRCS) $(CUDA_HDRS)
+	@mkdir -p $(LIBDIR)
+	$(NVCC) $(NVCCFLAGS) -shared -o $@ $(CUDA_SRCS) -lcudart -ldl
+
+$(LIBDIR)/liblh_host.so: $(HOST_SRCS) $(HOST_HDRS)
+	@mkdir -p $(LIBDIR)
+	$(CXX) $(CXXFLAGS) -shared -o $@ $(HOST_SRCS) $(LDFLAGS_SO)
+
+oracle/liblh_oracle.so: $(ORACLE_SRCS) $(ORACLE_HDRS)
+	$(CXX) $(CXXFLAGS) -fvisibility=default -pthread -shared -o $@ $(ORACLE_SRCS) $(LDFLAGS_SO)
+
+# The reference's scene-prep path compiles from its own few sources; its full
+# build (Vulkan, fastgltf download) does not -- see DESIGN.md.
+REF_GLM := $(REF)/external/VulkanMemoryAllocator-Hpp/Vulkan-Hpp/glm
+REF_MESHOPT := $(REF)/external/meshoptimizer/src
+ref:
+	@if [ -d $(REF)/src ]; then $(MAKE) --no-print-directory oracle/_ref/libref_sceneprep.so; \
+	 else echo "no $(REF): keeping prebuilt oracle/_ref"; fi
+
+oracle/_ref/libref_sceneprep.so: oracle/ref_shim/ref_exports.cpp oracle/ref_shim/ref_pch.h
+	@mkdir -p oracle/_ref
+	$(CXX) -O2 -std=c++20 -fPIC -fvisibility=hidden -w -shared -o $@ \
+	    -include oracle/ref_shim/ref_pch.h -Ioracle/ref_shim -I$(REF)/src -I$(REF_GLM) -I$(REF_MESHOPT) \
+	    oracle/ref_shim/ref_exports.cpp $(REF_MESHOPT)/clusterizer.cpp $(REF_MESHOPT)/allocator.cpp $(LDFLAGS_SO)
+
+clean:
+	rm -f $(LIBDIR)/*.so oracle/*.so oracle/_ref/*.so
+
+.PHONY: all cuda host oracle ref clean

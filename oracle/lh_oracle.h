@@ -1,0 +1,94 @@
+/*
+ * lh_oracle.h -- CPU restatement of the reference's geometry pipeline.
+ *
+ * TEST INFRASTRUCTURE ONLY.  Nothing under lighthugger_b200/ may include,
+ * link or call this: only tests/, __graft_entry__.smoke() and bench.py's
+ * cpu_baseline / --impl reference legs use it, as the checker / CPU baseline.
+ *
+ * PARITY STATUS: "parity unpinned" by the reference -- the reference ships no
+ * tests, golden vectors or fixtures for this path and
+ * its GLSL cannot be executed in this image (no Vulkan loader / lavapipe /
+ * glslc).  What IS pinned against the reference: struct layouts and constants
+ * (include/lh_shared_cpu_gpu.h static_asserts), and the scene-prep inputs
+ * (meshlet bounds, bounding sphere) against the reference's own
+ * src/resources/meshlets.cpp + vendored meshoptimizer compiled into
+ * oracle/_ref (see oracle/Makefile, tests/golden/).
+ *
+ * The functions operate on the same byte layouts as the device path; every
+ * "address" field of LhUniforms / LhInstance / LhMeshInfo is a HOST pointer
+ * here.  Each function cites the reference file:line it follows.
+ *
+ * Pinned arithmetic model (the reference leaves these implementation-defined,
+ * SURVEY.md 8c): IEEE-754 binary32, round-to-nearest-even, no FMA contraction
+ * (build with -ffp-contract=off), mat4*vec4 = (c0*x + c1*y) + (c2*z + c3*w),
+ * mat3*vec3 = (c0*x + c1*y) + c2*z, dot = (ax*bx + ay*by) + az*bz,
+ * length = sqrt(dot(v,v)), normalize(v) = v / length(v) (true division),
+ * appends in ascending invocation order.
+ */
+#ifndef LH_ORACLE_H
+#define LH_ORACLE_H
+
+#include "lh_shared_cpu_gpu.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct LhoTexture {
+    const uint8_t* rgba8;   /* all mips, tightly packed, largest first */
+    uint32_t width, height, mip_levels;
+    uint32_t srgb;          /* decode sRGB -> linear on fetch (reference registers every BC texture as sRGB) */
+} LhoTexture;
+
+typedef struct LhoConfig {
+    uint32_t max_instances;
+    uint32_t max_opaque_draws;
+    uint32_t max_alpha_clip_draws;
+    uint32_t shadowmap_size;
+    uint32_t threads;            /* 0 = hardware_concurrency */
+    uint32_t instance_first;     /* sort-last partition: instances [first, first+count) */
+    uint32_t instance_count;     /* 0xFFFFFFFF = all */
+    const LhoTexture* textures;  /* bindless table, may be NULL */
+    uint32_t num_textures;
+    const float* skybox;         /* 6 faces RGBA32F or NULL */
+    uint32_t skybox_size;
+} LhoConfig;
+
+void lho_config_default(LhoConfig* cfg);
+
+/* reset_buffers_a (compute/reset_buffers.glsl:9-29) + reset_counters (common/util.glsl:61-70) */
+int lho_reset(const LhUniforms* u, const LhoConfig* cfg);
+/* cull_instances (cull_instances.comp:7-27) + prefix_sum_inclusive_append (common/prefix_sum.glsl:17-30),
+ * appends in ascending instance order */
+int lho_cull_instances(const LhUniforms* u, const LhoConfig* cfg);
+/* reset_buffers_b + write_draw_calls (write_draw_calls.comp:7-57) incl. get_meshlet_reference
+ * (common/util.glsl:42-59) and prefix_sum_binary_search (common/prefix_sum.glsl:33-46) */
+int lho_cull_meshlets(const LhUniforms* u, const LhoConfig* cfg);
+/* visbuffer_opaque_* / visbuffer_alpha_clip_* (rasterization.glsl:38-97) + fixed-function state
+ * (pipelines.cpp:10-25,67-71; rendering.cpp:195-266).  vis holds width*height packed keys and is cleared first. */
+int lho_raster_visbuffer(const LhUniforms* u, const LhoConfig* cfg, uint64_t* vis);
+/* read_depth (compute/read_depth.glsl:22-83) */
+int lho_reduce_depth(const LhUniforms* u, const LhoConfig* cfg, const uint64_t* vis);
+/* generate_shadow_matrices (compute/generate_shadow_matrices.glsl:15-110) */
+int lho_generate_shadow_matrices(const LhUniforms* u, const LhoConfig* cfg);
+/* cull_instances_shadows (cull_instances.comp:31-56) */
+int lho_cull_instances_shadows(const LhUniforms* u, const LhoConfig* cfg);
+/* reset_buffers_c + write_draw_calls_shadows (write_draw_calls.comp:61-117) + shadowmap_* raster
+ * (rasterization.glsl:101-145; pipelines.cpp:15-19,73-77; rendering.cpp:379-436).
+ * shadow holds 4 layers of shadowmap_size^2 floats; layer `cascade` is cleared to 1.0 and rendered. */
+int lho_shadow_cascade(const LhUniforms* u, const LhoConfig* cfg, uint32_t cascade, float* shadow);
+/* render_geometry main (render_geometry.comp:70-266); out = width*height RGBA32F (the device stores RGBA16F) */
+int lho_resolve(const LhUniforms* u, const LhoConfig* cfg, const uint64_t* vis, const float* shadow, float* out_rgba32f);
+/* steps 1-11 of rendering.cpp (reset ... resolve); out_rgba32f may be NULL to skip the resolve */
+int lho_render_frame(const LhUniforms* u, const LhoConfig* cfg, uint64_t* vis, float* shadow, float* out_rgba32f);
+
+/* sort-last composite: dst[i] = min(dst[i], src[i]) (new) */
+void lho_composite_min(uint64_t* dst, const uint64_t* src, uint64_t count);
+
+/* pinned pow used by generate_shadow_matrices (double arithmetic, identical op sequence on host and device) */
+float lho_pinned_powf(float x, float p);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,386 @@
+// CPU restatement of the lighting resolve (render_geometry.comp:70-266) and of
+// the texture sampling it and the alpha-clip raster need.  TEST INFRASTRUCTURE
+// -- see lh_oracle.h.  Floating-point output, compared with a tolerance (the
+// reference's texture filtering, rcp/pow/normalize precision and fp16 store are
+// implementation-defined).
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <vector>
+
+#include "lh_oracle.h"
+#include "lh_oracle_internal.hpp"
+
+namespace lho {
+
+static float srgb_to_linear(uint8_t v) {
+    static float table[256];
+    static bool init = false;
+    if (!init) {
+        for (int i = 0; i < 256; i++) {
+            float c = (float)i / 255.0f;
+            table[i] = c <= 0.04045f ? c / 12.92f : powf((c + 0.055f) / 1.055f, 2.4f);
+        }
+        init = true;
+    }
+    return table[v];
+}
+
+static void fetch_texel(const LhoTexture& t, uint32_t level, int x, int y, float out[4]) {
+    uint32_t w = std::max(1u, t.width >> level), h = std::max(1u, t.height >> level);
+    const uint8_t* base = t.rgba8;
+    for (uint32_t l = 0; l < level; l++) base += (uint64_t)std::max(1u, t.width >> l) * std::max(1u, t.height >> l) * 4;
+    // repeat addressing (repeat_sampler, src/main.cpp:550-560)
+    int xi = ((x % (int)w) + (int)w) % (int)w, yi = ((y % (int)h) + (int)h) % (int)h;
+    const uint8_t* px = base + ((uint64_t)yi * w + xi) * 4;
+    for (int c = 0; c < 3; c++) out[c] = t.srgb ? srgb_to_linear(px[c]) : (float)px[c] / 255.0f;
+    out[3] = (float)px[3] / 255.0f;
+}
+
+static void sample_bilinear_level(const LhoTexture& t, float u, float v, uint32_t level, float out[4]) {
+    uint32_t w = std::max(1u, t.width >> level), h = std::max(1u, t.height >> level);
+    float x = u * (float)w - 0.5f, y = v * (float)h - 0.5f;
+    float fx = floorf(x), fy = floorf(y);
+    float ax = x - fx, ay = y - fy;
+    int x0 = (int)fx, y0 = (int)fy;
+    float t00[4], t10[4], t01[4], t11[4];
+    fetch_texel(t, level, x0, y0, t00);
+    fetch_texel(t, level, x0 + 1, y0, t10);
+    fetch_texel(t, level, x0, y0 + 1, t01);
+    fetch_texel(t, level, x0 + 1, y0 + 1, t11);
+    for (int c = 0; c < 4; c++) {
+        float top = t00[c] + ax * (t10[c] - t00[c]);
+        float bot = t01[c] + ax * (t11[c] - t01[c]);
+        out[c] = top + ay * (bot - top);
+    }
+}
+
+void sample_texture_lod(const LhoTexture& t, float u, float v, float lod, float out[4]) {
+    // keep the wrapped coordinate small so the float texel address stays precise
+    u = u - floorf(u);
+    v = v - floorf(v);
+    float maxl = (float)(t.mip_levels - 1);
+    lod = fminf(fmaxf(lod, 0.0f), maxl);
+    uint32_t l0 = (uint32_t)floorf(lod);
+    float f = lod - (float)l0;
+    sample_bilinear_level(t, u, v, l0, out);
+    if (f > 0.0f && l0 + 1 < t.mip_levels) {
+        float hi[4];
+        sample_bilinear_level(t, u, v, l0 + 1, hi);
+        for (int c = 0; c < 4; c++) out[c] = out[c] + f * (hi[c] - out[c]);
+    }
+}
+
+// textureGrad with the reference's repeat_sampler: trilinear, anisotropy 16.
+// The Vulkan spec's anisotropic model: N = min(ceil(Pmax/Pmin), 16) probes
+// along the major axis, lod = log2(Pmax / N).
+static void sample_texture_grad(const LhoTexture& t, const float uv[2], const float dx[2], const float dy[2], float out[4]) {
+    float w = (float)t.width, h = (float)t.height;
+    float ax[2] = {dx[0] * w, dx[1] * h}, ay[2] = {dy[0] * w, dy[1] * h};
+    float px = sqrtf(ax[0] * ax[0] + ax[1] * ax[1]), py = sqrtf(ay[0] * ay[0] + ay[1] * ay[1]);
+    float pmax = fmaxf(px, py), pmin = fminf(px, py);
+    if (!(pmax > 0.0f) || !std::isfinite(pmax)) {
+        sample_texture_lod(t, uv[0], uv[1], 0.0f, out);
+        return;
+    }
+    float n = pmin > 0.0f ? fminf(ceilf(pmax / pmin), 16.0f) : 16.0f;
+    if (pmax <= 1.0f) n = 1.0f;  // magnification: a single bilinear probe
+    float lod = log2f(pmax / n);
+    int probes = (int)n;
+    const float* major = px >= py ? dx : dy;
+    float acc[4] = {0, 0, 0, 0};
+    for (int i = 0; i < probes; i++) {
+        float o = ((float)i + 0.5f) / (float)probes - 0.5f;
+        float s[4];
+        sample_texture_lod(t, uv[0] + o * major[0], uv[1] + o * major[1], lod, s);
+        for (int c = 0; c < 4; c++) acc[c] += s[c];
+    }
+    for (int c = 0; c < 4; c++) out[c] = acc[c] / (float)probes;
+}
+
+// textureLod(samplerCube, ray, 0): bilinear inside the selected face
+static void sample_skybox(const LhoConfig* cfg, V3 d, float out[3]) {
+    if (!cfg->skybox || cfg->skybox_size == 0) {
+        out[0] = out[1] = out[2] = 0.0f;
+        return;
+    }
+    float ax = fabsf(d.x), ay = fabsf(d.y), az = fabsf(d.z);
+    int face;
+    float sc, tc, ma;
+    if (ax >= ay && ax >= az) {
+        face = d.x >= 0 ? 0 : 1; ma = ax; sc = d.x >= 0 ? -d.z : d.z; tc = -d.y;
+    } else if (ay >= az) {
+        face = d.y >= 0 ? 2 : 3; ma = ay; sc = d.x; tc = d.y >= 0 ? d.z : -d.z;
+    } else {
+        face = d.z >= 0 ? 4 : 5; ma = az; sc = d.z >= 0 ? d.x : -d.x; tc = -d.y;
+    }
+    uint32_t n = cfg->skybox_size;
+    float u = 0.5f * (sc / ma + 1.0f), v = 0.5f * (tc / ma + 1.0f);
+    float x = u * (float)n - 0.5f, y = v * (float)n - 0.5f;
+    float fx = floorf(x), fy = floorf(y), wx = x - fx, wy = y - fy;
+    auto tex = [&](int xi, int yi, int c) {
+        xi = std::min(std::max(xi, 0), (int)n - 1);
+        yi = std::min(std::max(yi, 0), (int)n - 1);
+        return cfg->skybox[(((uint64_t)face * n + yi) * n + xi) * 4 + c];
+    };
+    for (int c = 0; c < 3; c++) {
+        float top = tex((int)fx, (int)fy, c) + wx * (tex((int)fx + 1, (int)fy, c) - tex((int)fx, (int)fy, c));
+        float bot = tex((int)fx, (int)fy + 1, c) + wx * (tex((int)fx + 1, (int)fy + 1, c) - tex((int)fx, (int)fy + 1, c));
+        out[c] = top + wy * (bot - top);
+    }
+}
+
+// sampler2DArrayShadow + shadowmap_comparison_sampler (src/main.cpp:569-581):
+// 4 texels, each compared `ref < texel`, bilinearly weighted, clamp to edge.
+static float sample_shadow(const float* layer, uint32_t n, float u, float v, float ref) {
+    float x = u * (float)n - 0.5f, y = v * (float)n - 0.5f;
+    float fx = floorf(x), fy = floorf(y), wx = x - fx, wy = y - fy;
+    auto cmp = [&](int xi, int yi) {
+        xi = std::min(std::max(xi, 0), (int)n - 1);
+        yi = std::min(std::max(yi, 0), (int)n - 1);
+        return ref < layer[(uint64_t)yi * n + xi] ? 1.0f : 0.0f;
+    };
+    if (!std::isfinite(x) || !std::isfinite(y)) return 0.0f;
+    fx = fminf(fmaxf(fx, -2.0f), (float)n + 1.0f);
+    fy = fminf(fmaxf(fy, -2.0f), (float)n + 1.0f);
+    float c00 = cmp((int)fx, (int)fy), c10 = cmp((int)fx + 1, (int)fy);
+    float c01 = cmp((int)fx, (int)fy + 1), c11 = cmp((int)fx + 1, (int)fy + 1);
+    float top = c00 + wx * (c10 - c00), bot = c01 + wx * (c11 - c01);
+    return top + wy * (bot - top);
+}
+
+struct Bary {
+    V3 lambda, ddx, ddy;
+};
+
+// CalcFullBary, common/vbuffer.glsl:11-63
+static Bary calc_full_bary(V4 p0, V4 p1, V4 p2, float ndc_x, float ndc_y, float win_w, float win_h) {
+    Bary r;
+    V3 invw{1.0f / p0.w, 1.0f / p1.w, 1.0f / p2.w};
+    float n0x = p0.x * invw.x, n0y = p0.y * invw.x;
+    float n1x = p1.x * invw.y, n1y = p1.y * invw.y;
+    float n2x = p2.x * invw.z, n2y = p2.y * invw.z;
+    // determinant(float2x2(ndc2 - ndc1, ndc0 - ndc1)): columns
+    float det = (n2x - n1x) * (n0y - n1y) - (n0x - n1x) * (n2y - n1y);
+    float inv_det = 1.0f / det;
+    r.ddx = V3{(n1y - n2y) * inv_det * invw.x, (n2y - n0y) * inv_det * invw.y, (n0y - n1y) * inv_det * invw.z};
+    r.ddy = V3{(n2x - n1x) * inv_det * invw.x, (n0x - n2x) * inv_det * invw.y, (n1x - n0x) * inv_det * invw.z};
+    float ddx_sum = r.ddx.x + r.ddx.y + r.ddx.z;
+    float ddy_sum = r.ddy.x + r.ddy.y + r.ddy.z;
+    float dvx = ndc_x - n0x, dvy = ndc_y - n0y;
+    float interp_inv_w = invw.x + dvx * ddx_sum + dvy * ddy_sum;
+    float interp_w = 1.0f / interp_inv_w;
+    r.lambda.x = interp_w * (invw.x + dvx * r.ddx.x + dvy * r.ddy.x);
+    r.lambda.y = interp_w * (0.0f + dvx * r.ddx.y + dvy * r.ddy.y);
+    r.lambda.z = interp_w * (0.0f + dvx * r.ddx.z + dvy * r.ddy.z);
+    float sx = 2.0f / win_w, sy = 2.0f / win_h;
+    r.ddx = V3{r.ddx.x * sx, r.ddx.y * sx, r.ddx.z * sx};
+    r.ddy = V3{r.ddy.x * sy, r.ddy.y * sy, r.ddy.z * sy};
+    ddx_sum *= sx;
+    ddy_sum *= sy;
+    r.ddy = V3{-r.ddy.x, -r.ddy.y, -r.ddy.z};
+    ddy_sum *= -1.0f;
+    float iw_ddx = 1.0f / (interp_inv_w + ddx_sum);
+    float iw_ddy = 1.0f / (interp_inv_w + ddy_sum);
+    r.ddx = V3{iw_ddx * (r.lambda.x * interp_inv_w + r.ddx.x) - r.lambda.x,
+               iw_ddx * (r.lambda.y * interp_inv_w + r.ddx.y) - r.lambda.y,
+               iw_ddx * (r.lambda.z * interp_inv_w + r.ddx.z) - r.lambda.z};
+    r.ddy = V3{iw_ddy * (r.lambda.x * interp_inv_w + r.ddy.x) - r.lambda.x,
+               iw_ddy * (r.lambda.y * interp_inv_w + r.ddy.y) - r.lambda.y,
+               iw_ddy * (r.lambda.z * interp_inv_w + r.ddy.z) - r.lambda.z};
+    return r;
+}
+
+struct Interp {
+    float value, dx, dy;
+};
+static Interp interp1(const Bary& b, float v0, float v1, float v2) {  // InterpolateWithDeriv, vbuffer.glsl:65-74
+    V3 m{v0, v1, v2};
+    return Interp{dot3(m, b.lambda), dot3(m, b.ddx), dot3(m, b.ddy)};
+}
+
+// common/pbr.glsl:3-96
+static const float kPi = 3.14159265358979323846f;
+static float f_schlick1(float u, float f0, float f90) { return f0 + (f90 - f0) * powf(1.0f - u, 5.0f); }
+static float fd_burley(float nov, float nol, float loh, float roughness) {
+    float f90 = 0.5f + 2.0f * roughness * loh * loh;
+    return f_schlick1(nol, 1.0f, f90) * f_schlick1(nov, 1.0f, f90) * (1.0f / kPi);
+}
+static float clampf(float x, float lo, float hi) { return fminf(fmaxf(x, lo), hi); }
+static void brdf(V3 v, V3 l, V3 n, float perceptual_roughness, float metallic, const float base[3], bool thin_walled, float out[3]) {
+    V3 h = normalize3(V3{v.x + l.x, v.y + l.y, v.z + l.z});
+    float diffuse[3], f0[3];
+    float refl = ((1.5f - 1.0f) / (1.5f + 1.0f)) * ((1.5f - 1.0f) / (1.5f + 1.0f));
+    for (int c = 0; c < 3; c++) {
+        diffuse[c] = (1.0f - metallic) * base[c];
+        f0[c] = refl * (1.0f - metallic) + base[c] * metallic;
+    }
+    float nov = clampf(dot3(n, v), 1e-5f, 1.0f);
+    float nol = clampf(dot3(n, l), 0.0f, 1.0f);
+    float noh = clampf(dot3(n, h), 0.0f, 1.0f);
+    float loh = clampf(dot3(l, h), 0.0f, 1.0f);
+    float roughness = perceptual_roughness * perceptual_roughness;
+    float a2 = roughness * roughness;
+    float f = (noh * a2 - noh) * noh + 1.0f;
+    float D = a2 / (kPi * f * f);
+    float ggxl = nov * sqrtf((-nol * a2 + nol) * nol + a2);
+    float ggxv = nol * sqrtf((-nov * a2 + nov) * nov + a2);
+    float V = 0.5f / (ggxv + ggxl);
+    float p5 = powf(1.0f - loh, 5.0f);
+    float burley = fd_burley(nov, nol, loh, roughness);
+    V3 nn{-n.x, -n.y, -n.z};
+    float rev_nov = clampf(dot3(nn, v), 1e-5f, 1.0f);
+    float rev_nol = clampf(dot3(nn, l), 0.0f, 1.0f);
+    float rev_burley = fd_burley(rev_nov, rev_nol, loh, roughness);
+    for (int c = 0; c < 3; c++) {
+        float F = f0[c] + (1.0f - f0[c]) * p5;
+        float fr = (D * V) * F;
+        float fd = diffuse[c] * burley;
+        float irr = (fd + fr) * nol;
+        irr = fmaxf(irr, 0.0f);
+        if (thin_walled) irr += diffuse[c] * rev_burley * rev_nol;
+        out[c] = std::isnan(irr) ? 0.0f : irr;
+    }
+}
+
+static void resolve_pixel(const LhUniforms* u, const LhoConfig* cfg, const uint64_t* vis, const float* shadow, uint32_t x,
+                          uint32_t y, float out[4]) {
+    const uint32_t W = u->window_size[0], H = u->window_size[1];
+    float ndc_x = (float)x / (float)W * 2.0f - 1.0f;  // pixel corner, render_geometry.comp:82-84
+    float ndc_y = (float)y / (float)H * 2.0f - 1.0f;
+    uint64_t key = vis[(uint64_t)y * W + x];
+    out[3] = 1.0f;
+    if (lh_vis_depth_bits(key) == 0) {  // depth == 0.0: sky, :86-101
+        V4 un = mat4_mul(u->perspective_inverse, V4{ndc_x, ndc_y, 0.0f, 1.0f});
+        V3 ray_local = normalize3(V3{un.x, un.y, un.z});
+        V4 ray = mat4_mul(u->view_inverse, V4{ray_local.x, ray_local.y, ray_local.z, 0.0f});
+        float s[3];
+        sample_skybox(cfg, V3{ray.x, ray.y, ray.z}, s);
+        for (int c = 0; c < 3; c++) out[c] = s[c] * 8.0f;  // pow(2, exposure = 3)
+        return;
+    }
+    uint32_t slot = lh_vis_slot(key), tri = lh_vis_tri(key);
+    const LhMeshletReference* refs = (const LhMeshletReference*)(uintptr_t)u->meshlet_references;
+    const LhInstance* instances = (const LhInstance*)(uintptr_t)u->instances;
+    const LhMiscStorage* misc = (const LhMiscStorage*)(uintptr_t)u->misc_storage;
+    LhMeshletReference ref = refs[slot];
+    const LhInstance* inst = &instances[ref.instance_index];
+    const LhMeshInfo* mi = (const LhMeshInfo*)(uintptr_t)inst->mesh_info_address;
+    const LhMeshlet* m = (const LhMeshlet*)(uintptr_t)mi->meshlets + ref.meshlet_index;
+    const uint8_t* micro = (const uint8_t*)(uintptr_t)mi->micro_indices + m->triangle_offset + 3 * tri;
+    bool wide = (mi->flags & LH_MESH_INFO_FLAGS_32_BIT_INDICES) != 0;
+    bool alpha = (mi->flags & LH_MESH_INFO_FLAGS_ALPHA_CLIP) != 0;
+    uint32_t idx[3];
+    for (int k = 0; k < 3; k++) {
+        uint32_t vi = m->index_offset + micro[k];
+        idx[k] = wide ? ((const uint32_t*)(uintptr_t)mi->indices)[vi] : ((const uint16_t*)(uintptr_t)mi->indices)[vi];
+    }
+    const uint16_t* positions = (const uint16_t*)(uintptr_t)mi->positions;
+    const uint16_t* uvs = (const uint16_t*)(uintptr_t)mi->uvs;
+    const int8_t* normals = (const int8_t*)(uintptr_t)mi->normals;
+    V3 pos[3];
+    V4 clip[3];
+    for (int k = 0; k < 3; k++) {
+        V4 p{(float)positions[3 * idx[k]], (float)positions[3 * idx[k] + 1], (float)positions[3 * idx[k] + 2], 1.0f};
+        V4 w = mat4_mul(inst->transform, p);
+        pos[k] = V3{w.x, w.y, w.z};
+        clip[k] = mat4_mul(u->combined_perspective_view, V4{w.x, w.y, w.z, 1.0f});
+    }
+    Bary bary = calc_full_bary(clip[0], clip[1], clip[2], ndc_x, ndc_y, (float)W, (float)H);
+    Interp wx = interp1(bary, pos[0].x, pos[1].x, pos[2].x);
+    Interp wy = interp1(bary, pos[0].y, pos[1].y, pos[2].y);
+    Interp wz = interp1(bary, pos[0].z, pos[1].z, pos[2].z);
+    V3 world{wx.value, wy.value, wz.value};
+    float tu[3], tv[3];
+    for (int k = 0; k < 3; k++) {
+        tu[k] = (float)uvs[2 * idx[k]] * mi->texture_scale[0];
+        tv[k] = (float)uvs[2 * idx[k] + 1] * mi->texture_scale[1];
+    }
+    Interp iu = interp1(bary, tu[0], tu[1], tu[2]);
+    Interp iv = interp1(bary, tv[0], tv[1], tv[2]);
+    float uv[2] = {iu.value + mi->texture_offset[0], iv.value + mi->texture_offset[1]};
+    float uv_dx[2] = {iu.dx, iv.dx}, uv_dy[2] = {iu.dy, iv.dy};
+
+    V3 view_vec = normalize3(V3{u->camera_pos[0] - world.x, u->camera_pos[1] - world.y, u->camera_pos[2] - world.z});
+    V3 nrm[3];
+    for (int k = 0; k < 3; k++)
+        nrm[k] = normalize3(V3{(float)normals[3 * idx[k]], (float)normals[3 * idx[k] + 1], (float)normals[3 * idx[k] + 2]});
+    V3 normal{interp1(bary, nrm[0].x, nrm[1].x, nrm[2].x).value, interp1(bary, nrm[0].y, nrm[1].y, nrm[2].y).value,
+              interp1(bary, nrm[0].z, nrm[1].z, nrm[2].z).value};
+    normal = normalize3(mat3_mul(inst->normal_transform, normal));
+    V3 e1{pos[1].x - pos[0].x, pos[1].y - pos[0].y, pos[1].z - pos[0].z};
+    V3 e2{pos[2].x - pos[0].x, pos[2].y - pos[0].y, pos[2].z - pos[0].z};
+    V3 gn = cross3(e1, e2);
+    if (dot3(gn, view_vec) < 0.0f) normal = V3{-normal.x, -normal.y, -normal.z};
+
+    // cascade selection, :183-196
+    uint32_t cascade;
+    V4 sc{0, 0, 0, 0};
+    for (cascade = 0; cascade < 4; cascade++) {
+        sc = mat4_mul(misc->uv_space_shadow_matrices[cascade], V4{world.x, world.y, world.z, 1.0f});
+        if (fabsf(sc.x - 0.5f) < 0.5f && fabsf(sc.y - 0.5f) < 0.5f) break;
+    }
+    float bias = alpha ? 0.000002f : 0.0f;
+    sc = V4{sc.x / sc.w, sc.y / sc.w, sc.z / sc.w, 1.0f};
+    uint32_t layer = std::min(cascade, 3u);
+    uint32_t sn = cfg->shadowmap_size;
+    const float* layer_ptr = shadow + (uint64_t)layer * sn * sn;
+    float shadow_sum = 0.0f;
+    for (int ox = -1; ox <= 1; ox++)
+        for (int oy = -1; oy <= 1; oy++)
+            shadow_sum += sample_shadow(layer_ptr, sn, sc.x + (float)ox / 1024.0f, sc.y + (float)oy / 1024.0f, sc.z - bias);
+    shadow_sum /= 9.0f;
+    if (sc.z > 1.0f) shadow_sum = 1.0f;
+
+    float base[3] = {1, 1, 1}, mr[4] = {1, 1, 1, 1};
+    auto texture_at = [&](uint16_t index) -> const LhoTexture* {
+        return (cfg->textures && index < cfg->num_textures) ? &cfg->textures[index] : nullptr;
+    };
+    if (const LhoTexture* t = texture_at(mi->base_color_texture_index)) {
+        float s[4];
+        sample_texture_grad(*t, uv, uv_dx, uv_dy, s);
+        for (int c = 0; c < 3; c++) base[c] = s[c];
+    }
+    for (int c = 0; c < 3; c++) base[c] *= mi->base_color_factor[c];
+    if (const LhoTexture* t = texture_at(mi->metallic_roughness_texture_index)) sample_texture_grad(*t, uv, uv_dx, uv_dy, mr);
+    float roughness = mr[1], metallic = mr[2];
+    if (mi->normal_texture_index != LH_UNUSED_TEXTURE_INDEX) {
+        if (const LhoTexture* t = texture_at(mi->normal_texture_index)) {
+            float s[4];
+            sample_texture_grad(*t, uv, uv_dx, uv_dy, s);
+            V3 mn{s[0] * 255.0f / 127.0f - 128.0f / 127.0f, s[1] * 255.0f / 127.0f - 128.0f / 127.0f,
+                  s[2] * 255.0f / 127.0f - 128.0f / 127.0f};
+            // compute_cotangent_frame, :25-38
+            V3 pdx{wx.dx, wy.dx, wz.dx}, pdy{wx.dy, wy.dy, wz.dy};
+            V3 dpy_perp = cross3(pdy, normal), dpx_perp = cross3(normal, pdx);
+            V3 t3{dpy_perp.x * uv_dx[0] + dpx_perp.x * uv_dy[0], dpy_perp.y * uv_dx[0] + dpx_perp.y * uv_dy[0],
+                  dpy_perp.z * uv_dx[0] + dpx_perp.z * uv_dy[0]};
+            V3 b3{dpy_perp.x * uv_dx[1] + dpx_perp.x * uv_dy[1], dpy_perp.y * uv_dx[1] + dpx_perp.y * uv_dy[1],
+                  dpy_perp.z * uv_dx[1] + dpx_perp.z * uv_dy[1]};
+            float invmax = 1.0f / sqrtf(fmaxf(dot3(t3, t3), dot3(b3, b3)));
+            V3 nn{(t3.x * invmax) * mn.x + (b3.x * invmax) * mn.y + normal.x * mn.z,
+                  (t3.y * invmax) * mn.x + (b3.y * invmax) * mn.y + normal.y * mn.z,
+                  (t3.z * invmax) * mn.x + (b3.z * invmax) * mn.y + normal.z * mn.z};
+            normal = normalize3(nn);
+        }
+    }
+    // ambient: SH with sh[0] = sh[2] = 0.025 (:40-57)
+    float amb = 0.025f + 0.025f * normal.y;
+    float sun[3];
+    brdf(view_vec, V3{u->sun_dir[0], u->sun_dir[1], u->sun_dir[2]}, normal, roughness, metallic, base, alpha, sun);
+    float sun_intensity = kPi * shadow_sum;
+    for (int c = 0; c < 3; c++) out[c] = sun[c] * sun_intensity + amb * ((1.0f - metallic) * base[c]);
+}
+
+}  // namespace lho
+
+using namespace lho;
+
+extern "C" int lho_resolve(const LhUniforms* u, const LhoConfig* cfg, const uint64_t* vis, const float* shadow, float* out) {
+    const uint32_t W = u->window_size[0], H = u->window_size[1];
+    parallel_for(H, thread_count(cfg), [&](uint64_t b, uint64_t e) {
+        for (uint64_t y = b; y < e; y++)
+            for (uint32_t x = 0; x < W; x++) resolve_pixel(u, cfg, vis, shadow, x, (uint32_t)y, out + ((uint64_t)y * W + x) * 4);
+    });
+    return 0;
+}
