@@ -16,8 +16,8 @@ HOST_HDRS := $(wildcard lighthugger_b200/host/*.hpp include/*.h)
 ORACLE_SRCS := $(wildcard oracle/*.cpp)
 ORACLE_HDRS := $(wildcard oracle/*.h oracle/*.hpp include/*.h)
 
-# -fmad=false: the pinned arithmetic model has no FMA contraction
-NVCCFLAGS := -gencode arch=compute_100a,code=sm_100a -O3 -std=c++20 -lineinfo -fmad=false \
+# the pinned arithmetic (no FMA contraction, IEEE div/sqrt) is written with explicit _rn intrinsics (lh_internal.cuh)
+NVCCFLAGS := -gencode arch=compute_100a,code=sm_100a -O3 -std=c++20 -lineinfo \
              -Xcompiler -fPIC,-fvisibility=hidden -Iinclude -Ilighthugger_b200/csrc
 LDFLAGS_SO := -Wl,--exclude-libs,ALL
 CXXFLAGS := -O2 -std=c++20 -fPIC -fvisibility=hidden -ffp-contract=off -Iinclude -Wall -Wextra -Wno-unused-parameter
@@ -28,9 +28,14 @@ cuda: $(LIBDIR)/liblighthugger_b200.so
 host: $(LIBDIR)/liblh_host.so
 oracle: oracle/liblh_oracle.so
 
-$(LIBDIR)/liblighthugger_b200.so: $(CUDA_SRCS) $(CUDA_HDRS)
+CUDA_OBJS := $(patsubst lighthugger_b200/csrc/%.cu,build/%.o,$(CUDA_SRCS))
+build/%.o: lighthugger_b200/csrc/%.cu $(CUDA_HDRS)
+	@mkdir -p build
+	$(NVCC) $(NVCCFLAGS) -c -o $@ $<
+
+$(LIBDIR)/liblighthugger_b200.so: $(CUDA_OBJS)
 	@mkdir -p $(LIBDIR)
-	$(NVCC) $(NVCCFLAGS) -shared -o $@ $(CUDA_SRCS) -lcudart -ldl
+	$(NVCC) -shared -o $@ $(CUDA_OBJS) -lcudart_static -ldl -lrt -lpthread
 
 $(LIBDIR)/liblh_host.so: $(HOST_SRCS) $(HOST_HDRS)
 	@mkdir -p $(LIBDIR)

@@ -1,0 +1,374 @@
+#!/usr/bin/env python
+"""Benchmark of the per-frame geometry pipeline (BASELINE.json metric: 4K
+visibility-buffer frames/s, culled Mtri/s, % HBM roofline).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c2]
+
+A step is one frame: reset -> instance cull + scan -> meshlet cull -> vis-buffer
+raster -> (composite) -> depth min/max -> cascade matrices -> shadow cull/raster x4
+-> lighting resolve (src/rendering.cpp steps 1-11) of BASELINE config 2
+(10 000 instances of a 100 000-triangle torus at 3840x2160).  `value` times the
+frame with every input resident in HBM (CUDA events on the context stream, L2
+flushed between frames); `e2e` times lh_render_frame_host: host Uniforms +
+host Instance array in, frame statistics out, copies inside the timed region.
+--impl reference times the CPU restatement of the reference (oracle/) on the
+host cores; it is a reported baseline, not the target.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for p in (ROOT, os.path.join(ROOT, "tests")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+import numpy as np  # noqa: E402
+
+METRIC = "visbuffer_frames_per_s"
+UNIT = "frames/s"
+WORKLOADS = {
+    "c1": "BASELINE config 1: 1000 x torus 20k tri, 1920x1080",
+    "c2": "BASELINE config 2: 10000 x torus 100k tri (1.0 G tri), 3840x2160, frustum+cone cull, vis-buffer, 4 cascades, lighting resolve",
+    "c4": "BASELINE config 4: ~100 M tri mixed meshes, 5% alpha-clip, BC7 textures, 3840x2160",
+    "c5": "BASELINE config 5: 10000 x torus 100k tri, 7680x4320",
+    "tiny": "unit-test scene",
+}
+
+
+def measured_peak():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device):
+        self.device = device
+        self.proc = None
+        self.path = None
+
+    def start(self):
+        try:
+            fd, self.path = tempfile.mkstemp(suffix=".csv")
+            os.close(fd)
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.device}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in open(self.path):
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for k, n in enumerate(names):
+                if f[5 + k].lower().startswith("active"):
+                    reasons.add(n)
+        os.unlink(self.path)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def dist_env():
+    return int(os.environ.get("RANK", 0)), int(os.environ.get("LOCAL_RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
+
+
+def build_scene(workload):
+    from lighthugger_b200.scene import Scene
+    return Scene.preset(workload)
+
+
+def scene_textures(scene, size):
+    from helpers import Textures
+    return Textures(scene, size) if scene.num_texture_sets else None
+
+
+# ---------------------------------------------------------------- reference arm / cpu baseline
+def cpu_frame_times(scene, tex, sky, sample_instances, threads=0):
+    """Times the oracle (CPU restatement of the reference) pass by pass on the first `sample_instances` instances at
+    the workload's full resolution.  Returns (seconds of instance-proportional passes, seconds of per-pixel passes)."""
+    from helpers import make_oracle
+    o = make_oracle(scene, textures=tex, skybox=sky, threads=threads, instance_range=(0, sample_instances))
+    t = {}
+
+    def run(name, fn):
+        t0 = time.perf_counter()
+        fn()
+        t[name] = time.perf_counter() - t0
+
+    run("reset", o.reset)
+    run("cull_instances", o.cull_instances)
+    run("cull_meshlets", o.cull_meshlets)
+    run("visbuffer", o.raster_visbuffer)
+    run("depth_reduction", o.reduce_depth)
+    run("shadow_matrices", o.generate_shadow_matrices)
+    run("cull_instances_shadows", o.cull_instances_shadows)
+    run("shadowmaps", lambda: [o.shadow_cascade(c) for c in range(4)])
+    run("render_geometry", o.resolve)
+    proportional = t["cull_instances"] + t["cull_meshlets"] + t["visbuffer"] + t["cull_instances_shadows"] + t["shadowmaps"]
+    fixed = t["reset"] + t["depth_reduction"] + t["shadow_matrices"] + t["render_geometry"]
+    return proportional, fixed, t
+
+
+def cpu_baseline(scene, tex, sky, budget_s):
+    """One bounded sample: instance subset sized from a calibration run so that the sample takes about `budget_s`."""
+    n = scene.num_instances
+    cores = os.cpu_count() or 1
+    probe = max(1, min(n, n // 100))
+    p, f, _ = cpu_frame_times(scene, tex, sky, probe)
+    per_instance = max(p / probe, 1e-9)
+    sample = int(max(probe, min(n, (budget_s - f) / per_instance)))
+    p, f, passes = cpu_frame_times(scene, tex, sky, sample)
+    full_frame_s = f + p * (n / sample)
+    return {
+        "value": 1.0 / full_frame_s, "unit": UNIT, "cores": cores, "kind": "port",
+        "sample": (f"oracle (CPU restatement of the reference; lavapipe not installed) on instances [0,{sample}) of {n} at full "
+                   f"resolution, all passes: {p + f:.2f} s measured; instance-proportional passes scaled x{n / sample:.2f}, "
+                   f"per-pixel passes as measured -> {full_frame_s:.2f} s/frame"),
+        "culled_mtri_per_s": scene.total_triangles / full_frame_s / 1e6,
+        "passes_s": {k: round(v, 4) for k, v in passes.items()},
+    }
+
+
+def run_reference(args):
+    rank, _, world = dist_env()
+    if rank != 0:
+        return
+    scene = build_scene(args.workload)
+    tex = scene_textures(scene, args.tex_size)
+    sky = scene.make_skybox(32)
+    total = max(1, args.steps + args.warmup)
+    budget = max(2.0, min(30.0, 150.0 / total))
+    times = []
+    base = None
+    for i in range(total):
+        base = cpu_baseline(scene, tex, sky, budget)
+        if i >= args.warmup:
+            times.append(1.0 / base["value"])
+    ms = 1e3 * float(np.mean(times))
+    value = 1e3 / ms
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "impl": "reference",
+        "config": {"workload": WORKLOADS[args.workload], "resolution": [scene.width, scene.height], "instances": scene.num_instances,
+                   "input_triangles": scene.total_triangles},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": base["cores"], "kind": base["kind"], "sample": base["sample"]},
+        "culled_mtri_per_s": scene.total_triangles / (ms / 1e3) / 1e6,
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------- our arm
+def run_ours(args):
+    import torch
+    from lighthugger_b200 import _structs as S
+    from helpers import make_context
+
+    rank, local_rank, world = dist_env()
+    n_gpus = world
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    scene = build_scene(args.workload)
+    tex = scene_textures(scene, args.tex_size)
+    sky = scene.make_skybox(32)
+    n = scene.num_instances
+    first, end = rank * n // world, (rank + 1) * n // world
+    caps = scene.default_capacities()
+    if world > 1:
+        # per-rank slot share: keys carry rank * slots_per_rank + local slot (25-bit field)
+        per_rank = -(-scene.total_meshlets // world)
+        caps = S.LhCapacities(max_instances=n, max_opaque_draws=per_rank + 1024, max_alpha_clip_draws=max(1024, per_rank // 8))
+    ctx = make_context(scene, textures=tex, skybox=sky, caps=caps, flags=S.LH_CONFIG_WRITE_DRAW_COMMANDS | S.LH_CONFIG_PASS_TIMINGS,
+                       device=local_rank)
+    if world > 1:
+        ids = [ctx.comm_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(ids, src=0)
+        ctx.comm_init(rank, world, ids[0])
+        ctx.set_instance_range(first, end - first)
+        # shadow cascades shard one per GPU (N=4); N=2: two each; N=8: a cascade per GPU pair, instance halves
+        ctx.set_shadow_cascade_mask(sum(1 << c for c in range(4) if c % min(world, 4) == rank % min(world, 4)))
+    u = ctx.uniforms()
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def frame_resident():
+        ctx.frame_begin(u)
+        ctx.render_frame()
+
+    # ---- warm-up (>= 3) ----
+    warm = max(3, args.warmup)
+    for _ in range(warm):
+        ctx.flush_l2()
+        frame_resident()
+    ctx.sync()
+    stats = ctx.stats()
+    launches_before = ctx.launch_count()
+
+    # ---- timed: device-resident frames, CUDA events on the context stream, L2 flushed between frames ----
+    sampler = ClockSampler(local_rank)
+    barrier()
+    sampler.start()
+    frame_ms, pass_ms = [], []
+    t_wall0 = time.perf_counter()
+    for _ in range(args.steps):
+        ctx.flush_l2()
+        ctx.timer_start()
+        frame_resident()
+        frame_ms.append(ctx.timer_stop())
+        pass_ms.append(ctx.timings())
+    barrier()
+    wall = time.perf_counter() - t_wall0
+    clocks = sampler.stop()
+    launches = (ctx.launch_count() - launches_before - args.steps) // max(1, args.steps)  # minus the L2 flush
+    total_ms = float(np.sum(frame_ms))
+    if dist:
+        t = torch.tensor([total_ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total_ms = float(t.item())
+    ms_per_step = total_ms / args.steps
+    value = 1e3 / ms_per_step
+
+    # ---- e2e: the public host call, host buffers in, stats out, copies inside the timed region ----
+    for _ in range(2):
+        ctx.render_frame_host(u)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        ctx.render_frame_host(u)
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    if dist:
+        t = torch.tensor([e2e_s], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t.item())
+    e2e_value = args.steps / e2e_s
+    h2d = C.sizeof(S.LhUniforms) + n * C.sizeof(S.LhInstance)
+    d2h = C.sizeof(S.LhFrameStats)
+
+    if rank != 0:
+        ctx.close()
+        if dist:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline: per-pass algorithmic bytes (SURVEY.md 8d / DESIGN.md) over the event-timed pass durations ----
+    peak, peak_src = measured_peak()
+    W, H = scene.width, scene.height
+    px = W * H
+    med = {k: float(np.median([p[k] for p in pass_ms])) for k in pass_ms[0]}
+    inst_here = end - first
+    avg_tris = scene.total_triangles / max(1, scene.total_meshlets)
+    survivors = stats.num_opaque + stats.num_alpha_clip
+    alg = {
+        "cull_instances": 112 * inst_here + 8 * stats.num_visible_instances,
+        "cull_meshlets": 56 * stats.num_candidate_meshlets + (8 + 16) * survivors + 8 * stats.num_visible_instances,
+        "depth_reduction": 8 * px,
+        "render_geometry": 16 * px,
+        # raster geometry fetch per rasterised meshlet: 56 + 3 tri + 2 idx + 6 pos per vertex + 64 B of instance transform
+        "raster_meshlets_kernel": survivors * (56 + 3 * avg_tris + (2 + 6) * 64 + 64),
+    }
+    passes = {}
+    for k, b in alg.items():
+        ms = med.get(k, 0.0)
+        if ms > 0:
+            passes[k] = {"ms": round(ms, 4), "alg_bytes": int(b), "gbs": round(b / ms / 1e6, 1), "frac": round(b / ms / 1e6 / peak, 4)}
+    kernel_share = {k: round(v / med["frame"], 4) for k, v in med.items() if k not in ("frame",) and med["frame"] > 0}
+    dom = "raster_meshlets_kernel"
+    roofline = {
+        "bound": "hbm", "kernel": "raster_meshlets_kernel<main view> (one warp per meshlet)",
+        "achieved": passes.get(dom, {}).get("gbs"), "peak": peak, "unit": "GB/s", "frac": passes.get(dom, {}).get("frac"),
+        "traffic": None, "peak_source": peak_src,
+        "note": "dominant kernel by time; it is issue/L2-atomic bound, not HBM bound (see DESIGN.md); HBM-bound passes under 'passes'",
+    }
+    cpu = None
+    if n_gpus == 1 and not args.no_cpu_baseline:
+        cpu = cpu_baseline(scene, tex, sky, budget_s=args.cpu_budget)
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": n_gpus, "steps": args.steps, "warmup": warm,
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic",
+        "config": {"workload": WORKLOADS[args.workload], "resolution": [W, H], "instances": n, "input_triangles": scene.total_triangles,
+                   "candidate_meshlets": scene.total_meshlets, "l2": "flushed between timed frames (256 MB write)",
+                   "parallelism": f"sort-last x{n_gpus}" if n_gpus > 1 else "single GPU", "texture_format": "BC7_SRGB",
+                   "texture_size": args.tex_size},
+        "culled_mtri_per_s": scene.total_triangles / (ms_per_step / 1e3) / 1e6,
+        "frame": {"visible_instances": stats.num_visible_instances, "candidate_meshlets": stats.num_candidate_meshlets,
+                  "rasterised_meshlets": survivors, "deferred_triangle_tiles": stats.num_large_triangles,
+                  "rasterised_triangles_nonempty": int(stats.rasterized_triangles)},
+        "pass_ms": {k: round(v, 4) for k, v in med.items()},
+        "pass_share": kernel_share,
+        "passes": passes,
+        "roofline": roofline,
+        "cpu_baseline": cpu,
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "call": "lh_render_frame_host (C ABI)"},
+        "gpu_launches": int(launches * args.steps),
+        "gpu_launches_per_frame": int(launches),
+        "clocks": clocks,
+        "wall_s_timed_region": round(wall, 3),
+    }
+    print(json.dumps(line), flush=True)
+    ctx.close()
+    if dist:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
+    ap.add_argument("--tex-size", type=int, default=256)
+    ap.add_argument("--cpu-budget", type=float, default=15.0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -119,7 +119,8 @@ enum {
 
 typedef struct LhPassTimes {
     float ms[LH_PASS_COUNT];
-    float frame_ms;   /* first pass start -> last pass end */
+    float frame_ms;                /* first pass start -> last pass end */
+    float raster_meshlets_kernel_ms; /* the main-view one-warp-per-meshlet raster kernel alone */
 } LhPassTimes;
 
 enum {
@@ -163,6 +164,9 @@ LH_API int lh_texture_destroy(LhContext* ctx, uint16_t slot);
 /* skybox cubemap, 6 faces (+X,-X,+Y,-Y,+Z,-Z) of size^2 RGBA32F texels
  * (the reference loads an RGB9E5 DDS cubemap, src/main.cpp:542-549). */
 LH_API int lh_skybox_create(LhContext* ctx, uint32_t size, const float* rgba32f_faces);
+/* display-transform LUT: size^3 RGB32F texels, x fastest (the reference loads the
+ * 48^3 RGB9E5 Tony McMapface DDS, src/main.cpp:534-541; decode on the host). */
+LH_API int lh_set_display_lut(LhContext* ctx, uint32_t size, const float* rgb32f);
 
 /* ---- render targets (replaces ResizingResources, src/frame_resources.h:7-73) ---- */
 LH_API int lh_targets_resize(LhContext* ctx, uint32_t width, uint32_t height);
@@ -170,19 +174,23 @@ LH_API int lh_targets_resize(LhContext* ctx, uint32_t width, uint32_t height);
 /* ---- sort-last partition (new; no reference counterpart).
  * The context culls and rasterises instances [first, first+count) only. ---- */
 LH_API int lh_set_instance_range(LhContext* ctx, uint32_t first, uint32_t count);
+/* cascades this context renders in lh_render_frame (bit c = cascade c; default 0xF).
+ * "One cascade per GPU" = mask 1 << rank; the layers are merged by lh_shadow_exchange. */
+LH_API int lh_set_shadow_cascade_mask(LhContext* ctx, uint32_t mask);
 
 /* ---- per frame (replaces uniform_buffer.flush + render() + submit + fence,
  * src/main.cpp:784-817).  One export per pass, in src/rendering.cpp order. ---- */
 LH_API int lh_frame_begin(LhContext* ctx, const LhUniforms* uniforms);          /* main.cpp:784 */
-LH_API int lh_reset(LhContext* ctx);                    /* reset_buffers_a, rendering.cpp:79; also clears the vis buffer (depth clear 0.0, :206-211) */
+LH_API int lh_reset(LhContext* ctx);                    /* reset_buffers_a, rendering.cpp:79 */
 LH_API int lh_cull_instances(LhContext* ctx);           /* cull_instances.comp:7-27, rendering.cpp:139-147 */
 LH_API int lh_cull_meshlets(LhContext* ctx);            /* reset_buffers_b + write_draw_calls.comp:7-57, rendering.cpp:156-183 */
-LH_API int lh_raster_visbuffer(LhContext* ctx);         /* rasterization.glsl:38-97 + fixed function, rendering.cpp:195-266 */
+LH_API int lh_raster_visbuffer(LhContext* ctx);         /* rasterization.glsl:38-97 + fixed function incl. the depth clear 0.0, rendering.cpp:195-266 */
 LH_API int lh_composite(LhContext* ctx);                /* new: sort-last u64-min over NCCL; no-op without lh_comm_init */
 LH_API int lh_reduce_depth(LhContext* ctx);             /* compute/read_depth.glsl:22-83, rendering.cpp:289-300 */
 LH_API int lh_generate_shadow_matrices(LhContext* ctx); /* compute/generate_shadow_matrices.glsl:15-110, rendering.cpp:302 */
 LH_API int lh_cull_instances_shadows(LhContext* ctx);   /* cull_instances.comp:31-56, rendering.cpp:304-312 */
 LH_API int lh_shadow_cascade(LhContext* ctx, uint32_t cascade); /* reset_buffers_c + write_draw_calls_shadows + shadowmap_*; rendering.cpp:325-438 */
+LH_API int lh_shadow_exchange(LhContext* ctx);          /* new: uint32-min merge of shadow layers over NCCL; no-op without lh_comm_init */
 LH_API int lh_resolve(LhContext* ctx);                  /* render_geometry.comp:70-266, rendering.cpp:462-474 */
 LH_API int lh_display_transform(LhContext* ctx);        /* display_transform.comp:37-81, rendering.cpp:491-502 */
 LH_API int lh_render_frame(LhContext* ctx);             /* all of the above in rendering.cpp order (display transform excluded) */
@@ -199,6 +207,7 @@ LH_API int lh_render_frame_host(LhContext* ctx, const LhUniforms* uniforms,
 LH_API int lh_get_frame_stats(LhContext* ctx, LhFrameStats* out);   /* synchronises */
 LH_API int lh_get_target(LhContext* ctx, int target, void* dst, uint64_t bytes);
 LH_API int lh_get_timings(LhContext* ctx, LhPassTimes* out);
+LH_API int lh_get_launch_count(LhContext* ctx, uint64_t* kernels_launched);   /* kernels this context has launched so far */
 LH_API int lh_get_target_address(LhContext* ctx, int target, uint64_t* dev_addr);
 /* time one span on the context stream (CUDA events): bench helpers */
 LH_API int lh_timer_start(LhContext* ctx);

@@ -114,7 +114,7 @@ class LhFrameStats(C.Structure):
 
 
 class LhPassTimes(C.Structure):
-    _fields_ = [("ms", f32 * LH_PASS_COUNT), ("frame_ms", f32)]
+    _fields_ = [("ms", f32 * LH_PASS_COUNT), ("frame_ms", f32), ("raster_meshlets_kernel_ms", f32)]
 
 
 # ---- include/lh_scene.h ----

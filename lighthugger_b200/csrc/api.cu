@@ -1,0 +1,698 @@
+// C ABI of the CUDA layer (include/lighthugger_b200.h): context, buffers,
+// textures, targets, the per-pass entry points in src/rendering.cpp order, and
+// readback.  There is no CPU fallback anywhere in this library.
+#include <cstdio>
+#include <cstring>
+#include <new>
+
+#include "lh_internal.cuh"
+
+using namespace lh;
+
+namespace {
+thread_local std::string g_create_error;
+}
+
+namespace lh {
+
+int fail(LhContext* ctx, int code, const char* what, cudaError_t e) {
+    std::string msg = what ? what : "";
+    if (e != cudaSuccess) {
+        msg += ": ";
+        msg += cudaGetErrorString(e);
+        if (e == cudaErrorMemoryAllocation) code = LH_ERR_OUT_OF_MEMORY;
+        cudaGetLastError();
+    }
+    if (ctx) ctx->error = msg;
+    else g_create_error = msg;
+    return code;
+}
+
+FrameParams make_params(LhContext* ctx) {
+    FrameParams p;
+    memset(&p, 0, sizeof(p));
+    p.u = ctx->uniforms;
+    p.max_instances = ctx->cfg.max_instances;
+    p.max_opaque = ctx->cfg.max_opaque_draws;
+    p.max_alpha = ctx->cfg.max_alpha_clip_draws;
+    uint32_t first = ctx->instance_first < p.u.num_instances ? ctx->instance_first : p.u.num_instances;
+    uint64_t end = (uint64_t)first + ctx->instance_count;
+    p.instance_first = first;
+    p.instance_end = (ctx->instance_count == 0xFFFFFFFFu || end > p.u.num_instances) ? p.u.num_instances : (uint32_t)end;
+    p.shadowmap_size = ctx->cfg.shadowmap_size;
+    p.flags = ctx->cfg.flags;
+    p.max_large = ctx->cfg.max_large_triangles;
+    p.state = ctx->state;
+    p.instance_tiles = ctx->instance_tiles;
+    p.meshlet_tiles = ctx->meshlet_tiles;
+    p.large_queue = ctx->large_queue;
+    p.vis = ctx->vis;
+    p.shadow = ctx->shadow;
+    p.textures = ctx->tex_dev;
+    p.slot_offset = ctx->slot_offset;
+    p.resolve_refs = ctx->gathered_refs ? (const LhMeshletReference*)ctx->gathered_refs : (const LhMeshletReference*)p.u.meshlet_references;
+    p.scene = ctx->scene;
+    p.display = ctx->display;
+    p.sky = ctx->sky_tex;
+    p.lut = ctx->lut_tex;
+    p.resolve_y0 = 0;
+    p.resolve_y1 = p.u.window_size[1];
+    return p;
+}
+
+}  // namespace lh
+
+namespace {
+
+struct PassScope {
+    LhContext* ctx;
+    int pass;
+    PassScope(LhContext* c, int p) : ctx(c), pass(p) {
+        if (ctx->cfg.flags & LH_CONFIG_PASS_TIMINGS) cudaEventRecord(ctx->pass_start[pass], ctx->stream);
+    }
+    ~PassScope() {
+        if (ctx->cfg.flags & LH_CONFIG_PASS_TIMINGS) {
+            cudaEventRecord(ctx->pass_stop[pass], ctx->stream);
+            ctx->pass_recorded[pass] = true;
+        }
+    }
+};
+
+int check_launch(LhContext* ctx, const char* what) {
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(ctx, LH_ERR_CUDA, what, e);
+    return LH_OK;
+}
+
+int require_frame(LhContext* ctx) {
+    if (!ctx) return LH_ERR_INVALID_ARGUMENT;
+    if (!ctx->have_uniforms) return fail(ctx, LH_ERR_NOT_READY, "lh_frame_begin has not been called");
+    return LH_OK;
+}
+
+int alloc_targets(LhContext* ctx, uint32_t w, uint32_t h) {
+    cudaFree(ctx->vis);
+    cudaFree(ctx->scene);
+    cudaFree(ctx->display);
+    cudaFree(ctx->depth_plane);
+    ctx->vis = nullptr;
+    ctx->scene = ctx->display = nullptr;
+    ctx->depth_plane = nullptr;
+    uint64_t px = (uint64_t)w * h;
+    if (px == 0) return fail(ctx, LH_ERR_INVALID_ARGUMENT, "zero-sized render target");
+    LH_CUDA(ctx, cudaMalloc(&ctx->vis, px * 8 + 16));
+    LH_CUDA(ctx, cudaMalloc(&ctx->scene, px * 8));
+    LH_CUDA(ctx, cudaMalloc(&ctx->display, px * 4));
+    LH_CUDA(ctx, cudaMalloc(&ctx->depth_plane, px * 4));
+    LH_CUDA(ctx, cudaMemset(ctx->vis, 0xFF, px * 8 + 16));
+    LH_CUDA(ctx, cudaMemset(ctx->scene, 0, px * 8));
+    LH_CUDA(ctx, cudaMemset(ctx->display, 0, px * 4));
+    ctx->cfg.width = w;
+    ctx->cfg.height = h;
+    return LH_OK;
+}
+
+int ensure_instance_tiles(LhContext* ctx, uint32_t num_instances) {
+    uint32_t tiles = (num_instances + kInstanceTile - 1) / kInstanceTile + 1;
+    if (tiles <= ctx->instance_tiles_per_sector) return LH_OK;
+    cudaStreamSynchronize(ctx->stream);
+    cudaFree(ctx->instance_tiles);
+    ctx->instance_tiles = nullptr;
+    LH_CUDA(ctx, cudaMalloc(&ctx->instance_tiles, (size_t)tiles * 4 * 8));
+    LH_CUDA(ctx, cudaMemset(ctx->instance_tiles, 0, (size_t)tiles * 4 * 8));
+    ctx->instance_tiles_per_sector = tiles;
+    return LH_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int lh_config_default(LhConfig* cfg) {
+    if (!cfg) return LH_ERR_INVALID_ARGUMENT;
+    memset(cfg, 0, sizeof(*cfg));
+    cfg->struct_size = sizeof(LhConfig);
+    cfg->device = 0;
+    cfg->max_instances = LH_MAX_INSTANCES;
+    cfg->max_opaque_draws = LH_MAX_OPAQUE_DRAWS;
+    cfg->max_alpha_clip_draws = LH_MAX_ALPHA_CLIP_DRAWS;
+    cfg->width = 640;   // src/main.cpp:103-106
+    cfg->height = 480;
+    cfg->shadowmap_size = LH_SHADOWMAP_SIZE;
+    cfg->flags = LH_CONFIG_WRITE_DRAW_COMMANDS;
+    cfg->max_large_triangles = 1u << 22;
+    return LH_OK;
+}
+
+int lh_buffer_sizes(const LhConfig* cfg, LhBufferSizes* out) {
+    if (!cfg || !out) return LH_ERR_INVALID_ARGUMENT;
+    uint64_t draws = (uint64_t)cfg->max_opaque_draws + cfg->max_alpha_clip_draws;
+    out->meshlet_references = 8 * draws * 2;
+    out->num_meshlets_prefix_sum = ((uint64_t)cfg->max_instances * 8 + 8) * 4;
+    out->draw_calls = 8 + 16 * draws;
+    out->dispatches = 12 * 3;
+    out->misc_storage = sizeof(LhMiscStorage);
+    out->uniforms = sizeof(LhUniforms);
+    return LH_OK;
+}
+
+const char* lh_version(void) { return "lighthugger_b200 0.1 (sm_100a)"; }
+
+const char* lh_last_error(const LhContext* ctx) { return ctx ? ctx->error.c_str() : g_create_error.c_str(); }
+
+int lh_context_create(const LhConfig* cfg, LhContext** out) {
+    if (!cfg || !out || cfg->struct_size != sizeof(LhConfig)) return fail(nullptr, LH_ERR_INVALID_ARGUMENT, "bad LhConfig");
+    if ((uint64_t)cfg->max_opaque_draws + cfg->max_alpha_clip_draws > LH_VIS_MAX_SLOTS)
+        return fail(nullptr, LH_ERR_INVALID_ARGUMENT, "max_opaque_draws + max_alpha_clip_draws exceeds the 25-bit slot field");
+    if (cfg->max_instances == 0 || cfg->shadowmap_size == 0) return fail(nullptr, LH_ERR_INVALID_ARGUMENT, "zero capacity");
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0) return fail(nullptr, LH_ERR_NO_DEVICE, "no CUDA device (there is no CPU fallback)", e);
+    if (cfg->device < 0 || cfg->device >= count) return fail(nullptr, LH_ERR_NO_DEVICE, "device ordinal out of range");
+    if ((e = cudaSetDevice(cfg->device)) != cudaSuccess) return fail(nullptr, LH_ERR_CUDA, "cudaSetDevice", e);
+    LhContext* ctx = new (std::nothrow) LhContext();
+    if (!ctx) return fail(nullptr, LH_ERR_OUT_OF_MEMORY, "host allocation");
+    ctx->device = cfg->device;
+    ctx->cfg = *cfg;
+    cudaDeviceProp prop;
+    cudaGetDeviceProperties(&prop, cfg->device);
+    ctx->num_sms = prop.multiProcessorCount;
+    auto bail = [&](int rc) {
+        g_create_error = ctx->error;
+        lh_context_destroy(ctx);
+        return rc;
+    };
+#define TRY(expr)                                                              \
+    do {                                                                       \
+        cudaError_t _e = (expr);                                               \
+        if (_e != cudaSuccess) return bail(fail(ctx, LH_ERR_CUDA, #expr, _e)); \
+    } while (0)
+    TRY(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+    int rc = alloc_targets(ctx, cfg->width, cfg->height);
+    if (rc) return bail(rc);
+    size_t shadow_bytes = (size_t)4 * cfg->shadowmap_size * cfg->shadowmap_size * 4;
+    TRY(cudaMalloc(&ctx->shadow, shadow_bytes));
+    TRY(cudaMemset(ctx->shadow, 0, shadow_bytes));
+    TRY(cudaMalloc(&ctx->state, sizeof(FrameState)));
+    TRY(cudaMemset(ctx->state, 0, sizeof(FrameState)));
+    TRY(cudaMalloc(&ctx->meshlet_tiles, kMaxMeshletTiles * 8));
+    TRY(cudaMemset(ctx->meshlet_tiles, 0, kMaxMeshletTiles * 8));
+    TRY(cudaMalloc(&ctx->large_queue, (size_t)(cfg->max_large_triangles ? cfg->max_large_triangles : 1) * 8));
+    TRY(cudaMalloc(&ctx->tex_dev, sizeof(cudaTextureObject_t) * LH_MAX_TEXTURES));
+    TRY(cudaMemset(ctx->tex_dev, 0, sizeof(cudaTextureObject_t) * LH_MAX_TEXTURES));
+    TRY(cudaMallocHost(&ctx->pinned_stats, sizeof(LhFrameStats)));
+    for (int i = 0; i < LH_PASS_COUNT; i++) {
+        TRY(cudaEventCreate(&ctx->pass_start[i]));
+        TRY(cudaEventCreate(&ctx->pass_stop[i]));
+    }
+    TRY(cudaEventCreate(&ctx->timer_a));
+    TRY(cudaEventCreate(&ctx->timer_b));
+    TRY(cudaEventCreate(&ctx->raster_kernel_a));
+    TRY(cudaEventCreate(&ctx->raster_kernel_b));
+    rc = ensure_instance_tiles(ctx, cfg->max_instances);
+    if (rc) return bail(rc);
+#undef TRY
+    *out = ctx;
+    return LH_OK;
+}
+
+int lh_context_destroy(LhContext* ctx) {
+    if (!ctx) return LH_OK;
+    cudaSetDevice(ctx->device);
+    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    lh_comm_destroy(ctx);
+    for (uint32_t i = 0; i < LH_MAX_TEXTURES; i++) {
+        if (ctx->tex_host[i]) cudaDestroyTextureObject(ctx->tex_host[i]);
+        if (ctx->tex_arrays[i]) cudaFreeMipmappedArray(ctx->tex_arrays[i]);
+    }
+    if (ctx->sky_tex) cudaDestroyTextureObject(ctx->sky_tex);
+    if (ctx->sky_array) cudaFreeArray(ctx->sky_array);
+    if (ctx->lut_tex) cudaDestroyTextureObject(ctx->lut_tex);
+    if (ctx->lut_array) cudaFreeArray(ctx->lut_array);
+    for (void* b : ctx->buffers) cudaFree(b);
+    cudaFree(ctx->vis);
+    cudaFree(ctx->scene);
+    cudaFree(ctx->display);
+    cudaFree(ctx->depth_plane);
+    cudaFree(ctx->shadow);
+    cudaFree(ctx->state);
+    cudaFree(ctx->instance_tiles);
+    cudaFree(ctx->meshlet_tiles);
+    cudaFree(ctx->large_queue);
+    cudaFree(ctx->tex_dev);
+    cudaFree(ctx->l2_flush);
+    cudaFree(ctx->gathered_refs);
+    if (ctx->pinned) cudaFreeHost(ctx->pinned);
+    if (ctx->pinned_stats) cudaFreeHost(ctx->pinned_stats);
+    for (int i = 0; i < LH_PASS_COUNT; i++) {
+        if (ctx->pass_start[i]) cudaEventDestroy(ctx->pass_start[i]);
+        if (ctx->pass_stop[i]) cudaEventDestroy(ctx->pass_stop[i]);
+    }
+    if (ctx->timer_a) cudaEventDestroy(ctx->timer_a);
+    if (ctx->timer_b) cudaEventDestroy(ctx->timer_b);
+    if (ctx->raster_kernel_a) cudaEventDestroy(ctx->raster_kernel_a);
+    if (ctx->raster_kernel_b) cudaEventDestroy(ctx->raster_kernel_b);
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+    return LH_OK;
+}
+
+// ---- buffers ----
+int lh_buffer_alloc(LhContext* ctx, uint64_t bytes, uint64_t* dev_addr) {
+    if (!ctx || !dev_addr) return LH_ERR_INVALID_ARGUMENT;
+    void* p = nullptr;
+    LH_CUDA(ctx, cudaMalloc(&p, bytes ? bytes : 16));
+    LH_CUDA(ctx, cudaMemsetAsync(p, 0, bytes ? bytes : 16, ctx->stream));
+    ctx->buffers.push_back(p);
+    *dev_addr = (uint64_t)(uintptr_t)p;
+    return LH_OK;
+}
+
+int lh_buffer_free(LhContext* ctx, uint64_t dev_addr) {
+    if (!ctx) return LH_ERR_INVALID_ARGUMENT;
+    void* p = (void*)(uintptr_t)dev_addr;
+    for (size_t i = 0; i < ctx->buffers.size(); i++)
+        if (ctx->buffers[i] == p) {
+            cudaStreamSynchronize(ctx->stream);
+            cudaFree(p);
+            ctx->buffers[i] = ctx->buffers.back();
+            ctx->buffers.pop_back();
+            return LH_OK;
+        }
+    return fail(ctx, LH_ERR_INVALID_ARGUMENT, "lh_buffer_free: unknown address");
+}
+
+int lh_upload(LhContext* ctx, uint64_t dev_addr, const void* src, uint64_t bytes) {
+    if (!ctx || (!src && bytes)) return LH_ERR_INVALID_ARGUMENT;
+    if (!bytes) return LH_OK;
+    LH_CUDA(ctx, cudaMemcpyAsync((void*)(uintptr_t)dev_addr, src, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    LH_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // no host pointer is retained past the call
+    return LH_OK;
+}
+
+int lh_download(LhContext* ctx, uint64_t dev_addr, void* dst, uint64_t bytes) {
+    if (!ctx || (!dst && bytes)) return LH_ERR_INVALID_ARGUMENT;
+    if (!bytes) return LH_OK;
+    LH_CUDA(ctx, cudaMemcpyAsync(dst, (const void*)(uintptr_t)dev_addr, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    LH_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return LH_OK;
+}
+
+// ---- textures ----
+int lh_texture_create(LhContext* ctx, int format, uint32_t width, uint32_t height, uint32_t mip_levels, const void* data,
+                      uint64_t bytes, uint16_t* slot_out) {
+    if (!ctx || !data || !slot_out || !width || !height || !mip_levels) return LH_ERR_INVALID_ARGUMENT;
+    uint32_t slot = 0;
+    while (slot < LH_MAX_TEXTURES && ctx->tex_host[slot]) slot++;
+    if (slot == LH_MAX_TEXTURES) return fail(ctx, LH_ERR_CAPACITY, "all 512 bindless texture slots are in use");
+    cudaChannelFormatDesc desc;
+    bool block = false, srgb = false;
+    switch (format) {
+    case LH_TEXTURE_RGBA8_SRGB: desc = cudaCreateChannelDesc<uchar4>(); srgb = true; break;
+    case LH_TEXTURE_RGBA8_UNORM: desc = cudaCreateChannelDesc<uchar4>(); break;
+    case LH_TEXTURE_BC7_SRGB: desc = cudaCreateChannelDesc<cudaChannelFormatKindUnsignedBlockCompressed7SRGB>(); block = true; break;
+    case LH_TEXTURE_BC1_SRGB: desc = cudaCreateChannelDesc<cudaChannelFormatKindUnsignedBlockCompressed1SRGB>(); block = true; break;
+    default: return fail(ctx, LH_ERR_UNSUPPORTED, "unknown texture format");
+    }
+    const uint32_t block_bytes = format == LH_TEXTURE_BC1_SRGB ? 8 : 16;
+    uint64_t need = 0;
+    for (uint32_t l = 0; l < mip_levels; l++) {
+        uint32_t w = width >> l ? width >> l : 1, h = height >> l ? height >> l : 1;
+        need += block ? (uint64_t)((w + 3) / 4) * ((h + 3) / 4) * block_bytes : (uint64_t)w * h * 4;
+    }
+    if (bytes < need) return fail(ctx, LH_ERR_INVALID_ARGUMENT, "texture data is smaller than its mip chain");
+    cudaMipmappedArray_t arr = nullptr;
+    LH_CUDA(ctx, cudaMallocMipmappedArray(&arr, &desc, make_cudaExtent(width, height, 0), mip_levels));
+    const uint8_t* src = (const uint8_t*)data;
+    for (uint32_t l = 0; l < mip_levels; l++) {
+        uint32_t w = width >> l ? width >> l : 1, h = height >> l ? height >> l : 1;
+        cudaArray_t level;
+        cudaError_t e = cudaGetMipmappedArrayLevel(&level, arr, l);
+        size_t row_bytes = block ? (size_t)((w + 3) / 4) * block_bytes : (size_t)w * 4;
+        size_t rows = block ? (h + 3) / 4 : h;
+        if (e == cudaSuccess) e = cudaMemcpy2DToArray(level, 0, 0, src, row_bytes, row_bytes, rows, cudaMemcpyHostToDevice);
+        if (e != cudaSuccess) {
+            cudaFreeMipmappedArray(arr);
+            return fail(ctx, LH_ERR_CUDA, "texture level upload", e);
+        }
+        src += row_bytes * rows;
+    }
+    // repeat_sampler (src/main.cpp:550-560): linear mag/min/mip, repeat, anisotropy 16
+    cudaResourceDesc res{};
+    res.resType = cudaResourceTypeMipmappedArray;
+    res.res.mipmap.mipmap = arr;
+    cudaTextureDesc td{};
+    td.addressMode[0] = td.addressMode[1] = td.addressMode[2] = cudaAddressModeWrap;
+    td.filterMode = cudaFilterModeLinear;
+    td.mipmapFilterMode = cudaFilterModeLinear;
+    td.readMode = cudaReadModeNormalizedFloat;
+    td.normalizedCoords = 1;
+    td.maxAnisotropy = 16;
+    td.minMipmapLevelClamp = 0.0f;
+    td.maxMipmapLevelClamp = (float)(mip_levels - 1);
+    td.sRGB = srgb ? 1 : 0;
+    cudaTextureObject_t tex = 0;
+    cudaError_t e = cudaCreateTextureObject(&tex, &res, &td, nullptr);
+    if (e != cudaSuccess) {
+        cudaFreeMipmappedArray(arr);
+        return fail(ctx, LH_ERR_CUDA, "cudaCreateTextureObject", e);
+    }
+    ctx->tex_host[slot] = tex;
+    ctx->tex_arrays[slot] = arr;
+    LH_CUDA(ctx, cudaMemcpyAsync(ctx->tex_dev + slot, &ctx->tex_host[slot], sizeof(tex), cudaMemcpyHostToDevice, ctx->stream));
+    LH_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    *slot_out = (uint16_t)slot;
+    return LH_OK;
+}
+
+int lh_texture_destroy(LhContext* ctx, uint16_t slot) {
+    if (!ctx || slot >= LH_MAX_TEXTURES || !ctx->tex_host[slot]) return LH_ERR_INVALID_ARGUMENT;
+    cudaStreamSynchronize(ctx->stream);
+    cudaDestroyTextureObject(ctx->tex_host[slot]);
+    cudaFreeMipmappedArray(ctx->tex_arrays[slot]);
+    ctx->tex_host[slot] = 0;
+    ctx->tex_arrays[slot] = nullptr;
+    LH_CUDA(ctx, cudaMemsetAsync(ctx->tex_dev + slot, 0, sizeof(cudaTextureObject_t), ctx->stream));
+    return LH_OK;
+}
+
+int lh_skybox_create(LhContext* ctx, uint32_t size, const float* faces) {
+    if (!ctx || !size || !faces) return LH_ERR_INVALID_ARGUMENT;
+    cudaStreamSynchronize(ctx->stream);
+    if (ctx->sky_tex) cudaDestroyTextureObject(ctx->sky_tex);
+    if (ctx->sky_array) cudaFreeArray(ctx->sky_array);
+    ctx->sky_tex = 0;
+    ctx->sky_array = nullptr;
+    cudaChannelFormatDesc desc = cudaCreateChannelDesc<float4>();
+    LH_CUDA(ctx, cudaMalloc3DArray(&ctx->sky_array, &desc, make_cudaExtent(size, size, 6), cudaArrayCubemap));
+    cudaMemcpy3DParms cp{};
+    cp.srcPtr = make_cudaPitchedPtr((void*)faces, (size_t)size * 16, size, size);
+    cp.dstArray = ctx->sky_array;
+    cp.extent = make_cudaExtent(size, size, 6);
+    cp.kind = cudaMemcpyHostToDevice;
+    LH_CUDA(ctx, cudaMemcpy3D(&cp));
+    cudaResourceDesc res{};
+    res.resType = cudaResourceTypeArray;
+    res.res.array.array = ctx->sky_array;
+    cudaTextureDesc td{};
+    td.addressMode[0] = td.addressMode[1] = td.addressMode[2] = cudaAddressModeClamp;
+    td.filterMode = cudaFilterModeLinear;
+    td.readMode = cudaReadModeElementType;
+    td.normalizedCoords = 1;
+    LH_CUDA(ctx, cudaCreateTextureObject(&ctx->sky_tex, &res, &td, nullptr));
+    return LH_OK;
+}
+
+int lh_set_display_lut(LhContext* ctx, uint32_t size, const float* rgb) {
+    if (!ctx || !size || !rgb) return LH_ERR_INVALID_ARGUMENT;
+    cudaStreamSynchronize(ctx->stream);
+    if (ctx->lut_tex) cudaDestroyTextureObject(ctx->lut_tex);
+    if (ctx->lut_array) cudaFreeArray(ctx->lut_array);
+    ctx->lut_tex = 0;
+    ctx->lut_array = nullptr;
+    std::vector<float> rgba((size_t)size * size * size * 4);
+    for (size_t i = 0; i < (size_t)size * size * size; i++) {
+        rgba[4 * i] = rgb[3 * i];
+        rgba[4 * i + 1] = rgb[3 * i + 1];
+        rgba[4 * i + 2] = rgb[3 * i + 2];
+        rgba[4 * i + 3] = 1.0f;
+    }
+    cudaChannelFormatDesc desc = cudaCreateChannelDesc<float4>();
+    LH_CUDA(ctx, cudaMalloc3DArray(&ctx->lut_array, &desc, make_cudaExtent(size, size, size), 0));
+    cudaMemcpy3DParms cp{};
+    cp.srcPtr = make_cudaPitchedPtr(rgba.data(), (size_t)size * 16, size, size);
+    cp.dstArray = ctx->lut_array;
+    cp.extent = make_cudaExtent(size, size, size);
+    cp.kind = cudaMemcpyHostToDevice;
+    LH_CUDA(ctx, cudaMemcpy3D(&cp));
+    cudaResourceDesc res{};
+    res.resType = cudaResourceTypeArray;
+    res.res.array.array = ctx->lut_array;
+    cudaTextureDesc td{};  // clamp_sampler (src/main.cpp:561-568)
+    td.addressMode[0] = td.addressMode[1] = td.addressMode[2] = cudaAddressModeClamp;
+    td.filterMode = cudaFilterModeLinear;
+    td.readMode = cudaReadModeElementType;
+    td.normalizedCoords = 1;
+    LH_CUDA(ctx, cudaCreateTextureObject(&ctx->lut_tex, &res, &td, nullptr));
+    return LH_OK;
+}
+
+int lh_targets_resize(LhContext* ctx, uint32_t width, uint32_t height) {
+    if (!ctx) return LH_ERR_INVALID_ARGUMENT;
+    cudaStreamSynchronize(ctx->stream);
+    return alloc_targets(ctx, width, height);
+}
+
+int lh_set_instance_range(LhContext* ctx, uint32_t first, uint32_t count) {
+    if (!ctx) return LH_ERR_INVALID_ARGUMENT;
+    ctx->instance_first = first;
+    ctx->instance_count = count;
+    return LH_OK;
+}
+
+int lh_set_shadow_cascade_mask(LhContext* ctx, uint32_t mask) {
+    if (!ctx) return LH_ERR_INVALID_ARGUMENT;
+    ctx->cascade_mask = mask & 0xFu;
+    return LH_OK;
+}
+
+// ---- per frame ----
+int lh_frame_begin(LhContext* ctx, const LhUniforms* u) {
+    if (!ctx || !u) return LH_ERR_INVALID_ARGUMENT;
+    if (u->window_size[0] != ctx->cfg.width || u->window_size[1] != ctx->cfg.height)
+        return fail(ctx, LH_ERR_INVALID_ARGUMENT, "uniforms.window_size differs from the render targets (call lh_targets_resize)");
+    if (!u->instances || !u->meshlet_references || !u->draw_calls || !u->misc_storage || !u->num_meshlets_prefix_sum || !u->dispatches)
+        return fail(ctx, LH_ERR_INVALID_ARGUMENT, "uniforms carry a null buffer address");
+    ctx->uniforms = *u;
+    ctx->have_uniforms = true;
+    for (int i = 0; i < LH_PASS_COUNT; i++) ctx->pass_recorded[i] = false;
+    ctx->raster_kernel_recorded = false;
+    return ensure_instance_tiles(ctx, u->num_instances);
+}
+
+int lh_reset(LhContext* ctx) {
+    if (int rc = require_frame(ctx)) return rc;
+    PassScope scope(ctx, LH_PASS_RESET);
+    launch_reset(ctx, make_params(ctx));
+    return check_launch(ctx, "reset");
+}
+
+int lh_cull_instances(LhContext* ctx) {
+    if (int rc = require_frame(ctx)) return rc;
+    PassScope scope(ctx, LH_PASS_CULL_INSTANCES);
+    launch_cull_instances(ctx, make_params(ctx), false);
+    return check_launch(ctx, "cull_instances");
+}
+
+int lh_cull_meshlets(LhContext* ctx) {
+    if (int rc = require_frame(ctx)) return rc;
+    PassScope scope(ctx, LH_PASS_CULL_MESHLETS);
+    launch_cull_meshlets(ctx, make_params(ctx), -1);
+    return check_launch(ctx, "cull_meshlets");
+}
+
+int lh_raster_visbuffer(LhContext* ctx) {
+    if (int rc = require_frame(ctx)) return rc;
+    PassScope scope(ctx, LH_PASS_VISBUFFER);
+    // render-pass begin: depth clear 0.0 (rendering.cpp:206-211) == all-ones key
+    launch_fill_u64(ctx, ctx->vis, (uint64_t)ctx->cfg.width * ctx->cfg.height, LH_VIS_CLEAR);
+    launch_raster(ctx, make_params(ctx), -1);
+    return check_launch(ctx, "raster_visbuffer");
+}
+
+int lh_composite(LhContext* ctx) {
+    if (int rc = require_frame(ctx)) return rc;
+    if (!ctx->nccl_comm || ctx->nranks <= 1) return LH_OK;
+    PassScope scope(ctx, LH_PASS_COMPOSITE);
+    return composite_allreduce_min(ctx);
+}
+
+int lh_reduce_depth(LhContext* ctx) {
+    if (int rc = require_frame(ctx)) return rc;
+    PassScope scope(ctx, LH_PASS_DEPTH_REDUCTION);
+    launch_reduce_depth(ctx, make_params(ctx));
+    return check_launch(ctx, "reduce_depth");
+}
+
+int lh_generate_shadow_matrices(LhContext* ctx) {
+    if (int rc = require_frame(ctx)) return rc;
+    PassScope scope(ctx, LH_PASS_SHADOW_MATRICES);
+    launch_shadow_matrices(ctx, make_params(ctx));
+    return check_launch(ctx, "generate_shadow_matrices");
+}
+
+int lh_cull_instances_shadows(LhContext* ctx) {
+    if (int rc = require_frame(ctx)) return rc;
+    PassScope scope(ctx, LH_PASS_CULL_INSTANCES_SHADOWS);
+    launch_cull_instances(ctx, make_params(ctx), true);
+    return check_launch(ctx, "cull_instances_shadows");
+}
+
+int lh_shadow_cascade(LhContext* ctx, uint32_t cascade) {
+    if (int rc = require_frame(ctx)) return rc;
+    if (cascade >= 4) return fail(ctx, LH_ERR_INVALID_ARGUMENT, "cascade index out of range");
+    FrameParams p = make_params(ctx);
+    launch_cull_meshlets(ctx, p, (int)cascade);
+    size_t texels = (size_t)ctx->cfg.shadowmap_size * ctx->cfg.shadowmap_size;
+    launch_fill_u32(ctx, ctx->shadow + texels * cascade, texels, 0x3F800000u);  // clear 1.0, rendering.cpp:384
+    launch_raster(ctx, p, (int)cascade);
+    return check_launch(ctx, "shadow_cascade");
+}
+
+int lh_resolve(LhContext* ctx) {
+    if (int rc = require_frame(ctx)) return rc;
+    PassScope scope(ctx, LH_PASS_RENDER_GEOMETRY);
+    launch_resolve(ctx, make_params(ctx));
+    return check_launch(ctx, "resolve");
+}
+
+int lh_display_transform(LhContext* ctx) {
+    if (int rc = require_frame(ctx)) return rc;
+    PassScope scope(ctx, LH_PASS_DISPLAY_TRANSFORM);
+    launch_display_transform(ctx, make_params(ctx));
+    return check_launch(ctx, "display_transform");
+}
+
+int lh_render_frame(LhContext* ctx) {
+    int rc;
+    if ((rc = lh_reset(ctx))) return rc;
+    if ((rc = lh_cull_instances(ctx))) return rc;
+    if ((rc = lh_cull_meshlets(ctx))) return rc;
+    if ((rc = lh_raster_visbuffer(ctx))) return rc;
+    if ((rc = lh_composite(ctx))) return rc;
+    if ((rc = lh_reduce_depth(ctx))) return rc;
+    if ((rc = lh_generate_shadow_matrices(ctx))) return rc;
+    if ((rc = lh_cull_instances_shadows(ctx))) return rc;
+    {
+        PassScope scope(ctx, LH_PASS_SHADOWMAPS);
+        for (uint32_t c = 0; c < 4; c++)
+            if ((ctx->cascade_mask >> c) & 1u)
+                if ((rc = lh_shadow_cascade(ctx, c))) return rc;
+    }
+    if ((rc = lh_shadow_exchange(ctx))) return rc;
+    return lh_resolve(ctx);
+}
+
+int lh_frame_sync(LhContext* ctx) {
+    if (!ctx) return LH_ERR_INVALID_ARGUMENT;
+    LH_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return check_launch(ctx, "frame");
+}
+
+int lh_get_frame_stats(LhContext* ctx, LhFrameStats* out) {
+    if (int rc = require_frame(ctx)) return rc;
+    if (!out) return LH_ERR_INVALID_ARGUMENT;
+    launch_gather_stats(ctx, make_params(ctx), ctx->pinned_stats);
+    LH_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (int rc = check_launch(ctx, "gather_stats")) return rc;
+    *out = *ctx->pinned_stats;
+    if (out->overflow) return fail(ctx, LH_ERR_CAPACITY, "a list overflowed its LhConfig capacity (see LhFrameStats.overflow)");
+    return LH_OK;
+}
+
+int lh_render_frame_host(LhContext* ctx, const LhUniforms* u, const LhInstance* instances, uint32_t num_instances, LhFrameStats* stats) {
+    if (!ctx || !u) return LH_ERR_INVALID_ARGUMENT;
+    int rc;
+    if ((rc = lh_frame_begin(ctx, u))) return rc;
+    if (instances && num_instances) {
+        // stage through pinned memory so the copy is a true async DMA
+        size_t bytes = (size_t)num_instances * sizeof(LhInstance);
+        if (bytes > ctx->pinned_bytes) {
+            if (ctx->pinned) cudaFreeHost(ctx->pinned);
+            ctx->pinned = nullptr;
+            ctx->pinned_bytes = 0;
+            LH_CUDA(ctx, cudaMallocHost(&ctx->pinned, bytes));
+            ctx->pinned_bytes = bytes;
+        }
+        memcpy(ctx->pinned, instances, bytes);
+        LH_CUDA(ctx, cudaMemcpyAsync((void*)(uintptr_t)u->instances, ctx->pinned, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    }
+    if ((rc = lh_render_frame(ctx))) return rc;
+    if (stats) return lh_get_frame_stats(ctx, stats);
+    return lh_frame_sync(ctx);
+}
+
+int lh_get_target(LhContext* ctx, int target, void* dst, uint64_t bytes) {
+    if (!ctx || !dst) return LH_ERR_INVALID_ARGUMENT;
+    uint64_t px = (uint64_t)ctx->cfg.width * ctx->cfg.height;
+    const void* src = nullptr;
+    uint64_t need = 0;
+    switch (target) {
+    case LH_TARGET_VIS64: src = ctx->vis; need = px * 8; break;
+    case LH_TARGET_DEPTH:
+        launch_extract_depth(ctx, make_params(ctx));
+        src = ctx->depth_plane; need = px * 4; break;
+    case LH_TARGET_SCENE_RGBA16F: src = ctx->scene; need = px * 8; break;
+    case LH_TARGET_SHADOW: src = ctx->shadow; need = (uint64_t)4 * ctx->cfg.shadowmap_size * ctx->cfg.shadowmap_size * 4; break;
+    case LH_TARGET_DISPLAY_BGRA8: src = ctx->display; need = px * 4; break;
+    default: return fail(ctx, LH_ERR_INVALID_ARGUMENT, "unknown target");
+    }
+    if (bytes < need) return fail(ctx, LH_ERR_INVALID_ARGUMENT, "lh_get_target: destination too small");
+    LH_CUDA(ctx, cudaMemcpyAsync(dst, src, need, cudaMemcpyDeviceToHost, ctx->stream));
+    LH_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return LH_OK;
+}
+
+int lh_get_target_address(LhContext* ctx, int target, uint64_t* dev_addr) {
+    if (!ctx || !dev_addr) return LH_ERR_INVALID_ARGUMENT;
+    switch (target) {
+    case LH_TARGET_VIS64: *dev_addr = (uint64_t)(uintptr_t)ctx->vis; break;
+    case LH_TARGET_DEPTH: *dev_addr = (uint64_t)(uintptr_t)ctx->depth_plane; break;
+    case LH_TARGET_SCENE_RGBA16F: *dev_addr = (uint64_t)(uintptr_t)ctx->scene; break;
+    case LH_TARGET_SHADOW: *dev_addr = (uint64_t)(uintptr_t)ctx->shadow; break;
+    case LH_TARGET_DISPLAY_BGRA8: *dev_addr = (uint64_t)(uintptr_t)ctx->display; break;
+    default: return fail(ctx, LH_ERR_INVALID_ARGUMENT, "unknown target");
+    }
+    return LH_OK;
+}
+
+int lh_get_timings(LhContext* ctx, LhPassTimes* out) {
+    if (!ctx || !out) return LH_ERR_INVALID_ARGUMENT;
+    if (!(ctx->cfg.flags & LH_CONFIG_PASS_TIMINGS)) return fail(ctx, LH_ERR_NOT_READY, "context was created without LH_CONFIG_PASS_TIMINGS");
+    LH_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    memset(out, 0, sizeof(*out));
+    int first = -1, last = -1;
+    for (int i = 0; i < LH_PASS_COUNT; i++) {
+        if (!ctx->pass_recorded[i]) continue;
+        cudaEventElapsedTime(&out->ms[i], ctx->pass_start[i], ctx->pass_stop[i]);
+        if (i == LH_PASS_DISPLAY_TRANSFORM) continue;
+        if (first < 0) first = i;
+        last = i;
+    }
+    if (first >= 0) cudaEventElapsedTime(&out->frame_ms, ctx->pass_start[first], ctx->pass_stop[last]);
+    if (ctx->raster_kernel_recorded) cudaEventElapsedTime(&out->raster_meshlets_kernel_ms, ctx->raster_kernel_a, ctx->raster_kernel_b);
+    return LH_OK;
+}
+
+int lh_get_launch_count(LhContext* ctx, uint64_t* n) {
+    if (!ctx || !n) return LH_ERR_INVALID_ARGUMENT;
+    *n = ctx->launches;
+    return LH_OK;
+}
+
+int lh_timer_start(LhContext* ctx) {
+    if (!ctx) return LH_ERR_INVALID_ARGUMENT;
+    LH_CUDA(ctx, cudaEventRecord(ctx->timer_a, ctx->stream));
+    return LH_OK;
+}
+
+int lh_timer_stop(LhContext* ctx, float* ms) {
+    if (!ctx || !ms) return LH_ERR_INVALID_ARGUMENT;
+    LH_CUDA(ctx, cudaEventRecord(ctx->timer_b, ctx->stream));
+    LH_CUDA(ctx, cudaEventSynchronize(ctx->timer_b));
+    LH_CUDA(ctx, cudaEventElapsedTime(ms, ctx->timer_a, ctx->timer_b));
+    return LH_OK;
+}
+
+int lh_flush_l2(LhContext* ctx) {
+    if (!ctx) return LH_ERR_INVALID_ARGUMENT;
+    const size_t bytes = (size_t)256 << 20;  // > 126 MB of L2
+    if (!ctx->l2_flush) {
+        LH_CUDA(ctx, cudaMalloc(&ctx->l2_flush, bytes));
+        ctx->l2_flush_bytes = bytes;
+    }
+    launch_fill_u32(ctx, (uint32_t*)ctx->l2_flush, bytes / 4, 0u);
+    return check_launch(ctx, "flush_l2");
+}
+
+}  // extern "C"

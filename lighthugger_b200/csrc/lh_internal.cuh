@@ -1,0 +1,191 @@
+// Internal declarations shared by the CUDA translation units: the context,
+// the per-launch parameter block and the pinned device arithmetic.
+//
+// Pinned arithmetic model: everything that decides a cull, a
+// coverage bit or a depth value is written with __fmul_rn / __fadd_rn /
+// __fdiv_rn / __fsqrt_rn so that no FMA contraction or approximate
+// division can occur whatever the compiler flags are.  The operation order
+// restates what the reference's GLSL leaves implementation-defined
+// (src/shaders/common/culling.glsl, rasterization.glsl) in glm's order
+// (mat4*vec4 = (c0*x + c1*y) + (c2*z + c3*w)).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+#include <vector>
+
+#include "lighthugger_b200.h"
+
+namespace lh {
+
+// ---- pinned scalar / vector arithmetic ------------------------------------
+__device__ __forceinline__ float pmul(float a, float b) { return __fmul_rn(a, b); }
+__device__ __forceinline__ float padd(float a, float b) { return __fadd_rn(a, b); }
+__device__ __forceinline__ float psub(float a, float b) { return __fsub_rn(a, b); }
+__device__ __forceinline__ float pdiv(float a, float b) { return __fdiv_rn(a, b); }
+__device__ __forceinline__ float psqrt(float a) { return __fsqrt_rn(a); }
+
+struct V3 {
+    float x, y, z;
+};
+struct V4 {
+    float x, y, z, w;
+};
+
+// (c0*x + c1*y) + (c2*z + c3*w); m points at 16 floats, column-major
+__device__ __forceinline__ V4 mat4_mul(const float* m, float x, float y, float z, float w) {
+    V4 r;
+    r.x = padd(padd(pmul(m[0], x), pmul(m[4], y)), padd(pmul(m[8], z), pmul(m[12], w)));
+    r.y = padd(padd(pmul(m[1], x), pmul(m[5], y)), padd(pmul(m[9], z), pmul(m[13], w)));
+    r.z = padd(padd(pmul(m[2], x), pmul(m[6], y)), padd(pmul(m[10], z), pmul(m[14], w)));
+    r.w = padd(padd(pmul(m[3], x), pmul(m[7], y)), padd(pmul(m[11], z), pmul(m[15], w)));
+    return r;
+}
+// (c0*x + c1*y) + c2*z; m points at 9 floats, column-major
+__device__ __forceinline__ V3 mat3_mul(const float* m, float x, float y, float z) {
+    V3 r;
+    r.x = padd(padd(pmul(m[0], x), pmul(m[3], y)), pmul(m[6], z));
+    r.y = padd(padd(pmul(m[1], x), pmul(m[4], y)), pmul(m[7], z));
+    r.z = padd(padd(pmul(m[2], x), pmul(m[5], y)), pmul(m[8], z));
+    return r;
+}
+__device__ __forceinline__ float dot3(V3 a, V3 b) { return padd(padd(pmul(a.x, b.x), pmul(a.y, b.y)), pmul(a.z, b.z)); }
+__device__ __forceinline__ float length3(V3 a) { return psqrt(dot3(a, a)); }
+__device__ __forceinline__ V3 normalize3(V3 a) {
+    float l = length3(a);
+    return V3{pdiv(a.x, l), pdiv(a.y, l), pdiv(a.z, l)};
+}
+__device__ __forceinline__ V3 cross3(V3 a, V3 b) {
+    return V3{psub(pmul(a.y, b.z), pmul(b.y, a.z)), psub(pmul(a.z, b.x), pmul(b.z, a.x)), psub(pmul(a.x, b.y), pmul(b.x, a.y))};
+}
+
+// ---- device-side scratch that lives across passes of one frame -------------
+struct FrameState {
+    uint32_t overflow;             // LH_OVERFLOW_* bits
+    uint32_t large_count;          // entries in the deferred-triangle queue (current raster pass)
+    uint32_t main_large_count;     // ... as left by the main-view pass (stats)
+    uint32_t main_visible, main_candidates, main_opaque, main_alpha_clip;  // main-view counts (the shared counters are reused by the cascades)
+    uint32_t shadow_opaque[4];     // draw counts of each cascade, saved for the stats
+    uint32_t shadow_alpha_clip[4];
+    uint32_t shadow_visible[4];
+    uint32_t shadow_candidates[4];
+    uint32_t tickets[8];           // tile tickets: [0] main meshlet cull, [1..4] cascades
+    uint32_t done[8];              // CTAs finished (self-cleaning of the tile states)
+    unsigned long long rasterized_triangles;
+};
+
+constexpr uint32_t kMeshletTile = 1024;        // candidate meshlets per scan tile
+constexpr uint32_t kInstanceTile = 256;        // instances per scan tile
+constexpr uint64_t kMaxMeshletTiles = (1ull << 32) / kMeshletTile;  // lo32 of the prefix counter bounds the candidates
+
+// Everything a kernel needs, passed by value (__grid_constant__).
+struct FrameParams {
+    LhUniforms u;
+    uint32_t max_instances, max_opaque, max_alpha;
+    uint32_t instance_first, instance_end;   // sort-last partition
+    uint32_t shadowmap_size;
+    uint32_t flags;
+    uint32_t max_large;
+    FrameState* state;
+    unsigned long long* instance_tiles;      // [4][tiles] decoupled-lookback states
+    unsigned long long* meshlet_tiles;       // [5][kMaxMeshletTiles]
+    uint32_t* large_queue;
+    unsigned long long* vis;
+    uint32_t* shadow;                        // 4 layers of float bits
+    const cudaTextureObject_t* textures;
+    uint32_t slot_offset;                    // sort-last: global slot of this rank's local slot 0
+    const LhMeshletReference* resolve_refs;  // table indexed by GLOBAL slot (== u.meshlet_references on one GPU)
+    void* scene;                             // RGBA16F target
+    void* display;                           // BGRA8 target
+    cudaTextureObject_t sky, lut;
+    uint32_t resolve_y0, resolve_y1;         // screen rows this rank resolves
+};
+
+}  // namespace lh
+
+struct LhContext {
+    int device = 0;
+    LhConfig cfg{};
+    cudaStream_t stream = nullptr;
+    std::string error;
+    LhUniforms uniforms{};
+    bool have_uniforms = false;
+    uint32_t instance_first = 0, instance_count = 0xFFFFFFFFu;
+    uint32_t cascade_mask = 0xF;
+
+    // targets
+    unsigned long long* vis = nullptr;
+    void* scene = nullptr;       // RGBA16F
+    uint32_t* shadow = nullptr;
+    void* display = nullptr;     // BGRA8
+    float* depth_plane = nullptr;
+
+    // scratch
+    lh::FrameState* state = nullptr;
+    unsigned long long* instance_tiles = nullptr;
+    uint32_t instance_tiles_per_sector = 0;
+    unsigned long long* meshlet_tiles = nullptr;
+    uint32_t* large_queue = nullptr;
+    void* l2_flush = nullptr;
+    size_t l2_flush_bytes = 0;
+    void* pinned = nullptr;
+    size_t pinned_bytes = 0;
+    LhFrameStats* pinned_stats = nullptr;
+
+    // textures
+    cudaTextureObject_t tex_host[LH_MAX_TEXTURES] = {};
+    cudaMipmappedArray_t tex_arrays[LH_MAX_TEXTURES] = {};
+    cudaTextureObject_t* tex_dev = nullptr;
+    cudaArray_t sky_array = nullptr;
+    cudaTextureObject_t sky_tex = 0;
+    cudaArray_t lut_array = nullptr;
+    cudaTextureObject_t lut_tex = 0;
+
+    // timing
+    cudaEvent_t pass_start[LH_PASS_COUNT] = {}, pass_stop[LH_PASS_COUNT] = {};
+    bool pass_recorded[LH_PASS_COUNT] = {};
+    cudaEvent_t timer_a = nullptr, timer_b = nullptr;
+    cudaEvent_t raster_kernel_a = nullptr, raster_kernel_b = nullptr;
+    bool raster_kernel_recorded = false;
+    uint64_t launches = 0;
+
+    // multi-GPU
+    void* nccl_comm = nullptr;
+    int rank = 0, nranks = 1;
+    uint32_t slot_offset = 0;          // rank * slots_per_rank
+    uint32_t slots_per_rank = 0;
+    void* gathered_refs = nullptr;     // all ranks' meshlet-reference tables, rank-major (multi-GPU only)
+    int num_sms = 148;
+
+    std::vector<void*> buffers;
+};
+
+namespace lh {
+
+int fail(LhContext* ctx, int code, const char* what, cudaError_t e = cudaSuccess);
+FrameParams make_params(LhContext* ctx);
+
+// pass launchers (one per translation unit)
+void launch_reset(LhContext* ctx, const FrameParams& p);
+void launch_cull_instances(LhContext* ctx, const FrameParams& p, bool shadows);
+void launch_cull_meshlets(LhContext* ctx, const FrameParams& p, int cascade);
+void launch_raster(LhContext* ctx, const FrameParams& p, int cascade);
+void launch_reduce_depth(LhContext* ctx, const FrameParams& p);
+void launch_shadow_matrices(LhContext* ctx, const FrameParams& p);
+void launch_resolve(LhContext* ctx, const FrameParams& p);
+void launch_display_transform(LhContext* ctx, const FrameParams& p);
+void launch_extract_depth(LhContext* ctx, const FrameParams& p);
+void launch_gather_stats(LhContext* ctx, const FrameParams& p, LhFrameStats* dst_dev_or_pinned);
+void launch_fill_u64(LhContext* ctx, unsigned long long* dst, uint64_t count, unsigned long long value);
+void launch_fill_u32(LhContext* ctx, uint32_t* dst, uint64_t count, uint32_t value);
+int composite_allreduce_min(LhContext* ctx);
+extern "C" int lh_shadow_exchange(LhContext* ctx);
+
+}  // namespace lh
+
+#define LH_CUDA(ctx, expr)                                              \
+    do {                                                                \
+        cudaError_t _e = (expr);                                        \
+        if (_e != cudaSuccess) return lh::fail(ctx, LH_ERR_CUDA, #expr, _e); \
+    } while (0)

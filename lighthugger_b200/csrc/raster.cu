@@ -1,0 +1,528 @@
+// Software rasteriser: visibility buffer (packed 64-bit depth|slot|triangle
+// words resolved by atomicMin) and the four shadow-map layers (u32 atomicMin
+// on float bits).
+//
+// Replaces the reference's hardware raster passes (file:line)
+//   load_vertex_data / visbuffer_* / shadowmap_*   src/shaders/rasterization.glsl:12-145
+//   calculate_world_pos, load_index, pack          src/shaders/common/util.glsl:3-20
+//   fixed-function state                           src/pipelines.cpp:10-25,67-77,255-315
+//   clears, drawIndirectCount                      src/rendering.cpp:195-266,379-436
+//
+// Rasterisation rules (Vulkan; pinned in DESIGN.md): clip against w - z >= 0,
+// ndc = clip / w, viewport transform, snap to 8 sub-pixel bits (round half
+// even), integer edge functions, samples at pixel centres, top-left rule,
+// front face = counter-clockwise (A2 < 0), screen-linear depth.
+//
+// B200 design.  The reference issues one indirect draw per surviving meshlet
+// and runs the vertex shader three times per triangle through a 6-deep
+// pointer chase.  Here one WARP owns a meshlet: its <= 64 vertices are
+// transformed once into shared memory (2 per lane), then every lane sets up
+// triangles (stride 32).  Sub-pixel and small triangles -- the overwhelming
+// majority at 1 G triangles per frame -- are finished by their lane with
+// 32-bit edge functions; triangles with a large footprint or crossing the
+// near plane are deferred, one queue entry per 128x32-pixel screen tile, to a
+// second kernel where a whole warp scans a tile in 8x4-pixel blocks with
+// 64-bit edge functions.  Both paths evaluate identical integer coverage and
+// the identical depth expression, so the result is independent of the split.
+#include "lh_internal.cuh"
+
+namespace lh {
+
+namespace {
+
+constexpr int kWarpsPerCta = 8;
+constexpr uint32_t kTileW = 128, kTileH = 32;   // deferred-triangle screen tile
+constexpr uint32_t kWholeTriangle = 0xFFFFFFFFu;
+constexpr int kSmallMaxSpan = 32;               // small path: pixel bbox < 32 on each axis ...
+constexpr int kSmallMaxArea = 64;               // ... and at most this many pixel tests
+constexpr int kSmallMaxExtent = 1 << 14;        // ... and sub-pixel extent < 2^14 (32-bit edge functions stay exact)
+
+enum { CULL_NONE = 0, CULL_BACK = 1, CULL_FRONT = 2 };
+enum { FLAG_INSIDE = 1, FLAG_SNAPPED = 2 };
+
+struct WarpVerts {
+    float4 clip[LH_MAX_MESHLET_UNIQUE_VERTICES];
+    int sx[LH_MAX_MESHLET_UNIQUE_VERTICES];
+    int sy[LH_MAX_MESHLET_UNIQUE_VERTICES];
+    float z[LH_MAX_MESHLET_UNIQUE_VERTICES];
+    uint8_t flags[LH_MAX_MESHLET_UNIQUE_VERTICES];
+};
+
+struct SnapVert {
+    int x, y;
+    float z, w, u, v;
+};
+
+// project_snap of the pinned model: false when the vertex is not finite
+__device__ __forceinline__ bool project_snap(float cx, float cy, float cz, float cw, float half_w, float half_h, int* sx, int* sy, float* z) {
+    float ndc_x = pdiv(cx, cw), ndc_y = pdiv(cy, cw);
+    *z = pdiv(cz, cw);
+    float fx = pmul(padd(pmul(ndc_x, half_w), half_w), 256.0f);
+    float fy = pmul(padd(pmul(ndc_y, half_h), half_h), 256.0f);
+    if (!(isfinite(fx) && isfinite(fy) && isfinite(*z))) return false;
+    const float lim = 536870912.0f;  // 2^29
+    fx = fminf(fmaxf(fx, -lim), lim);
+    fy = fminf(fmaxf(fy, -lim), lim);
+    *sx = __float2int_rn(fx);
+    *sy = __float2int_rn(fy);
+    return true;
+}
+
+template <bool SHADOW>
+struct Target {
+    unsigned long long* vis;
+    uint32_t* layer;
+    uint32_t width, height;
+    // depth test + write of one covered sample
+    __device__ __forceinline__ void emit(int x, int y, float z, uint32_t lo) const {
+        if (SHADOW) {
+            z = padd(z, 0.0f);                      // canonicalise -0
+            if (!(z >= 0.0f && z < 1.0f)) return;   // 0 <= z <= w clip; LESS against the 1.0 clear
+            uint32_t bits = __float_as_uint(z);
+            uint32_t* p = layer + (size_t)y * width + x;
+            if (bits < *p) atomicMin(p, bits);
+        } else {
+            z = fminf(fmaxf(z, 0.0f), 1.0f);
+            if (!(z > 0.0f)) return;                // GREATER against the 0.0 clear
+            unsigned long long key = ((unsigned long long)(~__float_as_uint(z)) << 32) | lo;
+            unsigned long long* p = vis + (size_t)y * width + x;
+            if (key < *p) atomicMin(p, key);
+        }
+    }
+};
+
+struct AlphaTest {
+    bool enabled;
+    cudaTextureObject_t tex;
+};
+
+__device__ __forceinline__ bool top_left(long long dx, long long dy) { return dy < 0 || (dy == 0 && dx > 0); }
+
+// visbuffer_alpha_clip_pixel (rasterization.glsl:90-97): perspective-correct uv, alpha < 0.5 discards
+__device__ __forceinline__ bool alpha_discard(const AlphaTest& at, float w0, float w1, float w2, float fA, const SnapVert& a,
+                                              const SnapVert& b, const SnapVert& c) {
+    float b0 = pdiv(w0, fA), b1 = pdiv(w1, fA), b2 = pdiv(w2, fA);
+    float q0 = pdiv(b0, a.w), q1 = pdiv(b1, b.w), q2 = pdiv(b2, c.w);
+    float den = padd(padd(q0, q1), q2);
+    float tu = pdiv(padd(padd(pmul(q0, a.u), pmul(q1, b.u)), pmul(q2, c.u)), den);
+    float tv = pdiv(padd(padd(pmul(q0, a.v), pmul(q1, b.v)), pmul(q2, c.v)), den);
+    return tex2DLod<float4>(at.tex, tu, tv, 0.0f).w < 0.5f;
+}
+
+// ---- warp-cooperative rasterisation of one snapped triangle inside a pixel rectangle ----
+template <bool SHADOW>
+__device__ void raster_snapped_coop(SnapVert a, SnapVert b, SnapVert c, int cull, const Target<SHADOW>& tg, int rx0, int ry0, int rx1,
+                                    int ry1, const AlphaTest& at, uint32_t lo) {
+    const uint32_t lane = threadIdx.x & 31;
+    long long A2 = (long long)(b.x - a.x) * (c.y - a.y) - (long long)(b.y - a.y) * (c.x - a.x);
+    if (A2 == 0) return;
+    bool front = A2 < 0;
+    if (cull == CULL_BACK && !front) return;
+    if (cull == CULL_FRONT && front) return;
+    if (A2 < 0) {
+        SnapVert t = b;
+        b = c;
+        c = t;
+        A2 = -A2;
+    }
+    int minx = min(a.x, min(b.x, c.x)), maxx = max(a.x, max(b.x, c.x));
+    int miny = min(a.y, min(b.y, c.y)), maxy = max(a.y, max(b.y, c.y));
+    int px0 = max(rx0, (minx - 128 + 255) >> 8), px1 = min(rx1, (maxx - 128) >> 8);
+    int py0 = max(ry0, (miny - 128 + 255) >> 8), py1 = min(ry1, (maxy - 128) >> 8);
+    if (px0 > px1 || py0 > py1) return;
+    const long long e0x = (long long)c.x - b.x, e0y = (long long)c.y - b.y;
+    const long long e1x = (long long)a.x - c.x, e1y = (long long)a.y - c.y;
+    const long long e2x = (long long)b.x - a.x, e2y = (long long)b.y - a.y;
+    const long long bias0 = top_left(e0x, e0y) ? 0 : -1, bias1 = top_left(e1x, e1y) ? 0 : -1, bias2 = top_left(e2x, e2y) ? 0 : -1;
+    const float fA = (float)A2;
+    const float inv_area = pdiv(1.0f, fA);
+    const float dz1 = psub(b.z, a.z), dz2 = psub(c.z, a.z);
+    const int nbx = (px1 - px0 + 8) >> 3, nby = (py1 - py0 + 4) >> 2;
+    for (int by = 0; by < nby; by++)
+        for (int bx = 0; bx < nbx; bx++) {
+            const int x0 = px0 + bx * 8, y0 = py0 + by * 4;
+            // trivial reject: the corner of the 8x4 block where each edge function is largest
+            {
+                const long long cx_lo = (long long)x0 * 256 + 128, cx_hi = cx_lo + 7 * 256;
+                const long long cy_lo = (long long)y0 * 256 + 128, cy_hi = cy_lo + 3 * 256;
+                long long m0 = e0x * ((e0x > 0 ? cy_hi : cy_lo) - b.y) - e0y * ((e0y < 0 ? cx_hi : cx_lo) - b.x);
+                long long m1 = e1x * ((e1x > 0 ? cy_hi : cy_lo) - c.y) - e1y * ((e1y < 0 ? cx_hi : cx_lo) - c.x);
+                long long m2 = e2x * ((e2x > 0 ? cy_hi : cy_lo) - a.y) - e2y * ((e2y < 0 ? cx_hi : cx_lo) - a.x);
+                if (((m0 + bias0) | (m1 + bias1) | (m2 + bias2)) < 0) continue;
+            }
+            const int px = x0 + (int)(lane & 7), py = y0 + (int)(lane >> 3);
+            if (px > px1 || py > py1) continue;
+            const long long cx = (long long)px * 256 + 128, cy = (long long)py * 256 + 128;
+            const long long w0 = e0x * (cy - b.y) - e0y * (cx - b.x);
+            const long long w1 = e1x * (cy - c.y) - e1y * (cx - c.x);
+            const long long w2 = e2x * (cy - a.y) - e2y * (cx - a.x);
+            if (((w0 + bias0) | (w1 + bias1) | (w2 + bias2)) < 0) continue;
+            if (at.enabled && alpha_discard(at, (float)w0, (float)w1, (float)w2, fA, a, b, c)) continue;
+            float z = padd(a.z, pmul(padd(pmul((float)w1, dz1), pmul((float)w2, dz2)), inv_area));
+            tg.emit(px, py, z, lo);
+        }
+}
+
+struct ClipVert {
+    float x, y, z, w, u, v;
+};
+
+// The generic path of the pinned model: near-plane clip, snap, then the
+// cooperative scan.  All 32 lanes pass identical arguments.
+template <bool SHADOW>
+__device__ void raster_clip_triangle_coop(const ClipVert v[3], int cull, const Target<SHADOW>& tg, int rx0, int ry0, int rx1, int ry1,
+                                          const AlphaTest& at, uint32_t lo) {
+    const float half_w = pmul((float)tg.width, 0.5f), half_h = pmul((float)tg.height, 0.5f);
+    bool in[3] = {true, true, true};
+    float d[3] = {0, 0, 0};
+    int n_in = 3;
+    if (!SHADOW) {
+        n_in = 0;
+        for (int k = 0; k < 3; k++) {
+            d[k] = psub(v[k].w, v[k].z);
+            in[k] = d[k] >= 0.0f;
+            n_in += in[k] ? 1 : 0;
+        }
+    }
+    if (n_in == 0) return;
+    ClipVert poly[4];
+    int n = 0;
+    if (n_in == 3) {
+        poly[0] = v[0];
+        poly[1] = v[1];
+        poly[2] = v[2];
+        n = 3;
+    } else {
+        for (int e = 0; e < 3; e++) {
+            int ia = e, ib = (e + 1) % 3;
+            if (in[ia]) poly[n++] = v[ia];
+            if (in[ia] != in[ib]) {
+                int ii = in[ia] ? ia : ib, io = in[ia] ? ib : ia;
+                float t = pdiv(d[ii], psub(d[ii], d[io]));
+                const ClipVert& I = v[ii];
+                const ClipVert& O = v[io];
+                poly[n++] = ClipVert{padd(I.x, pmul(t, psub(O.x, I.x))), padd(I.y, pmul(t, psub(O.y, I.y))),
+                                     padd(I.z, pmul(t, psub(O.z, I.z))), padd(I.w, pmul(t, psub(O.w, I.w))),
+                                     padd(I.u, pmul(t, psub(O.u, I.u))), padd(I.v, pmul(t, psub(O.v, I.v)))};
+            }
+        }
+    }
+    SnapVert s[4];
+    for (int k = 0; k < n; k++) {
+        if (!project_snap(poly[k].x, poly[k].y, poly[k].z, poly[k].w, half_w, half_h, &s[k].x, &s[k].y, &s[k].z)) return;
+        s[k].w = poly[k].w;
+        s[k].u = poly[k].u;
+        s[k].v = poly[k].v;
+    }
+    raster_snapped_coop<SHADOW>(s[0], s[1], s[2], cull, tg, rx0, ry0, rx1, ry1, at, lo);
+    if (n == 4) raster_snapped_coop<SHADOW>(s[0], s[2], s[3], cull, tg, rx0, ry0, rx1, ry1, at, lo);
+}
+
+// Everything needed to locate one meshlet's data; loaded by every lane from the same addresses (broadcast).
+struct MeshletHeader {
+    float T[16];
+    const uint16_t* positions;
+    const void* indices;
+    const uint16_t* uvs;
+    const uint8_t* micro;      // already offset by triangle_offset
+    uint32_t index_offset;
+    uint32_t tri_count, vert_count;
+    bool wide, alpha;
+    float tex_scale[2], tex_offset[2];
+    uint32_t base_color_texture;
+};
+
+__device__ __forceinline__ void load_header(const FrameParams& P, uint32_t slot, MeshletHeader& h) {
+    const LhMeshletReference* refs = (const LhMeshletReference*)P.u.meshlet_references;
+    const unsigned long long ref = __ldg((const unsigned long long*)(refs + slot));
+    const uint32_t instance_index = (uint32_t)ref, meshlet_index = (uint32_t)(ref >> 32) & 0xFFFFu;
+    const LhInstance* inst = (const LhInstance*)P.u.instances + instance_index;
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        float4 c = __ldg((const float4*)&inst->transform + k);
+        h.T[4 * k] = c.x; h.T[4 * k + 1] = c.y; h.T[4 * k + 2] = c.z; h.T[4 * k + 3] = c.w;
+    }
+    const LhMeshInfo* mi = (const LhMeshInfo*)__ldg((const unsigned long long*)&inst->mesh_info_address);
+    h.positions = (const uint16_t*)__ldg((const unsigned long long*)&mi->positions);
+    h.indices = (const void*)__ldg((const unsigned long long*)&mi->indices);
+    h.uvs = (const uint16_t*)__ldg((const unsigned long long*)&mi->uvs);
+    const uint8_t* micro = (const uint8_t*)__ldg((const unsigned long long*)&mi->micro_indices);
+    const LhMeshlet* m = (const LhMeshlet*)__ldg((const unsigned long long*)&mi->meshlets) + meshlet_index;
+    const uint32_t flags = __ldg(&mi->flags);
+    h.wide = (flags & LH_MESH_INFO_FLAGS_32_BIT_INDICES) != 0;
+    h.alpha = (flags & LH_MESH_INFO_FLAGS_ALPHA_CLIP) != 0;
+    const unsigned long long tail = __ldg((const unsigned long long*)m + 6);  // index_offset | counts
+    h.micro = micro + __ldg(&m->triangle_offset);
+    h.index_offset = (uint32_t)tail;
+    h.tri_count = (uint32_t)(tail >> 32) & 0xFFu;
+    h.vert_count = (uint32_t)(tail >> 40) & 0xFFu;
+    h.tex_scale[0] = __ldg(&mi->texture_scale[0]);
+    h.tex_scale[1] = __ldg(&mi->texture_scale[1]);
+    h.tex_offset[0] = __ldg(&mi->texture_offset[0]);
+    h.tex_offset[1] = __ldg(&mi->texture_offset[1]);
+    h.base_color_texture = __ldg(&mi->base_color_texture_index);
+}
+
+__device__ __forceinline__ uint32_t load_vertex_index(const MeshletHeader& h, uint32_t v) {
+    return h.wide ? __ldg((const uint32_t*)h.indices + h.index_offset + v) : (uint32_t)__ldg((const uint16_t*)h.indices + h.index_offset + v);
+}
+
+__device__ __forceinline__ AlphaTest make_alpha_test(const FrameParams& P, const MeshletHeader& h) {
+    AlphaTest at{false, 0};
+    if (h.alpha && h.base_color_texture < LH_MAX_TEXTURES) {
+        at.tex = P.textures[h.base_color_texture];
+        at.enabled = at.tex != 0;
+    }
+    return at;
+}
+
+// work item k of the pass -> (slot in the meshlet-reference table, low word of the vis key)
+__device__ __forceinline__ void work_to_slot(const FrameParams& P, uint32_t k, uint32_t n_opaque, bool shadow, uint32_t* slot, uint32_t* local) {
+    bool alpha = k >= n_opaque;
+    *local = alpha ? P.max_opaque + (k - n_opaque) : k;
+    *slot = *local + (shadow ? P.max_opaque + P.max_alpha : 0u);
+}
+
+__device__ __forceinline__ void push_deferred(const FrameParams& P, uint32_t lo, uint32_t tile) {
+    uint32_t at = atomicAdd(&P.state->large_count, 1u);
+    if (at < P.max_large) {
+        P.large_queue[2 * (size_t)at] = lo;
+        P.large_queue[2 * (size_t)at + 1] = tile;
+    } else {
+        atomicOr(&P.state->overflow, (uint32_t)LH_OVERFLOW_LARGE_TRIANGLES);
+    }
+}
+
+// ---- kernel 1: one warp per meshlet ----
+template <bool SHADOW>
+__global__ void __launch_bounds__(kWarpsPerCta * 32) raster_meshlets_kernel(const __grid_constant__ FrameParams P, uint32_t cascade) {
+    __shared__ WarpVerts verts_all[kWarpsPerCta];
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    WarpVerts& sv = verts_all[warp];
+    const uint32_t* draw = (const uint32_t*)P.u.draw_calls;
+    const uint32_t n_opaque = min(draw[0], P.max_opaque);   // drawIndirectCount clamps to maxDrawCount
+    const uint32_t n_alpha = min(draw[1], P.max_alpha);
+    const uint32_t total = n_opaque + n_alpha;
+
+    Target<SHADOW> tg;
+    tg.vis = P.vis;
+    tg.layer = SHADOW ? P.shadow + (size_t)cascade * P.shadowmap_size * P.shadowmap_size : nullptr;
+    tg.width = SHADOW ? P.shadowmap_size : P.u.window_size[0];
+    tg.height = SHADOW ? P.shadowmap_size : P.u.window_size[1];
+    const float half_w = pmul((float)tg.width, 0.5f), half_h = pmul((float)tg.height, 0.5f);
+    const int W = (int)tg.width, H = (int)tg.height;
+
+    float M[16];
+    {
+        const float* src = SHADOW ? &((const LhMiscStorage*)P.u.misc_storage)->shadow_matrices[cascade].m[0][0] : &P.u.combined_perspective_view.m[0][0];
+#pragma unroll
+        for (int k = 0; k < 16; k++) M[k] = src[k];
+    }
+    uint32_t tris_done = 0;
+
+    for (uint32_t k = blockIdx.x * kWarpsPerCta + warp; k < total; k += gridDim.x * kWarpsPerCta) {
+        uint32_t slot, local;
+        work_to_slot(P, k, n_opaque, SHADOW, &slot, &local);
+        MeshletHeader h;
+        load_header(P, slot, h);
+        const uint32_t nv = min(h.vert_count, (uint32_t)LH_MAX_MESHLET_UNIQUE_VERTICES);
+        // cull modes: pipelines.cpp:10-25,255-315
+        const int cull = h.alpha ? CULL_NONE : (SHADOW ? CULL_FRONT : CULL_BACK);
+        const AlphaTest at = make_alpha_test(P, h);
+
+        // vertex phase: load_vertex_data + calculate_world_pos + matrix * (world, 1)
+        for (uint32_t v = lane; v < nv; v += 32) {
+            const uint32_t idx = load_vertex_index(h, v);
+            const uint16_t* p = h.positions + 3 * (size_t)idx;
+            const float px = (float)__ldg(p), py = (float)__ldg(p + 1), pz = (float)__ldg(p + 2);
+            const V4 world = mat4_mul(h.T, px, py, pz, 1.0f);
+            const V4 clip = mat4_mul(M, world.x, world.y, world.z, 1.0f);
+            sv.clip[v] = make_float4(clip.x, clip.y, clip.z, clip.w);
+            uint8_t f = 0;
+            if (SHADOW || psub(clip.w, clip.z) >= 0.0f) {
+                f |= FLAG_INSIDE;
+                int sx, sy;
+                float z;
+                if (project_snap(clip.x, clip.y, clip.z, clip.w, half_w, half_h, &sx, &sy, &z)) {
+                    f |= FLAG_SNAPPED;
+                    sv.sx[v] = sx;
+                    sv.sy[v] = sy;
+                    sv.z[v] = z;
+                }
+            }
+            sv.flags[v] = f;
+        }
+        __syncwarp();
+
+        // triangle phase
+        for (uint32_t t = lane; t < h.tri_count; t += 32) {
+            const uint32_t i0 = __ldg(h.micro + 3 * t), i1 = __ldg(h.micro + 3 * t + 1), i2 = __ldg(h.micro + 3 * t + 2);
+            if (max(i0, max(i1, i2)) >= nv) continue;
+            const uint32_t lo = ((P.slot_offset + local) << LH_VIS_TRI_BITS) | t;
+            const uint32_t f0 = sv.flags[i0], f1 = sv.flags[i1], f2 = sv.flags[i2];
+            const uint32_t f_and = f0 & f1 & f2, f_or = f0 | f1 | f2;
+            if (!(f_or & FLAG_INSIDE)) continue;                       // entirely behind the near plane
+            if (!(f_and & FLAG_INSIDE)) {                              // crosses it: generic path
+                push_deferred(P, lo, kWholeTriangle);
+                continue;
+            }
+            if (!(f_and & FLAG_SNAPPED)) continue;                     // non-finite vertex
+            int ax = sv.sx[i0], ay = sv.sy[i0], bx = sv.sx[i1], by = sv.sy[i1], cx = sv.sx[i2], cy = sv.sy[i2];
+            const int minx = min(ax, min(bx, cx)), maxx = max(ax, max(bx, cx));
+            const int miny = min(ay, min(by, cy)), maxy = max(ay, max(by, cy));
+            const int px0 = max(0, (minx - 128 + 255) >> 8), px1 = min(W - 1, (maxx - 128) >> 8);
+            const int py0 = max(0, (miny - 128 + 255) >> 8), py1 = min(H - 1, (maxy - 128) >> 8);
+            if (px0 > px1 || py0 > py1) continue;                      // covers no sample: the common case
+            tris_done++;
+            const bool small_extent = (maxx - minx) < kSmallMaxExtent && (maxy - miny) < kSmallMaxExtent;
+            if (small_extent) {
+                // exact in 32 bits: |d| < 2^14 so every product is < 2^28
+                int A2 = (bx - ax) * (cy - ay) - (by - ay) * (cx - ax);
+                if (A2 == 0) continue;
+                const bool front = A2 < 0;
+                if ((cull == CULL_BACK && !front) || (cull == CULL_FRONT && front)) continue;
+                const int spanx = px1 - px0 + 1, spany = py1 - py0 + 1;
+                if (spanx <= kSmallMaxSpan && spany <= kSmallMaxSpan && spanx * spany <= kSmallMaxArea) {
+                    float az = sv.z[i0], bz = sv.z[i1], cz = sv.z[i2];
+                    uint32_t ia = i0, ib = i1, ic = i2;
+                    if (A2 < 0) {
+                        int t0 = bx; bx = cx; cx = t0;
+                        t0 = by; by = cy; cy = t0;
+                        float tz = bz; bz = cz; cz = tz;
+                        ib = i2; ic = i1;
+                        A2 = -A2;
+                    }
+                    const int e0x = cx - bx, e0y = cy - by, e1x = ax - cx, e1y = ay - cy, e2x = bx - ax, e2y = by - ay;
+                    const int bias0 = top_left(e0x, e0y) ? 0 : -1, bias1 = top_left(e1x, e1y) ? 0 : -1, bias2 = top_left(e2x, e2y) ? 0 : -1;
+                    const float fA = (float)A2;
+                    const float inv_area = pdiv(1.0f, fA);
+                    const float dz1 = psub(bz, az), dz2 = psub(cz, az);
+                    const int ccx = px0 * 256 + 128, ccy = py0 * 256 + 128;
+                    int w0_row = e0x * (ccy - by) - e0y * (ccx - bx);
+                    int w1_row = e1x * (ccy - cy) - e1y * (ccx - cx);
+                    int w2_row = e2x * (ccy - ay) - e2y * (ccx - ax);
+                    SnapVert A, B, C;
+                    if (at.enabled) {
+                        // perspective-correct uv needs the clip w and the vertex uvs
+                        const uint32_t ids[3] = {ia, ib, ic};
+                        SnapVert* out[3] = {&A, &B, &C};
+                        for (int q = 0; q < 3; q++) {
+                            const uint32_t idx = load_vertex_index(h, ids[q]);
+                            out[q]->w = sv.clip[ids[q]].w;
+                            out[q]->u = padd(pmul((float)__ldg(h.uvs + 2 * (size_t)idx), h.tex_scale[0]), h.tex_offset[0]);
+                            out[q]->v = padd(pmul((float)__ldg(h.uvs + 2 * (size_t)idx + 1), h.tex_scale[1]), h.tex_offset[1]);
+                        }
+                    }
+                    for (int py = py0; py <= py1; py++) {
+                        int w0 = w0_row, w1 = w1_row, w2 = w2_row;
+                        for (int px = px0; px <= px1; px++) {
+                            if (((w0 + bias0) | (w1 + bias1) | (w2 + bias2)) >= 0) {
+                                if (!(at.enabled && alpha_discard(at, (float)w0, (float)w1, (float)w2, fA, A, B, C))) {
+                                    float z = padd(az, pmul(padd(pmul((float)w1, dz1), pmul((float)w2, dz2)), inv_area));
+                                    tg.emit(px, py, z, lo);
+                                }
+                            }
+                            w0 -= e0y * 256;
+                            w1 -= e1y * 256;
+                            w2 -= e2y * 256;
+                        }
+                        w0_row += e0x * 256;
+                        w1_row += e1x * 256;
+                        w2_row += e2x * 256;
+                    }
+                    continue;
+                }
+            }
+            else {
+                const long long A2 = (long long)(bx - ax) * (cy - ay) - (long long)(by - ay) * (cx - ax);
+                if (A2 == 0) continue;
+                const bool front = A2 < 0;
+                if ((cull == CULL_BACK && !front) || (cull == CULL_FRONT && front)) continue;
+            }
+            // large footprint: one queue entry per 128x32 screen tile the bounding box touches
+            const uint32_t tx0 = (uint32_t)px0 / kTileW, tx1 = (uint32_t)px1 / kTileW;
+            const uint32_t ty0 = (uint32_t)py0 / kTileH, ty1 = (uint32_t)py1 / kTileH;
+            for (uint32_t ty = ty0; ty <= ty1; ty++)
+                for (uint32_t tx = tx0; tx <= tx1; tx++) push_deferred(P, lo, tx | (ty << 16));
+        }
+        __syncwarp();
+    }
+    if (P.flags & LH_CONFIG_PASS_TIMINGS) {
+        for (int o = 16; o > 0; o >>= 1) tris_done += __shfl_xor_sync(0xFFFFFFFFu, tris_done, o);
+        if (lane == 0 && tris_done && !SHADOW) atomicAdd(&P.state->rasterized_triangles, (unsigned long long)tris_done);
+    }
+}
+
+// ---- kernel 2: one warp per deferred (triangle, screen tile) ----
+template <bool SHADOW>
+__global__ void __launch_bounds__(kWarpsPerCta * 32) raster_deferred_kernel(const __grid_constant__ FrameParams P, uint32_t cascade) {
+    const uint32_t warp = threadIdx.x >> 5;
+    const uint32_t count = min(P.state->large_count, P.max_large);
+    Target<SHADOW> tg;
+    tg.vis = P.vis;
+    tg.layer = SHADOW ? P.shadow + (size_t)cascade * P.shadowmap_size * P.shadowmap_size : nullptr;
+    tg.width = SHADOW ? P.shadowmap_size : P.u.window_size[0];
+    tg.height = SHADOW ? P.shadowmap_size : P.u.window_size[1];
+    const float* M = SHADOW ? &((const LhMiscStorage*)P.u.misc_storage)->shadow_matrices[cascade].m[0][0] : &P.u.combined_perspective_view.m[0][0];
+    const uint32_t section = SHADOW ? P.max_opaque + P.max_alpha : 0u;
+
+    for (uint32_t e = blockIdx.x * kWarpsPerCta + warp; e < count; e += gridDim.x * kWarpsPerCta) {
+        const uint32_t lo = P.large_queue[2 * (size_t)e], tile = P.large_queue[2 * (size_t)e + 1];
+        const uint32_t local = (lo >> LH_VIS_TRI_BITS) - P.slot_offset, t = lo & LH_VIS_TRI_MASK;
+        MeshletHeader h;
+        load_header(P, section + local, h);
+        const int cull = h.alpha ? CULL_NONE : (SHADOW ? CULL_FRONT : CULL_BACK);
+        const AlphaTest at = make_alpha_test(P, h);
+        ClipVert v[3];
+        for (int q = 0; q < 3; q++) {
+            const uint32_t mi = __ldg(h.micro + 3 * t + q);
+            const uint32_t idx = load_vertex_index(h, mi);
+            const uint16_t* p = h.positions + 3 * (size_t)idx;
+            const V4 world = mat4_mul(h.T, (float)__ldg(p), (float)__ldg(p + 1), (float)__ldg(p + 2), 1.0f);
+            const V4 clip = mat4_mul(M, world.x, world.y, world.z, 1.0f);
+            v[q] = ClipVert{clip.x, clip.y, clip.z, clip.w, 0.0f, 0.0f};
+            if (at.enabled) {
+                v[q].u = padd(pmul((float)__ldg(h.uvs + 2 * (size_t)idx), h.tex_scale[0]), h.tex_offset[0]);
+                v[q].v = padd(pmul((float)__ldg(h.uvs + 2 * (size_t)idx + 1), h.tex_scale[1]), h.tex_offset[1]);
+            }
+        }
+        int rx0 = 0, ry0 = 0, rx1 = (int)tg.width - 1, ry1 = (int)tg.height - 1;
+        if (tile != kWholeTriangle) {
+            rx0 = (int)((tile & 0xFFFFu) * kTileW);
+            ry0 = (int)((tile >> 16) * kTileH);
+            rx1 = min(rx1, rx0 + (int)kTileW - 1);
+            ry1 = min(ry1, ry0 + (int)kTileH - 1);
+        }
+        raster_clip_triangle_coop<SHADOW>(v, cull, tg, rx0, ry0, rx1, ry1, at, lo);
+    }
+}
+
+__global__ void begin_raster_pass_kernel(const __grid_constant__ FrameParams P) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) P.state->large_count = 0;
+}
+__global__ void end_main_pass_kernel(const __grid_constant__ FrameParams P) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) P.state->main_large_count = P.state->large_count;
+}
+
+}  // namespace
+
+void launch_raster(LhContext* ctx, const FrameParams& p, int cascade) {
+    const uint32_t grid = (uint32_t)ctx->num_sms * 8;  // 64 resident warps per SM
+    begin_raster_pass_kernel<<<1, 32, 0, ctx->stream>>>(p); ctx->launches++;
+    if (cascade < 0) {
+        const bool timed = (ctx->cfg.flags & LH_CONFIG_PASS_TIMINGS) != 0;
+        if (timed) cudaEventRecord(ctx->raster_kernel_a, ctx->stream);
+        raster_meshlets_kernel<false><<<grid, kWarpsPerCta * 32, 0, ctx->stream>>>(p, 0); ctx->launches++;
+        if (timed) {
+            cudaEventRecord(ctx->raster_kernel_b, ctx->stream);
+            ctx->raster_kernel_recorded = true;
+        }
+        raster_deferred_kernel<false><<<grid, kWarpsPerCta * 32, 0, ctx->stream>>>(p, 0); ctx->launches++;
+        end_main_pass_kernel<<<1, 32, 0, ctx->stream>>>(p); ctx->launches++;
+    } else {
+        raster_meshlets_kernel<true><<<grid, kWarpsPerCta * 32, 0, ctx->stream>>>(p, (uint32_t)cascade); ctx->launches++;
+        raster_deferred_kernel<true><<<grid, kWarpsPerCta * 32, 0, ctx->stream>>>(p, (uint32_t)cascade); ctx->launches++;
+    }
+}
+
+}  // namespace lh

@@ -1,0 +1,333 @@
+// Full-screen lighting resolve from the visibility buffer, and the display
+// transform that follows it.
+//
+// Replaces (reference file:line)
+//   render_geometry main            src/shaders/render_geometry.comp:70-266
+//   CalcFullBary / interpolate      src/shaders/common/vbuffer.glsl:11-119
+//   BRDF and helpers                src/shaders/common/pbr.glsl:3-96
+//   display_transform               src/shaders/display_transform.comp:37-81
+//   samplers                        src/main.cpp:550-581
+//
+// B200 design.  One thread per pixel; each warp owns an 8x4 pixel block so the
+// three-vertex attribute refetch and the texture footprints of a warp stay
+// inside one or two meshlets.  Depth and ids arrive in ONE 8-byte word per
+// pixel (the reference reads a D32F image and an R32U image); material
+// textures are CUDA block-compressed (BC7 sRGB) mipmapped arrays sampled with
+// hardware anisotropic filtering (tex2DGrad, maxAnisotropy 16) from the
+// analytic barycentric derivatives; the shadow compare-and-filter, which CUDA
+// has no sampler for, is done by hand from the u32 depth layers.  Output is
+// written as one 8-byte RGBA16F store per pixel.
+//
+// This pass is floating-point and tolerance-checked (tests/test_resolve.py);
+// it may use fused multiply-adds and fast reciprocals.
+#include <cuda_fp16.h>
+
+#include "lh_internal.cuh"
+
+namespace lh {
+
+namespace {
+
+struct F3 {
+    float x, y, z;
+};
+__device__ __forceinline__ F3 operator+(F3 a, F3 b) { return F3{a.x + b.x, a.y + b.y, a.z + b.z}; }
+__device__ __forceinline__ F3 operator-(F3 a, F3 b) { return F3{a.x - b.x, a.y - b.y, a.z - b.z}; }
+__device__ __forceinline__ F3 operator*(F3 a, float s) { return F3{a.x * s, a.y * s, a.z * s}; }
+__device__ __forceinline__ float dot(F3 a, F3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+__device__ __forceinline__ F3 cross(F3 a, F3 b) { return F3{a.y * b.z - b.y * a.z, a.z * b.x - b.z * a.x, a.x * b.y - b.x * a.y}; }
+__device__ __forceinline__ F3 normalize(F3 a) {
+    float inv = 1.0f / sqrtf(dot(a, a));
+    return a * inv;
+}
+__device__ __forceinline__ float4 mul4(const float* m, float x, float y, float z, float w) {
+    return make_float4(m[0] * x + m[4] * y + m[8] * z + m[12] * w, m[1] * x + m[5] * y + m[9] * z + m[13] * w,
+                       m[2] * x + m[6] * y + m[10] * z + m[14] * w, m[3] * x + m[7] * y + m[11] * z + m[15] * w);
+}
+
+struct Bary {
+    F3 lambda, ddx, ddy;
+};
+
+// CalcFullBary, vbuffer.glsl:11-63
+__device__ Bary calc_full_bary(float4 p0, float4 p1, float4 p2, float ndc_x, float ndc_y, float win_w, float win_h) {
+    Bary r;
+    F3 invw{1.0f / p0.w, 1.0f / p1.w, 1.0f / p2.w};
+    float n0x = p0.x * invw.x, n0y = p0.y * invw.x;
+    float n1x = p1.x * invw.y, n1y = p1.y * invw.y;
+    float n2x = p2.x * invw.z, n2y = p2.y * invw.z;
+    float inv_det = 1.0f / ((n2x - n1x) * (n0y - n1y) - (n0x - n1x) * (n2y - n1y));
+    r.ddx = F3{(n1y - n2y) * inv_det * invw.x, (n2y - n0y) * inv_det * invw.y, (n0y - n1y) * inv_det * invw.z};
+    r.ddy = F3{(n2x - n1x) * inv_det * invw.x, (n0x - n2x) * inv_det * invw.y, (n1x - n0x) * inv_det * invw.z};
+    float ddx_sum = r.ddx.x + r.ddx.y + r.ddx.z;
+    float ddy_sum = r.ddy.x + r.ddy.y + r.ddy.z;
+    float dvx = ndc_x - n0x, dvy = ndc_y - n0y;
+    float interp_inv_w = invw.x + dvx * ddx_sum + dvy * ddy_sum;
+    float interp_w = 1.0f / interp_inv_w;
+    r.lambda.x = interp_w * (invw.x + dvx * r.ddx.x + dvy * r.ddy.x);
+    r.lambda.y = interp_w * (0.0f + dvx * r.ddx.y + dvy * r.ddy.y);
+    r.lambda.z = interp_w * (0.0f + dvx * r.ddx.z + dvy * r.ddy.z);
+    float sx = 2.0f / win_w, sy = -2.0f / win_h;  // the y derivative is flipped (vbuffer.glsl:50-51)
+    r.ddx = r.ddx * sx;
+    r.ddy = r.ddy * sy;
+    ddx_sum *= sx;
+    ddy_sum *= sy;
+    float iw_ddx = 1.0f / (interp_inv_w + ddx_sum), iw_ddy = 1.0f / (interp_inv_w + ddy_sum);
+    r.ddx = (r.lambda * interp_inv_w + r.ddx) * iw_ddx - r.lambda;
+    r.ddy = (r.lambda * interp_inv_w + r.ddy) * iw_ddy - r.lambda;
+    return r;
+}
+
+struct Interp {
+    float value, dx, dy;
+};
+__device__ __forceinline__ Interp interp1(const Bary& b, float v0, float v1, float v2) {
+    F3 m{v0, v1, v2};
+    return Interp{dot(m, b.lambda), dot(m, b.ddx), dot(m, b.ddy)};
+}
+
+// pbr.glsl:3-96
+constexpr float kPi = 3.14159265358979323846f;
+__device__ __forceinline__ float pow5(float x) {
+    float x2 = x * x;
+    return x2 * x2 * x;
+}
+__device__ __forceinline__ float fd_burley(float nov, float nol, float loh, float roughness) {
+    float f90 = 0.5f + 2.0f * roughness * loh * loh;
+    float ls = 1.0f + (f90 - 1.0f) * pow5(1.0f - nol), vs = 1.0f + (f90 - 1.0f) * pow5(1.0f - nov);
+    return ls * vs * (1.0f / kPi);
+}
+__device__ __forceinline__ float clampf(float x, float lo, float hi) { return fminf(fmaxf(x, lo), hi); }
+
+__device__ F3 brdf(F3 v, F3 l, F3 n, float perceptual_roughness, float metallic, F3 base, bool thin_walled) {
+    F3 h = normalize(v + l);
+    F3 diffuse = base * (1.0f - metallic);
+    const float refl = 0.04f;  // reflectance_for_ior(1.5) = ((1.5-1)/(1.5+1))^2
+    F3 f0 = F3{refl * (1.0f - metallic) + base.x * metallic, refl * (1.0f - metallic) + base.y * metallic,
+               refl * (1.0f - metallic) + base.z * metallic};
+    float nov = clampf(dot(n, v), 1e-5f, 1.0f), nol = clampf(dot(n, l), 0.0f, 1.0f);
+    float noh = clampf(dot(n, h), 0.0f, 1.0f), loh = clampf(dot(l, h), 0.0f, 1.0f);
+    float roughness = perceptual_roughness * perceptual_roughness;
+    float a2 = roughness * roughness;
+    float f = (noh * a2 - noh) * noh + 1.0f;
+    float D = a2 / (kPi * f * f);
+    float ggxl = nov * sqrtf((-nol * a2 + nol) * nol + a2), ggxv = nol * sqrtf((-nov * a2 + nov) * nov + a2);
+    float V = 0.5f / (ggxv + ggxl);
+    float p5 = pow5(1.0f - loh);
+    float burley = fd_burley(nov, nol, loh, roughness);
+    float rev_nov = clampf(-dot(n, v), 1e-5f, 1.0f), rev_nol = clampf(-dot(n, l), 0.0f, 1.0f);
+    float rev = thin_walled ? fd_burley(rev_nov, rev_nol, loh, roughness) * rev_nol : 0.0f;
+    float dv = D * V;
+    F3 out;
+    float* o = &out.x;
+    const float* f0p = &f0.x;
+    const float* dp = &diffuse.x;
+    for (int c = 0; c < 3; c++) {
+        float F = f0p[c] + (1.0f - f0p[c]) * p5;
+        float irr = fmaxf((dp[c] * burley + dv * F) * nol, 0.0f);
+        irr += dp[c] * rev;
+        o[c] = isnan(irr) ? 0.0f : irr;
+    }
+    return out;
+}
+
+// sampler2DArrayShadow + compare LESS + linear (src/main.cpp:569-581), by hand
+__device__ __forceinline__ float sample_shadow(const uint32_t* layer, int n, float u, float v, float ref) {
+    float x = u * (float)n - 0.5f, y = v * (float)n - 0.5f;
+    if (!(isfinite(x) && isfinite(y))) return 0.0f;
+    float fx = floorf(x), fy = floorf(y), wx = x - fx, wy = y - fy;
+    fx = fminf(fmaxf(fx, -2.0f), (float)n + 1.0f);
+    fy = fminf(fmaxf(fy, -2.0f), (float)n + 1.0f);
+    int x0 = min(max((int)fx, 0), n - 1), x1 = min(max((int)fx + 1, 0), n - 1);
+    int y0 = min(max((int)fy, 0), n - 1), y1 = min(max((int)fy + 1, 0), n - 1);
+    float c00 = ref < __uint_as_float(__ldg(layer + (size_t)y0 * n + x0)) ? 1.0f : 0.0f;
+    float c10 = ref < __uint_as_float(__ldg(layer + (size_t)y0 * n + x1)) ? 1.0f : 0.0f;
+    float c01 = ref < __uint_as_float(__ldg(layer + (size_t)y1 * n + x0)) ? 1.0f : 0.0f;
+    float c11 = ref < __uint_as_float(__ldg(layer + (size_t)y1 * n + x1)) ? 1.0f : 0.0f;
+    float top = c00 + wx * (c10 - c00), bot = c01 + wx * (c11 - c01);
+    return top + wy * (bot - top);
+}
+
+__device__ __forceinline__ void store_rgba16f(void* scene, size_t pixel, float r, float g, float b, float a) {
+    __half2 lo = __floats2half2_rn(r, g), hi = __floats2half2_rn(b, a);
+    uint2 packed;
+    packed.x = *reinterpret_cast<uint32_t*>(&lo);
+    packed.y = *reinterpret_cast<uint32_t*>(&hi);
+    reinterpret_cast<uint2*>(scene)[pixel] = packed;
+}
+
+__global__ void __launch_bounds__(256) resolve_kernel(const __grid_constant__ FrameParams P) {
+    const uint32_t W = P.u.window_size[0], H = P.u.window_size[1];
+    // 32x8 pixels per CTA, one 8x4 block per warp
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t x = blockIdx.x * 32 + (warp & 3) * 8 + (lane & 7);
+    const uint32_t y = P.resolve_y0 + blockIdx.y * 8 + (warp >> 2) * 4 + (lane >> 3);
+    if (x >= W || y >= min(H, P.resolve_y1)) return;
+    const size_t pixel = (size_t)y * W + x;
+    const float ndc_x = (float)x / (float)W * 2.0f - 1.0f;  // pixel corner, render_geometry.comp:82-84
+    const float ndc_y = (float)y / (float)H * 2.0f - 1.0f;
+    const unsigned long long key = P.vis[pixel];
+    if (lh_vis_depth_bits(key) == 0u) {  // depth == 0: sky (:86-101)
+        float4 un = mul4(&P.u.perspective_inverse.m[0][0], ndc_x, ndc_y, 0.0f, 1.0f);
+        F3 local = normalize(F3{un.x, un.y, un.z});
+        float4 ray = mul4(&P.u.view_inverse.m[0][0], local.x, local.y, local.z, 0.0f);
+        float4 s = P.sky ? texCubemapLod<float4>(P.sky, ray.x, ray.y, ray.z, 0.0f) : make_float4(0, 0, 0, 0);
+        store_rgba16f(P.scene, pixel, s.x * 8.0f, s.y * 8.0f, s.z * 8.0f, 1.0f);
+        return;
+    }
+    const uint32_t slot = lh_vis_slot(key), tri = lh_vis_tri(key);
+    const unsigned long long ref = __ldg((const unsigned long long*)(P.resolve_refs + slot));
+    const LhInstance* inst = (const LhInstance*)P.u.instances + (uint32_t)ref;
+    const uint32_t meshlet_index = (uint32_t)(ref >> 32) & 0xFFFFu;
+    float T[16];
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        float4 c = __ldg((const float4*)&inst->transform + k);
+        T[4 * k] = c.x; T[4 * k + 1] = c.y; T[4 * k + 2] = c.z; T[4 * k + 3] = c.w;
+    }
+    const LhMeshInfo* mi = (const LhMeshInfo*)__ldg((const unsigned long long*)&inst->mesh_info_address);
+    const uint16_t* positions = (const uint16_t*)__ldg((const unsigned long long*)&mi->positions);
+    const void* indices = (const void*)__ldg((const unsigned long long*)&mi->indices);
+    const int8_t* normals = (const int8_t*)__ldg((const unsigned long long*)&mi->normals);
+    const uint16_t* uvs = (const uint16_t*)__ldg((const unsigned long long*)&mi->uvs);
+    const uint8_t* micro = (const uint8_t*)__ldg((const unsigned long long*)&mi->micro_indices);
+    const LhMeshlet* m = (const LhMeshlet*)__ldg((const unsigned long long*)&mi->meshlets) + meshlet_index;
+    const uint32_t flags = __ldg(&mi->flags);
+    const bool wide = (flags & LH_MESH_INFO_FLAGS_32_BIT_INDICES) != 0, alpha = (flags & LH_MESH_INFO_FLAGS_ALPHA_CLIP) != 0;
+    const uint32_t index_offset = __ldg(&m->index_offset);
+    micro += __ldg(&m->triangle_offset) + 3 * tri;
+
+    F3 pos[3], nrm[3];
+    float4 clip[3];
+    float tu[3], tv[3];
+    const float ts0 = __ldg(&mi->texture_scale[0]), ts1 = __ldg(&mi->texture_scale[1]);
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+        const uint32_t vi = index_offset + __ldg(micro + k);
+        const uint32_t idx = wide ? __ldg((const uint32_t*)indices + vi) : (uint32_t)__ldg((const uint16_t*)indices + vi);
+        const uint16_t* p = positions + 3 * (size_t)idx;
+        float4 w = mul4(T, (float)__ldg(p), (float)__ldg(p + 1), (float)__ldg(p + 2), 1.0f);
+        pos[k] = F3{w.x, w.y, w.z};
+        clip[k] = mul4(&P.u.combined_perspective_view.m[0][0], w.x, w.y, w.z, 1.0f);
+        const int8_t* n = normals + 3 * (size_t)idx;
+        nrm[k] = normalize(F3{(float)__ldg(n), (float)__ldg(n + 1), (float)__ldg(n + 2)});
+        tu[k] = (float)__ldg(uvs + 2 * (size_t)idx) * ts0;
+        tv[k] = (float)__ldg(uvs + 2 * (size_t)idx + 1) * ts1;
+    }
+    const Bary bary = calc_full_bary(clip[0], clip[1], clip[2], ndc_x, ndc_y, (float)W, (float)H);
+    const Interp wx = interp1(bary, pos[0].x, pos[1].x, pos[2].x);
+    const Interp wy = interp1(bary, pos[0].y, pos[1].y, pos[2].y);
+    const Interp wz = interp1(bary, pos[0].z, pos[1].z, pos[2].z);
+    const F3 world{wx.value, wy.value, wz.value};
+    const Interp iu = interp1(bary, tu[0], tu[1], tu[2]), iv = interp1(bary, tv[0], tv[1], tv[2]);
+    const float u = iu.value + __ldg(&mi->texture_offset[0]), v = iv.value + __ldg(&mi->texture_offset[1]);
+    const float2 duv_dx = make_float2(iu.dx, iv.dx), duv_dy = make_float2(iu.dy, iv.dy);
+
+    const F3 view_vec = normalize(F3{P.u.camera_pos[0], P.u.camera_pos[1], P.u.camera_pos[2]} - world);
+    F3 normal{interp1(bary, nrm[0].x, nrm[1].x, nrm[2].x).value, interp1(bary, nrm[0].y, nrm[1].y, nrm[2].y).value,
+              interp1(bary, nrm[0].z, nrm[1].z, nrm[2].z).value};
+    {
+        const float* N = &inst->normal_transform.m[0][0];
+        float n9[9];
+#pragma unroll
+        for (int k = 0; k < 9; k++) n9[k] = __ldg(N + k);
+        normal = normalize(F3{n9[0] * normal.x + n9[3] * normal.y + n9[6] * normal.z, n9[1] * normal.x + n9[4] * normal.y + n9[7] * normal.z,
+                              n9[2] * normal.x + n9[5] * normal.y + n9[8] * normal.z});
+    }
+    if (dot(cross(pos[1] - pos[0], pos[2] - pos[0]), view_vec) < 0.0f) normal = normal * -1.0f;
+
+    // cascade selection (:183-196) and 3x3 PCF (:200-226)
+    const LhMiscStorage* misc = (const LhMiscStorage*)P.u.misc_storage;
+    uint32_t cascade;
+    float4 sc = make_float4(0, 0, 0, 0);
+    for (cascade = 0; cascade < 4; cascade++) {
+        sc = mul4(&misc->uv_space_shadow_matrices[cascade].m[0][0], world.x, world.y, world.z, 1.0f);
+        if (fabsf(sc.x - 0.5f) < 0.5f && fabsf(sc.y - 0.5f) < 0.5f) break;
+    }
+    const float bias = alpha ? 0.000002f : 0.0f;
+    const float inv_w = 1.0f / sc.w;
+    sc.x *= inv_w; sc.y *= inv_w; sc.z *= inv_w;
+    const int sn = (int)P.shadowmap_size;
+    const uint32_t* layer = P.shadow + (size_t)min(cascade, 3u) * sn * sn;
+    float shadow_sum = 0.0f;
+#pragma unroll
+    for (int ox = -1; ox <= 1; ox++)
+#pragma unroll
+        for (int oy = -1; oy <= 1; oy++)
+            shadow_sum += sample_shadow(layer, sn, sc.x + (float)ox / 1024.0f, sc.y + (float)oy / 1024.0f, sc.z - bias);
+    shadow_sum *= (1.0f / 9.0f);
+    if (sc.z > 1.0f) shadow_sum = 1.0f;
+
+    // material (:228-246)
+    F3 base{1, 1, 1};
+    float roughness = 1.0f, metallic = 1.0f;
+    const uint32_t t_base = __ldg(&mi->base_color_texture_index), t_mr = __ldg(&mi->metallic_roughness_texture_index);
+    const uint32_t t_nrm = __ldg(&mi->normal_texture_index);
+    if (t_base < LH_MAX_TEXTURES && P.textures[t_base]) {
+        float4 s = tex2DGrad<float4>(P.textures[t_base], u, v, duv_dx, duv_dy);
+        base = F3{s.x, s.y, s.z};
+    }
+    base = F3{base.x * __ldg(&mi->base_color_factor[0]), base.y * __ldg(&mi->base_color_factor[1]), base.z * __ldg(&mi->base_color_factor[2])};
+    if (t_mr < LH_MAX_TEXTURES && P.textures[t_mr]) {
+        float4 s = tex2DGrad<float4>(P.textures[t_mr], u, v, duv_dx, duv_dy);
+        roughness = s.y;
+        metallic = s.z;
+    }
+    if (t_nrm != LH_UNUSED_TEXTURE_INDEX && t_nrm < LH_MAX_TEXTURES && P.textures[t_nrm]) {
+        float4 s = tex2DGrad<float4>(P.textures[t_nrm], u, v, duv_dx, duv_dy);
+        F3 mn{s.x * (255.0f / 127.0f) - 128.0f / 127.0f, s.y * (255.0f / 127.0f) - 128.0f / 127.0f, s.z * (255.0f / 127.0f) - 128.0f / 127.0f};
+        // compute_cotangent_frame (:25-38)
+        F3 pdx{wx.dx, wy.dx, wz.dx}, pdy{wx.dy, wy.dy, wz.dy};
+        F3 dpy_perp = cross(pdy, normal), dpx_perp = cross(normal, pdx);
+        F3 t3 = dpy_perp * duv_dx.x + dpx_perp * duv_dy.x;
+        F3 b3 = dpy_perp * duv_dx.y + dpx_perp * duv_dy.y;
+        float invmax = 1.0f / sqrtf(fmaxf(dot(t3, t3), dot(b3, b3)));
+        normal = normalize(t3 * (invmax * mn.x) + b3 * (invmax * mn.y) + normal * mn.z);
+    }
+    const float amb = 0.025f + 0.025f * normal.y;  // SH with sh[0] = sh[2] = 0.025 (:40-57)
+    const F3 sun = brdf(view_vec, F3{P.u.sun_dir[0], P.u.sun_dir[1], P.u.sun_dir[2]}, normal, roughness, metallic, base, alpha);
+    const float sun_intensity = kPi * shadow_sum;
+    const float dm = 1.0f - metallic;
+    store_rgba16f(P.scene, pixel, sun.x * sun_intensity + amb * dm * base.x, sun.y * sun_intensity + amb * dm * base.y,
+                  sun.z * sun_intensity + amb * dm * base.z, 1.0f);
+}
+
+// display_transform.comp:37-81: Tony McMapface LUT (48^3) + sRGB OETF -> BGRA8
+__device__ __forceinline__ float srgb_oetf(float v) { return v <= 0.003130f ? 12.92f * v : 1.055f * __powf(v, 1.0f / 2.4f) - 0.055f; }
+
+__global__ void __launch_bounds__(256) display_transform_kernel(const __grid_constant__ FrameParams P) {
+    const uint32_t W = P.u.window_size[0], H = P.u.window_size[1];
+    const uint64_t pixels = (uint64_t)W * H;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < pixels; i += (uint64_t)gridDim.x * blockDim.x) {
+        uint2 packed = reinterpret_cast<const uint2*>(P.scene)[i];
+        __half2 lo = *reinterpret_cast<__half2*>(&packed.x), hi = *reinterpret_cast<__half2*>(&packed.y);
+        float3 c = make_float3(fmaxf(__low2float(lo), 0.0f), fmaxf(__high2float(lo), 0.0f), fmaxf(__low2float(hi), 0.0f));
+        // encoded = c / (c + 1); uv = encoded * 47/48 + 0.5/48 (display_transform.comp:5-20)
+        float3 e = make_float3(c.x / (c.x + 1.0f), c.y / (c.y + 1.0f), c.z / (c.z + 1.0f));
+        float3 mapped = e;
+        if (P.lut) {
+            const float s = 47.0f / 48.0f, o = 0.5f / 48.0f;
+            float4 t = tex3D<float4>(P.lut, e.x * s + o, e.y * s + o, e.z * s + o);
+            mapped = make_float3(t.x, t.y, t.z);
+        }
+        uint32_t r = (uint32_t)__float2int_rn(fminf(fmaxf(srgb_oetf(mapped.x), 0.0f), 1.0f) * 255.0f);
+        uint32_t g = (uint32_t)__float2int_rn(fminf(fmaxf(srgb_oetf(mapped.y), 0.0f), 1.0f) * 255.0f);
+        uint32_t b = (uint32_t)__float2int_rn(fminf(fmaxf(srgb_oetf(mapped.z), 0.0f), 1.0f) * 255.0f);
+        reinterpret_cast<uint32_t*>(P.display)[i] = b | (g << 8) | (r << 16) | 0xFF000000u;  // B8G8R8A8
+    }
+}
+
+}  // namespace
+
+void launch_resolve(LhContext* ctx, const FrameParams& p) {
+    uint32_t W = p.u.window_size[0], rows = min(p.u.window_size[1], p.resolve_y1) - p.resolve_y0;
+    if (!W || !rows) return;
+    dim3 grid((W + 31) / 32, (rows + 7) / 8);
+    resolve_kernel<<<grid, 256, 0, ctx->stream>>>(p); ctx->launches++;
+}
+
+void launch_display_transform(LhContext* ctx, const FrameParams& p) {
+    display_transform_kernel<<<ctx->num_sms * 8, 256, 0, ctx->stream>>>(p); ctx->launches++;
+}
+
+}  // namespace lh

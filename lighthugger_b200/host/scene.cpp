@@ -708,7 +708,7 @@ int lh_scene_build_preset(LhScene* scene, int preset, uint32_t instance_count, u
     // camera outside the -z face of the (wide, flat) box looking at +z: the frustum holds about 40 % of it
     out->camera.position[0] = 0.0f;
     out->camera.position[1] = 0.0f;
-    out->camera.position[2] = -extent * 1.05f;
+    out->camera.position[2] = -extent * 1.15f;
     out->camera.yaw = 1.57079632679f;
     out->camera.pitch = 0.0f;
     return 0;

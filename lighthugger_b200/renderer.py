@@ -19,8 +19,8 @@ EXPORTS = [
     "lh_cull_meshlets", "lh_raster_visbuffer", "lh_composite", "lh_reduce_depth", "lh_generate_shadow_matrices",
     "lh_cull_instances_shadows", "lh_shadow_cascade", "lh_resolve", "lh_display_transform", "lh_render_frame",
     "lh_frame_sync", "lh_render_frame_host", "lh_get_frame_stats", "lh_get_target", "lh_get_timings",
-    "lh_get_target_address", "lh_timer_start", "lh_timer_stop", "lh_flush_l2", "lh_comm_unique_id", "lh_comm_init",
-    "lh_comm_destroy", "lh_comm_info", "lh_set_display_lut", "lh_set_shadow_cascade_mask",
+    "lh_get_target_address", "lh_get_launch_count", "lh_timer_start", "lh_timer_stop", "lh_flush_l2", "lh_comm_unique_id", "lh_comm_init",
+    "lh_comm_destroy", "lh_comm_info", "lh_set_display_lut", "lh_set_shadow_cascade_mask", "lh_shadow_exchange",
 ]
 
 
@@ -64,7 +64,7 @@ def cuda_lib():
         for name in ("lh_reset", "lh_cull_instances", "lh_cull_meshlets", "lh_raster_visbuffer", "lh_composite",
                      "lh_reduce_depth", "lh_generate_shadow_matrices", "lh_cull_instances_shadows", "lh_resolve",
                      "lh_display_transform", "lh_render_frame", "lh_frame_sync", "lh_timer_start", "lh_flush_l2",
-                     "lh_comm_destroy"):
+                     "lh_comm_destroy", "lh_shadow_exchange"):
             getattr(lib, name).argtypes = [vp]
         lib.lh_shadow_cascade.argtypes = [vp, u32]
         lib.lh_render_frame_host.argtypes = [vp, C.POINTER(S.LhUniforms), vp, u32, C.POINTER(S.LhFrameStats)]
@@ -73,6 +73,7 @@ def cuda_lib():
         lib.lh_get_timings.argtypes = [vp, C.POINTER(S.LhPassTimes)]
         lib.lh_get_target_address.argtypes = [vp, C.c_int, C.POINTER(u64)]
         lib.lh_timer_stop.argtypes = [vp, C.POINTER(C.c_float)]
+        lib.lh_get_launch_count.argtypes = [vp, C.POINTER(u64)]
         lib.lh_comm_unique_id.argtypes = [vp]
         lib.lh_comm_init.argtypes = [vp, C.c_int, C.c_int, vp]
         lib.lh_comm_info.argtypes = [vp, C.POINTER(C.c_int), C.POINTER(C.c_int)]
@@ -214,7 +215,13 @@ class Context:
     def timings(self):
         t = S.LhPassTimes()
         self._check(self.lib.lh_get_timings(self.handle, C.byref(t)))
-        return {n: float(t.ms[i]) for i, n in enumerate(S.LH_PASS_NAMES)} | {"frame": float(t.frame_ms)}
+        return {n: float(t.ms[i]) for i, n in enumerate(S.LH_PASS_NAMES)} | {
+            "frame": float(t.frame_ms), "raster_meshlets_kernel": float(t.raster_meshlets_kernel_ms)}
+
+    def launch_count(self):
+        n = C.c_uint64()
+        self._check(self.lib.lh_get_launch_count(self.handle, C.byref(n)))
+        return int(n.value)
 
     def download(self, addr, nbytes, dtype=np.uint8):
         out = np.zeros(nbytes // np.dtype(dtype).itemsize, dtype)
@@ -237,7 +244,7 @@ class Context:
         self._check(self.lib.lh_get_target(self.handle, which, out.ctypes.data, out.nbytes))
         return out
 
-    # views of the pipeline buffers, same shapes as tests/oracle_api.Oracle
+    # views of the pipeline buffers (the test-side checker exposes the same shapes)
     def sector(self, cascade=0):
         base = self.addresses.num_meshlets_prefix_sum + cascade * (self.cfg.max_instances * 8 + 8)
         counter = int(self.download(base, 8, np.uint64)[0])

@@ -14,8 +14,8 @@
 //   * samples at pixel centres, 64-bit integer edge functions, top-left rule:
 //     an edge with direction d owns its boundary iff d.y < 0 or
 //     (d.y == 0 and d.x > 0) once the triangle is oriented A2 > 0;
-//   * depth interpolated linearly in screen space:
-//     z = (z0 + b1 * (z1 - z0)) + b2 * (z2 - z0), b_k = float(w_k) / float(A2).
+//   * depth interpolated linearly in screen space with one reciprocal per
+//     triangle: z = z0 + (float(w1) * (z1 - z0) + float(w2) * (z2 - z0)) * (1 / float(A2)).
 #pragma once
 #include <cmath>
 #include <cstdint>
@@ -160,6 +160,8 @@ void raster_snapped(SnapVert a, SnapVert b, SnapVert c, int cull, uint32_t width
     int64_t bias1 = top_left(e1x, e1y) ? 0 : -1;
     int64_t bias2 = top_left(e2x, e2y) ? 0 : -1;
     float fA = (float)A2;
+    float inv_area = 1.0f / fA;
+    float dz1 = b.z - a.z, dz2 = c.z - a.z;
     for (int32_t py = py0; py <= py1; py++) {
         int64_t cy = (int64_t)py * 256 + 128;
         for (int32_t px = px0; px <= px1; px++) {
@@ -168,8 +170,8 @@ void raster_snapped(SnapVert a, SnapVert b, SnapVert c, int cull, uint32_t width
             int64_t w1 = e1x * (cy - c.y) - e1y * (cx - c.x);
             int64_t w2 = e2x * (cy - a.y) - e2y * (cx - a.x);
             if (((w0 + bias0) | (w1 + bias1) | (w2 + bias2)) < 0) continue;
-            float b1 = (float)w1 / fA, b2 = (float)w2 / fA;
             if (at.enabled) {
+                float b1 = (float)w1 / fA, b2 = (float)w2 / fA;
                 // perspective-correct uv, then the alpha test of
                 // visbuffer_alpha_clip_pixel (rasterization.glsl:90-97), sampled at mip 0
                 float b0 = (float)w0 / fA;
@@ -181,7 +183,7 @@ void raster_snapped(SnapVert a, SnapVert b, SnapVert c, int cull, uint32_t width
                 sample_texture_lod(*at.texture, tu, tv, 0.0f, rgba);
                 if (rgba[3] < 0.5f) continue;
             }
-            float z = (a.z + b1 * (b.z - a.z)) + b2 * (c.z - a.z);
+            float z = a.z + ((float)w1 * dz1 + (float)w2 * dz2) * inv_area;
             emit(px, py, z);
         }
     }

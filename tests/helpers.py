@@ -1,0 +1,103 @@
+"""Shared test plumbing: builds a scene once, binds it for the oracle (host
+memory) and for the CUDA layer (device memory), with identical textures."""
+import numpy as np
+
+from lighthugger_b200 import _structs as S
+from lighthugger_b200.scene import HostBinding, Scene
+from oracle_api import Oracle
+
+TEX_SIZE = 64
+
+
+def bc7_decode_mode6(blocks, width, height):
+    """Decodes BC7 mode-6 blocks (the only mode lh_bc7_encode emits) to RGBA8, per the BC7 specification."""
+    weights = np.array([0, 4, 9, 13, 17, 21, 26, 30, 34, 38, 43, 47, 51, 55, 60, 64], np.int64)
+    bw, bh = (width + 3) // 4, (height + 3) // 4
+    raw = blocks.reshape(bh * bw, 16)
+    lo = raw[:, :8].copy().view(np.uint64).reshape(-1)
+    hi = raw[:, 8:].copy().view(np.uint64).reshape(-1)
+
+    def bits(pos, n):
+        pos = int(pos)
+        if pos + n <= 64:
+            return (lo >> np.uint64(pos)) & np.uint64((1 << n) - 1)
+        if pos >= 64:
+            return (hi >> np.uint64(pos - 64)) & np.uint64((1 << n) - 1)
+        nlo = 64 - pos
+        return ((lo >> np.uint64(pos)) | ((hi & np.uint64((1 << (n - nlo)) - 1)) << np.uint64(nlo))) & np.uint64((1 << n) - 1)
+
+    assert np.all(bits(0, 7) == 64), "only BC7 mode 6 is expected"
+    e = np.zeros((len(raw), 2, 4), np.int64)
+    pos = 7
+    for c in range(4):
+        for k in range(2):
+            e[:, k, c] = bits(pos, 7).astype(np.int64)
+            pos += 7
+    p0, p1 = bits(pos, 1).astype(np.int64), bits(pos + 1, 1).astype(np.int64)
+    pos += 2
+    e[:, 0, :] = (e[:, 0, :] << 1) | p0[:, None]
+    e[:, 1, :] = (e[:, 1, :] << 1) | p1[:, None]
+    out = np.zeros((bh * 4, bw * 4, 4), np.uint8)
+    for t in range(16):
+        n = 3 if t == 0 else 4
+        idx = bits(pos, n).astype(np.int64)
+        pos += n
+        w = weights[idx][:, None]
+        val = ((64 - w) * e[:, 0, :] + w * e[:, 1, :] + 32) >> 6
+        out[(t // 4)::4, (t % 4)::4, :] = val.reshape(bh, bw, 4).astype(np.uint8)
+    return out[:height, :width]
+
+
+class Textures:
+    """The preset's texture table, both as BC7 blocks (for the device) and as
+    the RGBA8 the hardware decodes them to (for the oracle)."""
+
+    def __init__(self, scene, size=TEX_SIZE, bc7=True):
+        self.size = size
+        self.bc7 = bc7
+        self.entries = []  # (device_bytes, levels, decoded_rgba8_chain)
+        for rgba, levels, _ in scene.texture_table(size):
+            if bc7:
+                blocks, decoded, off = [], [], 0
+                for l in range(levels):
+                    s = max(1, size >> l)
+                    level = rgba[off:off + s * s * 4]
+                    off += s * s * 4
+                    b = scene.bc7_encode(np.ascontiguousarray(level), s, s)
+                    blocks.append(b)
+                    decoded.append(bc7_decode_mode6(b, s, s).reshape(-1))
+                self.entries.append((np.concatenate(blocks), levels, np.ascontiguousarray(np.concatenate(decoded))))
+            else:
+                self.entries.append((rgba, levels, rgba))
+
+    def oracle_table(self):
+        return [(dec, levels, self.size, True) for (_, levels, dec) in self.entries]
+
+    def upload(self, ctx):
+        fmt = S.LH_TEXTURE_BC7_SRGB if self.bc7 else S.LH_TEXTURE_RGBA8_SRGB
+        for i, (data, levels, _) in enumerate(self.entries):
+            slot = ctx.create_texture(fmt, self.size, self.size, levels, data)
+            assert slot == i
+
+
+def make_oracle(scene, textures=None, skybox=None, **kw):
+    hb = HostBinding(scene, kw.pop("caps", None))
+    return Oracle(hb, textures=textures.oracle_table() if textures else None, skybox=skybox, **kw)
+
+
+def make_context(scene, textures=None, skybox=None, caps=None, flags=None, width=None, height=None, **kw):
+    from lighthugger_b200.renderer import Context
+    ctx = Context(width or scene.width, height or scene.height, caps or scene.default_capacities(), flags=flags, **kw)
+    ctx.bind_scene(scene)
+    if textures:
+        textures.upload(ctx)
+    if skybox is not None:
+        ctx.create_skybox(int(round((skybox.size // 24) ** 0.5)), skybox)
+    return ctx
+
+
+def vis_fields(vis):
+    vis = np.asarray(vis, np.uint64)
+    depth = (~(vis >> np.uint64(32))).astype(np.uint32)
+    lo = (vis & np.uint64(0xFFFFFFFF)).astype(np.uint32)
+    return depth, lo >> 7, lo & 0x7F

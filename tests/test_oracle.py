@@ -1,0 +1,204 @@
+"""The oracle checked against independent restatements and the domain's own
+properties (the reference ships no golden vectors for this path: SURVEY.md 8c)."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from lighthugger_b200 import _structs as S
+from lighthugger_b200.scene import HostBinding, Scene
+from oracle_api import Oracle, oracle_lib
+from helpers import make_oracle, vis_fields
+
+
+def _mat(m):
+    return np.array([[m.m[c][r] for c in range(4)] for r in range(4)], np.float32)  # math layout
+
+
+def _instances(scene, hb):
+    ptr = scene.lib.lh_binding_instances(hb.handle)
+    return np.ctypeslib.as_array(C.cast(ptr, C.POINTER(C.c_float)), (scene.num_instances, 28)).copy()
+
+
+def numpy_cull_instances(scene, hb, u):
+    """cull_bounding_sphere (common/culling.glsl:1-46) restated in numpy float32, glm operation order."""
+    f32 = np.float32
+    inst = _instances(scene, hb)
+    out = []
+    P = np.array([[u.perspective.m[c][r] for r in range(4)] for c in range(4)], f32)  # P[c][r]
+    V = np.array([[u.initial_view.m[c][r] for r in range(4)] for c in range(4)], f32)
+
+    def norm3(v):
+        l = np.sqrt(f32(f32(v[0] * v[0] + v[1] * v[1]) + v[2] * v[2]))
+        return np.array([v[0] / l, v[1] / l, v[2] / l], f32)
+
+    def mul(Mc, x, y, z, w):
+        return np.array([f32(f32(Mc[0][r] * x + Mc[1][r] * y) + f32(Mc[2][r] * z + Mc[3][r] * w)) for r in range(4)], f32)
+
+    fx = norm3(np.array([P[0][3] + P[0][0], P[1][3] + P[1][0], P[2][3] + P[2][0]], f32))
+    fy = norm3(np.array([P[0][3] + P[0][1], P[1][3] + P[1][1], P[2][3] + P[2][1]], f32))
+    info = scene.mesh_view(0).info
+    sphere = np.array(info.bounding_sphere[:], f32)
+    for i in range(len(inst)):
+        T = inst[i, :16].reshape(4, 4)  # T[c][r]
+        w = mul(T, sphere[0], sphere[1], sphere[2], f32(1))
+        lens = [np.sqrt(f32(f32(T[c][0] * T[c][0] + T[c][1] * T[c][1]) + T[c][2] * T[c][2])) for c in range(3)]
+        radius = f32(sphere[3] * max(lens))
+        v = mul(V, w[0], w[1], w[2], f32(1))
+        vz = f32(-v[2])
+        vis = (f32(vz + radius) > f32(0.01)) and (f32(f32(vz * fx[2]) + f32(abs(v[0]) * fx[0])) < radius) and \
+              (f32(f32(vz * fy[2]) - f32(abs(v[1]) * fy[1])) < radius)
+        if vis:
+            out.append(i)
+    return out
+
+
+def test_instance_cull_matches_numpy_restatement():
+    sc = Scene.preset("tiny")
+    o = make_oracle(sc)
+    o.reset()
+    o.cull_instances()
+    count, total, vals = o.sector(0)
+    expect = numpy_cull_instances(sc, o.binding, o.u)
+    assert list(vals[:, 0]) == expect
+    nm = sc.mesh_view(0).info.num_meshlets
+    assert list(vals[:, 1]) == [nm * (k + 1) for k in range(count)] and total == nm * count  # inclusive sums
+    assert 0 < count < sc.num_instances
+
+
+def test_reset_and_dispatch_sizes():
+    sc = Scene.preset("tiny")
+    o = make_oracle(sc)
+    o.reset()
+    d = o.dispatches()
+    assert list(d[0]) == [1, 1, 1] and list(d[1]) == [4, 1, 1]  # ceil(64/64), ceil(64/16): reset_buffers.glsl:9-29
+    m = o.misc()
+    assert m.min_depth == 0xFFFFFFFF and m.max_depth == 0
+    assert o.draw_counts() == (0, 0) and o.sector(0)[:2] == (0, 0)
+
+
+def test_meshlet_cull_is_the_inverse_of_the_prefix_sum():
+    sc = Scene.preset("tiny")
+    o = make_oracle(sc)
+    o.reset(); o.cull_instances(); o.cull_meshlets()
+    count, total, vals = o.sector(0)
+    n_opaque, n_alpha = o.draw_counts()
+    assert n_alpha == 0 and 0 < n_opaque < total
+    refs = o.meshlet_references(0, n_opaque)
+    cmds = o.draw_commands(0, n_opaque)
+    nm = sc.mesh_view(0).info.num_meshlets
+    # ascending global meshlet id: (visible-instance order, meshlet index) strictly increasing
+    order = {int(v): k for k, v in enumerate(vals[:, 0])}
+    g = np.array([order[int(i)] * nm + int(m) for i, m in refs])
+    assert np.all(np.diff(g) > 0)
+    tc = sc.mesh_arrays(0)["meshlets"][:, 52].astype(np.uint32)
+    assert np.array_equal(cmds[:, 0], tc[refs[:, 1]] * 3) and np.all(cmds[:, 1] == 1) and np.all(cmds[:, 2] == 0)
+    assert np.array_equal(cmds[:, 3], np.arange(n_opaque, dtype=np.uint32))  # firstInstance = slot
+    assert list(o.dispatches()[2]) == [(total - 1) // 64 + 1, 1, 1]  # reset_buffers_b
+
+
+def _single_triangle_scene(verts_px, width=64, height=64):
+    """One instance of a one-triangle plane-like mesh is not expressible through the generator; use a quad mesh
+    and an orthographic-like camera far away instead: covered by test_raster_properties below."""
+
+
+def test_raster_properties_watertight_and_deterministic():
+    # a dense plane facing the camera: every interior pixel covered exactly by one triangle id, no holes on shared edges
+    sc = Scene()
+    mid = sc.add_mesh(S.LH_MESH_PLANE, 24, 24)
+    # the plane lies in xz with +y normal; a half-turn about (0, 1, 1)/sqrt2 maps +y to +z, i.e. it faces a camera at -z looking +z? no: towards +z
+    s = 2 ** -0.5
+    sc.add_instance(mid, (0, 0, 0), (0, s, s, 0), 3.0)
+    sc.camera.position[:] = (0, 0, 2.0)
+    sc.camera.yaw = -np.pi / 2  # facing -z
+    sc.width, sc.height = 160, 96
+    o = make_oracle(sc)
+    o.reset(); o.cull_instances(); o.cull_meshlets(); o.raster_visbuffer()
+    depth, slot, tri = vis_fields(o.vis)
+    covered = (depth != 0).reshape(sc.height, sc.width)
+    # the 3x3 plane at distance 2 overfills a 45-degree view: the centre region is fully covered
+    assert covered[8:-8, 8:-8].all()
+    v1 = o.vis.copy()
+    o.cfg.threads = 1
+    o.raster_visbuffer()
+    assert np.array_equal(v1, o.vis)  # order independence of the atomic-min resolve
+
+
+def test_depth_reduction_matches_numpy():
+    sc = Scene.preset("tiny")
+    o = make_oracle(sc)
+    o.reset(); o.cull_instances(); o.cull_meshlets(); o.raster_visbuffer(); o.reduce_depth()
+    depth, _, _ = vis_fields(o.vis)
+    m = o.misc()
+    assert m.max_depth == depth.max() and m.min_depth == depth[depth != 0].min()
+
+
+def test_depth_reduction_of_an_empty_frame_keeps_the_reset_values():
+    sc = Scene.preset("tiny")
+    sc.camera.yaw = -np.pi / 2  # look away from the scene
+    o = make_oracle(sc)
+    o.render_frame(resolve=False)
+    depth, _, _ = vis_fields(o.vis)
+    assert (depth == 0).all()
+    m = o.misc()
+    assert m.min_depth == 0xFFFFFFFF and m.max_depth == 0
+
+
+def test_shadow_cascades_nest_and_partition():
+    sc = Scene.preset("tiny")
+    o = make_oracle(sc)
+    o.render_frame(resolve=False)
+    m = o.misc()
+    radii = list(m.shadow_sphere_radii)
+    assert all(r > 0 for r in radii) and radii == sorted(radii)
+    assert all((r * 16) == int(r * 16) for r in radii)  # ceil(r * 16) / 16
+    sh = o.shadow.reshape(4, 1024, 1024)
+    assert all((sh[c] < 1.0).any() for c in range(4)) and sh.min() >= 0.0 and sh.max() <= 1.0
+
+
+def test_sort_last_partition_composites_to_the_whole_frame():
+    sc = Scene.preset("tiny")
+    whole = make_oracle(sc)
+    whole.reset(); whole.cull_instances(); whole.cull_meshlets(); whole.raster_visbuffer()
+    ref_w = whole.meshlet_references(0, whole.draw_counts()[0])
+    n = sc.num_instances
+    acc = np.full_like(whole.vis, S.LH_VIS_CLEAR)
+    triples = {}
+    for first, count in ((0, n // 3), (n // 3, n - n // 3)):
+        part = make_oracle(sc, instance_range=(first, count))
+        part.reset(); part.cull_instances(); part.cull_meshlets(); part.raster_visbuffer()
+        oracle_lib().lho_composite_min(acc.ctypes.data, part.vis.ctypes.data, acc.size)
+        triples[first] = (part.vis.copy(), part.meshlet_references(0, part.draw_counts()[0]))
+    # depth bits are identical; ids are compared as (instance, meshlet, triangle) through each partition's own table
+    dw, sw, tw = vis_fields(whole.vis)
+    da, _, _ = vis_fields(acc)
+    assert np.array_equal(dw, da)
+    got = np.zeros((acc.size, 3), np.int64) - 1
+    for first, (vis, refs) in triples.items():
+        d, s, t = vis_fields(vis)
+        win = (vis == acc) & (d != 0)
+        got[win, 0] = refs[s[win], 0]
+        got[win, 1] = refs[s[win], 1]
+        got[win, 2] = t[win]
+    cov = dw != 0
+    want = np.stack([ref_w[sw[cov], 0], ref_w[sw[cov], 1], tw[cov]], 1)
+    assert np.array_equal(got[cov], want)
+
+
+def test_pinned_pow_is_close_to_libm():
+    lib = oracle_lib()
+    for x, p in ((0.5, 3.0), (0.75, 3.0), (0.5, 1.0), (0.75, 0.37), (0.5, 7.5)):
+        assert abs(lib.lho_pinned_powf(x, p) - x ** p) <= 2e-7 * x ** p + 1e-12
+
+
+def test_resolve_is_finite_and_sky_where_empty():
+    sc = Scene.preset("tiny")
+    from helpers import Textures
+    tex = Textures(sc, 32)
+    sky = sc.make_skybox(8)
+    o = make_oracle(sc, textures=tex, skybox=sky)
+    o.render_frame(resolve=True)
+    col = o.color.reshape(-1, 4)
+    assert np.isfinite(col).all() and (col[:, 3] == 1).all() and (col[:, :3] >= 0).all()
+    depth, _, _ = vis_fields(o.vis)
+    assert (depth == 0).any() and (depth != 0).any()
