@@ -310,8 +310,8 @@ int lh_texture_create(LhContext* ctx, int format, uint32_t width, uint32_t heigh
     switch (format) {
     case LH_TEXTURE_RGBA8_SRGB: desc = cudaCreateChannelDesc<uchar4>(); srgb = true; break;
     case LH_TEXTURE_RGBA8_UNORM: desc = cudaCreateChannelDesc<uchar4>(); break;
-    case LH_TEXTURE_BC7_SRGB: desc = cudaCreateChannelDesc<cudaChannelFormatKindUnsignedBlockCompressed7SRGB>(); block = true; break;
-    case LH_TEXTURE_BC1_SRGB: desc = cudaCreateChannelDesc<cudaChannelFormatKindUnsignedBlockCompressed1SRGB>(); block = true; break;
+    case LH_TEXTURE_BC7_SRGB: desc = cudaCreateChannelDesc<cudaChannelFormatKindUnsignedBlockCompressed7SRGB>(); block = true; srgb = true; break;
+    case LH_TEXTURE_BC1_SRGB: desc = cudaCreateChannelDesc<cudaChannelFormatKindUnsignedBlockCompressed1SRGB>(); block = true; srgb = true; break;
     default: return fail(ctx, LH_ERR_UNSUPPORTED, "unknown texture format");
     }
     const uint32_t block_bytes = format == LH_TEXTURE_BC1_SRGB ? 8 : 16;
@@ -350,7 +350,7 @@ int lh_texture_create(LhContext* ctx, int format, uint32_t width, uint32_t heigh
     td.maxAnisotropy = 16;
     td.minMipmapLevelClamp = 0.0f;
     td.maxMipmapLevelClamp = (float)(mip_levels - 1);
-    td.sRGB = srgb ? 1 : 0;
+    td.sRGB = srgb ? 1 : 0;  // the driver rejects a BC*_SRGB array unless the sRGB read flag is set too (probed on B200)
     cudaTextureObject_t tex = 0;
     cudaError_t e = cudaCreateTextureObject(&tex, &res, &td, nullptr);
     if (e != cudaSuccess) {
