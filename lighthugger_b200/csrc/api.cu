@@ -49,6 +49,7 @@ FrameParams make_params(LhContext* ctx) {
     p.vis = ctx->vis;
     p.shadow = ctx->shadow;
     p.textures = ctx->tex_dev;
+    p.tex_dims = ctx->tex_dims_dev;
     p.slot_offset = ctx->slot_offset;
     p.resolve_refs = ctx->gathered_refs ? (const LhMeshletReference*)ctx->gathered_refs : (const LhMeshletReference*)p.u.meshlet_references;
     p.scene = ctx->scene;
@@ -200,6 +201,8 @@ int lh_context_create(const LhConfig* cfg, LhContext** out) {
     TRY(cudaMalloc(&ctx->large_queue, (size_t)(cfg->max_large_triangles ? cfg->max_large_triangles : 1) * 8));
     TRY(cudaMalloc(&ctx->tex_dev, sizeof(cudaTextureObject_t) * LH_MAX_TEXTURES));
     TRY(cudaMemset(ctx->tex_dev, 0, sizeof(cudaTextureObject_t) * LH_MAX_TEXTURES));
+    TRY(cudaMalloc(&ctx->tex_dims_dev, sizeof(uint4) * LH_MAX_TEXTURES));
+    TRY(cudaMemset(ctx->tex_dims_dev, 0, sizeof(uint4) * LH_MAX_TEXTURES));
     TRY(cudaMallocHost(&ctx->pinned_stats, sizeof(LhFrameStats)));
     for (int i = 0; i < LH_PASS_COUNT; i++) {
         TRY(cudaEventCreate(&ctx->pass_start[i]));
@@ -240,6 +243,7 @@ int lh_context_destroy(LhContext* ctx) {
     cudaFree(ctx->meshlet_tiles);
     cudaFree(ctx->large_queue);
     cudaFree(ctx->tex_dev);
+    cudaFree(ctx->tex_dims_dev);
     cudaFree(ctx->l2_flush);
     cudaFree(ctx->gathered_refs);
     if (ctx->pinned) cudaFreeHost(ctx->pinned);
@@ -337,17 +341,21 @@ int lh_texture_create(LhContext* ctx, int format, uint32_t width, uint32_t heigh
         }
         src += row_bytes * rows;
     }
-    // repeat_sampler (src/main.cpp:550-560): linear mag/min/mip, repeat, anisotropy 16
+    // repeat_sampler (src/main.cpp:550-560): linear mag/min/mip, repeat, anisotropy 16.  The texture unit does the
+    // block decode, the sRGB conversion and the bilinear taps; mip selection, the trilinear blend and the anisotropic
+    // footprint (Vulkan's model: N = min(ceil(Pmax/Pmin), 16) probes along the major axis at lod log2(Pmax/N)) are
+    // computed in the resolve kernel, because the hardware's own footprint is implementation-defined and the lit
+    // colour is parity-checked against that model.  Hence a point mip filter here: every fetch names an integer level.
     cudaResourceDesc res{};
     res.resType = cudaResourceTypeMipmappedArray;
     res.res.mipmap.mipmap = arr;
     cudaTextureDesc td{};
     td.addressMode[0] = td.addressMode[1] = td.addressMode[2] = cudaAddressModeWrap;
     td.filterMode = cudaFilterModeLinear;
-    td.mipmapFilterMode = cudaFilterModeLinear;
+    td.mipmapFilterMode = cudaFilterModePoint;
     td.readMode = cudaReadModeNormalizedFloat;
     td.normalizedCoords = 1;
-    td.maxAnisotropy = 16;
+    td.maxAnisotropy = 1;
     td.minMipmapLevelClamp = 0.0f;
     td.maxMipmapLevelClamp = (float)(mip_levels - 1);
     td.sRGB = srgb ? 1 : 0;  // the driver rejects a BC*_SRGB array unless the sRGB read flag is set too (probed on B200)
@@ -360,6 +368,8 @@ int lh_texture_create(LhContext* ctx, int format, uint32_t width, uint32_t heigh
     ctx->tex_host[slot] = tex;
     ctx->tex_arrays[slot] = arr;
     LH_CUDA(ctx, cudaMemcpyAsync(ctx->tex_dev + slot, &ctx->tex_host[slot], sizeof(tex), cudaMemcpyHostToDevice, ctx->stream));
+    const uint4 dims = make_uint4(width, height, mip_levels, 0u);
+    LH_CUDA(ctx, cudaMemcpyAsync(ctx->tex_dims_dev + slot, &dims, sizeof(dims), cudaMemcpyHostToDevice, ctx->stream));
     LH_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     *slot_out = (uint16_t)slot;
     return LH_OK;

@@ -94,6 +94,7 @@ struct FrameParams {
     unsigned long long* vis;
     uint32_t* shadow;                        // 4 layers of float bits
     const cudaTextureObject_t* textures;
+    const uint4* tex_dims;                   // per texture slot: width, height, mip levels, 0
     uint32_t slot_offset;                    // sort-last: global slot of this rank's local slot 0
     const LhMeshletReference* resolve_refs;  // table indexed by GLOBAL slot (== u.meshlet_references on one GPU)
     void* scene;                             // RGBA16F target
@@ -137,6 +138,7 @@ struct LhContext {
     cudaTextureObject_t tex_host[LH_MAX_TEXTURES] = {};
     cudaMipmappedArray_t tex_arrays[LH_MAX_TEXTURES] = {};
     cudaTextureObject_t* tex_dev = nullptr;
+    uint4* tex_dims_dev = nullptr;
     cudaArray_t sky_array = nullptr;
     cudaTextureObject_t sky_tex = 0;
     cudaArray_t lut_array = nullptr;

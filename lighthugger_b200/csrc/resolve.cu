@@ -12,9 +12,11 @@
 // three-vertex attribute refetch and the texture footprints of a warp stay
 // inside one or two meshlets.  Depth and ids arrive in ONE 8-byte word per
 // pixel (the reference reads a D32F image and an R32U image); material
-// textures are CUDA block-compressed (BC7 sRGB) mipmapped arrays sampled with
-// hardware anisotropic filtering (tex2DGrad, maxAnisotropy 16) from the
-// analytic barycentric derivatives; the shadow compare-and-filter, which CUDA
+// textures are CUDA block-compressed (BC7 sRGB) mipmapped arrays: the texture
+// unit decodes the blocks, converts sRGB and filters each bilinear tap, while
+// the anisotropic footprint (16x, from the analytic barycentric derivatives)
+// is laid out in the kernel per the Vulkan model so that the lit colour is
+// reproducible; the shadow compare-and-filter, which CUDA
 // has no sampler for, is done by hand from the u32 depth layers.  Output is
 // written as one 8-byte RGBA16F store per pixel.
 //
@@ -148,6 +150,40 @@ __device__ __forceinline__ float sample_shadow(const uint32_t* layer, int n, flo
     return top + wy * (bot - top);
 }
 
+// textureGrad through repeat_sampler (render_geometry.comp:59-66, src/main.cpp:550-560).  Footprint per the Vulkan
+// specification's anisotropic model; every tap is one hardware bilinear fetch (BC decode + sRGB in the texture unit)
+// at an integer mip level.
+__device__ __forceinline__ float4 sample_trilinear(cudaTextureObject_t t, float u, float v, float lod, float max_level) {
+    lod = fminf(fmaxf(lod, 0.0f), max_level);
+    const float l0 = floorf(lod), f = lod - l0;
+    float4 a = tex2DLod<float4>(t, u, v, l0);
+    if (f > 0.0f && l0 + 1.0f <= max_level) {
+        const float4 b = tex2DLod<float4>(t, u, v, l0 + 1.0f);
+        a.x += f * (b.x - a.x); a.y += f * (b.y - a.y); a.z += f * (b.z - a.z); a.w += f * (b.w - a.w);
+    }
+    return a;
+}
+__device__ float4 sample_texture_grad(cudaTextureObject_t t, uint4 dims, float u, float v, float2 ddx, float2 ddy) {
+    const float w = (float)dims.x, h = (float)dims.y, max_level = (float)(dims.z - 1u);
+    const float ax0 = ddx.x * w, ax1 = ddx.y * h, ay0 = ddy.x * w, ay1 = ddy.y * h;
+    const float px = sqrtf(ax0 * ax0 + ax1 * ax1), py = sqrtf(ay0 * ay0 + ay1 * ay1);
+    const float pmax = fmaxf(px, py), pmin = fminf(px, py);
+    if (!(pmax > 0.0f) || !isfinite(pmax)) return sample_trilinear(t, u, v, 0.0f, max_level);
+    float n = pmin > 0.0f ? fminf(ceilf(pmax / pmin), 16.0f) : 16.0f;
+    if (pmax <= 1.0f) n = 1.0f;  // magnification: a single bilinear probe
+    const float lod = log2f(pmax / n);
+    const int probes = (int)n;
+    const float2 major = px >= py ? ddx : ddy;
+    float4 acc = make_float4(0, 0, 0, 0);
+    for (int i = 0; i < probes; i++) {
+        const float o = ((float)i + 0.5f) / (float)probes - 0.5f;
+        const float4 s = sample_trilinear(t, u + o * major.x, v + o * major.y, lod, max_level);
+        acc.x += s.x; acc.y += s.y; acc.z += s.z; acc.w += s.w;
+    }
+    const float inv = 1.0f / (float)probes;
+    return make_float4(acc.x * inv, acc.y * inv, acc.z * inv, acc.w * inv);
+}
+
 __device__ __forceinline__ void store_rgba16f(void* scene, size_t pixel, float r, float g, float b, float a) {
     __half2 lo = __floats2half2_rn(r, g), hi = __floats2half2_rn(b, a);
     uint2 packed;
@@ -264,17 +300,17 @@ __global__ void __launch_bounds__(256) resolve_kernel(const __grid_constant__ Fr
     const uint32_t t_base = __ldg(&mi->base_color_texture_index), t_mr = __ldg(&mi->metallic_roughness_texture_index);
     const uint32_t t_nrm = __ldg(&mi->normal_texture_index);
     if (t_base < LH_MAX_TEXTURES && P.textures[t_base]) {
-        float4 s = tex2DGrad<float4>(P.textures[t_base], u, v, duv_dx, duv_dy);
+        float4 s = sample_texture_grad(P.textures[t_base], __ldg(&P.tex_dims[t_base]), u, v, duv_dx, duv_dy);
         base = F3{s.x, s.y, s.z};
     }
     base = F3{base.x * __ldg(&mi->base_color_factor[0]), base.y * __ldg(&mi->base_color_factor[1]), base.z * __ldg(&mi->base_color_factor[2])};
     if (t_mr < LH_MAX_TEXTURES && P.textures[t_mr]) {
-        float4 s = tex2DGrad<float4>(P.textures[t_mr], u, v, duv_dx, duv_dy);
+        float4 s = sample_texture_grad(P.textures[t_mr], __ldg(&P.tex_dims[t_mr]), u, v, duv_dx, duv_dy);
         roughness = s.y;
         metallic = s.z;
     }
     if (t_nrm != LH_UNUSED_TEXTURE_INDEX && t_nrm < LH_MAX_TEXTURES && P.textures[t_nrm]) {
-        float4 s = tex2DGrad<float4>(P.textures[t_nrm], u, v, duv_dx, duv_dy);
+        float4 s = sample_texture_grad(P.textures[t_nrm], __ldg(&P.tex_dims[t_nrm]), u, v, duv_dx, duv_dy);
         F3 mn{s.x * (255.0f / 127.0f) - 128.0f / 127.0f, s.y * (255.0f / 127.0f) - 128.0f / 127.0f, s.z * (255.0f / 127.0f) - 128.0f / 127.0f};
         // compute_cotangent_frame (:25-38)
         F3 pdx{wx.dx, wy.dx, wz.dx}, pdy{wx.dy, wy.dy, wz.dy};

@@ -1,7 +1,8 @@
 """Lighting resolve and alpha-clip raster: floating point / texture filtering,
 so compared with stated tolerances:
-  lit colour: |delta| <= 2/255 per channel after the display transfer on >= 99.9 % of pixels, <= 8/255 on the rest
-              (we allow 0.5 % / 24/255: BC7 + hardware anisotropic filtering vs the oracle's trilinear model)
+  lit colour: |delta| <= 2/255 per channel after the display transfer on >= 99.8 % of pixels, <= 12/255 on the rest.
+              Measured on B200: 0.05-0.13 % of pixels above 2/255, maximum 8.7/255.  What remains is the texture unit's
+              8-bit bilinear weights against the oracle's float weights, fp16 stores and fused multiply-adds.
   vis ids with alpha-clip geometry: mismatch <= 0.1 % of covered pixels."""
 import numpy as np
 import pytest
@@ -19,14 +20,14 @@ def display(c):
     return np.where(c <= 0.0031308, 12.92 * c, 1.055 * np.power(c, 1 / 2.4) - 0.055)
 
 
-def compare_color(ctx, o, frac_tol=0.005, tight=2 / 255, loose=24 / 255):
+def compare_color(ctx, o, frac_tol=0.002, tight=2 / 255, loose=12 / 255):
     got = ctx.target(S.LH_TARGET_SCENE_RGBA16F).astype(np.float32).reshape(-1, 4)
     want = o.color.reshape(-1, 4)
     assert np.isfinite(got).all() and (got[:, 3] == 1).all()
     d = np.abs(display(got[:, :3]) - display(want[:, :3])).max(axis=1)
     bad = np.count_nonzero(d > tight) / len(d)
     assert bad <= frac_tol, f"{bad:.4%} of pixels differ by more than 2/255 (max {d.max():.4f})"
-    assert np.quantile(d, 0.9995) <= loose, f"99.95th percentile error {np.quantile(d, 0.9995):.4f}"
+    assert d.max() <= loose, f"maximum error {d.max():.4f} exceeds 12/255"
     return bad, float(d.max())
 
 
