@@ -201,6 +201,8 @@ __global__ void gather_stats_kernel(const __grid_constant__ FrameParams P, LhFra
     s.num_large_triangles = st->main_large_count;
     s.overflow = st->overflow;
     s.rasterized_triangles = st->rasterized_triangles;
+    s.meshlets_skipped_no_sample = st->skipped_empty;
+    s.meshlets_skipped_occluded = st->skipped_occluded;
     *out = s;
 }
 

@@ -73,6 +73,8 @@ struct FrameState {
     uint32_t tickets[8];           // tile tickets: [0] main meshlet cull, [1..4] cascades
     uint32_t done[8];              // CTAs finished (self-cleaning of the tile states)
     unsigned long long rasterized_triangles;
+    uint32_t raster_ticket;        // next unclaimed meshlet of the current raster pass
+    uint32_t skipped_empty, skipped_occluded;   // main-view meshlets dropped by the early-outs (stats)
 };
 
 constexpr uint32_t kMeshletTile = 1024;        // candidate meshlets per scan tile

@@ -40,13 +40,18 @@ constexpr int kSmallMaxExtent = 1 << 14;        // ... and sub-pixel extent < 2^
 enum { CULL_NONE = 0, CULL_BACK = 1, CULL_FRONT = 2 };
 enum { FLAG_INSIDE = 1, FLAG_SNAPPED = 2 };
 
-struct WarpVerts {
-    float4 clip[LH_MAX_MESHLET_UNIQUE_VERTICES];
+// Per-warp scratch of the meshlet kernel: snapped vertices and the compacted list of triangles that cover a sample.
+// sx holds two sentinels instead of a flag byte: kVertOutside (behind the w - z >= 0 plane) and kVertNonFinite.
+struct WarpScratch {
     int sx[LH_MAX_MESHLET_UNIQUE_VERTICES];
     int sy[LH_MAX_MESHLET_UNIQUE_VERTICES];
     float z[LH_MAX_MESHLET_UNIQUE_VERTICES];
-    uint8_t flags[LH_MAX_MESHLET_UNIQUE_VERTICES];
+    float w[LH_MAX_MESHLET_UNIQUE_VERTICES];   // clip w, written for alpha-clip meshlets only (perspective-correct uv)
+    uint8_t surv[128];
 };
+constexpr int kVertOutside = INT_MIN, kVertNonFinite = INT_MIN + 1;   // |snapped| <= 2^29, so neither can be a coordinate
+constexpr uint32_t kTicketChunk = 4;       // meshlets a warp takes per ticket
+constexpr int kMaxOcclusionBlocks = 16;    // early-out reads at most 16 blocks of 8x4 pixels (512 keys)
 
 struct SnapVert {
     int x, y;
@@ -221,6 +226,7 @@ __device__ void raster_clip_triangle_coop(const ClipVert v[3], int cull, const T
 // Everything needed to locate one meshlet's data; loaded by every lane from the same addresses (broadcast).
 struct MeshletHeader {
     float T[16];
+    float sphere[4];            // Meshlet.bounding_sphere (object space)
     const uint16_t* positions;
     const void* indices;
     const uint16_t* uvs;
@@ -251,8 +257,14 @@ __device__ __forceinline__ void load_header(const FrameParams& P, uint32_t slot,
     const uint32_t flags = __ldg(&mi->flags);
     h.wide = (flags & LH_MESH_INFO_FLAGS_32_BIT_INDICES) != 0;
     h.alpha = (flags & LH_MESH_INFO_FLAGS_ALPHA_CLIP) != 0;
-    const unsigned long long tail = __ldg((const unsigned long long*)m + 6);  // index_offset | counts
-    h.micro = micro + __ldg(&m->triangle_offset);
+    // bytes 24..55 of the 56-byte Meshlet as four 8-byte loads: cutoff|sphere.x, sphere.yz, sphere.w|triangle_offset, index_offset|counts
+    const unsigned long long q3 = __ldg((const unsigned long long*)m + 3), q4 = __ldg((const unsigned long long*)m + 4);
+    const unsigned long long q5 = __ldg((const unsigned long long*)m + 5), tail = __ldg((const unsigned long long*)m + 6);
+    h.sphere[0] = __uint_as_float((uint32_t)(q3 >> 32));
+    h.sphere[1] = __uint_as_float((uint32_t)q4);
+    h.sphere[2] = __uint_as_float((uint32_t)(q4 >> 32));
+    h.sphere[3] = __uint_as_float((uint32_t)q5);
+    h.micro = micro + (uint32_t)(q5 >> 32);
     h.index_offset = (uint32_t)tail;
     h.tri_count = (uint32_t)(tail >> 32) & 0xFFu;
     h.vert_count = (uint32_t)(tail >> 40) & 0xFFu;
@@ -294,11 +306,32 @@ __device__ __forceinline__ void push_deferred(const FrameParams& P, uint32_t lo,
 }
 
 // ---- kernel 1: one warp per meshlet ----
+//
+// Per meshlet: (0) early-outs from the meshlet's bounding sphere -- interval arithmetic through the same matrix gives
+// a conservative pixel rectangle and a conservative nearest depth; the meshlet is dropped when the rectangle holds no
+// pixel centre, or when every key already stored in it is nearer than anything the meshlet can produce (the software
+// counterpart of the hierarchical-Z reject the reference gets from its hardware rasteriser; keys only ever decrease, so
+// a stale read is conservative and the final buffer is bit-identical); (1) vertex phase, one lane per vertex;
+// (2) triangle cull phase, one lane per triangle: near-plane / bounding-box / facing tests, survivors compacted by
+// ballot into shared memory; (3) raster phase over the compacted list, so lanes are not idle behind rejected
+// triangles.  Meshlets are handed out by ticket (kTicketChunk per atomic) because the early-outs unbalance a static split.
+
+// sigma_max(T) * r bounds |T (v - c)| for v in the object-space sphere (c, r).  Gershgorin on the Gram matrix and the
+// Frobenius norm are both valid for any matrix; for rotation * scale the first equals the reference's max column length.
+__device__ __forceinline__ float sigma_max_bound(const float* T) {
+    const float c00 = T[0] * T[0] + T[1] * T[1] + T[2] * T[2], c11 = T[4] * T[4] + T[5] * T[5] + T[6] * T[6],
+                c22 = T[8] * T[8] + T[9] * T[9] + T[10] * T[10];
+    const float c01 = fabsf(T[0] * T[4] + T[1] * T[5] + T[2] * T[6]), c02 = fabsf(T[0] * T[8] + T[1] * T[9] + T[2] * T[10]),
+                c12 = fabsf(T[4] * T[8] + T[5] * T[9] + T[6] * T[10]);
+    const float gersh = fmaxf(fmaxf(c00 + c01 + c02, c11 + c01 + c12), c22 + c02 + c12);
+    return sqrtf(fminf(gersh, c00 + c11 + c22)) * 1.00001f;
+}
+
 template <bool SHADOW>
 __global__ void __launch_bounds__(kWarpsPerCta * 32) raster_meshlets_kernel(const __grid_constant__ FrameParams P, uint32_t cascade) {
-    __shared__ WarpVerts verts_all[kWarpsPerCta];
+    __shared__ WarpScratch scratch_all[kWarpsPerCta];
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    WarpVerts& sv = verts_all[warp];
+    WarpScratch& sv = scratch_all[warp];
     const uint32_t* draw = (const uint32_t*)P.u.draw_calls;
     const uint32_t n_opaque = min(draw[0], P.max_opaque);   // drawIndirectCount clamps to maxDrawCount
     const uint32_t n_alpha = min(draw[1], P.max_alpha);
@@ -312,144 +345,231 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) raster_meshlets_kernel(cons
     const float half_w = pmul((float)tg.width, 0.5f), half_h = pmul((float)tg.height, 0.5f);
     const int W = (int)tg.width, H = (int)tg.height;
 
-    float M[16];
-    {
-        const float* src = SHADOW ? &((const LhMiscStorage*)P.u.misc_storage)->shadow_matrices[cascade].m[0][0] : &P.u.combined_perspective_view.m[0][0];
+    // The main view multiplies by the kernel parameter itself (constant-bank operands, no registers); a cascade's
+    // matrix was generated on the device and is held in registers.
+    float Mreg[SHADOW ? 16 : 1];
+    if (SHADOW) {
+        const float* src = &((const LhMiscStorage*)P.u.misc_storage)->shadow_matrices[cascade].m[0][0];
 #pragma unroll
-        for (int k = 0; k < 16; k++) M[k] = src[k];
+        for (int k = 0; k < (SHADOW ? 16 : 1); k++) Mreg[k] = src[k];
     }
-    uint32_t tris_done = 0;
+    const float* M = SHADOW ? Mreg : &P.u.combined_perspective_view.m[0][0];
+    // |row_k.xyz| of M, for the interval bounds of the early-outs
+    const float nrm_x = sqrtf(M[0] * M[0] + M[4] * M[4] + M[8] * M[8]), nrm_y = sqrtf(M[1] * M[1] + M[5] * M[5] + M[9] * M[9]);
+    const float nrm_z = sqrtf(M[2] * M[2] + M[6] * M[6] + M[10] * M[10]), nrm_w = sqrtf(M[3] * M[3] + M[7] * M[7] + M[11] * M[11]);
+    uint32_t tris_done = 0, skipped_empty = 0, skipped_occluded = 0;
 
-    for (uint32_t k = blockIdx.x * kWarpsPerCta + warp; k < total; k += gridDim.x * kWarpsPerCta) {
-        uint32_t slot, local;
-        work_to_slot(P, k, n_opaque, SHADOW, &slot, &local);
-        MeshletHeader h;
-        load_header(P, slot, h);
-        const uint32_t nv = min(h.vert_count, (uint32_t)LH_MAX_MESHLET_UNIQUE_VERTICES);
-        // cull modes: pipelines.cpp:10-25,255-315
-        const int cull = h.alpha ? CULL_NONE : (SHADOW ? CULL_FRONT : CULL_BACK);
-        const AlphaTest at = make_alpha_test(P, h);
+    for (;;) {
+        uint32_t chunk = 0;
+        if (lane == 0) chunk = atomicAdd(&P.state->raster_ticket, kTicketChunk);
+        chunk = __shfl_sync(0xFFFFFFFFu, chunk, 0);
+        if (chunk >= total) break;
+        const uint32_t chunk_end = min(total, chunk + kTicketChunk);
+        for (uint32_t k = chunk; k < chunk_end; k++) {
+            uint32_t slot, local;
+            work_to_slot(P, k, n_opaque, SHADOW, &slot, &local);
+            MeshletHeader h;
+            load_header(P, slot, h);
 
-        // vertex phase: load_vertex_data + calculate_world_pos + matrix * (world, 1)
-        for (uint32_t v = lane; v < nv; v += 32) {
-            const uint32_t idx = load_vertex_index(h, v);
-            const uint16_t* p = h.positions + 3 * (size_t)idx;
-            const float px = (float)__ldg(p), py = (float)__ldg(p + 1), pz = (float)__ldg(p + 2);
-            const V4 world = mat4_mul(h.T, px, py, pz, 1.0f);
-            const V4 clip = mat4_mul(M, world.x, world.y, world.z, 1.0f);
-            sv.clip[v] = make_float4(clip.x, clip.y, clip.z, clip.w);
-            uint8_t f = 0;
-            if (SHADOW || psub(clip.w, clip.z) >= 0.0f) {
-                f |= FLAG_INSIDE;
-                int sx, sy;
-                float z;
-                if (project_snap(clip.x, clip.y, clip.z, clip.w, half_w, half_h, &sx, &sy, &z)) {
-                    f |= FLAG_SNAPPED;
-                    sv.sx[v] = sx;
-                    sv.sy[v] = sy;
-                    sv.z[v] = z;
-                }
-            }
-            sv.flags[v] = f;
-        }
-        __syncwarp();
-
-        // triangle phase
-        for (uint32_t t = lane; t < h.tri_count; t += 32) {
-            const uint32_t i0 = __ldg(h.micro + 3 * t), i1 = __ldg(h.micro + 3 * t + 1), i2 = __ldg(h.micro + 3 * t + 2);
-            if (max(i0, max(i1, i2)) >= nv) continue;
-            const uint32_t lo = ((P.slot_offset + local) << LH_VIS_TRI_BITS) | t;
-            const uint32_t f0 = sv.flags[i0], f1 = sv.flags[i1], f2 = sv.flags[i2];
-            const uint32_t f_and = f0 & f1 & f2, f_or = f0 | f1 | f2;
-            if (!(f_or & FLAG_INSIDE)) continue;                       // entirely behind the near plane
-            if (!(f_and & FLAG_INSIDE)) {                              // crosses it: generic path
-                push_deferred(P, lo, kWholeTriangle);
-                continue;
-            }
-            if (!(f_and & FLAG_SNAPPED)) continue;                     // non-finite vertex
-            int ax = sv.sx[i0], ay = sv.sy[i0], bx = sv.sx[i1], by = sv.sy[i1], cx = sv.sx[i2], cy = sv.sy[i2];
-            const int minx = min(ax, min(bx, cx)), maxx = max(ax, max(bx, cx));
-            const int miny = min(ay, min(by, cy)), maxy = max(ay, max(by, cy));
-            const int px0 = max(0, (minx - 128 + 255) >> 8), px1 = min(W - 1, (maxx - 128) >> 8);
-            const int py0 = max(0, (miny - 128 + 255) >> 8), py1 = min(H - 1, (maxy - 128) >> 8);
-            if (px0 > px1 || py0 > py1) continue;                      // covers no sample: the common case
-            tris_done++;
-            const bool small_extent = (maxx - minx) < kSmallMaxExtent && (maxy - miny) < kSmallMaxExtent;
-            if (small_extent) {
-                // exact in 32 bits: |d| < 2^14 so every product is < 2^28
-                int A2 = (bx - ax) * (cy - ay) - (by - ay) * (cx - ax);
-                if (A2 == 0) continue;
-                const bool front = A2 < 0;
-                if ((cull == CULL_BACK && !front) || (cull == CULL_FRONT && front)) continue;
-                const int spanx = px1 - px0 + 1, spany = py1 - py0 + 1;
-                if (spanx <= kSmallMaxSpan && spany <= kSmallMaxSpan && spanx * spany <= kSmallMaxArea) {
-                    float az = sv.z[i0], bz = sv.z[i1], cz = sv.z[i2];
-                    uint32_t ia = i0, ib = i1, ic = i2;
-                    if (A2 < 0) {
-                        int t0 = bx; bx = cx; cx = t0;
-                        t0 = by; by = cy; cy = t0;
-                        float tz = bz; bz = cz; cz = tz;
-                        ib = i2; ic = i1;
-                        A2 = -A2;
-                    }
-                    const int e0x = cx - bx, e0y = cy - by, e1x = ax - cx, e1y = ay - cy, e2x = bx - ax, e2y = by - ay;
-                    const int bias0 = top_left(e0x, e0y) ? 0 : -1, bias1 = top_left(e1x, e1y) ? 0 : -1, bias2 = top_left(e2x, e2y) ? 0 : -1;
-                    const float fA = (float)A2;
-                    const float inv_area = pdiv(1.0f, fA);
-                    const float dz1 = psub(bz, az), dz2 = psub(cz, az);
-                    const int ccx = px0 * 256 + 128, ccy = py0 * 256 + 128;
-                    int w0_row = e0x * (ccy - by) - e0y * (ccx - bx);
-                    int w1_row = e1x * (ccy - cy) - e1y * (ccx - cx);
-                    int w2_row = e2x * (ccy - ay) - e2y * (ccx - ax);
-                    SnapVert A, B, C;
-                    if (at.enabled) {
-                        // perspective-correct uv needs the clip w and the vertex uvs
-                        const uint32_t ids[3] = {ia, ib, ic};
-                        SnapVert* out[3] = {&A, &B, &C};
-                        for (int q = 0; q < 3; q++) {
-                            const uint32_t idx = load_vertex_index(h, ids[q]);
-                            out[q]->w = sv.clip[ids[q]].w;
-                            out[q]->u = padd(pmul((float)__ldg(h.uvs + 2 * (size_t)idx), h.tex_scale[0]), h.tex_offset[0]);
-                            out[q]->v = padd(pmul((float)__ldg(h.uvs + 2 * (size_t)idx + 1), h.tex_scale[1]), h.tex_offset[1]);
+            // ---- (0) early-outs ----
+            {
+                const float R0 = h.sphere[3] * sigma_max_bound(h.T);
+                const float wx = h.T[0] * h.sphere[0] + h.T[4] * h.sphere[1] + h.T[8] * h.sphere[2] + h.T[12];
+                const float wy = h.T[1] * h.sphere[0] + h.T[5] * h.sphere[1] + h.T[9] * h.sphere[2] + h.T[13];
+                const float wz = h.T[2] * h.sphere[0] + h.T[6] * h.sphere[1] + h.T[10] * h.sphere[2] + h.T[14];
+                // radius padded for the rounding of the vertex transform itself (a few ulp of the terms' magnitude)
+                const float R = R0 * 1.0001f + 2e-6f * (fabsf(wx) + fabsf(wy) + fabsf(wz) + fabsf(h.T[12]) + fabsf(h.T[13]) + fabsf(h.T[14]));
+                const float ccx = M[0] * wx + M[4] * wy + M[8] * wz + M[12], ccy = M[1] * wx + M[5] * wy + M[9] * wz + M[13];
+                const float ccz = M[2] * wx + M[6] * wy + M[10] * wz + M[14], ccw = M[3] * wx + M[7] * wy + M[11] * wz + M[15];
+                const float ex = R * nrm_x, ey = R * nrm_y, ez = R * nrm_z, ew = R * nrm_w;
+                const float w_lo = ccw - ew, w_hi = ccw + ew;
+                if (w_lo > 1e-6f) {   // otherwise the sphere reaches the w = 0 plane: no bound
+                    const float x_lo = ccx - ex, x_hi = ccx + ex, y_lo = ccy - ey, y_hi = ccy + ey;
+                    const float nx_lo = x_lo / (x_lo >= 0.0f ? w_hi : w_lo), nx_hi = x_hi / (x_hi >= 0.0f ? w_lo : w_hi);
+                    const float ny_lo = y_lo / (y_lo >= 0.0f ? w_hi : w_lo), ny_hi = y_hi / (y_hi >= 0.0f ? w_lo : w_hi);
+                    float fx_lo = nx_lo * half_w + half_w, fx_hi = nx_hi * half_w + half_w;
+                    float fy_lo = ny_lo * half_h + half_h, fy_hi = ny_hi * half_h + half_h;
+                    // nearest depth the meshlet can produce: largest z/w for the reverse-Z view, smallest for a cascade
+                    const float z_edge = SHADOW ? ccz - ez : ccz + ez;
+                    float d_edge = SHADOW ? z_edge / (z_edge >= 0.0f ? w_hi : w_lo) : z_edge / (z_edge >= 0.0f ? w_lo : w_hi);
+                    if (fabsf(fx_lo) + fabsf(fx_hi) + fabsf(fy_lo) + fabsf(fy_hi) + fabsf(d_edge) < 3.0e38f) {
+                        fx_lo -= 0.125f + 1e-5f * fabsf(fx_lo); fx_hi += 0.125f + 1e-5f * fabsf(fx_hi);
+                        fy_lo -= 0.125f + 1e-5f * fabsf(fy_lo); fy_hi += 0.125f + 1e-5f * fabsf(fy_hi);
+                        const int px0 = max(0, (int)ceilf(fx_lo - 0.5f)), px1 = min(W - 1, (int)floorf(fx_hi - 0.5f));
+                        const int py0 = max(0, (int)ceilf(fy_lo - 0.5f)), py1 = min(H - 1, (int)floorf(fy_hi - 0.5f));
+                        if (px0 > px1 || py0 > py1) {   // no pixel centre inside the bound
+                            skipped_empty++;
+                            continue;
+                        }
+                        const int nbx = ((px1 - px0) >> 3) + 1, nby = ((py1 - py0) >> 2) + 1;
+                        d_edge = SHADOW ? d_edge - (4e-5f * fabsf(d_edge) + 1e-7f) : d_edge + (4e-5f * fabsf(d_edge) + 1e-30f);
+                        if (nbx * nby <= kMaxOcclusionBlocks && d_edge > 0.0f) {
+                            uint32_t worst = 0;   // main view: largest stored key high word; cascade: largest stored depth
+                            for (int by = 0; by < nby; by++)
+                                for (int bx = 0; bx < nbx; bx++) {
+                                    const int x = px0 + bx * 8 + (int)(lane & 7), y = py0 + by * 4 + (int)(lane >> 3);
+                                    if (x <= px1 && y <= py1) {
+                                        const size_t at = (size_t)y * W + x;
+                                        const uint32_t v = SHADOW ? __ldcg(tg.layer + at) : __ldcg((const uint32_t*)tg.vis + 2 * at + 1);
+                                        worst = max(worst, v);
+                                    }
+                                }
+                            worst = __reduce_max_sync(0xFFFFFFFFu, worst);
+                            // main view: a fragment of depth d loses when floatBits(d) < ~hi(key) for the stored key, i.e.
+                            // hi(key) < ~floatBits(d); cascade: it loses when d >= stored depth (LESS test)
+                            const bool occluded = SHADOW ? __float_as_uint(d_edge) >= worst : worst < ~__float_as_uint(d_edge);
+                            if (occluded) {
+                                skipped_occluded++;
+                                continue;
+                            }
                         }
                     }
-                    for (int py = py0; py <= py1; py++) {
-                        int w0 = w0_row, w1 = w1_row, w2 = w2_row;
-                        for (int px = px0; px <= px1; px++) {
-                            if (((w0 + bias0) | (w1 + bias1) | (w2 + bias2)) >= 0) {
-                                if (!(at.enabled && alpha_discard(at, (float)w0, (float)w1, (float)w2, fA, A, B, C))) {
-                                    float z = padd(az, pmul(padd(pmul((float)w1, dz1), pmul((float)w2, dz2)), inv_area));
-                                    tg.emit(px, py, z, lo);
+                }
+            }
+
+            const uint32_t nv = min(h.vert_count, (uint32_t)LH_MAX_MESHLET_UNIQUE_VERTICES);
+            // cull modes: pipelines.cpp:10-25,255-315
+            const int cull = h.alpha ? CULL_NONE : (SHADOW ? CULL_FRONT : CULL_BACK);
+            const AlphaTest at = make_alpha_test(P, h);
+
+            // ---- (1) vertex phase: load_vertex_data + calculate_world_pos + matrix * (world, 1) ----
+            for (uint32_t v = lane; v < nv; v += 32) {
+                const uint32_t idx = load_vertex_index(h, v);
+                const uint16_t* p = h.positions + 3 * (size_t)idx;
+                const float px = (float)__ldg(p), py = (float)__ldg(p + 1), pz = (float)__ldg(p + 2);
+                const V4 world = mat4_mul(h.T, px, py, pz, 1.0f);
+                const V4 clip = mat4_mul(M, world.x, world.y, world.z, 1.0f);
+                int sx = kVertOutside, sy = 0;
+                float z = 0.0f;
+                if (SHADOW || psub(clip.w, clip.z) >= 0.0f) {
+                    if (!project_snap(clip.x, clip.y, clip.z, clip.w, half_w, half_h, &sx, &sy, &z)) sx = kVertNonFinite;
+                }
+                sv.sx[v] = sx;
+                sv.sy[v] = sy;
+                sv.z[v] = z;
+                if (h.alpha) sv.w[v] = clip.w;
+            }
+            __syncwarp();
+
+            // ---- (2) triangle cull phase ----
+            uint32_t n_surv = 0;
+            for (uint32_t t0 = 0; t0 < h.tri_count; t0 += 32) {
+                const uint32_t t = t0 + lane;
+                bool keep = false;
+                if (t < h.tri_count) {
+                    const uint32_t i0 = __ldg(h.micro + 3 * t), i1 = __ldg(h.micro + 3 * t + 1), i2 = __ldg(h.micro + 3 * t + 2);
+                    if (max(i0, max(i1, i2)) < nv) {
+                        const int ax = sv.sx[i0], bx = sv.sx[i1], cx = sv.sx[i2];
+                        const int n_out = (ax == kVertOutside) + (bx == kVertOutside) + (cx == kVertOutside);
+                        const uint32_t lo = ((P.slot_offset + local) << LH_VIS_TRI_BITS) | t;
+                        if (n_out == 0) {
+                            if (ax != kVertNonFinite && bx != kVertNonFinite && cx != kVertNonFinite) {
+                                const int ay = sv.sy[i0], by = sv.sy[i1], cy = sv.sy[i2];
+                                const int minx = min(ax, min(bx, cx)), maxx = max(ax, max(bx, cx));
+                                const int miny = min(ay, min(by, cy)), maxy = max(ay, max(by, cy));
+                                const int px0 = max(0, (minx - 128 + 255) >> 8), px1 = min(W - 1, (maxx - 128) >> 8);
+                                const int py0 = max(0, (miny - 128 + 255) >> 8), py1 = min(H - 1, (maxy - 128) >> 8);
+                                if (px0 <= px1 && py0 <= py1) {   // else it covers no sample: the common case
+                                    tris_done++;
+                                    // facing; exact in 32 bits when the sub-pixel extent is < 2^14 (every product < 2^28)
+                                    const bool small_extent = (maxx - minx) < kSmallMaxExtent && (maxy - miny) < kSmallMaxExtent;
+                                    const long long A2 = small_extent
+                                                             ? (long long)((bx - ax) * (cy - ay) - (by - ay) * (cx - ax))
+                                                             : (long long)(bx - ax) * (cy - ay) - (long long)(by - ay) * (cx - ax);
+                                    const bool front = A2 < 0;
+                                    if (A2 != 0 && !((cull == CULL_BACK && !front) || (cull == CULL_FRONT && front))) {
+                                        const int spanx = px1 - px0 + 1, spany = py1 - py0 + 1;
+                                        if (small_extent && spanx <= kSmallMaxSpan && spany <= kSmallMaxSpan && spanx * spany <= kSmallMaxArea) {
+                                            keep = true;
+                                        } else {
+                                            // large footprint: one queue entry per 128x32 screen tile the bounding box touches
+                                            const uint32_t tx0 = (uint32_t)px0 / kTileW, tx1 = (uint32_t)px1 / kTileW;
+                                            const uint32_t ty0 = (uint32_t)py0 / kTileH, ty1 = (uint32_t)py1 / kTileH;
+                                            for (uint32_t ty = ty0; ty <= ty1; ty++)
+                                                for (uint32_t tx = tx0; tx <= tx1; tx++) push_deferred(P, lo, tx | (ty << 16));
+                                        }
+                                    }
                                 }
                             }
-                            w0 -= e0y * 256;
-                            w1 -= e1y * 256;
-                            w2 -= e2y * 256;
+                        } else if (n_out < 3) {
+                            push_deferred(P, lo, kWholeTriangle);   // crosses the near plane: generic path
                         }
-                        w0_row += e0x * 256;
-                        w1_row += e1x * 256;
-                        w2_row += e2x * 256;
                     }
-                    continue;
+                }
+                const uint32_t ballot = __ballot_sync(0xFFFFFFFFu, keep);
+                if (keep) sv.surv[n_surv + __popc(ballot & ((1u << lane) - 1u))] = (uint8_t)t;
+                n_surv += __popc(ballot);
+            }
+            __syncwarp();
+
+            // ---- (3) raster phase over the compacted survivors ----
+            for (uint32_t s = lane; s < n_surv; s += 32) {
+                const uint32_t t = sv.surv[s];
+                const uint32_t lo = ((P.slot_offset + local) << LH_VIS_TRI_BITS) | t;
+                uint32_t ia = __ldg(h.micro + 3 * t), ib = __ldg(h.micro + 3 * t + 1), ic = __ldg(h.micro + 3 * t + 2);
+                int ax = sv.sx[ia], ay = sv.sy[ia], bx = sv.sx[ib], by = sv.sy[ib], cx = sv.sx[ic], cy = sv.sy[ic];
+                const int minx = min(ax, min(bx, cx)), maxx = max(ax, max(bx, cx));
+                const int miny = min(ay, min(by, cy)), maxy = max(ay, max(by, cy));
+                const int px0 = max(0, (minx - 128 + 255) >> 8), px1 = min(W - 1, (maxx - 128) >> 8);
+                const int py0 = max(0, (miny - 128 + 255) >> 8), py1 = min(H - 1, (maxy - 128) >> 8);
+                int A2 = (bx - ax) * (cy - ay) - (by - ay) * (cx - ax);
+                float az = sv.z[ia], bz = sv.z[ib], cz = sv.z[ic];
+                if (A2 < 0) {
+                    int t0 = bx; bx = cx; cx = t0;
+                    t0 = by; by = cy; cy = t0;
+                    float tz = bz; bz = cz; cz = tz;
+                    const uint32_t ti = ib; ib = ic; ic = ti;
+                    A2 = -A2;
+                }
+                const int e0x = cx - bx, e0y = cy - by, e1x = ax - cx, e1y = ay - cy, e2x = bx - ax, e2y = by - ay;
+                const int bias0 = top_left(e0x, e0y) ? 0 : -1, bias1 = top_left(e1x, e1y) ? 0 : -1, bias2 = top_left(e2x, e2y) ? 0 : -1;
+                const float fA = (float)A2;
+                const float inv_area = pdiv(1.0f, fA);
+                const float dz1 = psub(bz, az), dz2 = psub(cz, az);
+                const int ccx = px0 * 256 + 128, ccy = py0 * 256 + 128;
+                int w0_row = e0x * (ccy - by) - e0y * (ccx - bx);
+                int w1_row = e1x * (ccy - cy) - e1y * (ccx - cx);
+                int w2_row = e2x * (ccy - ay) - e2y * (ccx - ax);
+                SnapVert A, B, C;
+                if (at.enabled) {
+                    // perspective-correct uv needs the clip w and the vertex uvs
+                    const uint32_t ids[3] = {ia, ib, ic};
+                    SnapVert* out[3] = {&A, &B, &C};
+                    for (int q = 0; q < 3; q++) {
+                        const uint32_t idx = load_vertex_index(h, ids[q]);
+                        out[q]->w = sv.w[ids[q]];
+                        out[q]->u = padd(pmul((float)__ldg(h.uvs + 2 * (size_t)idx), h.tex_scale[0]), h.tex_offset[0]);
+                        out[q]->v = padd(pmul((float)__ldg(h.uvs + 2 * (size_t)idx + 1), h.tex_scale[1]), h.tex_offset[1]);
+                    }
+                }
+                for (int py = py0; py <= py1; py++) {
+                    int w0 = w0_row, w1 = w1_row, w2 = w2_row;
+                    for (int px = px0; px <= px1; px++) {
+                        if (((w0 + bias0) | (w1 + bias1) | (w2 + bias2)) >= 0) {
+                            if (!(at.enabled && alpha_discard(at, (float)w0, (float)w1, (float)w2, fA, A, B, C))) {
+                                float z = padd(az, pmul(padd(pmul((float)w1, dz1), pmul((float)w2, dz2)), inv_area));
+                                tg.emit(px, py, z, lo);
+                            }
+                        }
+                        w0 -= e0y * 256;
+                        w1 -= e1y * 256;
+                        w2 -= e2y * 256;
+                    }
+                    w0_row += e0x * 256;
+                    w1_row += e1x * 256;
+                    w2_row += e2x * 256;
                 }
             }
-            else {
-                const long long A2 = (long long)(bx - ax) * (cy - ay) - (long long)(by - ay) * (cx - ax);
-                if (A2 == 0) continue;
-                const bool front = A2 < 0;
-                if ((cull == CULL_BACK && !front) || (cull == CULL_FRONT && front)) continue;
-            }
-            // large footprint: one queue entry per 128x32 screen tile the bounding box touches
-            const uint32_t tx0 = (uint32_t)px0 / kTileW, tx1 = (uint32_t)px1 / kTileW;
-            const uint32_t ty0 = (uint32_t)py0 / kTileH, ty1 = (uint32_t)py1 / kTileH;
-            for (uint32_t ty = ty0; ty <= ty1; ty++)
-                for (uint32_t tx = tx0; tx <= tx1; tx++) push_deferred(P, lo, tx | (ty << 16));
+            __syncwarp();
         }
-        __syncwarp();
     }
     if (P.flags & LH_CONFIG_PASS_TIMINGS) {
-        for (int o = 16; o > 0; o >>= 1) tris_done += __shfl_xor_sync(0xFFFFFFFFu, tris_done, o);
-        if (lane == 0 && tris_done && !SHADOW) atomicAdd(&P.state->rasterized_triangles, (unsigned long long)tris_done);
+        tris_done = __reduce_add_sync(0xFFFFFFFFu, tris_done);
+        if (lane == 0 && !SHADOW) {
+            if (tris_done) atomicAdd(&P.state->rasterized_triangles, (unsigned long long)tris_done);
+            if (skipped_empty) atomicAdd(&P.state->skipped_empty, skipped_empty);
+            if (skipped_occluded) atomicAdd(&P.state->skipped_occluded, skipped_occluded);
+        }
     }
 }
 
@@ -498,7 +618,10 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) raster_deferred_kernel(cons
 }
 
 __global__ void begin_raster_pass_kernel(const __grid_constant__ FrameParams P) {
-    if (threadIdx.x == 0 && blockIdx.x == 0) P.state->large_count = 0;
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        P.state->large_count = 0;
+        P.state->raster_ticket = 0;
+    }
 }
 __global__ void end_main_pass_kernel(const __grid_constant__ FrameParams P) {
     if (threadIdx.x == 0 && blockIdx.x == 0) P.state->main_large_count = P.state->large_count;
