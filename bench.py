@@ -335,8 +335,8 @@ def run_ours(args):
         "frame": {"visible_instances": stats.num_visible_instances, "candidate_meshlets": stats.num_candidate_meshlets,
                   "rasterised_meshlets": survivors, "deferred_triangle_tiles": stats.num_large_triangles,
                   "rasterised_triangles_nonempty": int(stats.rasterized_triangles),
-                  "meshlets_skipped_no_sample": stats.meshlets_skipped_no_sample,
-                  "meshlets_skipped_occluded": stats.meshlets_skipped_occluded,
+                  "meshlets_skipped_no_sample": list(stats.meshlets_skipped_no_sample),
+                  "meshlets_skipped_occluded": list(stats.meshlets_skipped_occluded),
                   "shadow_rasterised_meshlets": [int(a) + int(b) for a, b in zip(stats.shadow_opaque, stats.shadow_alpha_clip)]},
         "pass_ms": {k: round(v, 4) for k, v in med.items()},
         "pass_share": kernel_share,

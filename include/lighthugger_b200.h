@@ -92,8 +92,9 @@ typedef struct LhFrameStats {
     uint32_t num_large_triangles;       /* triangles deferred to the binned path (main view) */
     uint32_t overflow;                  /* bit mask of LH_OVERFLOW_* */
     uint64_t rasterized_triangles;      /* main view, after cull / clip (0 unless LH_CONFIG_PASS_TIMINGS) */
-    uint32_t meshlets_skipped_no_sample; /* main view: rasteriser early-out, bound holds no pixel centre (LH_CONFIG_PASS_TIMINGS) */
-    uint32_t meshlets_skipped_occluded;  /* main view: rasteriser early-out, every stored key already nearer */
+    /* rasteriser early-outs, [0] main view, [1..4] cascades (counted only with LH_CONFIG_PASS_TIMINGS) */
+    uint32_t meshlets_skipped_no_sample[5]; /* the meshlet's bound holds no pixel centre */
+    uint32_t meshlets_skipped_occluded[5];  /* every key already stored in the bound is nearer */
 } LhFrameStats;
 
 enum {

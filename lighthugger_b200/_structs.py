@@ -110,7 +110,7 @@ class LhFrameStats(C.Structure):
         ("min_depth", u32), ("max_depth", u32), ("shadow_visible_instances", u32 * 4),
         ("shadow_candidate_meshlets", u32 * 4), ("shadow_opaque", u32 * 4), ("shadow_alpha_clip", u32 * 4),
         ("num_large_triangles", u32), ("overflow", u32), ("rasterized_triangles", u64),
-        ("meshlets_skipped_no_sample", u32), ("meshlets_skipped_occluded", u32),
+        ("meshlets_skipped_no_sample", u32 * 5), ("meshlets_skipped_occluded", u32 * 5),
     ]
 
 

@@ -201,8 +201,10 @@ __global__ void gather_stats_kernel(const __grid_constant__ FrameParams P, LhFra
     s.num_large_triangles = st->main_large_count;
     s.overflow = st->overflow;
     s.rasterized_triangles = st->rasterized_triangles;
-    s.meshlets_skipped_no_sample = st->skipped_empty;
-    s.meshlets_skipped_occluded = st->skipped_occluded;
+    for (int c = 0; c < 5; c++) {
+        s.meshlets_skipped_no_sample[c] = st->skipped_empty[c];
+        s.meshlets_skipped_occluded[c] = st->skipped_occluded[c];
+    }
     *out = s;
 }
 

@@ -74,7 +74,7 @@ struct FrameState {
     uint32_t done[8];              // CTAs finished (self-cleaning of the tile states)
     unsigned long long rasterized_triangles;
     uint32_t raster_ticket;        // next unclaimed meshlet of the current raster pass
-    uint32_t skipped_empty, skipped_occluded;   // main-view meshlets dropped by the early-outs (stats)
+    uint32_t skipped_empty[5], skipped_occluded[5];   // meshlets dropped by the rasteriser's early-outs: [0] main view, [1..4] cascades (stats)
 };
 
 constexpr uint32_t kMeshletTile = 1024;        // candidate meshlets per scan tile

@@ -30,6 +30,9 @@ namespace lh {
 
 namespace {
 
+#ifndef LH_TICKET_CHUNK
+#define LH_TICKET_CHUNK 4
+#endif
 constexpr int kWarpsPerCta = 8;
 constexpr uint32_t kTileW = 128, kTileH = 32;   // deferred-triangle screen tile
 constexpr uint32_t kWholeTriangle = 0xFFFFFFFFu;
@@ -50,7 +53,8 @@ struct WarpScratch {
     uint8_t surv[128];
 };
 constexpr int kVertOutside = INT_MIN, kVertNonFinite = INT_MIN + 1;   // |snapped| <= 2^29, so neither can be a coordinate
-constexpr uint32_t kTicketChunk = 4;       // meshlets a warp takes per ticket
+constexpr uint32_t kMaxTicketChunk = LH_TICKET_CHUNK;   // meshlets a warp takes per ticket: one lane per meshlet in the bounds phase
+enum { kBoundNone = 0, kBoundTest = 1, kBoundEmpty = 2 };
 constexpr int kMaxOcclusionBlocks = 16;    // early-out reads at most 16 blocks of 8x4 pixels (512 keys)
 
 struct SnapVert {
@@ -226,7 +230,6 @@ __device__ void raster_clip_triangle_coop(const ClipVert v[3], int cull, const T
 // Everything needed to locate one meshlet's data; loaded by every lane from the same addresses (broadcast).
 struct MeshletHeader {
     float T[16];
-    float sphere[4];            // Meshlet.bounding_sphere (object space)
     const uint16_t* positions;
     const void* indices;
     const uint16_t* uvs;
@@ -257,14 +260,8 @@ __device__ __forceinline__ void load_header(const FrameParams& P, uint32_t slot,
     const uint32_t flags = __ldg(&mi->flags);
     h.wide = (flags & LH_MESH_INFO_FLAGS_32_BIT_INDICES) != 0;
     h.alpha = (flags & LH_MESH_INFO_FLAGS_ALPHA_CLIP) != 0;
-    // bytes 24..55 of the 56-byte Meshlet as four 8-byte loads: cutoff|sphere.x, sphere.yz, sphere.w|triangle_offset, index_offset|counts
-    const unsigned long long q3 = __ldg((const unsigned long long*)m + 3), q4 = __ldg((const unsigned long long*)m + 4);
-    const unsigned long long q5 = __ldg((const unsigned long long*)m + 5), tail = __ldg((const unsigned long long*)m + 6);
-    h.sphere[0] = __uint_as_float((uint32_t)(q3 >> 32));
-    h.sphere[1] = __uint_as_float((uint32_t)q4);
-    h.sphere[2] = __uint_as_float((uint32_t)(q4 >> 32));
-    h.sphere[3] = __uint_as_float((uint32_t)q5);
-    h.micro = micro + (uint32_t)(q5 >> 32);
+    const unsigned long long tail = __ldg((const unsigned long long*)m + 6);  // index_offset | counts
+    h.micro = micro + __ldg(&m->triangle_offset);
     h.index_offset = (uint32_t)tail;
     h.tri_count = (uint32_t)(tail >> 32) & 0xFFu;
     h.vert_count = (uint32_t)(tail >> 40) & 0xFFu;
@@ -273,6 +270,26 @@ __device__ __forceinline__ void load_header(const FrameParams& P, uint32_t slot,
     h.tex_offset[0] = __ldg(&mi->texture_offset[0]);
     h.tex_offset[1] = __ldg(&mi->texture_offset[1]);
     h.base_color_texture = __ldg(&mi->base_color_texture_index);
+}
+
+// What the early-outs need of one meshlet: the instance transform (3x3 + translation, columns packed) and the
+// meshlet's object-space bounding sphere.  Called by one lane per meshlet.
+__device__ __forceinline__ void load_bounds(const FrameParams& P, uint32_t slot, float T[12], float sphere[4]) {
+    const LhMeshletReference* refs = (const LhMeshletReference*)P.u.meshlet_references;
+    const unsigned long long ref = __ldg((const unsigned long long*)(refs + slot));
+    const LhInstance* inst = (const LhInstance*)P.u.instances + (uint32_t)ref;
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        const float4 c = __ldg((const float4*)&inst->transform + k);
+        T[3 * k] = c.x; T[3 * k + 1] = c.y; T[3 * k + 2] = c.z;
+    }
+    const LhMeshInfo* mi = (const LhMeshInfo*)__ldg((const unsigned long long*)&inst->mesh_info_address);
+    const LhMeshlet* m = (const LhMeshlet*)__ldg((const unsigned long long*)&mi->meshlets) + ((uint32_t)(ref >> 32) & 0xFFFFu);
+    const unsigned long long q3 = __ldg((const unsigned long long*)m + 3), q4 = __ldg((const unsigned long long*)m + 4);
+    sphere[0] = __uint_as_float((uint32_t)(q3 >> 32));
+    sphere[1] = __uint_as_float((uint32_t)q4);
+    sphere[2] = __uint_as_float((uint32_t)(q4 >> 32));
+    sphere[3] = __ldg(&m->bounding_sphere[3]);
 }
 
 __device__ __forceinline__ uint32_t load_vertex_index(const MeshletHeader& h, uint32_t v) {
@@ -318,11 +335,12 @@ __device__ __forceinline__ void push_deferred(const FrameParams& P, uint32_t lo,
 
 // sigma_max(T) * r bounds |T (v - c)| for v in the object-space sphere (c, r).  Gershgorin on the Gram matrix and the
 // Frobenius norm are both valid for any matrix; for rotation * scale the first equals the reference's max column length.
+// T here is the 3x3 part + translation of the instance transform, columns packed: T[0..2], T[3..5], T[6..8], T[9..11].
 __device__ __forceinline__ float sigma_max_bound(const float* T) {
-    const float c00 = T[0] * T[0] + T[1] * T[1] + T[2] * T[2], c11 = T[4] * T[4] + T[5] * T[5] + T[6] * T[6],
-                c22 = T[8] * T[8] + T[9] * T[9] + T[10] * T[10];
-    const float c01 = fabsf(T[0] * T[4] + T[1] * T[5] + T[2] * T[6]), c02 = fabsf(T[0] * T[8] + T[1] * T[9] + T[2] * T[10]),
-                c12 = fabsf(T[4] * T[8] + T[5] * T[9] + T[6] * T[10]);
+    const float c00 = T[0] * T[0] + T[1] * T[1] + T[2] * T[2], c11 = T[3] * T[3] + T[4] * T[4] + T[5] * T[5],
+                c22 = T[6] * T[6] + T[7] * T[7] + T[8] * T[8];
+    const float c01 = fabsf(T[0] * T[3] + T[1] * T[4] + T[2] * T[5]), c02 = fabsf(T[0] * T[6] + T[1] * T[7] + T[2] * T[8]),
+                c12 = fabsf(T[3] * T[6] + T[4] * T[7] + T[5] * T[8]);
     const float gersh = fmaxf(fmaxf(c00 + c01 + c02, c11 + c01 + c12), c22 + c02 + c12);
     return sqrtf(fminf(gersh, c00 + c11 + c22)) * 1.00001f;
 }
@@ -359,73 +377,89 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) raster_meshlets_kernel(cons
     const float nrm_z = sqrtf(M[2] * M[2] + M[6] * M[6] + M[10] * M[10]), nrm_w = sqrtf(M[3] * M[3] + M[7] * M[7] + M[11] * M[11]);
     uint32_t tris_done = 0, skipped_empty = 0, skipped_occluded = 0;
 
+    // A warp takes up to 32 consecutive meshlets per ticket (fewer when the pass is small, so that every warp gets work).
+    const uint32_t ticket_chunk = max(1u, min(kMaxTicketChunk, total / (gridDim.x * kWarpsPerCta * 4u)));
     for (;;) {
         uint32_t chunk = 0;
-        if (lane == 0) chunk = atomicAdd(&P.state->raster_ticket, kTicketChunk);
+        if (lane == 0) chunk = atomicAdd(&P.state->raster_ticket, ticket_chunk);
         chunk = __shfl_sync(0xFFFFFFFFu, chunk, 0);
         if (chunk >= total) break;
-        const uint32_t chunk_end = min(total, chunk + kTicketChunk);
-        for (uint32_t k = chunk; k < chunk_end; k++) {
-            uint32_t slot, local;
-            work_to_slot(P, k, n_opaque, SHADOW, &slot, &local);
-            MeshletHeader h;
-            load_header(P, slot, h);
+        const uint32_t chunk_end = min(total, chunk + ticket_chunk);
 
-            // ---- (0) early-outs ----
-            {
-                const float R0 = h.sphere[3] * sigma_max_bound(h.T);
-                const float wx = h.T[0] * h.sphere[0] + h.T[4] * h.sphere[1] + h.T[8] * h.sphere[2] + h.T[12];
-                const float wy = h.T[1] * h.sphere[0] + h.T[5] * h.sphere[1] + h.T[9] * h.sphere[2] + h.T[13];
-                const float wz = h.T[2] * h.sphere[0] + h.T[6] * h.sphere[1] + h.T[10] * h.sphere[2] + h.T[14];
-                // radius padded for the rounding of the vertex transform itself (a few ulp of the terms' magnitude)
-                const float R = R0 * 1.0001f + 2e-6f * (fabsf(wx) + fabsf(wy) + fabsf(wz) + fabsf(h.T[12]) + fabsf(h.T[13]) + fabsf(h.T[14]));
-                const float ccx = M[0] * wx + M[4] * wy + M[8] * wz + M[12], ccy = M[1] * wx + M[5] * wy + M[9] * wz + M[13];
-                const float ccz = M[2] * wx + M[6] * wy + M[10] * wz + M[14], ccw = M[3] * wx + M[7] * wy + M[11] * wz + M[15];
-                const float ex = R * nrm_x, ey = R * nrm_y, ez = R * nrm_z, ew = R * nrm_w;
-                const float w_lo = ccw - ew, w_hi = ccw + ew;
-                if (w_lo > 1e-6f) {   // otherwise the sphere reaches the w = 0 plane: no bound
-                    const float x_lo = ccx - ex, x_hi = ccx + ex, y_lo = ccy - ey, y_hi = ccy + ey;
-                    const float nx_lo = x_lo / (x_lo >= 0.0f ? w_hi : w_lo), nx_hi = x_hi / (x_hi >= 0.0f ? w_lo : w_hi);
-                    const float ny_lo = y_lo / (y_lo >= 0.0f ? w_hi : w_lo), ny_hi = y_hi / (y_hi >= 0.0f ? w_lo : w_hi);
-                    float fx_lo = nx_lo * half_w + half_w, fx_hi = nx_hi * half_w + half_w;
-                    float fy_lo = ny_lo * half_h + half_h, fy_hi = ny_hi * half_h + half_h;
-                    // nearest depth the meshlet can produce: largest z/w for the reverse-Z view, smallest for a cascade
-                    const float z_edge = SHADOW ? ccz - ez : ccz + ez;
-                    float d_edge = SHADOW ? z_edge / (z_edge >= 0.0f ? w_hi : w_lo) : z_edge / (z_edge >= 0.0f ? w_lo : w_hi);
-                    if (fabsf(fx_lo) + fabsf(fx_hi) + fabsf(fy_lo) + fabsf(fy_hi) + fabsf(d_edge) < 3.0e38f) {
-                        fx_lo -= 0.125f + 1e-5f * fabsf(fx_lo); fx_hi += 0.125f + 1e-5f * fabsf(fx_hi);
-                        fy_lo -= 0.125f + 1e-5f * fabsf(fy_lo); fy_hi += 0.125f + 1e-5f * fabsf(fy_hi);
-                        const int px0 = max(0, (int)ceilf(fx_lo - 0.5f)), px1 = min(W - 1, (int)floorf(fx_hi - 0.5f));
-                        const int py0 = max(0, (int)ceilf(fy_lo - 0.5f)), py1 = min(H - 1, (int)floorf(fy_hi - 0.5f));
-                        if (px0 > px1 || py0 > py1) {   // no pixel centre inside the bound
-                            skipped_empty++;
-                            continue;
-                        }
-                        const int nbx = ((px1 - px0) >> 3) + 1, nby = ((py1 - py0) >> 2) + 1;
+        // ---- (0a) bounds of the chunk's meshlets, one lane per meshlet ----
+        // my_rect_x/y = px0 | px1 << 16 ...; my_state: kBoundNone (no usable bound: rasterise), kBoundTest, kBoundEmpty
+        uint32_t my_rect_x = 0, my_rect_y = 0, my_edge = 0, my_state = kBoundNone;
+        if (chunk + lane < chunk_end) {
+            uint32_t slot, local;
+            work_to_slot(P, chunk + lane, n_opaque, SHADOW, &slot, &local);
+            float T[12], sphere[4];
+            load_bounds(P, slot, T, sphere);
+            const float R0 = sphere[3] * sigma_max_bound(T);
+            const float wx = T[0] * sphere[0] + T[3] * sphere[1] + T[6] * sphere[2] + T[9];
+            const float wy = T[1] * sphere[0] + T[4] * sphere[1] + T[7] * sphere[2] + T[10];
+            const float wz = T[2] * sphere[0] + T[5] * sphere[1] + T[8] * sphere[2] + T[11];
+            // radius padded for the rounding of the vertex transform itself (a few ulp of the terms' magnitude)
+            const float R = R0 * 1.0001f + 2e-6f * (fabsf(wx) + fabsf(wy) + fabsf(wz) + fabsf(T[9]) + fabsf(T[10]) + fabsf(T[11]));
+            const float ccx = M[0] * wx + M[4] * wy + M[8] * wz + M[12], ccy = M[1] * wx + M[5] * wy + M[9] * wz + M[13];
+            const float ccz = M[2] * wx + M[6] * wy + M[10] * wz + M[14], ccw = M[3] * wx + M[7] * wy + M[11] * wz + M[15];
+            const float ex = R * nrm_x, ey = R * nrm_y, ez = R * nrm_z, ew = R * nrm_w;
+            const float w_lo = ccw - ew, w_hi = ccw + ew;
+            if (w_lo > 1e-6f) {   // otherwise the sphere reaches the w = 0 plane: no bound
+                const float x_lo = ccx - ex, x_hi = ccx + ex, y_lo = ccy - ey, y_hi = ccy + ey;
+                const float nx_lo = x_lo / (x_lo >= 0.0f ? w_hi : w_lo), nx_hi = x_hi / (x_hi >= 0.0f ? w_lo : w_hi);
+                const float ny_lo = y_lo / (y_lo >= 0.0f ? w_hi : w_lo), ny_hi = y_hi / (y_hi >= 0.0f ? w_lo : w_hi);
+                float fx_lo = nx_lo * half_w + half_w, fx_hi = nx_hi * half_w + half_w;
+                float fy_lo = ny_lo * half_h + half_h, fy_hi = ny_hi * half_h + half_h;
+                // nearest depth the meshlet can produce: largest z/w for the reverse-Z view, smallest for a cascade
+                const float z_edge = SHADOW ? ccz - ez : ccz + ez;
+                float d_edge = SHADOW ? z_edge / (z_edge >= 0.0f ? w_hi : w_lo) : z_edge / (z_edge >= 0.0f ? w_lo : w_hi);
+                if (fabsf(fx_lo) + fabsf(fx_hi) + fabsf(fy_lo) + fabsf(fy_hi) + fabsf(d_edge) < 3.0e38f) {
+                    fx_lo -= 0.125f + 1e-5f * fabsf(fx_lo); fx_hi += 0.125f + 1e-5f * fabsf(fx_hi);
+                    fy_lo -= 0.125f + 1e-5f * fabsf(fy_lo); fy_hi += 0.125f + 1e-5f * fabsf(fy_hi);
+                    const int px0 = max(0, (int)ceilf(fx_lo - 0.5f)), px1 = min(W - 1, (int)floorf(fx_hi - 0.5f));
+                    const int py0 = max(0, (int)ceilf(fy_lo - 0.5f)), py1 = min(H - 1, (int)floorf(fy_hi - 0.5f));
+                    if (px0 > px1 || py0 > py1) {
+                        my_state = kBoundEmpty;   // no pixel centre inside the bound
+                    } else {
                         d_edge = SHADOW ? d_edge - (4e-5f * fabsf(d_edge) + 1e-7f) : d_edge + (4e-5f * fabsf(d_edge) + 1e-30f);
+                        const int nbx = ((px1 - px0) >> 3) + 1, nby = ((py1 - py0) >> 2) + 1;
                         if (nbx * nby <= kMaxOcclusionBlocks && d_edge > 0.0f) {
-                            uint32_t worst = 0;   // main view: largest stored key high word; cascade: largest stored depth
-                            for (int by = 0; by < nby; by++)
-                                for (int bx = 0; bx < nbx; bx++) {
-                                    const int x = px0 + bx * 8 + (int)(lane & 7), y = py0 + by * 4 + (int)(lane >> 3);
-                                    if (x <= px1 && y <= py1) {
-                                        const size_t at = (size_t)y * W + x;
-                                        const uint32_t v = SHADOW ? __ldcg(tg.layer + at) : __ldcg((const uint32_t*)tg.vis + 2 * at + 1);
-                                        worst = max(worst, v);
-                                    }
-                                }
-                            worst = __reduce_max_sync(0xFFFFFFFFu, worst);
+                            my_state = kBoundTest;
+                            my_rect_x = (uint32_t)px0 | ((uint32_t)px1 << 16);
+                            my_rect_y = (uint32_t)py0 | ((uint32_t)py1 << 16);
                             // main view: a fragment of depth d loses when floatBits(d) < ~hi(key) for the stored key, i.e.
                             // hi(key) < ~floatBits(d); cascade: it loses when d >= stored depth (LESS test)
-                            const bool occluded = SHADOW ? __float_as_uint(d_edge) >= worst : worst < ~__float_as_uint(d_edge);
-                            if (occluded) {
-                                skipped_occluded++;
-                                continue;
-                            }
+                            my_edge = SHADOW ? __float_as_uint(d_edge) : ~__float_as_uint(d_edge);
                         }
                     }
                 }
             }
+        }
+        skipped_empty += __popc(__ballot_sync(0xFFFFFFFFu, my_state == kBoundEmpty));
+
+        for (uint32_t k = chunk; k < chunk_end; k++) {
+            // ---- (0b) occlusion test against the keys already stored, the whole warp reading the rectangle ----
+            const uint32_t state = __shfl_sync(0xFFFFFFFFu, my_state, k - chunk);
+            if (state == kBoundEmpty) continue;
+            if (state == kBoundTest) {
+                const uint32_t rx = __shfl_sync(0xFFFFFFFFu, my_rect_x, k - chunk), ry = __shfl_sync(0xFFFFFFFFu, my_rect_y, k - chunk);
+                const uint32_t edge = __shfl_sync(0xFFFFFFFFu, my_edge, k - chunk);
+                const int px0 = (int)(rx & 0xFFFFu), px1 = (int)(rx >> 16), py0 = (int)(ry & 0xFFFFu), py1 = (int)(ry >> 16);
+                uint32_t worst = 0;   // main view: largest stored key high word; cascade: largest stored depth
+                for (int y = py0 + (int)(lane >> 3); y <= py1; y += 4) {
+                    const uint32_t* row = SHADOW ? tg.layer + (size_t)y * W : (const uint32_t*)tg.vis + 2 * (size_t)y * W + 1;
+                    for (int x = px0 + (int)(lane & 7); x <= px1; x += 8) worst = max(worst, __ldcg(row + (SHADOW ? x : 2 * x)));
+                }
+                worst = __reduce_max_sync(0xFFFFFFFFu, worst);
+                if (SHADOW ? edge >= worst : worst < edge) {
+                    skipped_occluded++;
+                    continue;
+                }
+            }
+            uint32_t slot, local;
+            work_to_slot(P, k, n_opaque, SHADOW, &slot, &local);
+            MeshletHeader h;
+            load_header(P, slot, h);
 
             const uint32_t nv = min(h.vert_count, (uint32_t)LH_MAX_MESHLET_UNIQUE_VERTICES);
             // cull modes: pipelines.cpp:10-25,255-315
@@ -565,10 +599,11 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) raster_meshlets_kernel(cons
     }
     if (P.flags & LH_CONFIG_PASS_TIMINGS) {
         tris_done = __reduce_add_sync(0xFFFFFFFFu, tris_done);
-        if (lane == 0 && !SHADOW) {
-            if (tris_done) atomicAdd(&P.state->rasterized_triangles, (unsigned long long)tris_done);
-            if (skipped_empty) atomicAdd(&P.state->skipped_empty, skipped_empty);
-            if (skipped_occluded) atomicAdd(&P.state->skipped_occluded, skipped_occluded);
+        if (lane == 0) {
+            const uint32_t pass = SHADOW ? 1u + cascade : 0u;
+            if (tris_done && !SHADOW) atomicAdd(&P.state->rasterized_triangles, (unsigned long long)tris_done);
+            if (skipped_empty) atomicAdd(&P.state->skipped_empty[pass], skipped_empty);
+            if (skipped_occluded) atomicAdd(&P.state->skipped_occluded[pass], skipped_occluded);
         }
     }
 }

@@ -31,7 +31,8 @@ class LhError(RuntimeError):
 
 
 def cuda_lib_path():
-    return os.path.join(_HERE, "lib", "liblighthugger_b200.so")
+    # LH_CUDA_LIB: developer hook for A/B-testing a differently built library (still the CUDA library, never a fallback)
+    return os.environ.get("LH_CUDA_LIB") or os.path.join(_HERE, "lib", "liblighthugger_b200.so")
 
 
 def cuda_lib():
