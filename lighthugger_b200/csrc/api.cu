@@ -46,6 +46,10 @@ FrameParams make_params(LhContext* ctx) {
     p.instance_tiles = ctx->instance_tiles;
     p.meshlet_tiles = ctx->meshlet_tiles;
     p.large_queue = ctx->large_queue;
+    p.meshlet_bounds = ctx->meshlet_bounds;
+    p.raster_queue = ctx->raster_queue;
+    p.depth_hist = ctx->depth_hist;
+    p.hiz = ctx->hiz;
     p.vis = ctx->vis;
     p.shadow = ctx->shadow;
     p.textures = ctx->tex_dev;
@@ -105,6 +109,13 @@ int alloc_targets(LhContext* ctx, uint32_t w, uint32_t h) {
     LH_CUDA(ctx, cudaMalloc(&ctx->scene, px * 8));
     LH_CUDA(ctx, cudaMalloc(&ctx->display, px * 4));
     LH_CUDA(ctx, cudaMalloc(&ctx->depth_plane, px * 4));
+    {
+        cudaFree(ctx->hiz);
+        ctx->hiz = nullptr;
+        const size_t main_tiles = (size_t)((w + 7) / 8) * ((h + 7) / 8), sm = (ctx->cfg.shadowmap_size + 7) / 8;
+        ctx->hiz_tiles = main_tiles > sm * sm ? main_tiles : sm * sm;
+        LH_CUDA(ctx, cudaMalloc(&ctx->hiz, ctx->hiz_tiles * 4));
+    }
     LH_CUDA(ctx, cudaMemset(ctx->vis, 0xFF, px * 8 + 16));
     LH_CUDA(ctx, cudaMemset(ctx->scene, 0, px * 8));
     LH_CUDA(ctx, cudaMemset(ctx->display, 0, px * 4));
@@ -199,6 +210,13 @@ int lh_context_create(const LhConfig* cfg, LhContext** out) {
     TRY(cudaMalloc(&ctx->meshlet_tiles, kMaxMeshletTiles * 8));
     TRY(cudaMemset(ctx->meshlet_tiles, 0, kMaxMeshletTiles * 8));
     TRY(cudaMalloc(&ctx->large_queue, (size_t)(cfg->max_large_triangles ? cfg->max_large_triangles : 1) * 8));
+    {
+        const size_t draws = (size_t)cfg->max_opaque_draws + cfg->max_alpha_clip_draws;
+        TRY(cudaMalloc(&ctx->meshlet_bounds, draws * 16));
+        TRY(cudaMalloc(&ctx->raster_queue, draws * 4));
+        TRY(cudaMalloc(&ctx->depth_hist, 65536 * 4));
+        TRY(cudaMemset(ctx->depth_hist, 0, 65536 * 4));
+    }
     TRY(cudaMalloc(&ctx->tex_dev, sizeof(cudaTextureObject_t) * LH_MAX_TEXTURES));
     TRY(cudaMemset(ctx->tex_dev, 0, sizeof(cudaTextureObject_t) * LH_MAX_TEXTURES));
     TRY(cudaMalloc(&ctx->tex_dims_dev, sizeof(uint4) * LH_MAX_TEXTURES));
@@ -242,6 +260,10 @@ int lh_context_destroy(LhContext* ctx) {
     cudaFree(ctx->instance_tiles);
     cudaFree(ctx->meshlet_tiles);
     cudaFree(ctx->large_queue);
+    cudaFree(ctx->meshlet_bounds);
+    cudaFree(ctx->raster_queue);
+    cudaFree(ctx->depth_hist);
+    cudaFree(ctx->hiz);
     cudaFree(ctx->tex_dev);
     cudaFree(ctx->tex_dims_dev);
     cudaFree(ctx->l2_flush);

@@ -73,7 +73,10 @@ struct FrameState {
     uint32_t tickets[8];           // tile tickets: [0] main meshlet cull, [1..4] cascades
     uint32_t done[8];              // CTAs finished (self-cleaning of the tile states)
     unsigned long long rasterized_triangles;
-    uint32_t raster_ticket;        // next unclaimed meshlet of the current raster pass
+    uint32_t raster_ticket;        // next unclaimed entry of the raster queue
+    uint32_t queue_count;          // entries appended to the raster queue so far in this pass
+    uint32_t band_begin, band_end; // queue range of the band being rasterised
+    uint32_t band_key[8];          // exclusive upper depth key of each band
     uint32_t skipped_empty[5], skipped_occluded[5];   // meshlets dropped by the rasteriser's early-outs: [0] main view, [1..4] cascades (stats)
 };
 
@@ -93,6 +96,10 @@ struct FrameParams {
     unsigned long long* instance_tiles;      // [4][tiles] decoupled-lookback states
     unsigned long long* meshlet_tiles;       // [5][kMaxMeshletTiles]
     uint32_t* large_queue;
+    void* meshlet_bounds;                    // 16 B per surviving meshlet of the current raster pass (raster.cu MeshletBound)
+    uint32_t* raster_queue;                  // indices of the meshlets selected for rasterisation, band after band
+    uint32_t* depth_hist;                    // 8192 bins of the depth-key histogram (self-cleaning)
+    uint32_t* hiz;                           // farthest stored value per 8x8-pixel tile of the current raster target
     unsigned long long* vis;
     uint32_t* shadow;                        // 4 layers of float bits
     const cudaTextureObject_t* textures;
@@ -130,6 +137,11 @@ struct LhContext {
     uint32_t instance_tiles_per_sector = 0;
     unsigned long long* meshlet_tiles = nullptr;
     uint32_t* large_queue = nullptr;
+    void* meshlet_bounds = nullptr;
+    uint32_t* raster_queue = nullptr;
+    uint32_t* depth_hist = nullptr;
+    uint32_t* hiz = nullptr;
+    size_t hiz_tiles = 0;
     void* l2_flush = nullptr;
     size_t l2_flush_bytes = 0;
     void* pinned = nullptr;

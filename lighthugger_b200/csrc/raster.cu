@@ -30,9 +30,6 @@ namespace lh {
 
 namespace {
 
-#ifndef LH_TICKET_CHUNK
-#define LH_TICKET_CHUNK 4
-#endif
 constexpr int kWarpsPerCta = 8;
 constexpr uint32_t kTileW = 128, kTileH = 32;   // deferred-triangle screen tile
 constexpr uint32_t kWholeTriangle = 0xFFFFFFFFu;
@@ -53,8 +50,6 @@ struct WarpScratch {
     uint8_t surv[128];
 };
 constexpr int kVertOutside = INT_MIN, kVertNonFinite = INT_MIN + 1;   // |snapped| <= 2^29, so neither can be a coordinate
-constexpr uint32_t kMaxTicketChunk = LH_TICKET_CHUNK;   // meshlets a warp takes per ticket: one lane per meshlet in the bounds phase
-enum { kBoundNone = 0, kBoundTest = 1, kBoundEmpty = 2 };
 constexpr int kMaxOcclusionBlocks = 16;    // early-out reads at most 16 blocks of 8x4 pixels (512 keys)
 
 struct SnapVert {
@@ -322,16 +317,34 @@ __device__ __forceinline__ void push_deferred(const FrameParams& P, uint32_t lo,
     }
 }
 
-// ---- kernel 1: one warp per meshlet ----
+// ---- the meshlet rasteriser: bounds -> depth bands -> (select, rasterise) per band ----
 //
-// Per meshlet: (0) early-outs from the meshlet's bounding sphere -- interval arithmetic through the same matrix gives
-// a conservative pixel rectangle and a conservative nearest depth; the meshlet is dropped when the rectangle holds no
-// pixel centre, or when every key already stored in it is nearer than anything the meshlet can produce (the software
-// counterpart of the hierarchical-Z reject the reference gets from its hardware rasteriser; keys only ever decrease, so
-// a stale read is conservative and the final buffer is bit-identical); (1) vertex phase, one lane per vertex;
-// (2) triangle cull phase, one lane per triangle: near-plane / bounding-box / facing tests, survivors compacted by
-// ballot into shared memory; (3) raster phase over the compacted list, so lanes are not idle behind rejected
-// triangles.  Meshlets are handed out by ticket (kTicketChunk per atomic) because the early-outs unbalance a static split.
+// The reference's hardware rasteriser rejects hidden geometry early (hierarchical Z); a software rasteriser that
+// pushes 10^8 sub-pixel triangles through 64-bit atomics needs the same, and gets it at meshlet granularity:
+//
+//   raster_bounds_kernel   one lane per surviving meshlet: interval arithmetic through the view's matrix on the
+//                          meshlet's bounding sphere gives a conservative pixel rectangle, a conservative nearest
+//                          depth ("edge") and a depth key; stored as a 16-byte MeshletBound, keys histogrammed.
+//   raster_bands_kernel    one CTA: histogram -> kBands key thresholds at fixed count fractions (nearest band small).
+//   raster_select_kernel   per band, nearest first: meshlets of the band whose rectangle holds a pixel centre and in
+//                          which some stored key is NOT already nearer than the edge depth are appended to a queue.
+//   raster_meshlets_kernel per band: one warp per queued meshlet (ticketed), re-tests against the live buffer, then
+//                          vertex phase (lane per vertex) -> triangle cull phase (lane per triangle, ballot compaction)
+//                          -> raster phase over the compacted survivors.
+//
+// Keys only ever decrease and a dropped meshlet could not have won any pixel, so the final buffer is bit-identical to
+// rasterising everything (tests compare it with the oracle, which does exactly that).
+
+struct MeshletBound {
+    uint32_t rect_x, rect_y;   // px0 | px1 << 16, py0 | py1 << 16; rect_x == kUntestable: rasterise without a test
+    uint32_t edge;             // main view: ~floatBits(nearest depth); cascade: floatBits(nearest depth)
+    uint32_t key;              // depth key, smaller = nearer; kKeyEmpty: the rectangle holds no pixel centre
+};
+constexpr uint32_t kUntestable = 0xFFFFFFFFu, kKeyEmpty = 0xFFFFFFFFu;
+constexpr int kBands = 6;
+constexpr uint32_t kHistShift = 19, kHistBins = 1u << (32 - kHistShift);   // 8192 bins over the top bits of the depth key
+constexpr int kHizTile = 8;                // hierarchical-Z tiles are 8x8 pixels
+constexpr int kMaxHizTiles = 64;           // selection tests rectangles of up to this many tiles
 
 // sigma_max(T) * r bounds |T (v - c)| for v in the object-space sphere (c, r).  Gershgorin on the Gram matrix and the
 // Frobenius norm are both valid for any matrix; for rotation * scale the first equals the reference's max column length.
@@ -346,14 +359,226 @@ __device__ __forceinline__ float sigma_max_bound(const float* T) {
 }
 
 template <bool SHADOW>
+__global__ void __launch_bounds__(256) raster_bounds_kernel(const __grid_constant__ FrameParams P, uint32_t cascade) {
+    const uint32_t* draw = (const uint32_t*)P.u.draw_calls;
+    const uint32_t n_opaque = min(draw[0], P.max_opaque), n_alpha = min(draw[1], P.max_alpha);
+    const uint32_t total = n_opaque + n_alpha;
+    const int W = (int)(SHADOW ? P.shadowmap_size : P.u.window_size[0]), H = (int)(SHADOW ? P.shadowmap_size : P.u.window_size[1]);
+    const float half_w = (float)W * 0.5f, half_h = (float)H * 0.5f;
+    float Mreg[SHADOW ? 16 : 1];
+    if (SHADOW) {
+        const float* src = &((const LhMiscStorage*)P.u.misc_storage)->shadow_matrices[cascade].m[0][0];
+#pragma unroll
+        for (int k = 0; k < (SHADOW ? 16 : 1); k++) Mreg[k] = src[k];
+    }
+    const float* M = SHADOW ? Mreg : &P.u.combined_perspective_view.m[0][0];
+    // |row_k.xyz| of M
+    const float nrm_x = sqrtf(M[0] * M[0] + M[4] * M[4] + M[8] * M[8]), nrm_y = sqrtf(M[1] * M[1] + M[5] * M[5] + M[9] * M[9]);
+    const float nrm_z = sqrtf(M[2] * M[2] + M[6] * M[6] + M[10] * M[10]), nrm_w = sqrtf(M[3] * M[3] + M[7] * M[7] + M[11] * M[11]);
+    MeshletBound* bounds = (MeshletBound*)P.meshlet_bounds;
+    uint32_t empty = 0;
+    for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < total; k += gridDim.x * blockDim.x) {
+        uint32_t slot, local;
+        work_to_slot(P, k, n_opaque, SHADOW, &slot, &local);
+        float T[12], sphere[4];
+        load_bounds(P, slot, T, sphere);
+        MeshletBound mb{kUntestable, 0u, 0u, 0u};   // no usable bound: nearest band, rasterised without a test
+        const float R0 = sphere[3] * sigma_max_bound(T);
+        const float wx = T[0] * sphere[0] + T[3] * sphere[1] + T[6] * sphere[2] + T[9];
+        const float wy = T[1] * sphere[0] + T[4] * sphere[1] + T[7] * sphere[2] + T[10];
+        const float wz = T[2] * sphere[0] + T[5] * sphere[1] + T[8] * sphere[2] + T[11];
+        // radius padded for the rounding of the vertex transform itself (a few ulp of the terms' magnitude)
+        const float R = R0 * 1.0001f + 2e-6f * (fabsf(wx) + fabsf(wy) + fabsf(wz) + fabsf(T[9]) + fabsf(T[10]) + fabsf(T[11]));
+        const float ccx = M[0] * wx + M[4] * wy + M[8] * wz + M[12], ccy = M[1] * wx + M[5] * wy + M[9] * wz + M[13];
+        const float ccz = M[2] * wx + M[6] * wy + M[10] * wz + M[14], ccw = M[3] * wx + M[7] * wy + M[11] * wz + M[15];
+        const float ex = R * nrm_x, ey = R * nrm_y, ez = R * nrm_z, ew = R * nrm_w;
+        const float w_lo = ccw - ew, w_hi = ccw + ew;
+        if (w_lo > 1e-6f) {   // otherwise the sphere reaches the w = 0 plane: no bound
+            const float x_lo = ccx - ex, x_hi = ccx + ex, y_lo = ccy - ey, y_hi = ccy + ey;
+            const float nx_lo = x_lo / (x_lo >= 0.0f ? w_hi : w_lo), nx_hi = x_hi / (x_hi >= 0.0f ? w_lo : w_hi);
+            const float ny_lo = y_lo / (y_lo >= 0.0f ? w_hi : w_lo), ny_hi = y_hi / (y_hi >= 0.0f ? w_lo : w_hi);
+            float fx_lo = nx_lo * half_w + half_w, fx_hi = nx_hi * half_w + half_w;
+            float fy_lo = ny_lo * half_h + half_h, fy_hi = ny_hi * half_h + half_h;
+            // nearest depth the meshlet can produce: largest z/w for the reverse-Z view, smallest for a cascade
+            const float z_edge = SHADOW ? ccz - ez : ccz + ez;
+            float d_edge = SHADOW ? z_edge / (z_edge >= 0.0f ? w_hi : w_lo) : z_edge / (z_edge >= 0.0f ? w_lo : w_hi);
+            if (fabsf(fx_lo) + fabsf(fx_hi) + fabsf(fy_lo) + fabsf(fy_hi) + fabsf(d_edge) < 3.0e38f) {
+                fx_lo -= 0.125f + 1e-5f * fabsf(fx_lo); fx_hi += 0.125f + 1e-5f * fabsf(fx_hi);
+                fy_lo -= 0.125f + 1e-5f * fabsf(fy_lo); fy_hi += 0.125f + 1e-5f * fabsf(fy_hi);
+                const int px0 = max(0, (int)ceilf(fx_lo - 0.5f)), px1 = min(W - 1, (int)floorf(fx_hi - 0.5f));
+                const int py0 = max(0, (int)ceilf(fy_lo - 0.5f)), py1 = min(H - 1, (int)floorf(fy_hi - 0.5f));
+                // depth key, smaller = nearer.  Main view: float bits of the view distance of the nearest point (bins are
+                // logarithmic in distance); cascade: the nearest light-space depth in [0,1) as 31-bit fixed point (linear bins)
+                mb.key = SHADOW ? (uint32_t)(fminf(fmaxf(d_edge, 0.0f), 0.99999994f) * 2147483648.0f) : min(__float_as_uint(w_lo), 0x7F800000u);
+                if (px0 > px1 || py0 > py1) {
+                    mb.key = kKeyEmpty;   // no pixel centre inside the bound
+                    empty++;
+                } else {
+                    d_edge = SHADOW ? d_edge - (4e-5f * fabsf(d_edge) + 1e-7f) : d_edge + (4e-5f * fabsf(d_edge) + 1e-30f);
+                    const int ntx = (px1 >> 3) - (px0 >> 3) + 1, nty = (py1 >> 3) - (py0 >> 3) + 1;
+                    if (ntx * nty <= kMaxHizTiles && d_edge > 0.0f) {
+                        mb.rect_x = (uint32_t)px0 | ((uint32_t)px1 << 16);
+                        mb.rect_y = (uint32_t)py0 | ((uint32_t)py1 << 16);
+                        // main view: a fragment of depth d loses when floatBits(d) < ~hi(key) for the stored key, i.e.
+                        // hi(key) < ~floatBits(d); cascade: it loses when d >= stored depth (LESS test)
+                        mb.edge = SHADOW ? __float_as_uint(d_edge) : ~__float_as_uint(d_edge);
+                    }
+                }
+            }
+        }
+        *(uint4*)(bounds + k) = make_uint4(mb.rect_x, mb.rect_y, mb.edge, mb.key);
+        // histogram, aggregated over the lanes that fall into the same bin (neighbouring meshlets mostly do; an
+        // un-aggregated add serialises on a handful of addresses)
+        const uint32_t bin = mb.key == kKeyEmpty ? kHistBins : mb.key >> kHistShift;
+        const uint32_t active = __activemask();
+        const uint32_t peers = __match_any_sync(active, bin);
+        if (bin < kHistBins && (threadIdx.x & 31u) == (uint32_t)(__ffs(peers) - 1)) atomicAdd(P.depth_hist + bin, (uint32_t)__popc(peers));
+    }
+    if (P.flags & LH_CONFIG_PASS_TIMINGS) {
+        empty = __reduce_add_sync(0xFFFFFFFFu, empty);
+        if ((threadIdx.x & 31) == 0 && empty) atomicAdd(&P.state->skipped_empty[SHADOW ? 1u + cascade : 0u], empty);
+    }
+}
+
+// One CTA of 1024 threads: scans the key histogram and writes the kBands upper key bounds (exclusive) at fixed
+// fractions of the meshlet count -- a small nearest band, so that the next bands already find most of the screen
+// covered -- and zeroes the histogram for the next pass.
+__global__ void __launch_bounds__(1024) raster_bands_kernel(const __grid_constant__ FrameParams P) {
+    __shared__ uint32_t partial[1024];
+    __shared__ uint32_t grand_total;
+    const uint32_t tid = threadIdx.x;
+    constexpr uint32_t kPer = kHistBins / 1024;   // 8 consecutive bins per thread: two coalesced 16-byte loads
+    uint32_t local[kPer], sum = 0;
+    {
+        uint4* src = (uint4*)(P.depth_hist + tid * kPer);
+        const uint4 a = src[0], b = src[1];
+        src[0] = make_uint4(0, 0, 0, 0);
+        src[1] = make_uint4(0, 0, 0, 0);
+        local[0] = a.x; local[1] = a.y; local[2] = a.z; local[3] = a.w;
+        local[4] = b.x; local[5] = b.y; local[6] = b.z; local[7] = b.w;
+#pragma unroll
+        for (uint32_t j = 0; j < kPer; j++) sum += local[j];
+    }
+    partial[tid] = sum;
+    __syncthreads();
+    // inclusive scan of the 1024 partials (Hillis-Steele)
+    for (uint32_t o = 1; o < 1024; o <<= 1) {
+        const uint32_t v = tid >= o ? partial[tid - o] : 0u;
+        __syncthreads();
+        partial[tid] += v;
+        __syncthreads();
+    }
+    if (tid == 1023) grand_total = partial[1023];
+    __syncthreads();
+    const uint32_t total = grand_total, before = partial[tid] - sum;
+    const float fractions[kBands - 1] = {0.02f, 0.07f, 0.17f, 0.35f, 0.60f};
+    FrameState* st = P.state;
+    if (tid == 0) {
+        st->band_key[kBands - 1] = kKeyEmpty;   // the last band takes the rest (empty meshlets carry kKeyEmpty and are never selected)
+        st->queue_count = 0;
+        st->band_begin = 0;
+    }
+    for (int b = 0; b < kBands - 1; b++) {
+        const uint32_t target = (uint32_t)((float)total * fractions[b]);
+        // the thread whose bins hold the target-th meshlet names the bin after it as the band's upper bound
+        if (sum && target >= before && target < before + sum) {
+            uint32_t run = before, j = 0;
+            for (; j < kPer; j++) {
+                run += local[j];
+                if (run > target) break;
+            }
+            st->band_key[b] = (tid * kPer + min(j, kPer - 1) + 1u) << kHistShift;
+        }
+        if (total == 0 && tid == 0) st->band_key[b] = 0u;
+    }
+}
+
+// Hierarchical Z: per 8x8-pixel tile the FARTHEST value stored in it (main view: largest key high word, all-ones while
+// any pixel is uncovered; cascade: largest depth).  Built between bands; stored values only get nearer afterwards, so
+// a tile value stays a valid bound.  One warp per tile, two pixels per lane.
+template <bool SHADOW>
+__global__ void __launch_bounds__(256) raster_hiz_kernel(const __grid_constant__ FrameParams P, uint32_t cascade) {
+    const int W = (int)(SHADOW ? P.shadowmap_size : P.u.window_size[0]), H = (int)(SHADOW ? P.shadowmap_size : P.u.window_size[1]);
+    const int TW = (W + kHizTile - 1) / kHizTile, TH = (H + kHizTile - 1) / kHizTile;
+    const uint32_t* layer = SHADOW ? P.shadow + (size_t)cascade * P.shadowmap_size * P.shadowmap_size : nullptr;
+    const uint32_t lane = threadIdx.x & 31;
+    const int warps = (int)(gridDim.x * (blockDim.x >> 5));
+    for (int tile = (int)(blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)); tile < TW * TH; tile += warps) {
+        const int x = (tile % TW) * kHizTile + (int)(lane & 7), y0 = (tile / TW) * kHizTile + (int)(lane >> 3);
+        uint32_t worst = 0;
+#pragma unroll
+        for (int half = 0; half < 2; half++) {
+            const int y = y0 + 4 * half;
+            if (x < W && y < H) {
+                const size_t at = (size_t)y * W + x;
+                worst = max(worst, SHADOW ? __ldcg(layer + at) : (uint32_t)(__ldcg(P.vis + at) >> 32));
+            }
+        }
+        worst = __reduce_max_sync(0xFFFFFFFFu, worst);
+        if (lane == 0) P.hiz[tile] = worst;
+    }
+}
+
+// Band selection, one lane per meshlet: appends the band's meshlets that might still win a pixel to the raster queue.
+// A meshlet is hidden when its nearest possible depth is farther than the farthest value of every tile its rectangle touches.
+template <bool SHADOW>
+__global__ void __launch_bounds__(256) raster_select_kernel(const __grid_constant__ FrameParams P, uint32_t cascade, uint32_t band) {
+    const uint32_t* draw = (const uint32_t*)P.u.draw_calls;
+    const uint32_t total = min(draw[0], P.max_opaque) + min(draw[1], P.max_alpha);
+    const uint32_t lane = threadIdx.x & 31;
+    const int W = (int)(SHADOW ? P.shadowmap_size : P.u.window_size[0]);
+    const int TW = (W + kHizTile - 1) / kHizTile;
+    const uint32_t key_lo = band ? P.state->band_key[band - 1] : 0u, key_hi = P.state->band_key[band];
+    const MeshletBound* bounds = (const MeshletBound*)P.meshlet_bounds;
+    uint32_t occluded = 0;
+    const uint32_t stride = gridDim.x * blockDim.x;
+    for (uint32_t base = blockIdx.x * blockDim.x + (threadIdx.x & ~31u); base < total; base += stride) {
+        const uint32_t k = base + lane;
+        uint4 mb = make_uint4(kUntestable, 0u, 0u, kKeyEmpty);
+        if (k < total) mb = __ldg((const uint4*)(bounds + k));
+        bool keep = mb.w >= key_lo && mb.w < key_hi;
+        if (keep && band != 0 && mb.x != kUntestable) {
+            const int tx0 = (int)(mb.x & 0xFFFFu) >> 3, tx1 = (int)(mb.x >> 16) >> 3, ty0 = (int)(mb.y & 0xFFFFu) >> 3, ty1 = (int)(mb.y >> 16) >> 3;
+            uint32_t worst = 0;   // main view: largest stored key high word; cascade: largest stored depth
+            for (int ty = ty0; ty <= ty1; ty++)
+                for (int tx = tx0; tx <= tx1; tx++) worst = max(worst, __ldcg(P.hiz + ty * TW + tx));
+            if (SHADOW ? mb.z >= worst : worst < mb.z) {
+                keep = false;
+                occluded++;
+            }
+        }
+        const uint32_t ballot = __ballot_sync(0xFFFFFFFFu, keep);
+        if (ballot) {
+            uint32_t at = 0;
+            if (lane == 0) at = atomicAdd(&P.state->queue_count, (uint32_t)__popc(ballot));
+            at = __shfl_sync(0xFFFFFFFFu, at, 0);
+            if (keep) P.raster_queue[at + __popc(ballot & ((1u << lane) - 1u))] = k;
+        }
+    }
+    if (P.flags & LH_CONFIG_PASS_TIMINGS) {
+        occluded = __reduce_add_sync(0xFFFFFFFFu, occluded);
+        if (lane == 0 && occluded) atomicAdd(&P.state->skipped_occluded[SHADOW ? 1u + cascade : 0u], occluded);
+    }
+}
+
+// between a band's selection and its rasterisation: the raster kernel takes tickets in [raster_ticket, band_end)
+__global__ void raster_band_begin_kernel(const __grid_constant__ FrameParams P) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        FrameState* st = P.state;
+        st->raster_ticket = st->band_begin;
+        st->band_end = st->queue_count;
+        st->band_begin = st->queue_count;
+    }
+}
+
+template <bool SHADOW>
 __global__ void __launch_bounds__(kWarpsPerCta * 32) raster_meshlets_kernel(const __grid_constant__ FrameParams P, uint32_t cascade) {
     __shared__ WarpScratch scratch_all[kWarpsPerCta];
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     WarpScratch& sv = scratch_all[warp];
     const uint32_t* draw = (const uint32_t*)P.u.draw_calls;
     const uint32_t n_opaque = min(draw[0], P.max_opaque);   // drawIndirectCount clamps to maxDrawCount
-    const uint32_t n_alpha = min(draw[1], P.max_alpha);
-    const uint32_t total = n_opaque + n_alpha;
+    const uint32_t band_end = P.state->band_end;
 
     Target<SHADOW> tg;
     tg.vis = P.vis;
@@ -372,86 +597,27 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) raster_meshlets_kernel(cons
         for (int k = 0; k < (SHADOW ? 16 : 1); k++) Mreg[k] = src[k];
     }
     const float* M = SHADOW ? Mreg : &P.u.combined_perspective_view.m[0][0];
-    // |row_k.xyz| of M, for the interval bounds of the early-outs
-    const float nrm_x = sqrtf(M[0] * M[0] + M[4] * M[4] + M[8] * M[8]), nrm_y = sqrtf(M[1] * M[1] + M[5] * M[5] + M[9] * M[9]);
-    const float nrm_z = sqrtf(M[2] * M[2] + M[6] * M[6] + M[10] * M[10]), nrm_w = sqrtf(M[3] * M[3] + M[7] * M[7] + M[11] * M[11]);
-    uint32_t tris_done = 0, skipped_empty = 0, skipped_occluded = 0;
+    const MeshletBound* bounds = (const MeshletBound*)P.meshlet_bounds;
+    uint32_t tris_done = 0, skipped_occluded = 0;
 
-    // A warp takes up to 32 consecutive meshlets per ticket (fewer when the pass is small, so that every warp gets work).
-    const uint32_t ticket_chunk = max(1u, min(kMaxTicketChunk, total / (gridDim.x * kWarpsPerCta * 4u)));
     for (;;) {
-        uint32_t chunk = 0;
-        if (lane == 0) chunk = atomicAdd(&P.state->raster_ticket, ticket_chunk);
-        chunk = __shfl_sync(0xFFFFFFFFu, chunk, 0);
-        if (chunk >= total) break;
-        const uint32_t chunk_end = min(total, chunk + ticket_chunk);
-
-        // ---- (0a) bounds of the chunk's meshlets, one lane per meshlet ----
-        // my_rect_x/y = px0 | px1 << 16 ...; my_state: kBoundNone (no usable bound: rasterise), kBoundTest, kBoundEmpty
-        uint32_t my_rect_x = 0, my_rect_y = 0, my_edge = 0, my_state = kBoundNone;
-        if (chunk + lane < chunk_end) {
-            uint32_t slot, local;
-            work_to_slot(P, chunk + lane, n_opaque, SHADOW, &slot, &local);
-            float T[12], sphere[4];
-            load_bounds(P, slot, T, sphere);
-            const float R0 = sphere[3] * sigma_max_bound(T);
-            const float wx = T[0] * sphere[0] + T[3] * sphere[1] + T[6] * sphere[2] + T[9];
-            const float wy = T[1] * sphere[0] + T[4] * sphere[1] + T[7] * sphere[2] + T[10];
-            const float wz = T[2] * sphere[0] + T[5] * sphere[1] + T[8] * sphere[2] + T[11];
-            // radius padded for the rounding of the vertex transform itself (a few ulp of the terms' magnitude)
-            const float R = R0 * 1.0001f + 2e-6f * (fabsf(wx) + fabsf(wy) + fabsf(wz) + fabsf(T[9]) + fabsf(T[10]) + fabsf(T[11]));
-            const float ccx = M[0] * wx + M[4] * wy + M[8] * wz + M[12], ccy = M[1] * wx + M[5] * wy + M[9] * wz + M[13];
-            const float ccz = M[2] * wx + M[6] * wy + M[10] * wz + M[14], ccw = M[3] * wx + M[7] * wy + M[11] * wz + M[15];
-            const float ex = R * nrm_x, ey = R * nrm_y, ez = R * nrm_z, ew = R * nrm_w;
-            const float w_lo = ccw - ew, w_hi = ccw + ew;
-            if (w_lo > 1e-6f) {   // otherwise the sphere reaches the w = 0 plane: no bound
-                const float x_lo = ccx - ex, x_hi = ccx + ex, y_lo = ccy - ey, y_hi = ccy + ey;
-                const float nx_lo = x_lo / (x_lo >= 0.0f ? w_hi : w_lo), nx_hi = x_hi / (x_hi >= 0.0f ? w_lo : w_hi);
-                const float ny_lo = y_lo / (y_lo >= 0.0f ? w_hi : w_lo), ny_hi = y_hi / (y_hi >= 0.0f ? w_lo : w_hi);
-                float fx_lo = nx_lo * half_w + half_w, fx_hi = nx_hi * half_w + half_w;
-                float fy_lo = ny_lo * half_h + half_h, fy_hi = ny_hi * half_h + half_h;
-                // nearest depth the meshlet can produce: largest z/w for the reverse-Z view, smallest for a cascade
-                const float z_edge = SHADOW ? ccz - ez : ccz + ez;
-                float d_edge = SHADOW ? z_edge / (z_edge >= 0.0f ? w_hi : w_lo) : z_edge / (z_edge >= 0.0f ? w_lo : w_hi);
-                if (fabsf(fx_lo) + fabsf(fx_hi) + fabsf(fy_lo) + fabsf(fy_hi) + fabsf(d_edge) < 3.0e38f) {
-                    fx_lo -= 0.125f + 1e-5f * fabsf(fx_lo); fx_hi += 0.125f + 1e-5f * fabsf(fx_hi);
-                    fy_lo -= 0.125f + 1e-5f * fabsf(fy_lo); fy_hi += 0.125f + 1e-5f * fabsf(fy_hi);
-                    const int px0 = max(0, (int)ceilf(fx_lo - 0.5f)), px1 = min(W - 1, (int)floorf(fx_hi - 0.5f));
-                    const int py0 = max(0, (int)ceilf(fy_lo - 0.5f)), py1 = min(H - 1, (int)floorf(fy_hi - 0.5f));
-                    if (px0 > px1 || py0 > py1) {
-                        my_state = kBoundEmpty;   // no pixel centre inside the bound
-                    } else {
-                        d_edge = SHADOW ? d_edge - (4e-5f * fabsf(d_edge) + 1e-7f) : d_edge + (4e-5f * fabsf(d_edge) + 1e-30f);
-                        const int nbx = ((px1 - px0) >> 3) + 1, nby = ((py1 - py0) >> 2) + 1;
-                        if (nbx * nby <= kMaxOcclusionBlocks && d_edge > 0.0f) {
-                            my_state = kBoundTest;
-                            my_rect_x = (uint32_t)px0 | ((uint32_t)px1 << 16);
-                            my_rect_y = (uint32_t)py0 | ((uint32_t)py1 << 16);
-                            // main view: a fragment of depth d loses when floatBits(d) < ~hi(key) for the stored key, i.e.
-                            // hi(key) < ~floatBits(d); cascade: it loses when d >= stored depth (LESS test)
-                            my_edge = SHADOW ? __float_as_uint(d_edge) : ~__float_as_uint(d_edge);
-                        }
-                    }
-                }
-            }
-        }
-        skipped_empty += __popc(__ballot_sync(0xFFFFFFFFu, my_state == kBoundEmpty));
-
-        for (uint32_t k = chunk; k < chunk_end; k++) {
-            // ---- (0b) occlusion test against the keys already stored, the whole warp reading the rectangle ----
-            const uint32_t state = __shfl_sync(0xFFFFFFFFu, my_state, k - chunk);
-            if (state == kBoundEmpty) continue;
-            if (state == kBoundTest) {
-                const uint32_t rx = __shfl_sync(0xFFFFFFFFu, my_rect_x, k - chunk), ry = __shfl_sync(0xFFFFFFFFu, my_rect_y, k - chunk);
-                const uint32_t edge = __shfl_sync(0xFFFFFFFFu, my_edge, k - chunk);
-                const int px0 = (int)(rx & 0xFFFFu), px1 = (int)(rx >> 16), py0 = (int)(ry & 0xFFFFu), py1 = (int)(ry >> 16);
-                uint32_t worst = 0;   // main view: largest stored key high word; cascade: largest stored depth
+        uint32_t ticket = 0;
+        if (lane == 0) ticket = atomicAdd(&P.state->raster_ticket, 1u);
+        ticket = __shfl_sync(0xFFFFFFFFu, ticket, 0);
+        if (ticket >= band_end) break;
+        {
+            const uint32_t k = __ldg(P.raster_queue + ticket);
+            // ---- (0) re-test against the keys stored since the selection (the band's own meshlets occlude one another) ----
+            const uint4 mb = __ldg((const uint4*)(bounds + k));
+            const int px0 = (int)(mb.x & 0xFFFFu), px1 = (int)(mb.x >> 16), py0 = (int)(mb.y & 0xFFFFu), py1 = (int)(mb.y >> 16);
+            if (mb.x != kUntestable && (((px1 - px0) >> 3) + 1) * (((py1 - py0) >> 2) + 1) <= kMaxOcclusionBlocks) {
+                uint32_t worst = 0;
                 for (int y = py0 + (int)(lane >> 3); y <= py1; y += 4) {
                     const uint32_t* row = SHADOW ? tg.layer + (size_t)y * W : (const uint32_t*)tg.vis + 2 * (size_t)y * W + 1;
                     for (int x = px0 + (int)(lane & 7); x <= px1; x += 8) worst = max(worst, __ldcg(row + (SHADOW ? x : 2 * x)));
                 }
                 worst = __reduce_max_sync(0xFFFFFFFFu, worst);
-                if (SHADOW ? edge >= worst : worst < edge) {
+                if (SHADOW ? mb.z >= worst : worst < mb.z) {
                     skipped_occluded++;
                     continue;
                 }
@@ -602,7 +768,6 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) raster_meshlets_kernel(cons
         if (lane == 0) {
             const uint32_t pass = SHADOW ? 1u + cascade : 0u;
             if (tris_done && !SHADOW) atomicAdd(&P.state->rasterized_triangles, (unsigned long long)tris_done);
-            if (skipped_empty) atomicAdd(&P.state->skipped_empty[pass], skipped_empty);
             if (skipped_occluded) atomicAdd(&P.state->skipped_occluded[pass], skipped_occluded);
         }
     }
@@ -665,20 +830,35 @@ __global__ void end_main_pass_kernel(const __grid_constant__ FrameParams P) {
 }  // namespace
 
 void launch_raster(LhContext* ctx, const FrameParams& p, int cascade) {
-    const uint32_t grid = (uint32_t)ctx->num_sms * 8;  // 64 resident warps per SM
+    const uint32_t grid = (uint32_t)ctx->num_sms * 8;
+    const bool timed = cascade < 0 && (ctx->cfg.flags & LH_CONFIG_PASS_TIMINGS) != 0;
     begin_raster_pass_kernel<<<1, 32, 0, ctx->stream>>>(p); ctx->launches++;
-    if (cascade < 0) {
-        const bool timed = (ctx->cfg.flags & LH_CONFIG_PASS_TIMINGS) != 0;
-        if (timed) cudaEventRecord(ctx->raster_kernel_a, ctx->stream);
-        raster_meshlets_kernel<false><<<grid, kWarpsPerCta * 32, 0, ctx->stream>>>(p, 0); ctx->launches++;
-        if (timed) {
-            cudaEventRecord(ctx->raster_kernel_b, ctx->stream);
-            ctx->raster_kernel_recorded = true;
+    if (timed) cudaEventRecord(ctx->raster_kernel_a, ctx->stream);
+    if (cascade < 0) raster_bounds_kernel<false><<<grid, 256, 0, ctx->stream>>>(p, 0);
+    else raster_bounds_kernel<true><<<grid, 256, 0, ctx->stream>>>(p, (uint32_t)cascade);
+    raster_bands_kernel<<<1, 1024, 0, ctx->stream>>>(p);
+    ctx->launches += 2;
+    for (uint32_t band = 0; band < (uint32_t)kBands; band++) {
+        if (band != 0) {
+            if (cascade < 0) raster_hiz_kernel<false><<<grid, 256, 0, ctx->stream>>>(p, 0);
+            else raster_hiz_kernel<true><<<grid, 256, 0, ctx->stream>>>(p, (uint32_t)cascade);
+            ctx->launches++;
         }
+        if (cascade < 0) raster_select_kernel<false><<<grid, 256, 0, ctx->stream>>>(p, 0, band);
+        else raster_select_kernel<true><<<grid, 256, 0, ctx->stream>>>(p, (uint32_t)cascade, band);
+        raster_band_begin_kernel<<<1, 32, 0, ctx->stream>>>(p);
+        if (cascade < 0) raster_meshlets_kernel<false><<<grid, kWarpsPerCta * 32, 0, ctx->stream>>>(p, 0);
+        else raster_meshlets_kernel<true><<<grid, kWarpsPerCta * 32, 0, ctx->stream>>>(p, (uint32_t)cascade);
+        ctx->launches += 3;
+    }
+    if (timed) {
+        cudaEventRecord(ctx->raster_kernel_b, ctx->stream);
+        ctx->raster_kernel_recorded = true;
+    }
+    if (cascade < 0) {
         raster_deferred_kernel<false><<<grid, kWarpsPerCta * 32, 0, ctx->stream>>>(p, 0); ctx->launches++;
         end_main_pass_kernel<<<1, 32, 0, ctx->stream>>>(p); ctx->launches++;
     } else {
-        raster_meshlets_kernel<true><<<grid, kWarpsPerCta * 32, 0, ctx->stream>>>(p, (uint32_t)cascade); ctx->launches++;
         raster_deferred_kernel<true><<<grid, kWarpsPerCta * 32, 0, ctx->stream>>>(p, (uint32_t)cascade); ctx->launches++;
     }
 }
