@@ -75,7 +75,8 @@ struct FrameState {
     unsigned long long rasterized_triangles;
     uint32_t raster_ticket;        // next unclaimed entry of the raster queue
     uint32_t queue_count;          // entries appended to the raster queue so far in this pass
-    uint32_t band_begin, band_end; // queue range of the band being rasterised
+    uint32_t band_begin, band_end; // queue range of the band being rasterised (band_begin already names the next band's start)
+    uint32_t band_first;           // first queue entry of the band being rasterised
     uint32_t band_key[8];          // exclusive upper depth key of each band
     uint32_t skipped_empty[5], skipped_occluded[5];   // meshlets dropped by the rasteriser's early-outs: [0] main view, [1..4] cascades (stats)
 };

@@ -50,6 +50,7 @@ struct WarpScratch {
     uint8_t surv[128];
 };
 constexpr int kVertOutside = INT_MIN, kVertNonFinite = INT_MIN + 1;   // |snapped| <= 2^29, so neither can be a coordinate
+constexpr int kFrontChunk = 4;             // queue entries a warp takes per ticket
 constexpr int kMaxOcclusionBlocks = 16;    // early-out reads at most 16 blocks of 8x4 pixels (512 keys)
 
 struct SnapVert {
@@ -59,8 +60,14 @@ struct SnapVert {
 
 // project_snap of the pinned model: false when the vertex is not finite
 __device__ __forceinline__ bool project_snap(float cx, float cy, float cz, float cw, float half_w, float half_h, int* sx, int* sy, float* z) {
-    float ndc_x = pdiv(cx, cw), ndc_y = pdiv(cy, cw);
-    *z = pdiv(cz, cw);
+    // x / 1.0f == x exactly: an orthographic (cascade) matrix yields w == 1 and skips the three IEEE divisions
+    float ndc_x = cx, ndc_y = cy;
+    *z = cz;
+    if (cw != 1.0f) {
+        ndc_x = pdiv(cx, cw);
+        ndc_y = pdiv(cy, cw);
+        *z = pdiv(cz, cw);
+    }
     float fx = pmul(padd(pmul(ndc_x, half_w), half_w), 256.0f);
     float fy = pmul(padd(pmul(ndc_y, half_h), half_h), 256.0f);
     if (!(isfinite(fx) && isfinite(fy) && isfinite(*z))) return false;
@@ -566,13 +573,17 @@ __global__ void raster_band_begin_kernel(const __grid_constant__ FrameParams P) 
     if (threadIdx.x == 0 && blockIdx.x == 0) {
         FrameState* st = P.state;
         st->raster_ticket = st->band_begin;
+        st->band_first = st->band_begin;
         st->band_end = st->queue_count;
         st->band_begin = st->queue_count;
     }
 }
 
+#ifndef LH_RASTER_MIN_CTAS
+#define LH_RASTER_MIN_CTAS 4
+#endif
 template <bool SHADOW>
-__global__ void __launch_bounds__(kWarpsPerCta * 32) raster_meshlets_kernel(const __grid_constant__ FrameParams P, uint32_t cascade) {
+__global__ void __launch_bounds__(kWarpsPerCta * 32, LH_RASTER_MIN_CTAS) raster_meshlets_kernel(const __grid_constant__ FrameParams P, uint32_t cascade) {
     __shared__ WarpScratch scratch_all[kWarpsPerCta];
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     WarpScratch& sv = scratch_all[warp];
@@ -598,23 +609,52 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) raster_meshlets_kernel(cons
     }
     const float* M = SHADOW ? Mreg : &P.u.combined_perspective_view.m[0][0];
     const MeshletBound* bounds = (const MeshletBound*)P.meshlet_bounds;
-    uint32_t tris_done = 0, skipped_occluded = 0;
+    uint32_t tris_done = 0, skipped_occluded = 0, skipped_empty = 0;
 
+    // A warp takes up to kFrontChunk queue entries per ticket (one when the band is small, so that every warp gets
+    // work and a heavy near meshlet does not serialise its neighbours): the entries, their bounds and the first 8x4
+    // block of every rectangle are fetched before any entry is processed, so the dependent round trips
+    // ticket -> queue -> bounds -> stored keys are paid once per chunk instead of once per meshlet.
+    const uint32_t band_count = band_end - P.state->band_first;
+    const uint32_t chunk = max(1u, min((uint32_t)kFrontChunk, band_count / (gridDim.x * kWarpsPerCta * 8u)));
     for (;;) {
         uint32_t ticket = 0;
-        if (lane == 0) ticket = atomicAdd(&P.state->raster_ticket, 1u);
+        if (lane == 0) ticket = atomicAdd(&P.state->raster_ticket, chunk);
         ticket = __shfl_sync(0xFFFFFFFFu, ticket, 0);
         if (ticket >= band_end) break;
-        {
-            const uint32_t k = __ldg(P.raster_queue + ticket);
+        const uint32_t n = min(chunk, band_end - ticket);
+        uint32_t my_k = 0;
+        uint4 my_mb = make_uint4(kUntestable, 0u, 0u, 0u);
+        if (lane < n) {
+            my_k = __ldg(P.raster_queue + ticket + lane);
+            my_mb = __ldg((const uint4*)(bounds + my_k));
+        }
+        uint32_t first[kFrontChunk];
+#pragma unroll
+        for (int j = 0; j < kFrontChunk; j++) {
+            first[j] = 0;
+            const uint32_t rx = __shfl_sync(0xFFFFFFFFu, my_mb.x, j), ry = __shfl_sync(0xFFFFFFFFu, my_mb.y, j);
+            const int x = (int)(rx & 0xFFFFu) + (int)(lane & 7), y = (int)(ry & 0xFFFFu) + (int)(lane >> 3);
+            if ((uint32_t)j < n && rx != kUntestable && x <= (int)(rx >> 16) && y <= (int)(ry >> 16)) {
+                const size_t at = (size_t)y * W + x;
+                first[j] = SHADOW ? __ldcg(tg.layer + at) : __ldcg((const uint32_t*)tg.vis + 2 * at + 1);
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < kFrontChunk; j++) {
+            if ((uint32_t)j >= n) break;
+            const uint32_t k = __shfl_sync(0xFFFFFFFFu, my_k, j);
             // ---- (0) re-test against the keys stored since the selection (the band's own meshlets occlude one another) ----
-            const uint4 mb = __ldg((const uint4*)(bounds + k));
+            const uint4 mb = make_uint4(__shfl_sync(0xFFFFFFFFu, my_mb.x, j), __shfl_sync(0xFFFFFFFFu, my_mb.y, j),
+                                        __shfl_sync(0xFFFFFFFFu, my_mb.z, j), 0u);
             const int px0 = (int)(mb.x & 0xFFFFu), px1 = (int)(mb.x >> 16), py0 = (int)(mb.y & 0xFFFFu), py1 = (int)(mb.y >> 16);
             if (mb.x != kUntestable && (((px1 - px0) >> 3) + 1) * (((py1 - py0) >> 2) + 1) <= kMaxOcclusionBlocks) {
-                uint32_t worst = 0;
-                for (int y = py0 + (int)(lane >> 3); y <= py1; y += 4) {
-                    const uint32_t* row = SHADOW ? tg.layer + (size_t)y * W : (const uint32_t*)tg.vis + 2 * (size_t)y * W + 1;
-                    for (int x = px0 + (int)(lane & 7); x <= px1; x += 8) worst = max(worst, __ldcg(row + (SHADOW ? x : 2 * x)));
+                uint32_t worst = first[j];
+                if (px1 - px0 >= 8 || py1 - py0 >= 4) {   // more than the prefetched block
+                    for (int y = py0 + (int)(lane >> 3); y <= py1; y += 4) {
+                        const uint32_t* row = SHADOW ? tg.layer + (size_t)y * W : (const uint32_t*)tg.vis + 2 * (size_t)y * W + 1;
+                        for (int x = px0 + (int)(lane & 7); x <= px1; x += 8) worst = max(worst, __ldcg(row + (SHADOW ? x : 2 * x)));
+                    }
                 }
                 worst = __reduce_max_sync(0xFFFFFFFFu, worst);
                 if (SHADOW ? mb.z >= worst : worst < mb.z) {
@@ -633,6 +673,9 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) raster_meshlets_kernel(cons
             const AlphaTest at = make_alpha_test(P, h);
 
             // ---- (1) vertex phase: load_vertex_data + calculate_world_pos + matrix * (world, 1) ----
+            int vminx = INT_MAX, vmaxx = INT_MIN, vminy = INT_MAX, vmaxy = INT_MIN;
+            uint32_t vnear = SHADOW ? 0xFFFFFFFFu : 0u;   // bits of the nearest vertex depth (depths are >= 0, so bits order like values)
+            bool special = false;                          // some vertex is behind the near plane, non-finite or of negative depth
             for (uint32_t v = lane; v < nv; v += 32) {
                 const uint32_t idx = load_vertex_index(h, v);
                 const uint16_t* p = h.positions + 3 * (size_t)idx;
@@ -648,8 +691,45 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) raster_meshlets_kernel(cons
                 sv.sy[v] = sy;
                 sv.z[v] = z;
                 if (h.alpha) sv.w[v] = clip.w;
+                if (sx == kVertOutside || sx == kVertNonFinite || !(z >= 0.0f)) {
+                    special = true;
+                } else {
+                    vminx = min(vminx, sx); vmaxx = max(vmaxx, sx);
+                    vminy = min(vminy, sy); vmaxy = max(vmaxy, sy);
+                    vnear = SHADOW ? min(vnear, __float_as_uint(z)) : max(vnear, __float_as_uint(z));
+                }
             }
             __syncwarp();
+
+            // ---- (1b) the same two early-outs with the exact vertex bounds: every triangle lies inside the vertices'
+            // rectangle, and (screen-linear depth) no fragment is nearer than the nearest vertex ----
+            if (!__any_sync(0xFFFFFFFFu, special)) {
+                vminx = __reduce_min_sync(0xFFFFFFFFu, vminx); vmaxx = __reduce_max_sync(0xFFFFFFFFu, vmaxx);
+                vminy = __reduce_min_sync(0xFFFFFFFFu, vminy); vmaxy = __reduce_max_sync(0xFFFFFFFFu, vmaxy);
+                const int bx0 = max(0, (vminx - 128 + 255) >> 8), bx1 = min(W - 1, (vmaxx - 128) >> 8);
+                const int by0 = max(0, (vminy - 128 + 255) >> 8), by1 = min(H - 1, (vmaxy - 128) >> 8);
+                if (bx0 > bx1 || by0 > by1) {   // no pixel centre inside
+                    skipped_empty++;
+                    continue;
+                }
+                if (bx1 - bx0 < 8 && by1 - by0 < 4) {   // one 8x4 block: test the stored keys against the nearest vertex depth
+                    vnear = SHADOW ? __reduce_min_sync(0xFFFFFFFFu, vnear) : __reduce_max_sync(0xFFFFFFFFu, vnear);
+                    const float zn = __uint_as_float(vnear);
+                    // the interpolated depth can leave the vertices' range by rounding only: pad by a few ulp
+                    const float d = SHADOW ? zn - (4e-6f * zn + 1e-30f) : zn + (4e-6f * zn + 1e-30f);
+                    const int x = bx0 + (int)(lane & 7), y = by0 + (int)(lane >> 3);
+                    uint32_t worst = 0;
+                    if (x <= bx1 && y <= by1) {
+                        const size_t at = (size_t)y * W + x;
+                        worst = SHADOW ? __ldcg(tg.layer + at) : __ldcg((const uint32_t*)tg.vis + 2 * at + 1);
+                    }
+                    worst = __reduce_max_sync(0xFFFFFFFFu, worst);
+                    if (d > 0.0f && (SHADOW ? __float_as_uint(d) >= worst : worst < ~__float_as_uint(d))) {
+                        skipped_occluded++;
+                        continue;
+                    }
+                }
+            }
 
             // ---- (2) triangle cull phase ----
             uint32_t n_surv = 0;
@@ -769,6 +849,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) raster_meshlets_kernel(cons
             const uint32_t pass = SHADOW ? 1u + cascade : 0u;
             if (tris_done && !SHADOW) atomicAdd(&P.state->rasterized_triangles, (unsigned long long)tris_done);
             if (skipped_occluded) atomicAdd(&P.state->skipped_occluded[pass], skipped_occluded);
+            if (skipped_empty) atomicAdd(&P.state->skipped_empty[pass], skipped_empty);
         }
     }
 }
