@@ -112,8 +112,10 @@ int alloc_targets(LhContext* ctx, uint32_t w, uint32_t h) {
     {
         cudaFree(ctx->hiz);
         ctx->hiz = nullptr;
-        const size_t main_tiles = (size_t)((w + 7) / 8) * ((h + 7) / 8), sm = (ctx->cfg.shadowmap_size + 7) / 8;
-        ctx->hiz_tiles = main_tiles > sm * sm ? main_tiles : sm * sm;
+        // two levels (4x4 and 16x16 pixel tiles), sized for the larger of the main view and a shadow layer
+        auto tiles = [](size_t tw, size_t th) { return ((tw + 3) / 4) * ((th + 3) / 4) + ((tw + 15) / 16) * ((th + 15) / 16); };
+        const size_t main_tiles = tiles(w, h), shadow_tiles = tiles(ctx->cfg.shadowmap_size, ctx->cfg.shadowmap_size);
+        ctx->hiz_tiles = main_tiles > shadow_tiles ? main_tiles : shadow_tiles;
         LH_CUDA(ctx, cudaMalloc(&ctx->hiz, ctx->hiz_tiles * 4));
     }
     LH_CUDA(ctx, cudaMemset(ctx->vis, 0xFF, px * 8 + 16));

@@ -47,6 +47,9 @@ struct WarpScratch {
     int sy[LH_MAX_MESHLET_UNIQUE_VERTICES];
     float z[LH_MAX_MESHLET_UNIQUE_VERTICES];
     float w[LH_MAX_MESHLET_UNIQUE_VERTICES];   // clip w, written for alpha-clip meshlets only (perspective-correct uv)
+    // per vertex, packed int16 pairs (x | y << 16): .x = first pixel whose centre is >= the vertex, .y = last pixel whose
+    // centre is <= it.  min/max over a triangle's vertices (SIMD halfword ops) give its pixel rectangle directly.
+    uint2 cover[LH_MAX_MESHLET_UNIQUE_VERTICES];
     uint8_t surv[128];
 };
 constexpr int kVertOutside = INT_MIN, kVertNonFinite = INT_MIN + 1;   // |snapped| <= 2^29, so neither can be a coordinate
@@ -348,10 +351,13 @@ struct MeshletBound {
     uint32_t key;              // depth key, smaller = nearer; kKeyEmpty: the rectangle holds no pixel centre
 };
 constexpr uint32_t kUntestable = 0xFFFFFFFFu, kKeyEmpty = 0xFFFFFFFFu;
-constexpr int kBands = 6;
+#ifndef LH_BANDS
+#define LH_BANDS 6
+#endif
+constexpr int kBands = LH_BANDS;
 constexpr uint32_t kHistShift = 19, kHistBins = 1u << (32 - kHistShift);   // 8192 bins over the top bits of the depth key
-constexpr int kHizTile = 8;                // hierarchical-Z tiles are 8x8 pixels
-constexpr int kMaxHizTiles = 64;           // selection tests rectangles of up to this many tiles
+constexpr int kHizShift0 = 2, kHizShift1 = 4;   // hierarchical-Z levels: 4x4-pixel and 16x16-pixel tiles
+constexpr int kMaxHizTiles = 48;                // selection reads at most this many tiles of one level per meshlet
 
 // sigma_max(T) * r bounds |T (v - c)| for v in the object-space sphere (c, r).  Gershgorin on the Gram matrix and the
 // Frobenius norm are both valid for any matrix; for rotation * scale the first equals the reference's max column length.
@@ -422,7 +428,7 @@ __global__ void __launch_bounds__(256) raster_bounds_kernel(const __grid_constan
                     empty++;
                 } else {
                     d_edge = SHADOW ? d_edge - (4e-5f * fabsf(d_edge) + 1e-7f) : d_edge + (4e-5f * fabsf(d_edge) + 1e-30f);
-                    const int ntx = (px1 >> 3) - (px0 >> 3) + 1, nty = (py1 >> 3) - (py0 >> 3) + 1;
+                    const int ntx = (px1 >> kHizShift1) - (px0 >> kHizShift1) + 1, nty = (py1 >> kHizShift1) - (py0 >> kHizShift1) + 1;
                     if (ntx * nty <= kMaxHizTiles && d_edge > 0.0f) {
                         mb.rect_x = (uint32_t)px0 | ((uint32_t)px1 << 16);
                         mb.rect_y = (uint32_t)py0 | ((uint32_t)py1 << 16);
@@ -478,7 +484,15 @@ __global__ void __launch_bounds__(1024) raster_bands_kernel(const __grid_constan
     if (tid == 1023) grand_total = partial[1023];
     __syncthreads();
     const uint32_t total = grand_total, before = partial[tid] - sum;
+#if LH_BANDS == 6
     const float fractions[kBands - 1] = {0.02f, 0.07f, 0.17f, 0.35f, 0.60f};
+#elif LH_BANDS == 8
+    const float fractions[kBands - 1] = {0.01f, 0.03f, 0.07f, 0.14f, 0.26f, 0.42f, 0.65f};
+#elif LH_BANDS == 10
+    const float fractions[kBands - 1] = {0.01f, 0.025f, 0.05f, 0.09f, 0.15f, 0.24f, 0.36f, 0.52f, 0.72f};
+#elif LH_BANDS == 4
+    const float fractions[kBands - 1] = {0.03f, 0.12f, 0.40f};
+#endif
     FrameState* st = P.state;
     if (tid == 0) {
         st->band_key[kBands - 1] = kKeyEmpty;   // the last band takes the rest (empty meshlets carry kKeyEmpty and are never selected)
@@ -500,41 +514,68 @@ __global__ void __launch_bounds__(1024) raster_bands_kernel(const __grid_constan
     }
 }
 
-// Hierarchical Z: per 8x8-pixel tile the FARTHEST value stored in it (main view: largest key high word, all-ones while
-// any pixel is uncovered; cascade: largest depth).  Built between bands; stored values only get nearer afterwards, so
-// a tile value stays a valid bound.  One warp per tile, two pixels per lane.
+// Hierarchical Z, two levels: per 4x4-pixel and per 16x16-pixel tile the FARTHEST value stored in it (main view:
+// largest key high word, all-ones while any pixel is uncovered; cascade: largest depth).  Built between bands; stored
+// values only get nearer afterwards, so a tile value stays a valid bound.  One thread per 4x4 tile (rows read as two
+// 16-byte loads, a warp row covering 256 contiguous bytes); a warp owns 8x4 fine tiles = two coarse tiles, reduced by shuffles.
+__device__ __forceinline__ int hiz_dim(int pixels, int shift) { return (pixels + (1 << shift) - 1) >> shift; }
+
 template <bool SHADOW>
 __global__ void __launch_bounds__(256) raster_hiz_kernel(const __grid_constant__ FrameParams P, uint32_t cascade) {
     const int W = (int)(SHADOW ? P.shadowmap_size : P.u.window_size[0]), H = (int)(SHADOW ? P.shadowmap_size : P.u.window_size[1]);
-    const int TW = (W + kHizTile - 1) / kHizTile, TH = (H + kHizTile - 1) / kHizTile;
+    const int TW0 = hiz_dim(W, kHizShift0), TH0 = hiz_dim(H, kHizShift0), TW1 = hiz_dim(W, kHizShift1), TH1 = hiz_dim(H, kHizShift1);
+    uint32_t* level0 = P.hiz;
+    uint32_t* level1 = P.hiz + (size_t)TW0 * TH0;
     const uint32_t* layer = SHADOW ? P.shadow + (size_t)cascade * P.shadowmap_size * P.shadowmap_size : nullptr;
     const uint32_t lane = threadIdx.x & 31;
     const int warps = (int)(gridDim.x * (blockDim.x >> 5));
-    for (int tile = (int)(blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)); tile < TW * TH; tile += warps) {
-        const int x = (tile % TW) * kHizTile + (int)(lane & 7), y0 = (tile / TW) * kHizTile + (int)(lane >> 3);
+    const int groups_x = (TW0 + 7) >> 3, groups_y = (TH0 + 3) >> 2;   // warp groups of 8x4 fine tiles
+    for (int g = (int)(blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)); g < groups_x * groups_y; g += warps) {
+        const int tx = (g % groups_x) * 8 + (int)(lane & 7), ty = (g / groups_x) * 4 + (int)(lane >> 3);
         uint32_t worst = 0;
+        if (tx < TW0 && ty < TH0) {
+            const int x0 = tx << kHizShift0, y0 = ty << kHizShift0;
 #pragma unroll
-        for (int half = 0; half < 2; half++) {
-            const int y = y0 + 4 * half;
-            if (x < W && y < H) {
-                const size_t at = (size_t)y * W + x;
-                worst = max(worst, SHADOW ? __ldcg(layer + at) : (uint32_t)(__ldcg(P.vis + at) >> 32));
+            for (int r = 0; r < 4; r++) {
+                const int y = y0 + r;
+                if (y >= H) break;
+                if (x0 + 3 < W && (W & 3) == 0) {
+                    if (SHADOW) {
+                        const uint4 q = __ldcg((const uint4*)(layer + (size_t)y * W + x0));
+                        worst = max(worst, max(max(q.x, q.y), max(q.z, q.w)));
+                    } else {
+                        const uint4 a = __ldcg((const uint4*)(P.vis + (size_t)y * W + x0)), b = __ldcg((const uint4*)(P.vis + (size_t)y * W + x0 + 2));
+                        worst = max(worst, max(max(a.y, a.w), max(b.y, b.w)));
+                    }
+                } else {
+                    for (int x = x0; x < min(W, x0 + 4); x++)
+                        worst = max(worst, SHADOW ? __ldcg(layer + (size_t)y * W + x) : (uint32_t)(__ldcg(P.vis + (size_t)y * W + x) >> 32));
+                }
             }
+            level0[(size_t)ty * TW0 + tx] = worst;
         }
-        worst = __reduce_max_sync(0xFFFFFFFFu, worst);
-        if (lane == 0) P.hiz[tile] = worst;
+        // coarse tile = 4x4 fine tiles: lanes with equal bit 2 (tx >> 2) over all four rows
+        uint32_t coarse = worst;
+        coarse = max(coarse, __shfl_xor_sync(0xFFFFFFFFu, coarse, 1));
+        coarse = max(coarse, __shfl_xor_sync(0xFFFFFFFFu, coarse, 2));
+        coarse = max(coarse, __shfl_xor_sync(0xFFFFFFFFu, coarse, 8));
+        coarse = max(coarse, __shfl_xor_sync(0xFFFFFFFFu, coarse, 16));
+        if ((lane & 27u) == 0 && tx < TW0 && ty < TH0) level1[(size_t)(ty >> 2) * TW1 + (tx >> 2)] = coarse;
     }
 }
 
 // Band selection, one lane per meshlet: appends the band's meshlets that might still win a pixel to the raster queue.
-// A meshlet is hidden when its nearest possible depth is farther than the farthest value of every tile its rectangle touches.
+// A meshlet is hidden when its nearest possible depth is farther than the farthest value of every tile its rectangle
+// touches (fine tiles when the rectangle is small, coarse ones otherwise).
 template <bool SHADOW>
 __global__ void __launch_bounds__(256) raster_select_kernel(const __grid_constant__ FrameParams P, uint32_t cascade, uint32_t band) {
     const uint32_t* draw = (const uint32_t*)P.u.draw_calls;
     const uint32_t total = min(draw[0], P.max_opaque) + min(draw[1], P.max_alpha);
     const uint32_t lane = threadIdx.x & 31;
-    const int W = (int)(SHADOW ? P.shadowmap_size : P.u.window_size[0]);
-    const int TW = (W + kHizTile - 1) / kHizTile;
+    const int W = (int)(SHADOW ? P.shadowmap_size : P.u.window_size[0]), H = (int)(SHADOW ? P.shadowmap_size : P.u.window_size[1]);
+    const int TW0 = hiz_dim(W, kHizShift0), TH0 = hiz_dim(H, kHizShift0), TW1 = hiz_dim(W, kHizShift1);
+    const uint32_t* level0 = P.hiz;
+    const uint32_t* level1 = P.hiz + (size_t)TW0 * TH0;
     const uint32_t key_lo = band ? P.state->band_key[band - 1] : 0u, key_hi = P.state->band_key[band];
     const MeshletBound* bounds = (const MeshletBound*)P.meshlet_bounds;
     uint32_t occluded = 0;
@@ -545,10 +586,13 @@ __global__ void __launch_bounds__(256) raster_select_kernel(const __grid_constan
         if (k < total) mb = __ldg((const uint4*)(bounds + k));
         bool keep = mb.w >= key_lo && mb.w < key_hi;
         if (keep && band != 0 && mb.x != kUntestable) {
-            const int tx0 = (int)(mb.x & 0xFFFFu) >> 3, tx1 = (int)(mb.x >> 16) >> 3, ty0 = (int)(mb.y & 0xFFFFu) >> 3, ty1 = (int)(mb.y >> 16) >> 3;
+            const int px0 = (int)(mb.x & 0xFFFFu), px1 = (int)(mb.x >> 16), py0 = (int)(mb.y & 0xFFFFu), py1 = (int)(mb.y >> 16);
+            const bool fine = ((px1 >> kHizShift0) - (px0 >> kHizShift0) + 1) * ((py1 >> kHizShift0) - (py0 >> kHizShift0) + 1) <= kMaxHizTiles;
+            const int shift = fine ? kHizShift0 : kHizShift1, TW = fine ? TW0 : TW1;
+            const uint32_t* level = fine ? level0 : level1;
             uint32_t worst = 0;   // main view: largest stored key high word; cascade: largest stored depth
-            for (int ty = ty0; ty <= ty1; ty++)
-                for (int tx = tx0; tx <= tx1; tx++) worst = max(worst, __ldcg(P.hiz + ty * TW + tx));
+            for (int ty = py0 >> shift; ty <= (py1 >> shift); ty++)
+                for (int tx = px0 >> shift; tx <= (px1 >> shift); tx++) worst = max(worst, __ldcg(level + (size_t)ty * TW + tx));
             if (SHADOW ? mb.z >= worst : worst < mb.z) {
                 keep = false;
                 occluded++;
@@ -691,6 +735,11 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, LH_RASTER_MIN_CTAS) raster_
                 sv.sy[v] = sy;
                 sv.z[v] = z;
                 if (h.alpha) sv.w[v] = clip.w;
+                {
+                    const int fx = min(max((sx + 127) >> 8, -32768), 32767), fy = min(max((sy + 127) >> 8, -32768), 32767);
+                    const int lx = min(max((sx - 128) >> 8, -32768), 32767), ly = min(max((sy - 128) >> 8, -32768), 32767);
+                    sv.cover[v] = make_uint2(((uint32_t)fx & 0xFFFFu) | ((uint32_t)fy << 16), ((uint32_t)lx & 0xFFFFu) | ((uint32_t)ly << 16));
+                }
                 if (sx == kVertOutside || sx == kVertNonFinite || !(z >= 0.0f)) {
                     special = true;
                 } else {
@@ -703,7 +752,8 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, LH_RASTER_MIN_CTAS) raster_
 
             // ---- (1b) the same two early-outs with the exact vertex bounds: every triangle lies inside the vertices'
             // rectangle, and (screen-linear depth) no fragment is nearer than the nearest vertex ----
-            if (!__any_sync(0xFFFFFFFFu, special)) {
+            const bool any_special = __any_sync(0xFFFFFFFFu, special);
+            if (!any_special) {
                 vminx = __reduce_min_sync(0xFFFFFFFFu, vminx); vmaxx = __reduce_max_sync(0xFFFFFFFFu, vmaxx);
                 vminy = __reduce_min_sync(0xFFFFFFFFu, vminy); vmaxy = __reduce_max_sync(0xFFFFFFFFu, vmaxy);
                 const int bx0 = max(0, (vminx - 128 + 255) >> 8), bx1 = min(W - 1, (vmaxx - 128) >> 8);
@@ -733,46 +783,61 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, LH_RASTER_MIN_CTAS) raster_
 
             // ---- (2) triangle cull phase ----
             uint32_t n_surv = 0;
+            const uint32_t screen_max = (uint32_t)(W - 1) | ((uint32_t)(H - 1) << 16);
             for (uint32_t t0 = 0; t0 < h.tri_count; t0 += 32) {
                 const uint32_t t = t0 + lane;
                 bool keep = false;
                 if (t < h.tri_count) {
                     const uint32_t i0 = __ldg(h.micro + 3 * t), i1 = __ldg(h.micro + 3 * t + 1), i2 = __ldg(h.micro + 3 * t + 2);
                     if (max(i0, max(i1, i2)) < nv) {
-                        const int ax = sv.sx[i0], bx = sv.sx[i1], cx = sv.sx[i2];
-                        const int n_out = (ax == kVertOutside) + (bx == kVertOutside) + (cx == kVertOutside);
                         const uint32_t lo = ((P.slot_offset + local) << LH_VIS_TRI_BITS) | t;
-                        if (n_out == 0) {
-                            if (ax != kVertNonFinite && bx != kVertNonFinite && cx != kVertNonFinite) {
-                                const int ay = sv.sy[i0], by = sv.sy[i1], cy = sv.sy[i2];
-                                const int minx = min(ax, min(bx, cx)), maxx = max(ax, max(bx, cx));
-                                const int miny = min(ay, min(by, cy)), maxy = max(ay, max(by, cy));
-                                const int px0 = max(0, (minx - 128 + 255) >> 8), px1 = min(W - 1, (maxx - 128) >> 8);
-                                const int py0 = max(0, (miny - 128 + 255) >> 8), py1 = min(H - 1, (maxy - 128) >> 8);
-                                if (px0 <= px1 && py0 <= py1) {   // else it covers no sample: the common case
-                                    tris_done++;
-                                    // facing; exact in 32 bits when the sub-pixel extent is < 2^14 (every product < 2^28)
-                                    const bool small_extent = (maxx - minx) < kSmallMaxExtent && (maxy - miny) < kSmallMaxExtent;
-                                    const long long A2 = small_extent
-                                                             ? (long long)((bx - ax) * (cy - ay) - (by - ay) * (cx - ax))
-                                                             : (long long)(bx - ax) * (cy - ay) - (long long)(by - ay) * (cx - ax);
-                                    const bool front = A2 < 0;
-                                    if (A2 != 0 && !((cull == CULL_BACK && !front) || (cull == CULL_FRONT && front))) {
-                                        const int spanx = px1 - px0 + 1, spany = py1 - py0 + 1;
-                                        if (small_extent && spanx <= kSmallMaxSpan && spany <= kSmallMaxSpan && spanx * spany <= kSmallMaxArea) {
-                                            keep = true;
-                                        } else {
-                                            // large footprint: one queue entry per 128x32 screen tile the bounding box touches
-                                            const uint32_t tx0 = (uint32_t)px0 / kTileW, tx1 = (uint32_t)px1 / kTileW;
-                                            const uint32_t ty0 = (uint32_t)py0 / kTileH, ty1 = (uint32_t)py1 / kTileH;
-                                            for (uint32_t ty = ty0; ty <= ty1; ty++)
-                                                for (uint32_t tx = tx0; tx <= tx1; tx++) push_deferred(P, lo, tx | (ty << 16));
-                                        }
-                                    }
-                                }
+                        // facing test and routing of a triangle whose pixel rectangle [px0,px1] x [py0,py1] is not empty
+                        auto covered = [&](int px0, int px1, int py0, int py1) {
+                            const int ax = sv.sx[i0], bx = sv.sx[i1], cx = sv.sx[i2], ay = sv.sy[i0], by = sv.sy[i1], cy = sv.sy[i2];
+                            const int minx = min(ax, min(bx, cx)), maxx = max(ax, max(bx, cx));
+                            const int miny = min(ay, min(by, cy)), maxy = max(ay, max(by, cy));
+                            tris_done++;
+                            // exact in 32 bits when the sub-pixel extent is < 2^14 (every product < 2^28)
+                            const bool small_extent = (maxx - minx) < kSmallMaxExtent && (maxy - miny) < kSmallMaxExtent;
+                            const long long A2 = small_extent
+                                                     ? (long long)((bx - ax) * (cy - ay) - (by - ay) * (cx - ax))
+                                                     : (long long)(bx - ax) * (cy - ay) - (long long)(by - ay) * (cx - ax);
+                            const bool front = A2 < 0;
+                            if (A2 == 0 || (cull == CULL_BACK && !front) || (cull == CULL_FRONT && front)) return;
+                            const int spanx = px1 - px0 + 1, spany = py1 - py0 + 1;
+                            if (small_extent && spanx <= kSmallMaxSpan && spany <= kSmallMaxSpan && spanx * spany <= kSmallMaxArea) {
+                                keep = true;
+                            } else {
+                                // large footprint: one queue entry per 128x32 screen tile the bounding box touches
+                                const uint32_t tx0 = (uint32_t)px0 / kTileW, tx1 = (uint32_t)px1 / kTileW;
+                                const uint32_t ty0 = (uint32_t)py0 / kTileH, ty1 = (uint32_t)py1 / kTileH;
+                                for (uint32_t ty = ty0; ty <= ty1; ty++)
+                                    for (uint32_t tx = tx0; tx <= tx1; tx++) push_deferred(P, lo, tx | (ty << 16));
                             }
-                        } else if (n_out < 3) {
-                            push_deferred(P, lo, kWholeTriangle);   // crosses the near plane: generic path
+                        };
+                        if (!any_special) {
+                            // the common case: every vertex is in front of the near plane and finite.  Rectangle by
+                            // halfword min/max of the per-vertex pixel bounds; most triangles end here (no sample inside).
+                            const uint2 c0 = sv.cover[i0], c1 = sv.cover[i1], c2 = sv.cover[i2];
+                            const uint32_t first = __vmaxs2(__vmins2(__vmins2(c0.x, c1.x), c2.x), 0u);
+                            const uint32_t last = __vmins2(__vmaxs2(__vmaxs2(c0.y, c1.y), c2.y), screen_max);
+                            if (__vcmpgts2(first, last) == 0u)
+                                covered((int)(first & 0xFFFFu), (int)(last & 0xFFFFu), (int)(first >> 16), (int)(last >> 16));
+                        } else {
+                            const int ax = sv.sx[i0], bx = sv.sx[i1], cx = sv.sx[i2];
+                            const int n_out = (ax == kVertOutside) + (bx == kVertOutside) + (cx == kVertOutside);
+                            if (n_out == 0) {
+                                if (ax != kVertNonFinite && bx != kVertNonFinite && cx != kVertNonFinite) {
+                                    const int ay = sv.sy[i0], by = sv.sy[i1], cy = sv.sy[i2];
+                                    const int minx = min(ax, min(bx, cx)), maxx = max(ax, max(bx, cx));
+                                    const int miny = min(ay, min(by, cy)), maxy = max(ay, max(by, cy));
+                                    const int px0 = max(0, (minx - 128 + 255) >> 8), px1 = min(W - 1, (maxx - 128) >> 8);
+                                    const int py0 = max(0, (miny - 128 + 255) >> 8), py1 = min(H - 1, (maxy - 128) >> 8);
+                                    if (px0 <= px1 && py0 <= py1) covered(px0, px1, py0, py1);
+                                }
+                            } else if (n_out < 3) {
+                                push_deferred(P, lo, kWholeTriangle);   // crosses the near plane: generic path
+                            }
                         }
                     }
                 }
