@@ -206,22 +206,19 @@ def run_ours(args):
     scene = build_scene(args.workload)
     tex = scene_textures(scene, args.tex_size)
     sky = scene.make_skybox(32)
+    from lighthugger_b200 import sortlast
     n = scene.num_instances
-    first, end = rank * n // world, (rank + 1) * n // world
-    caps = scene.default_capacities()
-    if world > 1:
-        # per-rank slot share: keys carry rank * slots_per_rank + local slot (25-bit field)
-        per_rank = -(-scene.total_meshlets // world)
-        caps = S.LhCapacities(max_instances=n, max_opaque_draws=per_rank + 1024, max_alpha_clip_draws=max(1024, per_rank // 8))
+    first, count = sortlast.instance_range(n, rank, world)
+    end = first + count
+    caps = sortlast.capacities(scene, world)
     ctx = make_context(scene, textures=tex, skybox=sky, caps=caps, flags=S.LH_CONFIG_WRITE_DRAW_COMMANDS | S.LH_CONFIG_PASS_TIMINGS,
                        device=local_rank)
     if world > 1:
         ids = [ctx.comm_unique_id() if rank == 0 else None]
         dist.broadcast_object_list(ids, src=0)
         ctx.comm_init(rank, world, ids[0])
-        ctx.set_instance_range(first, end - first)
-        # shadow cascades shard one per GPU (N=4); N=2: two each; N=8: a cascade per GPU pair, instance halves
-        ctx.set_shadow_cascade_mask(sum(1 << c for c in range(4) if c % min(world, 4) == rank % min(world, 4)))
+        ctx.set_instance_range(first, count)
+        ctx.set_shadow_cascade_mask(sortlast.cascade_mask(rank, world))
     u = ctx.uniforms()
 
     def barrier():

@@ -86,6 +86,8 @@ LH_TARGET_VIS64, LH_TARGET_DEPTH, LH_TARGET_SCENE_RGBA16F, LH_TARGET_SHADOW, LH_
 LH_TEXTURE_RGBA8_SRGB, LH_TEXTURE_RGBA8_UNORM, LH_TEXTURE_BC7_SRGB, LH_TEXTURE_BC1_SRGB = range(4)
 LH_ERR_CAPACITY = -4
 LH_VIS_CLEAR = 0xFFFFFFFFFFFFFFFF
+LH_VIS_TRI_BITS = 7
+LH_VIS_MAX_SLOTS = 1 << 25
 LH_UNUSED_TEXTURE_INDEX = 0xFFFF
 LH_MESH_INFO_FLAGS_32_BIT_INDICES = 1
 LH_MESH_INFO_FLAGS_ALPHA_CLIP = 2

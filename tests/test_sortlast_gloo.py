@@ -1,0 +1,92 @@
+"""The N > 1 host logic on CPU: two processes over torch.distributed / gloo run the sort-last plan
+(lighthugger_b200/sortlast.py) with the oracle standing in for the device passes, exchange their key buffers with a
+MIN all-reduce and their shadow layers likewise, and must reproduce the single-process frame bit-exactly
+(SURVEY.md 8e "determinism": min is associative and commutative)."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _worker(rank, world, port, out_dir):
+    sys.path[:0] = [ROOT, os.path.join(ROOT, "tests")]
+    import torch
+    import torch.distributed as dist
+    from lighthugger_b200 import _structs as S, sortlast
+    from lighthugger_b200.scene import Scene
+    from helpers import make_oracle, vis_fields
+
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        sc = Scene.preset("tiny")
+        first, count = sortlast.instance_range(sc.num_instances, rank, world)
+        caps = sortlast.capacities(sc, world)
+        o = make_oracle(sc, caps=caps, instance_range=(first, count))
+        o.reset(); o.cull_instances(); o.cull_meshlets(); o.raster_visbuffer()
+        n_local = sum(o.draw_counts())
+        # keys carry GLOBAL slots: rank * slots_per_rank + local (what lh_comm_init sets up on the device)
+        vis = o.vis.copy()
+        covered = vis != S.LH_VIS_CLEAR
+        vis[covered] += np.uint64(sortlast.slot_offset(caps, rank) << 7)
+        t = torch.from_numpy(sortlast.to_ordered_int64(vis).copy())
+        dist.all_reduce(t, op=dist.ReduceOp.MIN)
+        composite = sortlast.from_ordered_int64(t.numpy())
+        # reference tables of every rank, rank-major, as the all-gather inside lh_composite lays them out
+        per_rank = caps.max_opaque_draws + caps.max_alpha_clip_draws
+        mine = torch.zeros((per_rank, 2), dtype=torch.int64)
+        refs = o.meshlet_references(0, o.draw_counts()[0])
+        mine[:len(refs)] = torch.from_numpy(np.asarray(refs, np.int64))
+        gathered = [torch.zeros_like(mine) for _ in range(world)]
+        dist.all_gather(gathered, mine)
+        table = torch.cat(gathered).numpy()
+        if rank == 0:
+            np.savez(os.path.join(out_dir, "composite.npz"), vis=composite, table=table, per_rank=per_rank,
+                     masks=np.array([sortlast.cascade_mask(r, world) for r in range(world)]), n_local=n_local)
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_rank_composite_equals_single_process_frame(tmp_path):
+    import torch.multiprocessing as mp
+    sys.path[:0] = [ROOT, os.path.join(ROOT, "tests")]
+    from lighthugger_b200 import _structs as S, sortlast
+    from lighthugger_b200.scene import Scene
+    from helpers import make_oracle, vis_fields
+
+    world, port = 2, 29000 + os.getpid() % 2000
+    mp.spawn(_worker, args=(world, port, str(tmp_path)), nprocs=world, join=True)
+    got = np.load(os.path.join(tmp_path, "composite.npz"))
+
+    sc = Scene.preset("tiny")
+    whole = make_oracle(sc)
+    whole.reset(); whole.cull_instances(); whole.cull_meshlets(); whole.raster_visbuffer()
+    dw, sw, tw = vis_fields(whole.vis)
+    dg, sg, tg = vis_fields(got["vis"])
+    assert np.array_equal(dw, dg), "composited depth differs from the single-process frame"
+    cov = dw != 0
+    ref_w = whole.meshlet_references(0, whole.draw_counts()[0])
+    want = np.stack([ref_w[sw[cov], 0], ref_w[sw[cov], 1], tw[cov]], 1)
+    table = got["table"]
+    have = np.stack([table[sg[cov], 0], table[sg[cov], 1], tg[cov]], 1)
+    assert np.array_equal(have, want), "(instance, meshlet, triangle) under the composited keys differ"
+    # the plan itself
+    assert sorted(sum(([c for c in range(4) if m >> c & 1] for m in got["masks"]), [])) == [0, 1, 2, 3]
+
+
+def test_plan_tiles_instances_and_cascades():
+    sys.path[:0] = [ROOT]
+    from lighthugger_b200 import sortlast
+    for world in (1, 2, 4, 8):
+        for n in (0, 1, 7, 1000, 10000):
+            ranges = [sortlast.instance_range(n, r, world) for r in range(world)]
+            assert ranges[0][0] == 0 and sum(c for _, c in ranges) == n
+            assert all(ranges[r][0] + ranges[r][1] == ranges[r + 1][0] for r in range(world - 1))
+        cover = [0] * 4
+        for r in range(world):
+            for c in range(4):
+                cover[c] += sortlast.cascade_mask(r, world) >> c & 1
+        assert all(k == max(1, world // 4) for k in cover), (world, cover)
