@@ -28,7 +28,7 @@ int fail(LhContext* ctx, int code, const char* what, cudaError_t e) {
     return code;
 }
 
-FrameParams make_params(LhContext* ctx) {
+FrameParams make_params(LhContext* ctx, int cascade, int set, bool internal_lists) {
     FrameParams p;
     memset(&p, 0, sizeof(p));
     p.u = ctx->uniforms;
@@ -44,12 +44,25 @@ FrameParams make_params(LhContext* ctx) {
     p.max_large = ctx->cfg.max_large_triangles;
     p.state = ctx->state;
     p.instance_tiles = ctx->instance_tiles;
-    p.meshlet_tiles = ctx->meshlet_tiles;
-    p.large_queue = ctx->large_queue;
-    p.meshlet_bounds = ctx->meshlet_bounds;
-    p.raster_queue = ctx->raster_queue;
-    p.depth_hist = ctx->depth_hist;
-    p.hiz = ctx->hiz;
+    const LhContext::PassScratch& sc = ctx->scratch[set];
+    p.pass = sc.pass;
+    p.meshlet_tiles = sc.meshlet_tiles;
+    p.large_queue = sc.large_queue;
+    p.meshlet_bounds = sc.meshlet_bounds;
+    p.raster_queue = sc.raster_queue;
+    p.depth_hist = sc.depth_hist;
+    p.hiz = sc.hiz;
+    // a cascade's lists live in section 1 of the host-visible buffers (MESHLET_INDICES_BUFFER_SECTION_OFFSET), unless it
+    // runs concurrently with another cascade, in which case they live in the scratch set
+    const uint64_t section = (uint64_t)p.max_opaque + p.max_alpha;
+    p.pass_slot_base = cascade < 0 ? 0u : (uint32_t)section;
+    if (internal_lists) {
+        p.pass_draw_calls = (uint64_t)(uintptr_t)sc.draw_calls;
+        p.pass_refs = (uint64_t)(uintptr_t)sc.refs;
+    } else {
+        p.pass_draw_calls = p.u.draw_calls;
+        p.pass_refs = p.u.meshlet_references + (cascade < 0 ? 0ull : section * sizeof(LhMeshletReference));
+    }
     p.vis = ctx->vis;
     p.shadow = ctx->shadow;
     p.textures = ctx->tex_dev;
@@ -109,14 +122,12 @@ int alloc_targets(LhContext* ctx, uint32_t w, uint32_t h) {
     LH_CUDA(ctx, cudaMalloc(&ctx->scene, px * 8));
     LH_CUDA(ctx, cudaMalloc(&ctx->display, px * 4));
     LH_CUDA(ctx, cudaMalloc(&ctx->depth_plane, px * 4));
-    {
-        cudaFree(ctx->hiz);
-        ctx->hiz = nullptr;
-        // two levels (4x4 and 16x16 pixel tiles), sized for the larger of the main view and a shadow layer
+    if (ctx->scratch[0].pass) {   // the main view's hierarchical-Z follows the target size
         auto tiles = [](size_t tw, size_t th) { return ((tw + 3) / 4) * ((th + 3) / 4) + ((tw + 15) / 16) * ((th + 15) / 16); };
         const size_t main_tiles = tiles(w, h), shadow_tiles = tiles(ctx->cfg.shadowmap_size, ctx->cfg.shadowmap_size);
-        ctx->hiz_tiles = main_tiles > shadow_tiles ? main_tiles : shadow_tiles;
-        LH_CUDA(ctx, cudaMalloc(&ctx->hiz, ctx->hiz_tiles * 4));
+        cudaFree(ctx->scratch[0].hiz);
+        ctx->scratch[0].hiz = nullptr;
+        LH_CUDA(ctx, cudaMalloc(&ctx->scratch[0].hiz, (main_tiles > shadow_tiles ? main_tiles : shadow_tiles) * 4));
     }
     LH_CUDA(ctx, cudaMemset(ctx->vis, 0xFF, px * 8 + 16));
     LH_CUDA(ctx, cudaMemset(ctx->scene, 0, px * 8));
@@ -124,6 +135,49 @@ int alloc_targets(LhContext* ctx, uint32_t w, uint32_t h) {
     ctx->cfg.width = w;
     ctx->cfg.height = h;
     return LH_OK;
+}
+
+// scratch of one view; sets 1..3 (concurrent cascades) also get internal draw-call counters and a reference list
+int alloc_pass_scratch(LhContext* ctx, int set) {
+    LhContext::PassScratch& sc = ctx->scratch[set];
+    if (sc.pass) return LH_OK;
+    const size_t draws = (size_t)ctx->cfg.max_opaque_draws + ctx->cfg.max_alpha_clip_draws;
+    // candidate meshlets <= max_instances * 65535 (u16 meshlets per mesh) and < 2^32 (lo32 of the prefix counter)
+    const unsigned long long cand = (unsigned long long)ctx->cfg.max_instances * 65535ull;
+    ctx->meshlet_tile_count = (size_t)((cand < (1ull << 32) ? cand : (1ull << 32)) / kMeshletTile + 2);
+    LH_CUDA(ctx, cudaMalloc(&sc.pass, sizeof(PassState)));
+    LH_CUDA(ctx, cudaMemset(sc.pass, 0, sizeof(PassState)));
+    LH_CUDA(ctx, cudaMalloc(&sc.meshlet_tiles, ctx->meshlet_tile_count * 8));
+    LH_CUDA(ctx, cudaMemset(sc.meshlet_tiles, 0, ctx->meshlet_tile_count * 8));
+    LH_CUDA(ctx, cudaMalloc(&sc.large_queue, (size_t)(ctx->cfg.max_large_triangles ? ctx->cfg.max_large_triangles : 1) * 8));
+    LH_CUDA(ctx, cudaMalloc(&sc.meshlet_bounds, (draws ? draws : 1) * 16));
+    LH_CUDA(ctx, cudaMalloc(&sc.raster_queue, (draws ? draws : 1) * 4));
+    LH_CUDA(ctx, cudaMalloc(&sc.depth_hist, 8192 * 4));
+    LH_CUDA(ctx, cudaMemset(sc.depth_hist, 0, 8192 * 4));
+    // two hierarchical-Z levels (4x4 and 16x16 pixel tiles): the main view only ever uses set 0
+    auto tiles = [](size_t tw, size_t th) { return ((tw + 3) / 4) * ((th + 3) / 4) + ((tw + 15) / 16) * ((th + 15) / 16); };
+    size_t hiz_tiles = tiles(ctx->cfg.shadowmap_size, ctx->cfg.shadowmap_size);
+    if (set == 0 && tiles(ctx->cfg.width, ctx->cfg.height) > hiz_tiles) hiz_tiles = tiles(ctx->cfg.width, ctx->cfg.height);
+    LH_CUDA(ctx, cudaMalloc(&sc.hiz, hiz_tiles * 4));
+    if (set != 0) {
+        LH_CUDA(ctx, cudaMalloc(&sc.draw_calls, 16));   // counters only: commands are not materialised for internal lists
+        LH_CUDA(ctx, cudaMemset(sc.draw_calls, 0, 16));
+        LH_CUDA(ctx, cudaMalloc(&sc.refs, (draws ? draws : 1) * sizeof(LhMeshletReference)));
+        if (!ctx->side_streams[set - 1]) {
+            LH_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->side_streams[set - 1], cudaStreamNonBlocking));
+            LH_CUDA(ctx, cudaEventCreateWithFlags(&ctx->join_events[set - 1], cudaEventDisableTiming));
+        }
+        if (!ctx->fork_event) LH_CUDA(ctx, cudaEventCreateWithFlags(&ctx->fork_event, cudaEventDisableTiming));
+    }
+    return LH_OK;
+}
+
+void free_pass_scratch(LhContext* ctx) {
+    for (auto& sc : ctx->scratch) {
+        cudaFree(sc.pass); cudaFree(sc.meshlet_tiles); cudaFree(sc.large_queue); cudaFree(sc.meshlet_bounds);
+        cudaFree(sc.raster_queue); cudaFree(sc.depth_hist); cudaFree(sc.hiz); cudaFree(sc.draw_calls); cudaFree(sc.refs);
+        sc = LhContext::PassScratch{};
+    }
 }
 
 int ensure_instance_tiles(LhContext* ctx, uint32_t num_instances) {
@@ -209,16 +263,8 @@ int lh_context_create(const LhConfig* cfg, LhContext** out) {
     TRY(cudaMemset(ctx->shadow, 0, shadow_bytes));
     TRY(cudaMalloc(&ctx->state, sizeof(FrameState)));
     TRY(cudaMemset(ctx->state, 0, sizeof(FrameState)));
-    TRY(cudaMalloc(&ctx->meshlet_tiles, kMaxMeshletTiles * 8));
-    TRY(cudaMemset(ctx->meshlet_tiles, 0, kMaxMeshletTiles * 8));
-    TRY(cudaMalloc(&ctx->large_queue, (size_t)(cfg->max_large_triangles ? cfg->max_large_triangles : 1) * 8));
-    {
-        const size_t draws = (size_t)cfg->max_opaque_draws + cfg->max_alpha_clip_draws;
-        TRY(cudaMalloc(&ctx->meshlet_bounds, draws * 16));
-        TRY(cudaMalloc(&ctx->raster_queue, draws * 4));
-        TRY(cudaMalloc(&ctx->depth_hist, 65536 * 4));
-        TRY(cudaMemset(ctx->depth_hist, 0, 65536 * 4));
-    }
+    rc = alloc_pass_scratch(ctx, 0);
+    if (rc) return bail(rc);
     TRY(cudaMalloc(&ctx->tex_dev, sizeof(cudaTextureObject_t) * LH_MAX_TEXTURES));
     TRY(cudaMemset(ctx->tex_dev, 0, sizeof(cudaTextureObject_t) * LH_MAX_TEXTURES));
     TRY(cudaMalloc(&ctx->tex_dims_dev, sizeof(uint4) * LH_MAX_TEXTURES));
@@ -260,12 +306,12 @@ int lh_context_destroy(LhContext* ctx) {
     cudaFree(ctx->shadow);
     cudaFree(ctx->state);
     cudaFree(ctx->instance_tiles);
-    cudaFree(ctx->meshlet_tiles);
-    cudaFree(ctx->large_queue);
-    cudaFree(ctx->meshlet_bounds);
-    cudaFree(ctx->raster_queue);
-    cudaFree(ctx->depth_hist);
-    cudaFree(ctx->hiz);
+    free_pass_scratch(ctx);
+    for (int i = 0; i < 3; i++) {
+        if (ctx->side_streams[i]) cudaStreamDestroy(ctx->side_streams[i]);
+        if (ctx->join_events[i]) cudaEventDestroy(ctx->join_events[i]);
+    }
+    if (ctx->fork_event) cudaEventDestroy(ctx->fork_event);
     cudaFree(ctx->tex_dev);
     cudaFree(ctx->tex_dims_dev);
     cudaFree(ctx->l2_flush);
@@ -562,14 +608,20 @@ int lh_cull_instances_shadows(LhContext* ctx) {
     return check_launch(ctx, "cull_instances_shadows");
 }
 
+// reset_buffers_c + write_draw_calls_shadows + the layer clear + the depth-only raster of one cascade
+static void enqueue_cascade(LhContext* ctx, uint32_t cascade, int set, bool internal_lists, cudaStream_t stream) {
+    FrameParams p = make_params(ctx, (int)cascade, set, internal_lists);
+    if (internal_lists) p.flags &= ~(uint32_t)LH_CONFIG_WRITE_DRAW_COMMANDS;
+    launch_cull_meshlets(ctx, p, (int)cascade, stream);
+    size_t texels = (size_t)ctx->cfg.shadowmap_size * ctx->cfg.shadowmap_size;
+    launch_fill_u32(ctx, ctx->shadow + texels * cascade, texels, 0x3F800000u, stream);  // clear 1.0, rendering.cpp:384
+    launch_raster(ctx, p, (int)cascade, stream);
+}
+
 int lh_shadow_cascade(LhContext* ctx, uint32_t cascade) {
     if (int rc = require_frame(ctx)) return rc;
     if (cascade >= 4) return fail(ctx, LH_ERR_INVALID_ARGUMENT, "cascade index out of range");
-    FrameParams p = make_params(ctx);
-    launch_cull_meshlets(ctx, p, (int)cascade);
-    size_t texels = (size_t)ctx->cfg.shadowmap_size * ctx->cfg.shadowmap_size;
-    launch_fill_u32(ctx, ctx->shadow + texels * cascade, texels, 0x3F800000u);  // clear 1.0, rendering.cpp:384
-    launch_raster(ctx, p, (int)cascade);
+    enqueue_cascade(ctx, cascade, 0, false, nullptr);
     return check_launch(ctx, "shadow_cascade");
 }
 
@@ -598,10 +650,29 @@ int lh_render_frame(LhContext* ctx) {
     if ((rc = lh_generate_shadow_matrices(ctx))) return rc;
     if ((rc = lh_cull_instances_shadows(ctx))) return rc;
     {
+        // The cascades are independent of one another (own layer, own prefix-sum sector).  The last one of the mask runs
+        // on the context stream with the host-visible lists, which is the state the reference leaves behind
+        // (rendering.cpp:325-438 reuses one scratch section); the others run concurrently on side streams with internal
+        // lists, so that a small cascade's latency-bound launches overlap a large cascade's.
         PassScope scope(ctx, LH_PASS_SHADOWMAPS);
-        for (uint32_t c = 0; c < 4; c++)
-            if ((ctx->cascade_mask >> c) & 1u)
-                if ((rc = lh_shadow_cascade(ctx, c))) return rc;
+        int last = -1, others[4], n_others = 0;
+        for (int c = 3; c >= 0; c--)
+            if ((ctx->cascade_mask >> c) & 1u) {
+                if (last < 0) last = c;
+                else others[n_others++] = c;
+            }
+        for (int i = 0; i < n_others; i++)
+            if ((rc = alloc_pass_scratch(ctx, 1 + i))) return rc;
+        if (n_others) LH_CUDA(ctx, cudaEventRecord(ctx->fork_event, ctx->stream));
+        for (int i = 0; i < n_others; i++) {
+            cudaStream_t s = ctx->side_streams[i];
+            LH_CUDA(ctx, cudaStreamWaitEvent(s, ctx->fork_event, 0));
+            enqueue_cascade(ctx, (uint32_t)others[i], 1 + i, true, s);
+            LH_CUDA(ctx, cudaEventRecord(ctx->join_events[i], s));
+        }
+        if (last >= 0) enqueue_cascade(ctx, (uint32_t)last, 0, false, nullptr);
+        for (int i = 0; i < n_others; i++) LH_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->join_events[i], 0));
+        if ((rc = check_launch(ctx, "shadow cascades"))) return rc;
     }
     if ((rc = lh_shadow_exchange(ctx))) return rc;
     return lh_resolve(ctx);

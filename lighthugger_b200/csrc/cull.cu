@@ -142,7 +142,6 @@ __global__ void reset_kernel(const __grid_constant__ FrameParams P) {
     for (uint32_t c = 0; c < 4; c++) *sector_counter(P, c) = 0ull;
     FrameState* s = P.state;
     s->overflow = 0;
-    s->large_count = 0;
     s->main_large_count = 0;
     s->main_visible = s->main_candidates = s->main_opaque = s->main_alpha_clip = 0;
     s->rasterized_triangles = 0ull;
@@ -303,11 +302,11 @@ __global__ void __launch_bounds__(256) cull_meshlets_kernel(const __grid_constan
     const uint32_t num_tiles = (total + kMeshletTile - 1) / kMeshletTile;
     const LhInstance* instances = (const LhInstance*)P.u.instances;
     const LhMiscStorage* misc = (const LhMiscStorage*)P.u.misc_storage;
-    uint32_t* draw = (uint32_t*)P.u.draw_calls;
+    uint32_t* draw = (uint32_t*)P.pass_draw_calls;
     LhDrawIndirectCommand* cmds = (LhDrawIndirectCommand*)(draw + 2);
-    LhMeshletReference* refs = (LhMeshletReference*)P.u.meshlet_references;
-    const uint32_t section = SHADOWS ? P.max_opaque + P.max_alpha : 0u;  // MESHLET_INDICES_BUFFER_SECTION_OFFSET
+    LhMeshletReference* refs = (LhMeshletReference*)P.pass_refs;   // the view's own list: slot = pass_slot_base + index
     FrameState* st = P.state;
+    PassState* ps = P.pass;
 
     if (tid == 0) planes = frustum_planes(P.u);
     if (blockIdx.x == 0 && tid == 0) {
@@ -328,7 +327,7 @@ __global__ void __launch_bounds__(256) cull_meshlets_kernel(const __grid_constan
 
     for (;;) {
         __syncthreads();
-        if (tid == 0) tile_ticket = atomicAdd(&st->tickets[0], 1u);
+        if (tid == 0) tile_ticket = atomicAdd(&ps->cull_ticket, 1u);
         __syncthreads();
         const uint32_t tile = tile_ticket;
         if (tile >= num_tiles) break;
@@ -438,12 +437,12 @@ __global__ void __launch_bounds__(256) cull_meshlets_kernel(const __grid_constan
                     continue;
                 }
                 Survivor s = staged[cls][k];
-                uint32_t draw_index = first_draw + n, slot = draw_index + section;
+                uint32_t draw_index = first_draw + n, slot = draw_index + P.pass_slot_base;
                 LhMeshletReference ref;
                 ref.instance_index = s.instance_index;
                 ref.meshlet_index = (uint16_t)(s.meshlet_and_tris & 0xFFFFu);
                 ref._pad0 = 0;
-                refs[slot] = ref;
+                refs[draw_index] = ref;
                 if (P.flags & LH_CONFIG_WRITE_DRAW_COMMANDS)
                     cmds[draw_index] = LhDrawIndirectCommand{(s.meshlet_and_tris >> 16) * 3u, 1u, 0u, slot};
             }
@@ -465,14 +464,14 @@ __global__ void __launch_bounds__(256) cull_meshlets_kernel(const __grid_constan
     __shared__ uint32_t last_out;
     if (tid == 0) {
         __threadfence();
-        last_out = atomicAdd(&st->done[4], 1u) == gridDim.x - 1;
+        last_out = atomicAdd(&ps->cull_done, 1u) == gridDim.x - 1;
     }
     __syncthreads();
     if (last_out) {
         for (uint32_t t = tid; t < num_tiles; t += 256) st_relaxed(&P.meshlet_tiles[t], 0ull);
         if (tid == 0) {
-            st->tickets[0] = 0;
-            st->done[4] = 0;
+            ps->cull_ticket = 0;
+            ps->cull_done = 0;
         }
     }
 }
@@ -508,11 +507,12 @@ void launch_cull_instances(LhContext* ctx, const FrameParams& p, bool shadows) {
     ctx->launches++;
 }
 
-void launch_cull_meshlets(LhContext* ctx, const FrameParams& p, int cascade) {
+void launch_cull_meshlets(LhContext* ctx, const FrameParams& p, int cascade, cudaStream_t stream) {
+    if (!stream) stream = ctx->stream;
     // persistent grid: tiles are taken by ticket, so any grid size is correct
     uint32_t grid = (uint32_t)ctx->num_sms * 4;
-    if (cascade < 0) cull_meshlets_kernel<false><<<grid, 256, 0, ctx->stream>>>(p, 0);
-    else cull_meshlets_kernel<true><<<grid, 256, 0, ctx->stream>>>(p, (uint32_t)cascade);
+    if (cascade < 0) cull_meshlets_kernel<false><<<grid, 256, 0, stream>>>(p, 0);
+    else cull_meshlets_kernel<true><<<grid, 256, 0, stream>>>(p, (uint32_t)cascade);
     ctx->launches++;
 }
 
@@ -520,9 +520,9 @@ void launch_fill_u64(LhContext* ctx, unsigned long long* dst, uint64_t count, un
     if (!count) return;
     fill_u64_kernel<<<ctx->num_sms * 8, 256, 0, ctx->stream>>>(dst, count, value); ctx->launches++;
 }
-void launch_fill_u32(LhContext* ctx, uint32_t* dst, uint64_t count, uint32_t value) {
+void launch_fill_u32(LhContext* ctx, uint32_t* dst, uint64_t count, uint32_t value, cudaStream_t stream) {
     if (!count) return;
-    fill_u32_kernel<<<ctx->num_sms * 8, 256, 0, ctx->stream>>>(dst, count, value); ctx->launches++;
+    fill_u32_kernel<<<ctx->num_sms * 8, 256, 0, stream ? stream : ctx->stream>>>(dst, count, value); ctx->launches++;
 }
 
 }  // namespace lh

@@ -63,22 +63,27 @@ __device__ __forceinline__ V3 cross3(V3 a, V3 b) {
 // ---- device-side scratch that lives across passes of one frame -------------
 struct FrameState {
     uint32_t overflow;             // LH_OVERFLOW_* bits
-    uint32_t large_count;          // entries in the deferred-triangle queue (current raster pass)
     uint32_t main_large_count;     // ... as left by the main-view pass (stats)
     uint32_t main_visible, main_candidates, main_opaque, main_alpha_clip;  // main-view counts (the shared counters are reused by the cascades)
     uint32_t shadow_opaque[4];     // draw counts of each cascade, saved for the stats
     uint32_t shadow_alpha_clip[4];
     uint32_t shadow_visible[4];
     uint32_t shadow_candidates[4];
-    uint32_t tickets[8];           // tile tickets: [0] main meshlet cull, [1..4] cascades
-    uint32_t done[8];              // CTAs finished (self-cleaning of the tile states)
+    uint32_t done[4];              // instance cull: CTAs finished per sector (self-cleaning of the tile states)
     unsigned long long rasterized_triangles;
-    uint32_t raster_ticket;        // next unclaimed entry of the raster queue
-    uint32_t queue_count;          // entries appended to the raster queue so far in this pass
-    uint32_t band_begin, band_end; // queue range of the band being rasterised (band_begin already names the next band's start)
-    uint32_t band_first;           // first queue entry of the band being rasterised
-    uint32_t band_key[8];          // exclusive upper depth key of each band
     uint32_t skipped_empty[5], skipped_occluded[5];   // meshlets dropped by the rasteriser's early-outs: [0] main view, [1..4] cascades (stats)
+};
+
+// Work counters of one view (the main view or one cascade) through meshlet cull and rasterisation.  Each view that
+// can be in flight at the same time has its own, with its own scratch buffers, so cascades can run on separate streams.
+struct PassState {
+    uint32_t cull_ticket, cull_done;   // meshlet cull: next tile, CTAs finished (self-cleaning)
+    uint32_t large_count;              // entries in the deferred-triangle queue
+    uint32_t raster_ticket;            // next unclaimed entry of the raster queue
+    uint32_t queue_count;              // entries appended to the raster queue so far
+    uint32_t band_begin, band_end;     // queue range of the band being rasterised (band_begin already names the next band's start)
+    uint32_t band_first;               // first queue entry of the band being rasterised
+    uint32_t band_key[8];              // exclusive upper depth key of each band
 };
 
 constexpr uint32_t kMeshletTile = 1024;        // candidate meshlets per scan tile
@@ -95,7 +100,12 @@ struct FrameParams {
     uint32_t max_large;
     FrameState* state;
     unsigned long long* instance_tiles;      // [4][tiles] decoupled-lookback states
-    unsigned long long* meshlet_tiles;       // [5][kMaxMeshletTiles]
+    // ---- the view being culled / rasterised (see PassState) ----
+    PassState* pass;
+    uint64_t pass_draw_calls;                // its DrawCallBuffer: u.draw_calls, or an internal one for a concurrent cascade
+    uint64_t pass_refs;                      // first MeshletReference of its list (u.meshlet_references + section, or internal)
+    uint32_t pass_slot_base;                 // DrawIndirectCommand.firstInstance of its first draw (MESHLET_INDICES_BUFFER_SECTION_OFFSET for cascades)
+    unsigned long long* meshlet_tiles;       // decoupled-lookback states of the meshlet cull
     uint32_t* large_queue;
     void* meshlet_bounds;                    // 16 B per surviving meshlet of the current raster pass (raster.cu MeshletBound)
     uint32_t* raster_queue;                  // indices of the meshlets selected for rasterisation, band after band
@@ -136,13 +146,23 @@ struct LhContext {
     lh::FrameState* state = nullptr;
     unsigned long long* instance_tiles = nullptr;
     uint32_t instance_tiles_per_sector = 0;
-    unsigned long long* meshlet_tiles = nullptr;
-    uint32_t* large_queue = nullptr;
-    void* meshlet_bounds = nullptr;
-    uint32_t* raster_queue = nullptr;
-    uint32_t* depth_hist = nullptr;
-    uint32_t* hiz = nullptr;
-    size_t hiz_tiles = 0;
+    // Per-view scratch.  Set 0 serves the main view and whichever cascade runs on the context stream with the
+    // host-visible lists (u.draw_calls, u.meshlet_references); sets 1..3 serve cascades that lh_render_frame runs
+    // concurrently on side streams, with internal lists (allocated on first use).
+    struct PassScratch {
+        lh::PassState* pass = nullptr;
+        unsigned long long* meshlet_tiles = nullptr;
+        uint32_t* large_queue = nullptr;
+        void* meshlet_bounds = nullptr;
+        uint32_t* raster_queue = nullptr;
+        uint32_t* depth_hist = nullptr;
+        uint32_t* hiz = nullptr;
+        void* draw_calls = nullptr;   // internal lists (sets 1..3)
+        void* refs = nullptr;
+    } scratch[4];
+    size_t meshlet_tile_count = 0;
+    cudaStream_t side_streams[3] = {};
+    cudaEvent_t fork_event = nullptr, join_events[3] = {};
     void* l2_flush = nullptr;
     size_t l2_flush_bytes = 0;
     void* pinned = nullptr;
@@ -181,13 +201,14 @@ struct LhContext {
 namespace lh {
 
 int fail(LhContext* ctx, int code, const char* what, cudaError_t e = cudaSuccess);
-FrameParams make_params(LhContext* ctx);
+// cascade < 0: the main view.  set: which PassScratch; internal_lists: the view's lists live in the set's own buffers
+FrameParams make_params(LhContext* ctx, int cascade = -1, int set = 0, bool internal_lists = false);
 
-// pass launchers (one per translation unit)
+// pass launchers (one per translation unit); stream == nullptr means the context stream
 void launch_reset(LhContext* ctx, const FrameParams& p);
 void launch_cull_instances(LhContext* ctx, const FrameParams& p, bool shadows);
-void launch_cull_meshlets(LhContext* ctx, const FrameParams& p, int cascade);
-void launch_raster(LhContext* ctx, const FrameParams& p, int cascade);
+void launch_cull_meshlets(LhContext* ctx, const FrameParams& p, int cascade, cudaStream_t stream = nullptr);
+void launch_raster(LhContext* ctx, const FrameParams& p, int cascade, cudaStream_t stream = nullptr);
 void launch_reduce_depth(LhContext* ctx, const FrameParams& p);
 void launch_shadow_matrices(LhContext* ctx, const FrameParams& p);
 void launch_resolve(LhContext* ctx, const FrameParams& p);
@@ -195,7 +216,7 @@ void launch_display_transform(LhContext* ctx, const FrameParams& p);
 void launch_extract_depth(LhContext* ctx, const FrameParams& p);
 void launch_gather_stats(LhContext* ctx, const FrameParams& p, LhFrameStats* dst_dev_or_pinned);
 void launch_fill_u64(LhContext* ctx, unsigned long long* dst, uint64_t count, unsigned long long value);
-void launch_fill_u32(LhContext* ctx, uint32_t* dst, uint64_t count, uint32_t value);
+void launch_fill_u32(LhContext* ctx, uint32_t* dst, uint64_t count, uint32_t value, cudaStream_t stream = nullptr);
 int composite_allreduce_min(LhContext* ctx);
 extern "C" int lh_shadow_exchange(LhContext* ctx);
 

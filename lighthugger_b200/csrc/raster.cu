@@ -247,7 +247,7 @@ struct MeshletHeader {
 };
 
 __device__ __forceinline__ void load_header(const FrameParams& P, uint32_t slot, MeshletHeader& h) {
-    const LhMeshletReference* refs = (const LhMeshletReference*)P.u.meshlet_references;
+    const LhMeshletReference* refs = (const LhMeshletReference*)P.pass_refs;
     const unsigned long long ref = __ldg((const unsigned long long*)(refs + slot));
     const uint32_t instance_index = (uint32_t)ref, meshlet_index = (uint32_t)(ref >> 32) & 0xFFFFu;
     const LhInstance* inst = (const LhInstance*)P.u.instances + instance_index;
@@ -280,7 +280,7 @@ __device__ __forceinline__ void load_header(const FrameParams& P, uint32_t slot,
 // What the early-outs need of one meshlet: the instance transform (3x3 + translation, columns packed) and the
 // meshlet's object-space bounding sphere.  Called by one lane per meshlet.
 __device__ __forceinline__ void load_bounds(const FrameParams& P, uint32_t slot, float T[12], float sphere[4]) {
-    const LhMeshletReference* refs = (const LhMeshletReference*)P.u.meshlet_references;
+    const LhMeshletReference* refs = (const LhMeshletReference*)P.pass_refs;
     const unsigned long long ref = __ldg((const unsigned long long*)(refs + slot));
     const LhInstance* inst = (const LhInstance*)P.u.instances + (uint32_t)ref;
 #pragma unroll
@@ -310,15 +310,16 @@ __device__ __forceinline__ AlphaTest make_alpha_test(const FrameParams& P, const
     return at;
 }
 
-// work item k of the pass -> (slot in the meshlet-reference table, low word of the vis key)
+// work item k of the view -> index into the view's meshlet-reference list (P.pass_refs); the alpha-clip draws start at
+// max_opaque (ALPHA_CLIP_DRAWS_OFFSET).  slot and local are the same index: the list pointer already carries the section.
 __device__ __forceinline__ void work_to_slot(const FrameParams& P, uint32_t k, uint32_t n_opaque, bool shadow, uint32_t* slot, uint32_t* local) {
     bool alpha = k >= n_opaque;
     *local = alpha ? P.max_opaque + (k - n_opaque) : k;
-    *slot = *local + (shadow ? P.max_opaque + P.max_alpha : 0u);
+    *slot = *local;
 }
 
 __device__ __forceinline__ void push_deferred(const FrameParams& P, uint32_t lo, uint32_t tile) {
-    uint32_t at = atomicAdd(&P.state->large_count, 1u);
+    uint32_t at = atomicAdd(&P.pass->large_count, 1u);
     if (at < P.max_large) {
         P.large_queue[2 * (size_t)at] = lo;
         P.large_queue[2 * (size_t)at + 1] = tile;
@@ -373,7 +374,7 @@ __device__ __forceinline__ float sigma_max_bound(const float* T) {
 
 template <bool SHADOW>
 __global__ void __launch_bounds__(256) raster_bounds_kernel(const __grid_constant__ FrameParams P, uint32_t cascade) {
-    const uint32_t* draw = (const uint32_t*)P.u.draw_calls;
+    const uint32_t* draw = (const uint32_t*)P.pass_draw_calls;
     const uint32_t n_opaque = min(draw[0], P.max_opaque), n_alpha = min(draw[1], P.max_alpha);
     const uint32_t total = n_opaque + n_alpha;
     const int W = (int)(SHADOW ? P.shadowmap_size : P.u.window_size[0]), H = (int)(SHADOW ? P.shadowmap_size : P.u.window_size[1]);
@@ -493,7 +494,7 @@ __global__ void __launch_bounds__(1024) raster_bands_kernel(const __grid_constan
 #elif LH_BANDS == 4
     const float fractions[kBands - 1] = {0.03f, 0.12f, 0.40f};
 #endif
-    FrameState* st = P.state;
+    PassState* st = P.pass;
     if (tid == 0) {
         st->band_key[kBands - 1] = kKeyEmpty;   // the last band takes the rest (empty meshlets carry kKeyEmpty and are never selected)
         st->queue_count = 0;
@@ -569,14 +570,14 @@ __global__ void __launch_bounds__(256) raster_hiz_kernel(const __grid_constant__
 // touches (fine tiles when the rectangle is small, coarse ones otherwise).
 template <bool SHADOW>
 __global__ void __launch_bounds__(256) raster_select_kernel(const __grid_constant__ FrameParams P, uint32_t cascade, uint32_t band) {
-    const uint32_t* draw = (const uint32_t*)P.u.draw_calls;
+    const uint32_t* draw = (const uint32_t*)P.pass_draw_calls;
     const uint32_t total = min(draw[0], P.max_opaque) + min(draw[1], P.max_alpha);
     const uint32_t lane = threadIdx.x & 31;
     const int W = (int)(SHADOW ? P.shadowmap_size : P.u.window_size[0]), H = (int)(SHADOW ? P.shadowmap_size : P.u.window_size[1]);
     const int TW0 = hiz_dim(W, kHizShift0), TH0 = hiz_dim(H, kHizShift0), TW1 = hiz_dim(W, kHizShift1);
     const uint32_t* level0 = P.hiz;
     const uint32_t* level1 = P.hiz + (size_t)TW0 * TH0;
-    const uint32_t key_lo = band ? P.state->band_key[band - 1] : 0u, key_hi = P.state->band_key[band];
+    const uint32_t key_lo = band ? P.pass->band_key[band - 1] : 0u, key_hi = P.pass->band_key[band];
     const MeshletBound* bounds = (const MeshletBound*)P.meshlet_bounds;
     uint32_t occluded = 0;
     const uint32_t stride = gridDim.x * blockDim.x;
@@ -601,7 +602,7 @@ __global__ void __launch_bounds__(256) raster_select_kernel(const __grid_constan
         const uint32_t ballot = __ballot_sync(0xFFFFFFFFu, keep);
         if (ballot) {
             uint32_t at = 0;
-            if (lane == 0) at = atomicAdd(&P.state->queue_count, (uint32_t)__popc(ballot));
+            if (lane == 0) at = atomicAdd(&P.pass->queue_count, (uint32_t)__popc(ballot));
             at = __shfl_sync(0xFFFFFFFFu, at, 0);
             if (keep) P.raster_queue[at + __popc(ballot & ((1u << lane) - 1u))] = k;
         }
@@ -615,7 +616,7 @@ __global__ void __launch_bounds__(256) raster_select_kernel(const __grid_constan
 // between a band's selection and its rasterisation: the raster kernel takes tickets in [raster_ticket, band_end)
 __global__ void raster_band_begin_kernel(const __grid_constant__ FrameParams P) {
     if (threadIdx.x == 0 && blockIdx.x == 0) {
-        FrameState* st = P.state;
+        PassState* st = P.pass;
         st->raster_ticket = st->band_begin;
         st->band_first = st->band_begin;
         st->band_end = st->queue_count;
@@ -631,9 +632,9 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, LH_RASTER_MIN_CTAS) raster_
     __shared__ WarpScratch scratch_all[kWarpsPerCta];
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     WarpScratch& sv = scratch_all[warp];
-    const uint32_t* draw = (const uint32_t*)P.u.draw_calls;
+    const uint32_t* draw = (const uint32_t*)P.pass_draw_calls;
     const uint32_t n_opaque = min(draw[0], P.max_opaque);   // drawIndirectCount clamps to maxDrawCount
-    const uint32_t band_end = P.state->band_end;
+    const uint32_t band_end = P.pass->band_end;
 
     Target<SHADOW> tg;
     tg.vis = P.vis;
@@ -659,11 +660,11 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, LH_RASTER_MIN_CTAS) raster_
     // work and a heavy near meshlet does not serialise its neighbours): the entries, their bounds and the first 8x4
     // block of every rectangle are fetched before any entry is processed, so the dependent round trips
     // ticket -> queue -> bounds -> stored keys are paid once per chunk instead of once per meshlet.
-    const uint32_t band_count = band_end - P.state->band_first;
+    const uint32_t band_count = band_end - P.pass->band_first;
     const uint32_t chunk = max(1u, min((uint32_t)kFrontChunk, band_count / (gridDim.x * kWarpsPerCta * 8u)));
     for (;;) {
         uint32_t ticket = 0;
-        if (lane == 0) ticket = atomicAdd(&P.state->raster_ticket, chunk);
+        if (lane == 0) ticket = atomicAdd(&P.pass->raster_ticket, chunk);
         ticket = __shfl_sync(0xFFFFFFFFu, ticket, 0);
         if (ticket >= band_end) break;
         const uint32_t n = min(chunk, band_end - ticket);
@@ -923,20 +924,19 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, LH_RASTER_MIN_CTAS) raster_
 template <bool SHADOW>
 __global__ void __launch_bounds__(kWarpsPerCta * 32) raster_deferred_kernel(const __grid_constant__ FrameParams P, uint32_t cascade) {
     const uint32_t warp = threadIdx.x >> 5;
-    const uint32_t count = min(P.state->large_count, P.max_large);
+    const uint32_t count = min(P.pass->large_count, P.max_large);
     Target<SHADOW> tg;
     tg.vis = P.vis;
     tg.layer = SHADOW ? P.shadow + (size_t)cascade * P.shadowmap_size * P.shadowmap_size : nullptr;
     tg.width = SHADOW ? P.shadowmap_size : P.u.window_size[0];
     tg.height = SHADOW ? P.shadowmap_size : P.u.window_size[1];
     const float* M = SHADOW ? &((const LhMiscStorage*)P.u.misc_storage)->shadow_matrices[cascade].m[0][0] : &P.u.combined_perspective_view.m[0][0];
-    const uint32_t section = SHADOW ? P.max_opaque + P.max_alpha : 0u;
 
     for (uint32_t e = blockIdx.x * kWarpsPerCta + warp; e < count; e += gridDim.x * kWarpsPerCta) {
         const uint32_t lo = P.large_queue[2 * (size_t)e], tile = P.large_queue[2 * (size_t)e + 1];
         const uint32_t local = (lo >> LH_VIS_TRI_BITS) - P.slot_offset, t = lo & LH_VIS_TRI_MASK;
         MeshletHeader h;
-        load_header(P, section + local, h);
+        load_header(P, local, h);
         const int cull = h.alpha ? CULL_NONE : (SHADOW ? CULL_FRONT : CULL_BACK);
         const AlphaTest at = make_alpha_test(P, h);
         ClipVert v[3];
@@ -965,47 +965,48 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) raster_deferred_kernel(cons
 
 __global__ void begin_raster_pass_kernel(const __grid_constant__ FrameParams P) {
     if (threadIdx.x == 0 && blockIdx.x == 0) {
-        P.state->large_count = 0;
-        P.state->raster_ticket = 0;
+        P.pass->large_count = 0;
+        P.pass->raster_ticket = 0;
     }
 }
 __global__ void end_main_pass_kernel(const __grid_constant__ FrameParams P) {
-    if (threadIdx.x == 0 && blockIdx.x == 0) P.state->main_large_count = P.state->large_count;
+    if (threadIdx.x == 0 && blockIdx.x == 0) P.state->main_large_count = P.pass->large_count;
 }
 
 }  // namespace
 
-void launch_raster(LhContext* ctx, const FrameParams& p, int cascade) {
+void launch_raster(LhContext* ctx, const FrameParams& p, int cascade, cudaStream_t stream) {
+    if (!stream) stream = ctx->stream;
     const uint32_t grid = (uint32_t)ctx->num_sms * 8;
     const bool timed = cascade < 0 && (ctx->cfg.flags & LH_CONFIG_PASS_TIMINGS) != 0;
-    begin_raster_pass_kernel<<<1, 32, 0, ctx->stream>>>(p); ctx->launches++;
-    if (timed) cudaEventRecord(ctx->raster_kernel_a, ctx->stream);
-    if (cascade < 0) raster_bounds_kernel<false><<<grid, 256, 0, ctx->stream>>>(p, 0);
-    else raster_bounds_kernel<true><<<grid, 256, 0, ctx->stream>>>(p, (uint32_t)cascade);
-    raster_bands_kernel<<<1, 1024, 0, ctx->stream>>>(p);
+    begin_raster_pass_kernel<<<1, 32, 0, stream>>>(p); ctx->launches++;
+    if (timed) cudaEventRecord(ctx->raster_kernel_a, stream);
+    if (cascade < 0) raster_bounds_kernel<false><<<grid, 256, 0, stream>>>(p, 0);
+    else raster_bounds_kernel<true><<<grid, 256, 0, stream>>>(p, (uint32_t)cascade);
+    raster_bands_kernel<<<1, 1024, 0, stream>>>(p);
     ctx->launches += 2;
     for (uint32_t band = 0; band < (uint32_t)kBands; band++) {
         if (band != 0) {
-            if (cascade < 0) raster_hiz_kernel<false><<<grid, 256, 0, ctx->stream>>>(p, 0);
-            else raster_hiz_kernel<true><<<grid, 256, 0, ctx->stream>>>(p, (uint32_t)cascade);
+            if (cascade < 0) raster_hiz_kernel<false><<<grid, 256, 0, stream>>>(p, 0);
+            else raster_hiz_kernel<true><<<grid, 256, 0, stream>>>(p, (uint32_t)cascade);
             ctx->launches++;
         }
-        if (cascade < 0) raster_select_kernel<false><<<grid, 256, 0, ctx->stream>>>(p, 0, band);
-        else raster_select_kernel<true><<<grid, 256, 0, ctx->stream>>>(p, (uint32_t)cascade, band);
-        raster_band_begin_kernel<<<1, 32, 0, ctx->stream>>>(p);
-        if (cascade < 0) raster_meshlets_kernel<false><<<grid, kWarpsPerCta * 32, 0, ctx->stream>>>(p, 0);
-        else raster_meshlets_kernel<true><<<grid, kWarpsPerCta * 32, 0, ctx->stream>>>(p, (uint32_t)cascade);
+        if (cascade < 0) raster_select_kernel<false><<<grid, 256, 0, stream>>>(p, 0, band);
+        else raster_select_kernel<true><<<grid, 256, 0, stream>>>(p, (uint32_t)cascade, band);
+        raster_band_begin_kernel<<<1, 32, 0, stream>>>(p);
+        if (cascade < 0) raster_meshlets_kernel<false><<<grid, kWarpsPerCta * 32, 0, stream>>>(p, 0);
+        else raster_meshlets_kernel<true><<<grid, kWarpsPerCta * 32, 0, stream>>>(p, (uint32_t)cascade);
         ctx->launches += 3;
     }
     if (timed) {
-        cudaEventRecord(ctx->raster_kernel_b, ctx->stream);
+        cudaEventRecord(ctx->raster_kernel_b, stream);
         ctx->raster_kernel_recorded = true;
     }
     if (cascade < 0) {
-        raster_deferred_kernel<false><<<grid, kWarpsPerCta * 32, 0, ctx->stream>>>(p, 0); ctx->launches++;
-        end_main_pass_kernel<<<1, 32, 0, ctx->stream>>>(p); ctx->launches++;
+        raster_deferred_kernel<false><<<grid, kWarpsPerCta * 32, 0, stream>>>(p, 0); ctx->launches++;
+        end_main_pass_kernel<<<1, 32, 0, stream>>>(p); ctx->launches++;
     } else {
-        raster_deferred_kernel<true><<<grid, kWarpsPerCta * 32, 0, ctx->stream>>>(p, (uint32_t)cascade); ctx->launches++;
+        raster_deferred_kernel<true><<<grid, kWarpsPerCta * 32, 0, stream>>>(p, (uint32_t)cascade); ctx->launches++;
     }
 }
 
