@@ -79,6 +79,7 @@ struct FrameState {
 struct PassState {
     uint32_t cull_ticket, cull_done;   // meshlet cull: next tile, CTAs finished (self-cleaning)
     uint32_t large_count;              // entries in the deferred-triangle queue
+    uint32_t deferred_begin, deferred_end;   // queue range the current deferred launch processes
     uint32_t raster_ticket;            // next unclaimed entry of the raster queue
     uint32_t queue_count;              // entries appended to the raster queue so far
     uint32_t band_begin, band_end;     // queue range of the band being rasterised (band_begin already names the next band's start)

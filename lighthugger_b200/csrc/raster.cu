@@ -152,40 +152,53 @@ __device__ void raster_snapped_coop(SnapVert a, SnapVert b, SnapVert c, int cull
     const float inv_area = pdiv(1.0f, fA);
     const float dz1 = psub(b.z, a.z), dz2 = psub(c.z, a.z);
     const int nbx = (px1 - px0 + 8) >> 3, nby = (py1 - py0 + 4) >> 2;
-    for (int by = 0; by < nby; by++)
+    // The edge functions are affine in the pixel position, so everything below is additions: E_k at the centre of the
+    // block's first pixel is carried from block to block (step_x per 8 pixels, step_y per 4 rows); the lane's own pixel
+    // and the block corner where E_k is largest (for the trivial reject) are fixed offsets from it.
+    const long long cx0 = (long long)px0 * 256 + 128, cy0 = (long long)py0 * 256 + 128;
+    const long long dx0 = -e0y * 256, dx1 = -e1y * 256, dx2 = -e2y * 256;   // E_k(x + 1 pixel) - E_k(x)
+    const long long dy0 = e0x * 256, dy1 = e1x * 256, dy2 = e2x * 256;      // E_k(y + 1 pixel) - E_k(y)
+    long long row0 = e0x * (cy0 - b.y) - e0y * (cx0 - b.x) + bias0;          // top-left bias folded in: inside <=> all >= 0
+    long long row1 = e1x * (cy0 - c.y) - e1y * (cx0 - c.x) + bias1;
+    long long row2 = e2x * (cy0 - a.y) - e2y * (cx0 - a.x) + bias2;
+    const long long corner0 = (dx0 > 0 ? 7 * dx0 : 0) + (dy0 > 0 ? 3 * dy0 : 0);
+    const long long corner1 = (dx1 > 0 ? 7 * dx1 : 0) + (dy1 > 0 ? 3 * dy1 : 0);
+    const long long corner2 = (dx2 > 0 ? 7 * dx2 : 0) + (dy2 > 0 ? 3 * dy2 : 0);
+    const int lx = (int)(lane & 7), ly = (int)(lane >> 3);
+    const long long mine0 = lx * dx0 + ly * dy0, mine1 = lx * dx1 + ly * dy1, mine2 = lx * dx2 + ly * dy2;
+    for (int by = 0; by < nby; by++) {
+        long long blk0 = row0, blk1 = row1, blk2 = row2;
+        const int py = py0 + by * 4 + ly;
         for (int bx = 0; bx < nbx; bx++) {
-            const int x0 = px0 + bx * 8, y0 = py0 + by * 4;
-            // trivial reject: the corner of the 8x4 block where each edge function is largest
-            {
-                const long long cx_lo = (long long)x0 * 256 + 128, cx_hi = cx_lo + 7 * 256;
-                const long long cy_lo = (long long)y0 * 256 + 128, cy_hi = cy_lo + 3 * 256;
-                long long m0 = e0x * ((e0x > 0 ? cy_hi : cy_lo) - b.y) - e0y * ((e0y < 0 ? cx_hi : cx_lo) - b.x);
-                long long m1 = e1x * ((e1x > 0 ? cy_hi : cy_lo) - c.y) - e1y * ((e1y < 0 ? cx_hi : cx_lo) - c.x);
-                long long m2 = e2x * ((e2x > 0 ? cy_hi : cy_lo) - a.y) - e2y * ((e2y < 0 ? cx_hi : cx_lo) - a.x);
-                if (((m0 + bias0) | (m1 + bias1) | (m2 + bias2)) < 0) continue;
-            }
-            const int px = x0 + (int)(lane & 7), py = y0 + (int)(lane >> 3);
+            // trivial reject: the block corner where each (biased) edge function is largest is still outside
+            const bool reject = ((blk0 + corner0) | (blk1 + corner1) | (blk2 + corner2)) < 0;
+            const long long w0b = blk0 + mine0, w1b = blk1 + mine1, w2b = blk2 + mine2;
+            blk0 += 8 * dx0;
+            blk1 += 8 * dx1;
+            blk2 += 8 * dx2;
+            if (reject) continue;
+            const int px = px0 + bx * 8 + lx;
             if (px > px1 || py > py1) continue;
-            const long long cx = (long long)px * 256 + 128, cy = (long long)py * 256 + 128;
-            const long long w0 = e0x * (cy - b.y) - e0y * (cx - b.x);
-            const long long w1 = e1x * (cy - c.y) - e1y * (cx - c.x);
-            const long long w2 = e2x * (cy - a.y) - e2y * (cx - a.x);
-            if (((w0 + bias0) | (w1 + bias1) | (w2 + bias2)) < 0) continue;
+            if ((w0b | w1b | w2b) < 0) continue;
+            const long long w0 = w0b - bias0, w1 = w1b - bias1, w2 = w2b - bias2;
             if (at.enabled && alpha_discard(at, (float)w0, (float)w1, (float)w2, fA, a, b, c)) continue;
             float z = padd(a.z, pmul(padd(pmul((float)w1, dz1), pmul((float)w2, dz2)), inv_area));
             tg.emit(px, py, z, lo);
         }
+        row0 += 4 * dy0;
+        row1 += 4 * dy1;
+        row2 += 4 * dy2;
+    }
 }
 
 struct ClipVert {
     float x, y, z, w, u, v;
 };
 
-// The generic path of the pinned model: near-plane clip, snap, then the
-// cooperative scan.  All 32 lanes pass identical arguments.
+// The generic path of the pinned model: near-plane clip (w - z >= 0; a cascade has no such plane) and snap.
+// Returns the number of vertices of the clipped polygon in s[] (0: nothing to draw, else 3 or 4).
 template <bool SHADOW>
-__device__ void raster_clip_triangle_coop(const ClipVert v[3], int cull, const Target<SHADOW>& tg, int rx0, int ry0, int rx1, int ry1,
-                                          const AlphaTest& at, uint32_t lo) {
+__device__ int clip_and_snap(const ClipVert v[3], const Target<SHADOW>& tg, SnapVert s[4]) {
     const float half_w = pmul((float)tg.width, 0.5f), half_h = pmul((float)tg.height, 0.5f);
     bool in[3] = {true, true, true};
     float d[3] = {0, 0, 0};
@@ -198,7 +211,7 @@ __device__ void raster_clip_triangle_coop(const ClipVert v[3], int cull, const T
             n_in += in[k] ? 1 : 0;
         }
     }
-    if (n_in == 0) return;
+    if (n_in == 0) return 0;
     ClipVert poly[4];
     int n = 0;
     if (n_in == 3) {
@@ -221,15 +234,13 @@ __device__ void raster_clip_triangle_coop(const ClipVert v[3], int cull, const T
             }
         }
     }
-    SnapVert s[4];
     for (int k = 0; k < n; k++) {
-        if (!project_snap(poly[k].x, poly[k].y, poly[k].z, poly[k].w, half_w, half_h, &s[k].x, &s[k].y, &s[k].z)) return;
+        if (!project_snap(poly[k].x, poly[k].y, poly[k].z, poly[k].w, half_w, half_h, &s[k].x, &s[k].y, &s[k].z)) return 0;
         s[k].w = poly[k].w;
         s[k].u = poly[k].u;
         s[k].v = poly[k].v;
     }
-    raster_snapped_coop<SHADOW>(s[0], s[1], s[2], cull, tg, rx0, ry0, rx1, ry1, at, lo);
-    if (n == 4) raster_snapped_coop<SHADOW>(s[0], s[2], s[3], cull, tg, rx0, ry0, rx1, ry1, at, lo);
+    return n;
 }
 
 // Everything needed to locate one meshlet's data; loaded by every lane from the same addresses (broadcast).
@@ -812,8 +823,12 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, LH_RASTER_MIN_CTAS) raster_
                                 // large footprint: one queue entry per 128x32 screen tile the bounding box touches
                                 const uint32_t tx0 = (uint32_t)px0 / kTileW, tx1 = (uint32_t)px1 / kTileW;
                                 const uint32_t ty0 = (uint32_t)py0 / kTileH, ty1 = (uint32_t)py1 / kTileH;
-                                for (uint32_t ty = ty0; ty <= ty1; ty++)
-                                    for (uint32_t tx = tx0; tx <= tx1; tx++) push_deferred(P, lo, tx | (ty << 16));
+                                if ((tx1 - tx0 + 1) * (ty1 - ty0 + 1) > 2) {
+                                    push_deferred(P, lo, kWholeTriangle);   // split by the deferred kernel, a warp per triangle
+                                } else {
+                                    for (uint32_t ty = ty0; ty <= ty1; ty++)
+                                        for (uint32_t tx = tx0; tx <= tx1; tx++) push_deferred(P, lo, tx | (ty << 16));
+                                }
                             }
                         };
                         if (!any_special) {
@@ -920,11 +935,29 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, LH_RASTER_MIN_CTAS) raster_
     }
 }
 
-// ---- kernel 2: one warp per deferred (triangle, screen tile) ----
+// ---- the deferred queue: large and near-plane-crossing triangles, one warp per entry ----
+// An entry is (key low word, screen tile) or (key low word, kWholeTriangle).  Whole-triangle entries are clipped and,
+// when their rectangle spans more than two 128x32 tiles, split into per-tile entries appended to the queue -- a
+// screen-filling triangle would otherwise be scanned by a single warp -- which the next launch rasterises.
+// A warp takes 32 entries at a time: (a) one lane per entry walks the pointer chain, fetches and transforms the three
+// vertices, clips and snaps, and parks the result in shared memory -- the chain's seven dependent round trips are paid
+// once per 32 entries; (b) the warp then goes through the parked triangles one by one, all lanes scanning 8x4 blocks.
+struct DeferredTriangle {
+    SnapVert s[4];
+    cudaTextureObject_t tex;     // 0: no alpha test
+    uint32_t lo;
+    uint32_t rect_x, rect_y;     // x0 | x1 << 16, y0 | y1 << 16 (pixels); split: tile range instead
+    uint16_t n;                  // vertices after clipping; 0: nothing to do
+    uint8_t cull, split;         // split: append one entry per tile of the rectangle instead of rasterising
+};
+constexpr int kDeferredWarps = 4;
+
 template <bool SHADOW>
-__global__ void __launch_bounds__(kWarpsPerCta * 32) raster_deferred_kernel(const __grid_constant__ FrameParams P, uint32_t cascade) {
-    const uint32_t warp = threadIdx.x >> 5;
-    const uint32_t count = min(P.pass->large_count, P.max_large);
+__global__ void __launch_bounds__(kDeferredWarps * 32) raster_deferred_kernel(const __grid_constant__ FrameParams P, uint32_t cascade) {
+    __shared__ DeferredTriangle parked_all[kDeferredWarps][32];
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    DeferredTriangle* parked = parked_all[warp];
+    const uint32_t range_begin = P.pass->deferred_begin, range_end = P.pass->deferred_end;
     Target<SHADOW> tg;
     tg.vis = P.vis;
     tg.layer = SHADOW ? P.shadow + (size_t)cascade * P.shadowmap_size * P.shadowmap_size : nullptr;
@@ -932,40 +965,112 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) raster_deferred_kernel(cons
     tg.height = SHADOW ? P.shadowmap_size : P.u.window_size[1];
     const float* M = SHADOW ? &((const LhMiscStorage*)P.u.misc_storage)->shadow_matrices[cascade].m[0][0] : &P.u.combined_perspective_view.m[0][0];
 
-    for (uint32_t e = blockIdx.x * kWarpsPerCta + warp; e < count; e += gridDim.x * kWarpsPerCta) {
-        const uint32_t lo = P.large_queue[2 * (size_t)e], tile = P.large_queue[2 * (size_t)e + 1];
-        const uint32_t local = (lo >> LH_VIS_TRI_BITS) - P.slot_offset, t = lo & LH_VIS_TRI_MASK;
-        MeshletHeader h;
-        load_header(P, local, h);
-        const int cull = h.alpha ? CULL_NONE : (SHADOW ? CULL_FRONT : CULL_BACK);
-        const AlphaTest at = make_alpha_test(P, h);
-        ClipVert v[3];
-        for (int q = 0; q < 3; q++) {
-            const uint32_t mi = __ldg(h.micro + 3 * t + q);
-            const uint32_t idx = load_vertex_index(h, mi);
-            const uint16_t* p = h.positions + 3 * (size_t)idx;
-            const V4 world = mat4_mul(h.T, (float)__ldg(p), (float)__ldg(p + 1), (float)__ldg(p + 2), 1.0f);
-            const V4 clip = mat4_mul(M, world.x, world.y, world.z, 1.0f);
-            v[q] = ClipVert{clip.x, clip.y, clip.z, clip.w, 0.0f, 0.0f};
-            if (at.enabled) {
-                v[q].u = padd(pmul((float)__ldg(h.uvs + 2 * (size_t)idx), h.tex_scale[0]), h.tex_offset[0]);
-                v[q].v = padd(pmul((float)__ldg(h.uvs + 2 * (size_t)idx + 1), h.tex_scale[1]), h.tex_offset[1]);
+    for (uint32_t base = range_begin + (blockIdx.x * kDeferredWarps + warp) * 32; base < range_end; base += gridDim.x * kDeferredWarps * 32) {
+        // ---- (a) one lane per entry ----
+        {
+            DeferredTriangle& d = parked[lane];
+            d.n = 0;
+            const uint32_t e = base + lane;
+            if (e < range_end) {
+                const uint32_t lo = P.large_queue[2 * (size_t)e], tile = P.large_queue[2 * (size_t)e + 1];
+                const uint32_t local = (lo >> LH_VIS_TRI_BITS) - P.slot_offset, t = lo & LH_VIS_TRI_MASK;
+                MeshletHeader h;
+                load_header(P, local, h);
+                const AlphaTest at = make_alpha_test(P, h);
+                ClipVert v[3];
+                for (int q = 0; q < 3; q++) {
+                    const uint32_t mi = __ldg(h.micro + 3 * t + q);
+                    const uint32_t idx = load_vertex_index(h, mi);
+                    const uint16_t* p = h.positions + 3 * (size_t)idx;
+                    const V4 world = mat4_mul(h.T, (float)__ldg(p), (float)__ldg(p + 1), (float)__ldg(p + 2), 1.0f);
+                    const V4 clip = mat4_mul(M, world.x, world.y, world.z, 1.0f);
+                    v[q] = ClipVert{clip.x, clip.y, clip.z, clip.w, 0.0f, 0.0f};
+                    if (at.enabled) {
+                        v[q].u = padd(pmul((float)__ldg(h.uvs + 2 * (size_t)idx), h.tex_scale[0]), h.tex_offset[0]);
+                        v[q].v = padd(pmul((float)__ldg(h.uvs + 2 * (size_t)idx + 1), h.tex_scale[1]), h.tex_offset[1]);
+                    }
+                }
+                int n = clip_and_snap<SHADOW>(v, tg, d.s);
+                int rx0 = 0, ry0 = 0, rx1 = (int)tg.width - 1, ry1 = (int)tg.height - 1;
+                bool split = false;
+                if (n != 0) {
+                    if (tile != kWholeTriangle) {
+                        rx0 = (int)((tile & 0xFFFFu) * kTileW);
+                        ry0 = (int)((tile >> 16) * kTileH);
+                        rx1 = min(rx1, rx0 + (int)kTileW - 1);
+                        ry1 = min(ry1, ry0 + (int)kTileH - 1);
+                    } else {
+                        int minx = d.s[0].x, maxx = d.s[0].x, miny = d.s[0].y, maxy = d.s[0].y;
+                        for (int k = 1; k < n; k++) {
+                            minx = min(minx, d.s[k].x); maxx = max(maxx, d.s[k].x);
+                            miny = min(miny, d.s[k].y); maxy = max(maxy, d.s[k].y);
+                        }
+                        const int px0 = max(0, (minx - 128 + 255) >> 8), px1 = min(rx1, (maxx - 128) >> 8);
+                        const int py0 = max(0, (miny - 128 + 255) >> 8), py1 = min(ry1, (maxy - 128) >> 8);
+                        if (px0 > px1 || py0 > py1) {
+                            n = 0;
+                        } else {
+                            const int tx0 = px0 / (int)kTileW, tx1 = px1 / (int)kTileW, ty0 = py0 / (int)kTileH, ty1 = py1 / (int)kTileH;
+                            if ((tx1 - tx0 + 1) * (ty1 - ty0 + 1) > 2) {
+                                split = true;
+                                rx0 = tx0; rx1 = tx1; ry0 = ty0; ry1 = ty1;
+                            }
+                        }
+                    }
+                }
+                d.n = (uint16_t)n;
+                d.lo = lo;
+                d.rect_x = (uint32_t)rx0 | ((uint32_t)rx1 << 16);
+                d.rect_y = (uint32_t)ry0 | ((uint32_t)ry1 << 16);
+                d.cull = (uint8_t)(h.alpha ? CULL_NONE : (SHADOW ? CULL_FRONT : CULL_BACK));
+                d.split = split ? 1 : 0;
+                d.tex = at.enabled ? at.tex : 0;
             }
         }
-        int rx0 = 0, ry0 = 0, rx1 = (int)tg.width - 1, ry1 = (int)tg.height - 1;
-        if (tile != kWholeTriangle) {
-            rx0 = (int)((tile & 0xFFFFu) * kTileW);
-            ry0 = (int)((tile >> 16) * kTileH);
-            rx1 = min(rx1, rx0 + (int)kTileW - 1);
-            ry1 = min(ry1, ry0 + (int)kTileH - 1);
+        __syncwarp();
+        // ---- (b) the warp, one parked triangle at a time ----
+        for (int i = 0; i < 32; i++) {
+            const DeferredTriangle& d = parked[i];
+            const int n = d.n;
+            if (n == 0) continue;
+            const int x0 = (int)(d.rect_x & 0xFFFFu), x1 = (int)(d.rect_x >> 16), y0 = (int)(d.rect_y & 0xFFFFu), y1 = (int)(d.rect_y >> 16);
+            const uint32_t lo = d.lo;
+            if (d.split) {
+                const uint32_t ntx = (uint32_t)(x1 - x0 + 1), ntiles = ntx * (uint32_t)(y1 - y0 + 1);
+                uint32_t at = 0;
+                if (lane == 0) at = atomicAdd(&P.pass->large_count, ntiles);
+                at = __shfl_sync(0xFFFFFFFFu, at, 0);
+                for (uint32_t k = lane; k < ntiles; k += 32) {
+                    if (at + k < P.max_large) {
+                        P.large_queue[2 * (size_t)(at + k)] = lo;
+                        P.large_queue[2 * (size_t)(at + k) + 1] = ((uint32_t)x0 + k % ntx) | (((uint32_t)y0 + k / ntx) << 16);
+                    } else {
+                        atomicOr(&P.state->overflow, (uint32_t)LH_OVERFLOW_LARGE_TRIANGLES);
+                    }
+                }
+                continue;
+            }
+            const AlphaTest at{d.tex != 0, d.tex};
+            raster_snapped_coop<SHADOW>(d.s[0], d.s[1], d.s[2], (int)d.cull, tg, x0, y0, x1, y1, at, lo);
+            if (n == 4) raster_snapped_coop<SHADOW>(d.s[0], d.s[2], d.s[3], (int)d.cull, tg, x0, y0, x1, y1, at, lo);
         }
-        raster_clip_triangle_coop<SHADOW>(v, cull, tg, rx0, ry0, rx1, ry1, at, lo);
+        __syncwarp();
+    }
+}
+
+// the next deferred launch takes the entries appended since the previous one
+__global__ void raster_deferred_begin_kernel(const __grid_constant__ FrameParams P) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        PassState* st = P.pass;
+        st->deferred_begin = st->deferred_end;
+        st->deferred_end = min(st->large_count, P.max_large);
     }
 }
 
 __global__ void begin_raster_pass_kernel(const __grid_constant__ FrameParams P) {
     if (threadIdx.x == 0 && blockIdx.x == 0) {
         P.pass->large_count = 0;
+        P.pass->deferred_begin = P.pass->deferred_end = 0;
         P.pass->raster_ticket = 0;
     }
 }
@@ -997,16 +1102,23 @@ void launch_raster(LhContext* ctx, const FrameParams& p, int cascade, cudaStream
         if (cascade < 0) raster_meshlets_kernel<false><<<grid, kWarpsPerCta * 32, 0, stream>>>(p, 0);
         else raster_meshlets_kernel<true><<<grid, kWarpsPerCta * 32, 0, stream>>>(p, (uint32_t)cascade);
         ctx->launches += 3;
+        // The deferred queue is drained after the near bands (whose large triangles are the best occluders for the
+        // bands that follow) and at the end; twice each time: the first launch splits, the second rasterises the pieces.
+        if (band < 3 || band + 1 == (uint32_t)kBands) {
+            for (int round = 0; round < 2; round++) {
+                raster_deferred_begin_kernel<<<1, 32, 0, stream>>>(p);
+                if (cascade < 0) raster_deferred_kernel<false><<<grid, kDeferredWarps * 32, 0, stream>>>(p, 0);
+                else raster_deferred_kernel<true><<<grid, kDeferredWarps * 32, 0, stream>>>(p, (uint32_t)cascade);
+                ctx->launches += 2;
+            }
+        }
     }
     if (timed) {
         cudaEventRecord(ctx->raster_kernel_b, stream);
         ctx->raster_kernel_recorded = true;
     }
     if (cascade < 0) {
-        raster_deferred_kernel<false><<<grid, kWarpsPerCta * 32, 0, stream>>>(p, 0); ctx->launches++;
         end_main_pass_kernel<<<1, 32, 0, stream>>>(p); ctx->launches++;
-    } else {
-        raster_deferred_kernel<true><<<grid, kWarpsPerCta * 32, 0, stream>>>(p, (uint32_t)cascade); ctx->launches++;
     }
 }
 
