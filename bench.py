@@ -210,15 +210,18 @@ def run_ours(args):
     n = scene.num_instances
     first, count = sortlast.instance_range(n, rank, world)
     end = first + count
-    caps = sortlast.capacities(scene, world)
+    caps = sortlast.capacities(scene, world, args.shadow_split)
     ctx = make_context(scene, textures=tex, skybox=sky, caps=caps, flags=S.LH_CONFIG_WRITE_DRAW_COMMANDS | S.LH_CONFIG_PASS_TIMINGS,
                        device=local_rank)
     if world > 1:
         ids = [ctx.comm_unique_id() if rank == 0 else None]
         dist.broadcast_object_list(ids, src=0)
         ctx.comm_init(rank, world, ids[0])
+        ctx.comm_set_exchange(S.LH_EXCHANGE_NCCL if args.exchange == "nccl" else S.LH_EXCHANGE_PEER)
         ctx.set_instance_range(first, count)
-        ctx.set_shadow_cascade_mask(sortlast.cascade_mask(rank, world))
+        mask, sfirst, scount = sortlast.shadow_plan(n, rank, world, args.shadow_split)
+        ctx.set_shadow_cascade_mask(mask)
+        ctx.set_shadow_instance_range(sfirst, scount)
     u = ctx.uniforms()
 
     def barrier():
@@ -295,18 +298,24 @@ def run_ours(args):
     inst_here = end - first
     avg_tris = scene.total_triangles / max(1, scene.total_meshlets)
     survivors = stats.num_opaque + stats.num_alpha_clip
+    y0, y1 = ctx.comm_rows()           # rows rank 0 composites and resolves (the whole frame on one GPU)
+    px_here = (y1 - y0) * W
+    peer = n_gpus > 1 and args.exchange == "peer"
     alg = {
         "cull_instances": 112 * inst_here + 8 * stats.num_visible_instances,
         "cull_meshlets": 56 * stats.num_candidate_meshlets + (8 + 16) * survivors + 8 * stats.num_visible_instances,
-        "depth_reduction": 8 * px,
-        "render_geometry": 16 * px,
+        # peer exchange: the composite kernel reads this rank's rows of every rank's keys and writes them once, with
+        # the depth bounds folded in (the depth pass is then an 8-byte all-reduce)
+        "composite": 8 * px_here * (n_gpus + 1) if peer else (2 * 8 * px * (n_gpus - 1) // n_gpus if n_gpus > 1 else 0),
+        "depth_reduction": 0 if peer else 8 * px,
+        "render_geometry": 16 * px_here,
         # raster geometry fetch per rasterised meshlet: 56 + 3 tri + 2 idx + 6 pos per vertex + 64 B of instance transform
         "raster_meshlets_kernel": survivors * (56 + 3 * avg_tris + (2 + 6) * 64 + 64),
     }
     passes = {}
     for k, b in alg.items():
         ms = med.get(k, 0.0)
-        if ms > 0:
+        if ms > 0 and b > 0:
             passes[k] = {"ms": round(ms, 4), "alg_bytes": int(b), "gbs": round(b / ms / 1e6, 1), "frac": round(b / ms / 1e6 / peak, 4)}
     kernel_share = {k: round(v / med["frame"], 4) for k, v in med.items() if k not in ("frame",) and med["frame"] > 0}
     dom = "raster_meshlets_kernel"
@@ -326,7 +335,8 @@ def run_ours(args):
         "data": "synthetic",
         "config": {"workload": WORKLOADS[args.workload], "resolution": [W, H], "instances": n, "input_triangles": scene.total_triangles,
                    "candidate_meshlets": scene.total_meshlets, "l2": "flushed between timed frames (256 MB write)",
-                   "parallelism": f"sort-last x{n_gpus}" if n_gpus > 1 else "single GPU", "texture_format": "BC7_SRGB",
+                   "parallelism": (f"sort-last x{n_gpus}: instances split, {args.exchange} exchange, shadows split by {args.shadow_split}"
+                                   if n_gpus > 1 else "single GPU"), "texture_format": "BC7_SRGB",
                    "texture_size": args.tex_size},
         "culled_mtri_per_s": scene.total_triangles / (ms_per_step / 1e3) / 1e6,
         "frame": {"visible_instances": stats.num_visible_instances, "candidate_meshlets": stats.num_candidate_meshlets,
@@ -363,6 +373,8 @@ def main():
     ap.add_argument("--tex-size", type=int, default=256)
     ap.add_argument("--cpu-budget", type=float, default=15.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"], help="multi-GPU: peer-memory kernels or whole-buffer NCCL")
+    ap.add_argument("--shadow-split", default="instances", choices=["instances", "cascades"])
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

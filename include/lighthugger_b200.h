@@ -180,6 +180,10 @@ LH_API int lh_set_instance_range(LhContext* ctx, uint32_t first, uint32_t count)
 /* cascades this context renders in lh_render_frame (bit c = cascade c; default 0xF).
  * "One cascade per GPU" = mask 1 << rank; the layers are merged by lh_shadow_exchange. */
 LH_API int lh_set_shadow_cascade_mask(LhContext* ctx, uint32_t mask);
+/* instances this context's cascades draw, [first, first+count); default: the range of lh_set_instance_range.
+ * Over all ranks the (cascade, instance) pairs must be covered exactly once: either every rank draws all four
+ * cascades of its own instances, or one cascade per GPU over all instances (BASELINE config 3). */
+LH_API int lh_set_shadow_instance_range(LhContext* ctx, uint32_t first, uint32_t count);
 
 /* ---- per frame (replaces uniform_buffer.flush + render() + submit + fence,
  * src/main.cpp:784-817).  One export per pass, in src/rendering.cpp order. ---- */
@@ -223,9 +227,16 @@ LH_API int lh_flush_l2(LhContext* ctx);                 /* writes a buffer large
 LH_API int lh_comm_unique_id(void* id128);
 LH_API int lh_comm_init(LhContext* ctx, int rank, int nranks, const void* id128);
 LH_API int lh_comm_destroy(LhContext* ctx);
-/* global slot offset of this rank's meshlet references (exclusive sum of the
- * ranks' visible counts); valid after lh_composite */
 LH_API int lh_comm_info(LhContext* ctx, int* rank, int* nranks);
+/* How the exchange steps move data.  LH_EXCHANGE_PEER (default when every rank can map its peers' buffers through
+ * CUDA IPC over NVLink): each rank owns the screen rows [y0, y1) of lh_comm_rows; lh_composite is ONE kernel that
+ * pulls those rows of every peer's key buffer through peer memory, takes the uint64 min and folds the depth min/max
+ * in; the resolve reads the winners' MeshletReference from the owning rank's table through peer memory and stores
+ * its rows of lit colour into rank 0's frame.  LH_EXCHANGE_NCCL: ncclAllReduce(uint64, min) of whole buffers and an
+ * all-gather of the reference tables; every rank then holds and resolves the whole frame. */
+enum { LH_EXCHANGE_PEER = 0, LH_EXCHANGE_NCCL = 1 };
+LH_API int lh_comm_set_exchange(LhContext* ctx, int mode);
+LH_API int lh_comm_rows(LhContext* ctx, uint32_t* y0, uint32_t* y1);   /* rows this rank composites and resolves */
 
 #ifdef __cplusplus
 }

@@ -85,6 +85,7 @@ LH_CONFIG_PASS_TIMINGS = 2
 LH_TARGET_VIS64, LH_TARGET_DEPTH, LH_TARGET_SCENE_RGBA16F, LH_TARGET_SHADOW, LH_TARGET_DISPLAY_BGRA8 = range(5)
 LH_TEXTURE_RGBA8_SRGB, LH_TEXTURE_RGBA8_UNORM, LH_TEXTURE_BC7_SRGB, LH_TEXTURE_BC1_SRGB = range(4)
 LH_ERR_CAPACITY = -4
+LH_EXCHANGE_PEER, LH_EXCHANGE_NCCL = 0, 1
 LH_VIS_CLEAR = 0xFFFFFFFFFFFFFFFF
 LH_VIS_TRI_BITS = 7
 LH_VIS_MAX_SLOTS = 1 << 25

@@ -39,6 +39,14 @@ FrameParams make_params(LhContext* ctx, int cascade, int set, bool internal_list
     uint64_t end = (uint64_t)first + ctx->instance_count;
     p.instance_first = first;
     p.instance_end = (ctx->instance_count == 0xFFFFFFFFu || end > p.u.num_instances) ? p.u.num_instances : (uint32_t)end;
+    p.shadow_instance_first = p.instance_first;
+    p.shadow_instance_end = p.instance_end;
+    if (ctx->shadow_range_set) {
+        const uint32_t sfirst = ctx->shadow_instance_first < p.u.num_instances ? ctx->shadow_instance_first : p.u.num_instances;
+        const uint64_t send = (uint64_t)sfirst + ctx->shadow_instance_count;
+        p.shadow_instance_first = sfirst;
+        p.shadow_instance_end = send > p.u.num_instances ? p.u.num_instances : (uint32_t)send;
+    }
     p.shadowmap_size = ctx->cfg.shadowmap_size;
     p.flags = ctx->cfg.flags;
     p.max_large = ctx->cfg.max_large_triangles;
@@ -75,6 +83,17 @@ FrameParams make_params(LhContext* ctx, int cascade, int set, bool internal_list
     p.lut = ctx->lut_tex;
     p.resolve_y0 = 0;
     p.resolve_y1 = p.u.window_size[1];
+    p.rank = (uint32_t)ctx->rank;
+    p.nranks = (uint32_t)ctx->nranks;
+    p.slots_per_rank = ctx->slots_per_rank;
+    p.depth_pair = ctx->comm_scratch;
+    if (peer_exchange(ctx)) {
+        p.peer_vis = (const unsigned long long* const*)ctx->peer_vis_dev;
+        p.peer_refs = (const LhMeshletReference* const*)ctx->peer_refs_dev;
+        p.scene_remote = ctx->scene_remote;
+        p.resolve_y0 = ctx->row0;
+        p.resolve_y1 = ctx->row1;
+    }
     return p;
 }
 
@@ -530,6 +549,14 @@ int lh_set_instance_range(LhContext* ctx, uint32_t first, uint32_t count) {
     return LH_OK;
 }
 
+int lh_set_shadow_instance_range(LhContext* ctx, uint32_t first, uint32_t count) {
+    if (!ctx) return LH_ERR_INVALID_ARGUMENT;
+    ctx->shadow_range_set = true;
+    ctx->shadow_instance_first = first;
+    ctx->shadow_instance_count = count;
+    return LH_OK;
+}
+
 int lh_set_shadow_cascade_mask(LhContext* ctx, uint32_t mask) {
     if (!ctx) return LH_ERR_INVALID_ARGUMENT;
     ctx->cascade_mask = mask & 0xFu;
@@ -547,6 +574,7 @@ int lh_frame_begin(LhContext* ctx, const LhUniforms* u) {
     ctx->have_uniforms = true;
     for (int i = 0; i < LH_PASS_COUNT; i++) ctx->pass_recorded[i] = false;
     ctx->raster_kernel_recorded = false;
+    if (int rc = ensure_peer_maps(ctx)) return rc;
     return ensure_instance_tiles(ctx, u->num_instances);
 }
 
@@ -584,13 +612,22 @@ int lh_composite(LhContext* ctx) {
     if (int rc = require_frame(ctx)) return rc;
     if (!ctx->nccl_comm || ctx->nranks <= 1) return LH_OK;
     PassScope scope(ctx, LH_PASS_COMPOSITE);
+    if (peer_exchange(ctx)) {
+        if (int rc = composite_pull(ctx)) return rc;
+        return check_launch(ctx, "composite");
+    }
     return composite_allreduce_min(ctx);
 }
 
 int lh_reduce_depth(LhContext* ctx) {
     if (int rc = require_frame(ctx)) return rc;
     PassScope scope(ctx, LH_PASS_DEPTH_REDUCTION);
-    launch_reduce_depth(ctx, make_params(ctx));
+    if (peer_exchange(ctx)) {
+        // the composite kernel already reduced this rank's rows; what is left is the 8-byte exchange
+        if (int rc = reduce_depth_exchange(ctx)) return rc;
+    } else {
+        launch_reduce_depth(ctx, make_params(ctx));
+    }
     return check_launch(ctx, "reduce_depth");
 }
 
@@ -675,7 +712,10 @@ int lh_render_frame(LhContext* ctx) {
         if ((rc = check_launch(ctx, "shadow cascades"))) return rc;
     }
     if ((rc = lh_shadow_exchange(ctx))) return rc;
-    return lh_resolve(ctx);
+    if ((rc = lh_resolve(ctx))) return rc;
+    // rank 0's frame is complete, and every table a peer reads may be rewritten, once all ranks have resolved their rows
+    if (peer_exchange(ctx)) return frame_barrier(ctx);
+    return LH_OK;
 }
 
 int lh_frame_sync(LhContext* ctx) {

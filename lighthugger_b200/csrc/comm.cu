@@ -3,8 +3,25 @@
 // One process / context per GPU.  Instances are partitioned across ranks; each
 // rank rasterises its partition into a full-resolution packed visibility
 // buffer whose keys carry GLOBAL slots (rank * slots_per_rank + local), so the
-// per-pixel uint64 MIN over ranks is exactly the single-GPU buffer.  Exchange
-// steps, all on the context stream:
+// per-pixel uint64 MIN over ranks is exactly the single-GPU buffer.
+//
+// LH_EXCHANGE_PEER (default).  Every rank maps its peers' key buffer,
+// MeshletReference table and rank 0's colour target through CUDA IPC (NVLink
+// peer memory; the handles travel through one ncclAllGather) and owns the
+// screen rows [row0, row1).  Per frame, on the context stream:
+//   composite        barrier, then ONE kernel: for its rows, 128-bit loads of
+//                    every rank's keys straight from peer memory, uint64 min,
+//                    result stored in place, depth min/max of the rows folded in
+//                    (in place is safe: a rank writes only its own rows of its
+//                    own buffer, and its peers read only THEIR rows of it)
+//   depth bounds     ncclAllReduce(min) of {min, ~max}: 8 bytes, doubles as the
+//                    barrier after which key buffers may be reused
+//   shadow layers    ncclAllReduce(uint32, min) over the 4 depth layers
+//   resolve          rows [row0,row1) only; the winner's MeshletReference is read
+//                    from the owning rank's table through peer memory; the lit
+//                    colour is stored into rank 0's frame through peer memory
+//   frame barrier    4-byte all-reduce: rank 0's frame is complete
+// LH_EXCHANGE_NCCL.  Whole-buffer collectives; every rank resolves everything:
 //   composite        ncclAllReduce(uint64, min) over width*height keys
 //   reference table  ncclAllGather of each rank's MeshletReference section
 //   shadow layers    ncclAllReduce(uint32, min) over the 4 depth layers
@@ -68,9 +85,155 @@ int nccl_fail(LhContext* ctx, const char* what, ncclResult_t r) {
     return fail(ctx, LH_ERR_NCCL, msg.c_str());
 }
 
+// Maps `local` (a cudaMalloc allocation of this rank) on every peer and the peers' counterparts here.  Collective:
+// every rank must call it with its own counterpart at the same point of the stream.
+int peer_map(LhContext* ctx, void* local, LhContext::PeerMap** out) {
+    for (auto& m : ctx->peer_maps)
+        if (m.local == local) {
+            *out = &m;
+            return LH_OK;
+        }
+    const int n = ctx->nranks;
+    cudaIpcMemHandle_t mine;
+    LH_CUDA(ctx, cudaIpcGetMemHandle(&mine, local));
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "handle staging assumes 64-byte IPC handles");
+    uint8_t* stage = (uint8_t*)(ctx->comm_scratch + 16);
+    LH_CUDA(ctx, cudaMemcpyAsync(stage + 64 * (size_t)ctx->rank, &mine, 64, cudaMemcpyHostToDevice, ctx->stream));
+    ncclResult_t r = g_nccl.AllGather(stage + 64 * (size_t)ctx->rank, stage, 64, ncclUint8, (ncclComm_t)ctx->nccl_comm, ctx->stream);
+    if (r != ncclSuccess) return nccl_fail(ctx, "ncclAllGather(ipc handles)", r);
+    std::vector<cudaIpcMemHandle_t> all((size_t)n);
+    LH_CUDA(ctx, cudaMemcpyAsync(all.data(), stage, 64 * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
+    LH_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    LhContext::PeerMap m;
+    m.local = local;
+    m.ptrs.assign((size_t)n, nullptr);
+    for (int q = 0; q < n; q++) {
+        if (q == ctx->rank) {
+            m.ptrs[q] = local;
+            continue;
+        }
+        cudaError_t e = cudaIpcOpenMemHandle(&m.ptrs[q], all[q], cudaIpcMemLazyEnablePeerAccess);
+        if (e != cudaSuccess) {
+            for (int k = 0; k < q; k++)
+                if (k != ctx->rank && m.ptrs[k]) cudaIpcCloseMemHandle(m.ptrs[k]);
+            return fail(ctx, LH_ERR_CUDA, "cudaIpcOpenMemHandle (peer buffer; LH_EXCHANGE_NCCL does not need peer memory)", e);
+        }
+    }
+    LH_CUDA(ctx, cudaMalloc(&m.table_dev, sizeof(void*) * (size_t)n));
+    LH_CUDA(ctx, cudaMemcpy(m.table_dev, m.ptrs.data(), sizeof(void*) * (size_t)n, cudaMemcpyHostToDevice));
+    ctx->peer_maps.push_back(std::move(m));
+    *out = &ctx->peer_maps.back();
+    return LH_OK;
+}
+
+void peer_unmap_all(LhContext* ctx) {
+    for (auto& m : ctx->peer_maps) {
+        for (size_t q = 0; q < m.ptrs.size(); q++)
+            if ((int)q != ctx->rank && m.ptrs[q]) cudaIpcCloseMemHandle(m.ptrs[q]);
+        cudaFree(m.table_dev);
+    }
+    ctx->peer_maps.clear();
+}
+
+// A collective on 4 bytes: nothing after it on any rank's stream starts before everything ahead of it on every rank's
+// stream has finished.
+int stream_barrier(LhContext* ctx) {
+    ncclResult_t r = g_nccl.AllReduce(ctx->comm_scratch + 2, ctx->comm_scratch + 2, 1, ncclUint32, ncclMin, (ncclComm_t)ctx->nccl_comm, ctx->stream);
+    if (r != ncclSuccess) return nccl_fail(ctx, "ncclAllReduce(barrier)", r);
+    return LH_OK;
+}
+
+__global__ void depth_pair_init_kernel(uint32_t* pair) {
+    if (threadIdx.x < 2) pair[threadIdx.x] = 0xFFFFFFFFu;   // min identity for both {min, ~max}
+}
+
+__global__ void depth_pair_store_kernel(const __grid_constant__ FrameParams P) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        LhMiscStorage* misc = (LhMiscStorage*)P.u.misc_storage;
+        misc->min_depth = P.depth_pair[0];     // 0xFFFFFFFF / 0 when nothing was drawn, like read_depth.glsl
+        misc->max_depth = ~P.depth_pair[1];
+    }
+}
+
+// The sort-last composite of this rank's rows: min over every rank's keys, read through peer memory.  Two pixels per
+// 128-bit load; the loads of all ranks are issued before the first min so that up to nranks NVLink round trips overlap.
+constexpr int kMaxRanks = 16;
+__global__ void __launch_bounds__(256) composite_pull_kernel(const __grid_constant__ FrameParams P, uint64_t first_pair, uint64_t pairs) {
+    const uint32_t n = P.nranks, self = P.rank;
+    uint32_t mn = 0xFFFFFFFFu, inv_mx = 0xFFFFFFFFu;
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < pairs; i += stride) {
+        ulonglong2 v[kMaxRanks];
+#pragma unroll
+        for (uint32_t q = 0; q < (uint32_t)kMaxRanks; q++)
+            if (q < n) v[q] = __ldcg((const ulonglong2*)P.peer_vis[q] + first_pair + i);
+        ulonglong2 best = v[0];
+#pragma unroll
+        for (uint32_t q = 1; q < (uint32_t)kMaxRanks; q++)
+            if (q < n) {
+                best.x = min(best.x, v[q].x);
+                best.y = min(best.y, v[q].y);
+            }
+        ((ulonglong2*)P.peer_vis[self])[first_pair + i] = best;
+        const uint32_t d0 = ~(uint32_t)(best.x >> 32), d1 = ~(uint32_t)(best.y >> 32);
+        if (d0) mn = min(mn, d0);                 // min_if_not_zero, read_depth.glsl:3-7
+        if (d1) mn = min(mn, d1);
+        inv_mx = min(inv_mx, min(~d0, ~d1));
+    }
+    mn = __reduce_min_sync(0xFFFFFFFFu, mn);
+    inv_mx = __reduce_min_sync(0xFFFFFFFFu, inv_mx);
+    if ((threadIdx.x & 31) == 0) {
+        if (mn != 0xFFFFFFFFu) atomicMin(P.depth_pair, mn);
+        if (inv_mx != 0xFFFFFFFFu) atomicMin(P.depth_pair + 1, inv_mx);
+    }
+}
+
 }  // namespace
 
 namespace lh {
+
+bool peer_exchange(const LhContext* ctx) { return ctx->nccl_comm && ctx->nranks > 1 && ctx->exchange == LH_EXCHANGE_PEER; }
+
+// Called by lh_frame_begin.  The first frame (and any frame after the host moved its MeshletReference buffer or
+// resized the targets -- which all ranks must do together) exchanges IPC handles; afterwards this is three lookups.
+int ensure_peer_maps(LhContext* ctx) {
+    ctx->peer_vis_dev = ctx->peer_refs_dev = nullptr;
+    ctx->scene_remote = nullptr;
+    if (!peer_exchange(ctx)) return LH_OK;
+    LhContext::PeerMap* m = nullptr;
+    if (int rc = peer_map(ctx, ctx->vis, &m)) return rc;
+    ctx->peer_vis_dev = m->table_dev;
+    if (int rc = peer_map(ctx, (void*)(uintptr_t)ctx->uniforms.meshlet_references, &m)) return rc;
+    ctx->peer_refs_dev = m->table_dev;
+    if (int rc = peer_map(ctx, ctx->scene, &m)) return rc;
+    ctx->scene_remote = ctx->rank == 0 ? nullptr : m->ptrs[0];
+    return LH_OK;
+}
+
+int composite_pull(LhContext* ctx) {
+    if (ctx->nranks > kMaxRanks) return fail(ctx, LH_ERR_UNSUPPORTED, "LH_EXCHANGE_PEER supports at most 16 ranks");
+    FrameParams p = make_params(ctx);
+    depth_pair_init_kernel<<<1, 32, 0, ctx->stream>>>(ctx->comm_scratch); ctx->launches++;
+    if (int rc = stream_barrier(ctx)) return rc;   // every rank has rasterised its instances
+    const uint64_t W = ctx->cfg.width;
+    const uint64_t first = (uint64_t)ctx->row0 * W, count = (uint64_t)(ctx->row1 - ctx->row0) * W;
+    // row slices hold an even number of rows (lh_comm_init), so they are whole 16-byte key pairs unless both the
+    // width and the last slice's height are odd
+    if ((first | count) & 1ull) return fail(ctx, LH_ERR_UNSUPPORTED, "LH_EXCHANGE_PEER needs an even number of pixels per row slice");
+    if (count) {
+        composite_pull_kernel<<<ctx->num_sms * 8, 256, 0, ctx->stream>>>(p, first / 2, count / 2); ctx->launches++;
+    }
+    return LH_OK;
+}
+
+int reduce_depth_exchange(LhContext* ctx) {
+    ncclResult_t r = g_nccl.AllReduce(ctx->comm_scratch, ctx->comm_scratch, 2, ncclUint32, ncclMin, (ncclComm_t)ctx->nccl_comm, ctx->stream);
+    if (r != ncclSuccess) return nccl_fail(ctx, "ncclAllReduce(depth bounds)", r);
+    depth_pair_store_kernel<<<1, 32, 0, ctx->stream>>>(make_params(ctx)); ctx->launches++;
+    return LH_OK;
+}
+
+int frame_barrier(LhContext* ctx) { return stream_barrier(ctx); }
 
 int composite_allreduce_min(LhContext* ctx) {
     ncclComm_t comm = (ncclComm_t)ctx->nccl_comm;
@@ -115,12 +278,33 @@ int lh_comm_init(LhContext* ctx, int rank, int nranks, const void* id128) {
     ctx->nranks = nranks;
     ctx->slots_per_rank = (uint32_t)per_rank;
     ctx->slot_offset = (uint32_t)(per_rank * rank);
-    if (nranks > 1) {
-        cudaFree(ctx->gathered_refs);
-        ctx->gathered_refs = nullptr;
-        LH_CUDA(ctx, cudaMalloc(&ctx->gathered_refs, per_rank * nranks * sizeof(LhMeshletReference)));
-        LH_CUDA(ctx, cudaMemset(ctx->gathered_refs, 0, per_rank * nranks * sizeof(LhMeshletReference)));
+    cudaFree(ctx->comm_scratch);
+    ctx->comm_scratch = nullptr;
+    LH_CUDA(ctx, cudaMalloc(&ctx->comm_scratch, 64 + 64 * (size_t)nranks));
+    LH_CUDA(ctx, cudaMemset(ctx->comm_scratch, 0, 64 + 64 * (size_t)nranks));
+    // screen rows of this rank: even row counts so that a slice is a whole number of 16-byte key pairs
+    const uint32_t H = ctx->cfg.height, per = ((H + nranks - 1) / nranks + 1) & ~1u;
+    ctx->row0 = per * rank < H ? per * rank : H;
+    ctx->row1 = ctx->row0 + per < H ? ctx->row0 + per : H;
+    return LH_OK;
+}
+
+int lh_comm_set_exchange(LhContext* ctx, int mode) {
+    if (!ctx || (mode != LH_EXCHANGE_PEER && mode != LH_EXCHANGE_NCCL)) return LH_ERR_INVALID_ARGUMENT;
+    ctx->exchange = mode;
+    if (mode == LH_EXCHANGE_NCCL && ctx->nranks > 1 && !ctx->gathered_refs) {
+        const size_t bytes = (size_t)ctx->slots_per_rank * ctx->nranks * sizeof(LhMeshletReference);
+        LH_CUDA(ctx, cudaMalloc(&ctx->gathered_refs, bytes));
+        LH_CUDA(ctx, cudaMemset(ctx->gathered_refs, 0, bytes));
     }
+    return LH_OK;
+}
+
+int lh_comm_rows(LhContext* ctx, uint32_t* y0, uint32_t* y1) {
+    if (!ctx) return LH_ERR_INVALID_ARGUMENT;
+    const bool split = peer_exchange(ctx);
+    if (y0) *y0 = split ? ctx->row0 : 0u;
+    if (y1) *y1 = split ? ctx->row1 : ctx->cfg.height;
     return LH_OK;
 }
 
@@ -128,8 +312,13 @@ int lh_comm_destroy(LhContext* ctx) {
     if (!ctx) return LH_ERR_INVALID_ARGUMENT;
     if (ctx->nccl_comm && g_nccl.CommDestroy) {
         cudaStreamSynchronize(ctx->stream);
+        peer_unmap_all(ctx);
         g_nccl.CommDestroy((ncclComm_t)ctx->nccl_comm);
     }
+    cudaFree(ctx->comm_scratch);
+    ctx->comm_scratch = nullptr;
+    cudaFree(ctx->gathered_refs);
+    ctx->gathered_refs = nullptr;
     ctx->nccl_comm = nullptr;
     ctx->rank = 0;
     ctx->nranks = 1;

@@ -173,8 +173,8 @@ __global__ void __launch_bounds__(kInstanceTile) cull_instances_kernel(const __g
 
     const uint32_t tile = blockIdx.x, cascade = SHADOWS ? blockIdx.y : 0u;
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const uint32_t first = P.instance_first + tile * kInstanceTile;
-    const uint32_t n_here = min(kInstanceTile, P.instance_end - first);
+    const uint32_t first = (SHADOWS ? P.shadow_instance_first : P.instance_first) + tile * kInstanceTile;
+    const uint32_t n_here = min(kInstanceTile, (SHADOWS ? P.shadow_instance_end : P.instance_end) - first);
 
     // coalesced 128-bit loads of the tile's Instance records
     const int4* src = (const int4*)((const LhInstance*)P.u.instances + first);
@@ -499,7 +499,7 @@ void launch_reset(LhContext* ctx, const FrameParams& p) { reset_kernel<<<1, 32, 
 void launch_reset_counters(LhContext* ctx, const FrameParams& p) { reset_counters_kernel<<<1, 32, 0, ctx->stream>>>(p); ctx->launches++; }
 
 void launch_cull_instances(LhContext* ctx, const FrameParams& p, bool shadows) {
-    uint32_t n = p.instance_end - p.instance_first;
+    uint32_t n = shadows ? p.shadow_instance_end - p.shadow_instance_first : p.instance_end - p.instance_first;
     if (n == 0) return;
     uint32_t tiles = (n + kInstanceTile - 1) / kInstanceTile;
     if (shadows) cull_instances_kernel<true><<<dim3(tiles, 4), kInstanceTile, 0, ctx->stream>>>(p, ctx->instance_tiles_per_sector);

@@ -96,6 +96,7 @@ struct FrameParams {
     LhUniforms u;
     uint32_t max_instances, max_opaque, max_alpha;
     uint32_t instance_first, instance_end;   // sort-last partition
+    uint32_t shadow_instance_first, shadow_instance_end;   // ... of the cascades (lh_set_shadow_instance_range)
     uint32_t shadowmap_size;
     uint32_t flags;
     uint32_t max_large;
@@ -118,6 +119,12 @@ struct FrameParams {
     const uint4* tex_dims;                   // per texture slot: width, height, mip levels, 0
     uint32_t slot_offset;                    // sort-last: global slot of this rank's local slot 0
     const LhMeshletReference* resolve_refs;  // table indexed by GLOBAL slot (== u.meshlet_references on one GPU)
+    // peer exchange (multi-GPU, LH_EXCHANGE_PEER): device arrays of one pointer per rank into the peers' memory
+    const LhMeshletReference* const* peer_refs;   // rank q's table, indexed by q's LOCAL slot; nullptr: use resolve_refs
+    const unsigned long long* const* peer_vis;    // rank q's key buffer
+    uint32_t slots_per_rank, rank, nranks;
+    void* scene_remote;                      // rank 0's RGBA16F target mapped here (ranks != 0), else nullptr
+    uint32_t* depth_pair;                    // {min depth bits, ~max depth bits} of this rank's rows, then of the frame
     void* scene;                             // RGBA16F target
     void* display;                           // BGRA8 target
     cudaTextureObject_t sky, lut;
@@ -134,6 +141,8 @@ struct LhContext {
     LhUniforms uniforms{};
     bool have_uniforms = false;
     uint32_t instance_first = 0, instance_count = 0xFFFFFFFFu;
+    bool shadow_range_set = false;
+    uint32_t shadow_instance_first = 0, shadow_instance_count = 0xFFFFFFFFu;
     uint32_t cascade_mask = 0xF;
 
     // targets
@@ -193,7 +202,20 @@ struct LhContext {
     int rank = 0, nranks = 1;
     uint32_t slot_offset = 0;          // rank * slots_per_rank
     uint32_t slots_per_rank = 0;
-    void* gathered_refs = nullptr;     // all ranks' meshlet-reference tables, rank-major (multi-GPU only)
+    void* gathered_refs = nullptr;     // all ranks' meshlet-reference tables, rank-major (LH_EXCHANGE_NCCL only)
+    // LH_EXCHANGE_PEER: buffers of the peers mapped through CUDA IPC (comm.cu)
+    int exchange = LH_EXCHANGE_PEER;
+    struct PeerMap {
+        void* local = nullptr;             // this rank's buffer
+        std::vector<void*> ptrs;           // per rank: the buffer as seen from this device (own entry == local)
+        void** table_dev = nullptr;        // the same, on the device
+    };
+    std::vector<PeerMap> peer_maps;
+    uint32_t* comm_scratch = nullptr;      // [0..1] depth pair, [2] barrier word, [16..] handle staging
+    void** peer_vis_dev = nullptr;         // device tables of the current frame (owned by peer_maps)
+    void** peer_refs_dev = nullptr;
+    void* scene_remote = nullptr;
+    uint32_t row0 = 0, row1 = 0;           // screen rows this rank composites and resolves
     int num_sms = 148;
 
     std::vector<void*> buffers;
@@ -219,6 +241,11 @@ void launch_gather_stats(LhContext* ctx, const FrameParams& p, LhFrameStats* dst
 void launch_fill_u64(LhContext* ctx, unsigned long long* dst, uint64_t count, unsigned long long value);
 void launch_fill_u32(LhContext* ctx, uint32_t* dst, uint64_t count, uint32_t value, cudaStream_t stream = nullptr);
 int composite_allreduce_min(LhContext* ctx);
+int composite_pull(LhContext* ctx);          // LH_EXCHANGE_PEER: barrier + pull-min kernel with the depth bounds folded in
+int reduce_depth_exchange(LhContext* ctx);   // ... the frame's depth bounds from the ranks' row bounds
+int frame_barrier(LhContext* ctx);           // every rank has finished its part of the frame
+bool peer_exchange(const LhContext* ctx);    // multi-GPU and LH_EXCHANGE_PEER
+int ensure_peer_maps(LhContext* ctx);        // maps what the frame needs of the peers (collective the first time)
 extern "C" int lh_shadow_exchange(LhContext* ctx);
 
 }  // namespace lh

@@ -184,12 +184,19 @@ __device__ float4 sample_texture_grad(cudaTextureObject_t t, uint4 dims, float u
     return make_float4(acc.x * inv, acc.y * inv, acc.z * inv, acc.w * inv);
 }
 
-__device__ __forceinline__ void store_rgba16f(void* scene, size_t pixel, float r, float g, float b, float a) {
+// scene_remote: rank 0's target in peer memory (sort-last ranks != 0 deliver their rows there; a warp row is 64 B)
+__device__ __forceinline__ void store_rgba16f(void* scene, void* scene_remote, size_t pixel, float r, float g, float b, float a) {
     __half2 lo = __floats2half2_rn(r, g), hi = __floats2half2_rn(b, a);
     uint2 packed;
     packed.x = *reinterpret_cast<uint32_t*>(&lo);
     packed.y = *reinterpret_cast<uint32_t*>(&hi);
     reinterpret_cast<uint2*>(scene)[pixel] = packed;
+    if (scene_remote) reinterpret_cast<uint2*>(scene_remote)[pixel] = packed;
+}
+
+// a MeshletReference, possibly in a peer's memory (which the read-only cache path must not serve)
+__device__ __forceinline__ unsigned long long owner_load(const LhMeshletReference* p) {
+    return __ldcg((const unsigned long long*)p);
 }
 
 __global__ void __launch_bounds__(256) resolve_kernel(const __grid_constant__ FrameParams P) {
@@ -208,11 +215,17 @@ __global__ void __launch_bounds__(256) resolve_kernel(const __grid_constant__ Fr
         F3 local = normalize(F3{un.x, un.y, un.z});
         float4 ray = mul4(&P.u.view_inverse.m[0][0], local.x, local.y, local.z, 0.0f);
         float4 s = P.sky ? texCubemapLod<float4>(P.sky, ray.x, ray.y, ray.z, 0.0f) : make_float4(0, 0, 0, 0);
-        store_rgba16f(P.scene, pixel, s.x * 8.0f, s.y * 8.0f, s.z * 8.0f, 1.0f);
+        store_rgba16f(P.scene, P.scene_remote, pixel, s.x * 8.0f, s.y * 8.0f, s.z * 8.0f, 1.0f);
         return;
     }
     const uint32_t slot = lh_vis_slot(key), tri = lh_vis_tri(key);
-    const unsigned long long ref = __ldg((const unsigned long long*)(P.resolve_refs + slot));
+    // sort-last: the slot is global (rank * slots_per_rank + local) and the reference lives in the owning rank's table
+    const LhMeshletReference* ref_at = P.resolve_refs + slot;
+    if (P.peer_refs) {
+        const uint32_t owner = slot / P.slots_per_rank;
+        ref_at = P.peer_refs[owner] + (slot - owner * P.slots_per_rank);
+    }
+    const unsigned long long ref = owner_load(ref_at);
     const LhInstance* inst = (const LhInstance*)P.u.instances + (uint32_t)ref;
     const uint32_t meshlet_index = (uint32_t)(ref >> 32) & 0xFFFFu;
     float T[16];
@@ -324,7 +337,7 @@ __global__ void __launch_bounds__(256) resolve_kernel(const __grid_constant__ Fr
     const F3 sun = brdf(view_vec, F3{P.u.sun_dir[0], P.u.sun_dir[1], P.u.sun_dir[2]}, normal, roughness, metallic, base, alpha);
     const float sun_intensity = kPi * shadow_sum;
     const float dm = 1.0f - metallic;
-    store_rgba16f(P.scene, pixel, sun.x * sun_intensity + amb * dm * base.x, sun.y * sun_intensity + amb * dm * base.y,
+    store_rgba16f(P.scene, P.scene_remote, pixel, sun.x * sun_intensity + amb * dm * base.x, sun.y * sun_intensity + amb * dm * base.y,
                   sun.z * sun_intensity + amb * dm * base.z, 1.0f);
 }
 

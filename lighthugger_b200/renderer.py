@@ -20,7 +20,7 @@ EXPORTS = [
     "lh_cull_instances_shadows", "lh_shadow_cascade", "lh_resolve", "lh_display_transform", "lh_render_frame",
     "lh_frame_sync", "lh_render_frame_host", "lh_get_frame_stats", "lh_get_target", "lh_get_timings",
     "lh_get_target_address", "lh_get_launch_count", "lh_timer_start", "lh_timer_stop", "lh_flush_l2", "lh_comm_unique_id", "lh_comm_init",
-    "lh_comm_destroy", "lh_comm_info", "lh_set_display_lut", "lh_set_shadow_cascade_mask", "lh_shadow_exchange",
+    "lh_comm_destroy", "lh_comm_info", "lh_comm_set_exchange", "lh_comm_rows", "lh_set_shadow_instance_range", "lh_set_display_lut", "lh_set_shadow_cascade_mask", "lh_shadow_exchange",
 ]
 
 
@@ -61,6 +61,9 @@ def cuda_lib():
         lib.lh_targets_resize.argtypes = [vp, u32, u32]
         lib.lh_set_instance_range.argtypes = [vp, u32, u32]
         lib.lh_set_shadow_cascade_mask.argtypes = [vp, u32]
+        lib.lh_set_shadow_instance_range.argtypes = [vp, u32, u32]
+        lib.lh_comm_set_exchange.argtypes = [vp, C.c_int]
+        lib.lh_comm_rows.argtypes = [vp, C.POINTER(u32), C.POINTER(u32)]
         lib.lh_frame_begin.argtypes = [vp, C.POINTER(S.LhUniforms)]
         for name in ("lh_reset", "lh_cull_instances", "lh_cull_meshlets", "lh_raster_visbuffer", "lh_composite",
                      "lh_reduce_depth", "lh_generate_shadow_matrices", "lh_cull_instances_shadows", "lh_resolve",
@@ -169,6 +172,17 @@ class Context:
 
     def set_instance_range(self, first, count):
         self._check(self.lib.lh_set_instance_range(self.handle, first, count))
+
+    def set_shadow_instance_range(self, first, count):
+        self._check(self.lib.lh_set_shadow_instance_range(self.handle, first, count))
+
+    def comm_set_exchange(self, mode):
+        self._check(self.lib.lh_comm_set_exchange(self.handle, mode))
+
+    def comm_rows(self):
+        y0, y1 = C.c_uint32(0), C.c_uint32(0)
+        self._check(self.lib.lh_comm_rows(self.handle, C.byref(y0), C.byref(y1)))
+        return y0.value, y1.value
 
     def set_shadow_cascade_mask(self, mask):
         self._check(self.lib.lh_set_shadow_cascade_mask(self.handle, mask))

@@ -11,14 +11,20 @@ def instance_range(num_instances, rank, world):
     return first, end - first
 
 
-def capacities(scene, world):
+def capacities(scene, world, split="instances"):
     """Per-rank list capacities.  Keys carry rank * (max_opaque + max_alpha) + local slot in a 25-bit field, so the
-    per-rank share shrinks with the world size; every rank still culls against the full instance list capacity."""
+    per-rank share shrinks with the world size; every rank still culls against the full instance list capacity.
+    With split == "cascades" a rank's cascade lists hold meshlets of ALL instances, so the opaque capacity is the whole
+    scene's meshlet count where the slot field allows it (a cascade list that still overflows is reported as
+    LH_ERR_CAPACITY at run time)."""
     if world == 1:
         return scene.default_capacities()
     per_rank = -(-scene.total_meshlets // world)
-    caps = S.LhCapacities(max_instances=scene.num_instances, max_opaque_draws=per_rank + 1024,
-                          max_alpha_clip_draws=max(1024, per_rank // 8))
+    alpha = max(1024, per_rank // 8)
+    opaque = per_rank + 1024
+    if split == "cascades":
+        opaque = max(opaque, min(scene.total_meshlets + 1024, S.LH_VIS_MAX_SLOTS // world - alpha))
+    caps = S.LhCapacities(max_instances=scene.num_instances, max_opaque_draws=opaque, max_alpha_clip_draws=alpha)
     if (caps.max_opaque_draws + caps.max_alpha_clip_draws) * world > S.LH_VIS_MAX_SLOTS:
         raise ValueError("world * per-rank slots exceeds the 25-bit slot field of the visibility key")
     return caps
@@ -29,12 +35,29 @@ def slot_offset(caps, rank):
     return rank * (caps.max_opaque_draws + caps.max_alpha_clip_draws)
 
 
-def cascade_mask(rank, world):
-    """Shadow cascades rendered by `rank`: one cascade per GPU at 4 GPUs, two each at 2; at 8 GPUs a cascade is shared by
-    the two ranks r and r + 4, which split its instances (each rank rasterises its own instance range) and the layers
-    are merged by the uint32-min exchange."""
-    g = min(world, 4)
-    return sum(1 << c for c in range(4) if c % g == rank % g)
+def shadow_plan(num_instances, rank, world, split="instances"):
+    """(cascade mask, first instance, instance count) of the shadow work of `rank`.  Over the ranks the (cascade,
+    instance) pairs are covered exactly once, so the uint32-min merge of the layers equals the single-GPU layers.
+      "instances": every rank draws all four cascades of its own instance range (even load whatever the cascade sizes);
+      "cascades":  one cascade per GPU over ALL instances (BASELINE config 3: 4 GPUs); 2 GPUs take two cascades each, and
+                   with more than 4 GPUs the ranks c, c + 4, ... split cascade c's instances between them."""
+    if split == "instances" or world == 1:
+        first, count = instance_range(num_instances, rank, world)
+        return 0xF, first, count
+    if split != "cascades":
+        raise ValueError(f"unknown shadow split {split!r}")
+    groups = min(world, 4)                       # ranks with equal rank % groups share their cascades
+    mask = sum(1 << c for c in range(4) if c % groups == rank % groups)
+    members = [r for r in range(world) if r % groups == rank % groups]
+    first, count = instance_range(num_instances, members.index(rank), len(members))
+    return mask, first, count
+
+
+def row_range(height, rank, world):
+    """Screen rows [y0, y1) a rank composites and resolves (what lh_comm_init derives): even-sized slices."""
+    per = ((height + world - 1) // world + 1) & ~1
+    y0 = min(per * rank, height)
+    return y0, min(y0 + per, height)
 
 
 def to_ordered_int64(keys_u64):

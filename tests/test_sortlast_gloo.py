@@ -24,7 +24,7 @@ def _worker(rank, world, port, out_dir):
     try:
         sc = Scene.preset("tiny")
         first, count = sortlast.instance_range(sc.num_instances, rank, world)
-        caps = sortlast.capacities(sc, world)
+        caps = sortlast.capacities(sc, world, "cascades")
         o = make_oracle(sc, caps=caps, instance_range=(first, count))
         o.reset(); o.cull_instances(); o.cull_meshlets(); o.raster_visbuffer()
         n_local = sum(o.draw_counts())
@@ -43,9 +43,27 @@ def _worker(rank, world, port, out_dir):
         gathered = [torch.zeros_like(mine) for _ in range(world)]
         dist.all_gather(gathered, mine)
         table = torch.cat(gathered).numpy()
+        # shadows: depth bounds and cascade matrices from the COMPOSITED frame (every rank derives the same ones), then
+        # each rank draws its share of the (cascade, instance) pairs and the layers are merged with a MIN
+        shadows = {}
+        o.vis[:] = composite
+        o.reduce_depth()
+        for split in ("instances", "cascades"):
+            o.generate_shadow_matrices()   # also resets the list counters (generate_shadow_matrices.glsl ends in reset_counters)
+            mask, sfirst, scount = sortlast.shadow_plan(sc.num_instances, rank, world, split)
+            o.cfg.instance_first, o.cfg.instance_count = sfirst, scount
+            o.shadow[:] = 1.0
+            o.cull_instances_shadows()
+            for c in range(4):
+                if mask >> c & 1:
+                    o.shadow_cascade(c)
+            layers = torch.from_numpy(o.shadow.view(np.int32).copy())   # depths in [0, 1]: bits order like values
+            dist.all_reduce(layers, op=dist.ReduceOp.MIN)
+            shadows[split] = layers.numpy().view(np.float32)
         if rank == 0:
-            np.savez(os.path.join(out_dir, "composite.npz"), vis=composite, table=table, per_rank=per_rank,
-                     masks=np.array([sortlast.cascade_mask(r, world) for r in range(world)]), n_local=n_local)
+            np.savez(os.path.join(out_dir, "composite.npz"), vis=composite, table=table, per_rank=per_rank, n_local=n_local,
+                     misc=np.frombuffer(bytes(o.misc()), np.uint8), shadow_instances=shadows["instances"],
+                     shadow_cascades=shadows["cascades"])
     finally:
         dist.destroy_process_group()
 
@@ -73,8 +91,13 @@ def test_two_rank_composite_equals_single_process_frame(tmp_path):
     table = got["table"]
     have = np.stack([table[sg[cov], 0], table[sg[cov], 1], tg[cov]], 1)
     assert np.array_equal(have, want), "(instance, meshlet, triangle) under the composited keys differ"
-    # the plan itself
-    assert sorted(sum(([c for c in range(4) if m >> c & 1] for m in got["masks"]), [])) == [0, 1, 2, 3]
+    # depth bounds + cascade matrices from the composite, and the merged shadow layers under both shadow splits
+    whole.reduce_depth(); whole.generate_shadow_matrices(); whole.cull_instances_shadows()
+    for c in range(4):
+        whole.shadow_cascade(c)
+    assert bytes(got["misc"]) == bytes(whole.misc())
+    for split in ("instances", "cascades"):
+        assert np.array_equal(got["shadow_" + split].view(np.uint32), whole.shadow.view(np.uint32)), split
 
 
 def test_plan_tiles_instances_and_cascades():
@@ -85,8 +108,17 @@ def test_plan_tiles_instances_and_cascades():
             ranges = [sortlast.instance_range(n, r, world) for r in range(world)]
             assert ranges[0][0] == 0 and sum(c for _, c in ranges) == n
             assert all(ranges[r][0] + ranges[r][1] == ranges[r + 1][0] for r in range(world - 1))
-        cover = [0] * 4
-        for r in range(world):
-            for c in range(4):
-                cover[c] += sortlast.cascade_mask(r, world) >> c & 1
-        assert all(k == max(1, world // 4) for k in cover), (world, cover)
+            # every (cascade, instance) pair is drawn by exactly one rank, under both shadow splits
+            for split in ("instances", "cascades"):
+                cover = np.zeros((4, n), np.int32)
+                for r in range(world):
+                    mask, first, count = sortlast.shadow_plan(n, r, world, split)
+                    for c in range(4):
+                        if mask >> c & 1:
+                            cover[c, first:first + count] += 1
+                assert np.all(cover == 1), (world, n, split)
+        if world == 4:
+            assert [sortlast.shadow_plan(100, r, 4, "cascades") for r in range(4)] == [(1 << r, 0, 100) for r in range(4)]
+        for h in (1, 2, 1080, 2160, 4320, 37):
+            rows = [sortlast.row_range(h, r, world) for r in range(world)]
+            assert rows[0][0] == 0 and rows[-1][1] == h and all(rows[r][1] == rows[r + 1][0] for r in range(world - 1))
