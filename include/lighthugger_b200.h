@@ -177,6 +177,13 @@ LH_API int lh_targets_resize(LhContext* ctx, uint32_t width, uint32_t height);
 /* ---- sort-last partition (new; no reference counterpart).
  * The context culls and rasterises instances [first, first+count) only. ---- */
 LH_API int lh_set_instance_range(LhContext* ctx, uint32_t first, uint32_t count);
+/* Sort-last ownership by SCREEN STRIPES instead of (or on top of) an index range: the view is cut into `stripes`
+ * vertical stripes and an instance belongs to the context whose `index` equals (stripe of its bounding-sphere centre)
+ * % `count`.  view 0: the main view (stripes of the camera image); view 1: the cascades (stripes of each cascade's
+ * light-space square).  Neighbouring instances then land on the same GPU, so each GPU's own geometry keeps occluding
+ * itself (an index range hands every GPU a sparse copy of the whole scene whose hidden layers all get rasterised);
+ * interleaving several stripes per GPU evens the load.  stripes == 0 turns it off (default). */
+LH_API int lh_set_instance_stripes(LhContext* ctx, int view, uint32_t stripes, uint32_t index, uint32_t count);
 /* cascades this context renders in lh_render_frame (bit c = cascade c; default 0xF).
  * "One cascade per GPU" = mask 1 << rank; the layers are merged by lh_shadow_exchange. */
 LH_API int lh_set_shadow_cascade_mask(LhContext* ctx, uint32_t mask);

@@ -47,6 +47,11 @@ FrameParams make_params(LhContext* ctx, int cascade, int set, bool internal_list
         p.shadow_instance_first = sfirst;
         p.shadow_instance_end = send > p.u.num_instances ? p.u.num_instances : (uint32_t)send;
     }
+    for (int v = 0; v < 2; v++) {
+        p.stripes[v] = ctx->stripes[v];
+        p.stripe_index[v] = ctx->stripe_index[v];
+        p.stripe_count[v] = ctx->stripe_count[v];
+    }
     p.shadowmap_size = ctx->cfg.shadowmap_size;
     p.flags = ctx->cfg.flags;
     p.max_large = ctx->cfg.max_large_triangles;
@@ -58,6 +63,7 @@ FrameParams make_params(LhContext* ctx, int cascade, int set, bool internal_list
     p.large_queue = sc.large_queue;
     p.meshlet_bounds = sc.meshlet_bounds;
     p.raster_queue = sc.raster_queue;
+    p.depth_keys = sc.depth_keys;
     p.depth_hist = sc.depth_hist;
     p.hiz = sc.hiz;
     // a cascade's lists live in section 1 of the host-visible buffers (MESHLET_INDICES_BUFFER_SECTION_OFFSET), unless it
@@ -171,6 +177,7 @@ int alloc_pass_scratch(LhContext* ctx, int set) {
     LH_CUDA(ctx, cudaMalloc(&sc.large_queue, (size_t)(ctx->cfg.max_large_triangles ? ctx->cfg.max_large_triangles : 1) * 8));
     LH_CUDA(ctx, cudaMalloc(&sc.meshlet_bounds, (draws ? draws : 1) * 16));
     LH_CUDA(ctx, cudaMalloc(&sc.raster_queue, (draws ? draws : 1) * 4));
+    LH_CUDA(ctx, cudaMalloc(&sc.depth_keys, (draws ? draws : 1) * 4));
     LH_CUDA(ctx, cudaMalloc(&sc.depth_hist, 8192 * 4));
     LH_CUDA(ctx, cudaMemset(sc.depth_hist, 0, 8192 * 4));
     // two hierarchical-Z levels (4x4 and 16x16 pixel tiles): the main view only ever uses set 0
@@ -194,7 +201,7 @@ int alloc_pass_scratch(LhContext* ctx, int set) {
 void free_pass_scratch(LhContext* ctx) {
     for (auto& sc : ctx->scratch) {
         cudaFree(sc.pass); cudaFree(sc.meshlet_tiles); cudaFree(sc.large_queue); cudaFree(sc.meshlet_bounds);
-        cudaFree(sc.raster_queue); cudaFree(sc.depth_hist); cudaFree(sc.hiz); cudaFree(sc.draw_calls); cudaFree(sc.refs);
+        cudaFree(sc.raster_queue); cudaFree(sc.depth_keys); cudaFree(sc.depth_hist); cudaFree(sc.hiz); cudaFree(sc.draw_calls); cudaFree(sc.refs);
         sc = LhContext::PassScratch{};
     }
 }
@@ -554,6 +561,14 @@ int lh_set_shadow_instance_range(LhContext* ctx, uint32_t first, uint32_t count)
     ctx->shadow_range_set = true;
     ctx->shadow_instance_first = first;
     ctx->shadow_instance_count = count;
+    return LH_OK;
+}
+
+int lh_set_instance_stripes(LhContext* ctx, int view, uint32_t stripes, uint32_t index, uint32_t count) {
+    if (!ctx || view < 0 || view > 1 || (stripes && (count == 0 || index >= count))) return LH_ERR_INVALID_ARGUMENT;
+    ctx->stripes[view] = stripes;
+    ctx->stripe_index[view] = index;
+    ctx->stripe_count[view] = count ? count : 1;
     return LH_OK;
 }
 

@@ -80,11 +80,11 @@ struct PassState {
     uint32_t cull_ticket, cull_done;   // meshlet cull: next tile, CTAs finished (self-cleaning)
     uint32_t large_count;              // entries in the deferred-triangle queue
     uint32_t deferred_begin, deferred_end;   // queue range the current deferred launch processes
-    uint32_t raster_ticket;            // next unclaimed entry of the raster queue
     uint32_t queue_count;              // entries appended to the raster queue so far
-    uint32_t band_begin, band_end;     // queue range of the band being rasterised (band_begin already names the next band's start)
-    uint32_t band_first;               // first queue entry of the band being rasterised
+    uint32_t band_mark[9];             // queue_count when band b's rasterisation began: band b owns [band_mark[b], band_mark[b+1])
+    uint32_t band_ticket[8];           // next unclaimed entry of band b's range, relative to band_mark[b]
     uint32_t band_key[8];              // exclusive upper depth key of each band
+    uint32_t cta_done;                 // CTAs of the running raster / deferred launch that have finished (self-cleaning)
 };
 
 constexpr uint32_t kMeshletTile = 1024;        // candidate meshlets per scan tile
@@ -97,6 +97,9 @@ struct FrameParams {
     uint32_t max_instances, max_opaque, max_alpha;
     uint32_t instance_first, instance_end;   // sort-last partition
     uint32_t shadow_instance_first, shadow_instance_end;   // ... of the cascades (lh_set_shadow_instance_range)
+    // sort-last ownership by screen stripes (lh_set_instance_stripes): stripes == 0 means off; otherwise an instance
+    // belongs to the context whose index equals (stripe of its projected centre) % count.  [0] main view, [1] cascades
+    uint32_t stripes[2], stripe_index[2], stripe_count[2];
     uint32_t shadowmap_size;
     uint32_t flags;
     uint32_t max_large;
@@ -111,6 +114,7 @@ struct FrameParams {
     uint32_t* large_queue;
     void* meshlet_bounds;                    // 16 B per surviving meshlet of the current raster pass (raster.cu MeshletBound)
     uint32_t* raster_queue;                  // indices of the meshlets selected for rasterisation, band after band
+    uint32_t* depth_keys;                    // the bounds' depth keys on their own (4 B per meshlet): what band selection scans
     uint32_t* depth_hist;                    // 8192 bins of the depth-key histogram (self-cleaning)
     uint32_t* hiz;                           // farthest stored value per 8x8-pixel tile of the current raster target
     unsigned long long* vis;
@@ -142,6 +146,7 @@ struct LhContext {
     bool have_uniforms = false;
     uint32_t instance_first = 0, instance_count = 0xFFFFFFFFu;
     bool shadow_range_set = false;
+    uint32_t stripes[2] = {0, 0}, stripe_index[2] = {0, 0}, stripe_count[2] = {1, 1};
     uint32_t shadow_instance_first = 0, shadow_instance_count = 0xFFFFFFFFu;
     uint32_t cascade_mask = 0xF;
 
@@ -165,6 +170,7 @@ struct LhContext {
         uint32_t* large_queue = nullptr;
         void* meshlet_bounds = nullptr;
         uint32_t* raster_queue = nullptr;
+        uint32_t* depth_keys = nullptr;
         uint32_t* depth_hist = nullptr;
         uint32_t* hiz = nullptr;
         void* draw_calls = nullptr;   // internal lists (sets 1..3)

@@ -452,6 +452,7 @@ __global__ void __launch_bounds__(256) raster_bounds_kernel(const __grid_constan
             }
         }
         *(uint4*)(bounds + k) = make_uint4(mb.rect_x, mb.rect_y, mb.edge, mb.key);
+        P.depth_keys[k] = mb.key;
         // histogram, aggregated over the lanes that fall into the same bin (neighbouring meshlets mostly do; an
         // un-aggregated add serialises on a handful of addresses)
         const uint32_t bin = mb.key == kKeyEmpty ? kHistBins : mb.key >> kHistShift;
@@ -509,8 +510,13 @@ __global__ void __launch_bounds__(1024) raster_bands_kernel(const __grid_constan
     if (tid == 0) {
         st->band_key[kBands - 1] = kKeyEmpty;   // the last band takes the rest (empty meshlets carry kKeyEmpty and are never selected)
         st->queue_count = 0;
-        st->band_begin = 0;
+        st->band_mark[0] = 0;
+        // a raster pass begins: empty deferred queue
+        st->large_count = 0;
+        st->deferred_begin = st->deferred_end = 0;
+        st->cta_done = 0;
     }
+    if (tid < 8) st->band_ticket[tid] = 0;
     for (int b = 0; b < kBands - 1; b++) {
         const uint32_t target = (uint32_t)((float)total * fractions[b]);
         // the thread whose bins hold the target-th meshlet names the bin after it as the band's upper bound
@@ -594,9 +600,11 @@ __global__ void __launch_bounds__(256) raster_select_kernel(const __grid_constan
     const uint32_t stride = gridDim.x * blockDim.x;
     for (uint32_t base = blockIdx.x * blockDim.x + (threadIdx.x & ~31u); base < total; base += stride) {
         const uint32_t k = base + lane;
+        // the scan reads the 4-byte keys only; the 16-byte bound is fetched for the band's own meshlets
+        const uint32_t key = k < total ? __ldg(P.depth_keys + k) : kKeyEmpty;
+        bool keep = key >= key_lo && key < key_hi;
         uint4 mb = make_uint4(kUntestable, 0u, 0u, kKeyEmpty);
-        if (k < total) mb = __ldg((const uint4*)(bounds + k));
-        bool keep = mb.w >= key_lo && mb.w < key_hi;
+        if (keep && band != 0) mb = __ldg((const uint4*)(bounds + k));
         if (keep && band != 0 && mb.x != kUntestable) {
             const int px0 = (int)(mb.x & 0xFFFFu), px1 = (int)(mb.x >> 16), py0 = (int)(mb.y & 0xFFFFu), py1 = (int)(mb.y >> 16);
             const bool fine = ((px1 >> kHizShift0) - (px0 >> kHizShift0) + 1) * ((py1 >> kHizShift0) - (py0 >> kHizShift0) + 1) <= kMaxHizTiles;
@@ -624,14 +632,21 @@ __global__ void __launch_bounds__(256) raster_select_kernel(const __grid_constan
     }
 }
 
-// between a band's selection and its rasterisation: the raster kernel takes tickets in [raster_ticket, band_end)
-__global__ void raster_band_begin_kernel(const __grid_constant__ FrameParams P) {
-    if (threadIdx.x == 0 && blockIdx.x == 0) {
+// What the last CTA of a raster or deferred launch to finish does: the deferred entries appended so far become the
+// range of the next deferred launch.  consumed: this launch was a deferred one and has processed its range.
+__device__ __forceinline__ void finish_launch(const FrameParams& P, bool consumed) {
+    __shared__ bool last;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        last = atomicAdd(&P.pass->cta_done, 1u) == gridDim.x - 1u;
+    }
+    __syncthreads();
+    if (last && threadIdx.x == 0) {
         PassState* st = P.pass;
-        st->raster_ticket = st->band_begin;
-        st->band_first = st->band_begin;
-        st->band_end = st->queue_count;
-        st->band_begin = st->queue_count;
+        st->cta_done = 0;
+        if (consumed) st->deferred_begin = st->deferred_end;
+        st->deferred_end = min(*(volatile uint32_t*)&st->large_count, P.max_large);
     }
 }
 
@@ -639,13 +654,16 @@ __global__ void raster_band_begin_kernel(const __grid_constant__ FrameParams P) 
 #define LH_RASTER_MIN_CTAS 4
 #endif
 template <bool SHADOW>
-__global__ void __launch_bounds__(kWarpsPerCta * 32, LH_RASTER_MIN_CTAS) raster_meshlets_kernel(const __grid_constant__ FrameParams P, uint32_t cascade) {
+__global__ void __launch_bounds__(kWarpsPerCta * 32, LH_RASTER_MIN_CTAS) raster_meshlets_kernel(const __grid_constant__ FrameParams P, uint32_t cascade, uint32_t band) {
     __shared__ WarpScratch scratch_all[kWarpsPerCta];
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     WarpScratch& sv = scratch_all[warp];
     const uint32_t* draw = (const uint32_t*)P.pass_draw_calls;
     const uint32_t n_opaque = min(draw[0], P.max_opaque);   // drawIndirectCount clamps to maxDrawCount
-    const uint32_t band_end = P.pass->band_end;
+    // band b owns the queue entries appended by its selection: [band_mark[b], queue_count); nothing appends while
+    // this kernel runs, and the mark it leaves for band b + 1 is read by that band's launch only
+    const uint32_t band_first = P.pass->band_mark[band], band_end = P.pass->queue_count;
+    if (blockIdx.x == 0 && threadIdx.x == 0) P.pass->band_mark[band + 1] = band_end;
 
     Target<SHADOW> tg;
     tg.vis = P.vis;
@@ -671,11 +689,11 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, LH_RASTER_MIN_CTAS) raster_
     // work and a heavy near meshlet does not serialise its neighbours): the entries, their bounds and the first 8x4
     // block of every rectangle are fetched before any entry is processed, so the dependent round trips
     // ticket -> queue -> bounds -> stored keys are paid once per chunk instead of once per meshlet.
-    const uint32_t band_count = band_end - P.pass->band_first;
+    const uint32_t band_count = band_end - band_first;
     const uint32_t chunk = max(1u, min((uint32_t)kFrontChunk, band_count / (gridDim.x * kWarpsPerCta * 8u)));
     for (;;) {
         uint32_t ticket = 0;
-        if (lane == 0) ticket = atomicAdd(&P.pass->raster_ticket, chunk);
+        if (lane == 0) ticket = band_first + atomicAdd(&P.pass->band_ticket[band], chunk);
         ticket = __shfl_sync(0xFFFFFFFFu, ticket, 0);
         if (ticket >= band_end) break;
         const uint32_t n = min(chunk, band_end - ticket);
@@ -933,6 +951,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, LH_RASTER_MIN_CTAS) raster_
             if (skipped_empty) atomicAdd(&P.state->skipped_empty[pass], skipped_empty);
         }
     }
+    finish_launch(P, false);
 }
 
 // ---- the deferred queue: large and near-plane-crossing triangles, one warp per entry ----
@@ -1056,24 +1075,9 @@ __global__ void __launch_bounds__(kDeferredWarps * 32) raster_deferred_kernel(co
         }
         __syncwarp();
     }
+    finish_launch(P, true);
 }
 
-// the next deferred launch takes the entries appended since the previous one
-__global__ void raster_deferred_begin_kernel(const __grid_constant__ FrameParams P) {
-    if (threadIdx.x == 0 && blockIdx.x == 0) {
-        PassState* st = P.pass;
-        st->deferred_begin = st->deferred_end;
-        st->deferred_end = min(st->large_count, P.max_large);
-    }
-}
-
-__global__ void begin_raster_pass_kernel(const __grid_constant__ FrameParams P) {
-    if (threadIdx.x == 0 && blockIdx.x == 0) {
-        P.pass->large_count = 0;
-        P.pass->deferred_begin = P.pass->deferred_end = 0;
-        P.pass->raster_ticket = 0;
-    }
-}
 __global__ void end_main_pass_kernel(const __grid_constant__ FrameParams P) {
     if (threadIdx.x == 0 && blockIdx.x == 0) P.state->main_large_count = P.pass->large_count;
 }
@@ -1084,11 +1088,10 @@ void launch_raster(LhContext* ctx, const FrameParams& p, int cascade, cudaStream
     if (!stream) stream = ctx->stream;
     const uint32_t grid = (uint32_t)ctx->num_sms * 8;
     const bool timed = cascade < 0 && (ctx->cfg.flags & LH_CONFIG_PASS_TIMINGS) != 0;
-    begin_raster_pass_kernel<<<1, 32, 0, stream>>>(p); ctx->launches++;
     if (timed) cudaEventRecord(ctx->raster_kernel_a, stream);
     if (cascade < 0) raster_bounds_kernel<false><<<grid, 256, 0, stream>>>(p, 0);
     else raster_bounds_kernel<true><<<grid, 256, 0, stream>>>(p, (uint32_t)cascade);
-    raster_bands_kernel<<<1, 1024, 0, stream>>>(p);
+    raster_bands_kernel<<<1, 1024, 0, stream>>>(p);   // also opens the pass: empty raster and deferred queues
     ctx->launches += 2;
     for (uint32_t band = 0; band < (uint32_t)kBands; band++) {
         if (band != 0) {
@@ -1098,18 +1101,17 @@ void launch_raster(LhContext* ctx, const FrameParams& p, int cascade, cudaStream
         }
         if (cascade < 0) raster_select_kernel<false><<<grid, 256, 0, stream>>>(p, 0, band);
         else raster_select_kernel<true><<<grid, 256, 0, stream>>>(p, (uint32_t)cascade, band);
-        raster_band_begin_kernel<<<1, 32, 0, stream>>>(p);
-        if (cascade < 0) raster_meshlets_kernel<false><<<grid, kWarpsPerCta * 32, 0, stream>>>(p, 0);
-        else raster_meshlets_kernel<true><<<grid, kWarpsPerCta * 32, 0, stream>>>(p, (uint32_t)cascade);
-        ctx->launches += 3;
+        if (cascade < 0) raster_meshlets_kernel<false><<<grid, kWarpsPerCta * 32, 0, stream>>>(p, 0, band);
+        else raster_meshlets_kernel<true><<<grid, kWarpsPerCta * 32, 0, stream>>>(p, (uint32_t)cascade, band);
+        ctx->launches += 2;
         // The deferred queue is drained after the near bands (whose large triangles are the best occluders for the
         // bands that follow) and at the end; twice each time: the first launch splits, the second rasterises the pieces.
+        // Each launch takes the entries appended before it began (finish_launch of the launch ahead of it).
         if (band < 3 || band + 1 == (uint32_t)kBands) {
             for (int round = 0; round < 2; round++) {
-                raster_deferred_begin_kernel<<<1, 32, 0, stream>>>(p);
                 if (cascade < 0) raster_deferred_kernel<false><<<grid, kDeferredWarps * 32, 0, stream>>>(p, 0);
                 else raster_deferred_kernel<true><<<grid, kDeferredWarps * 32, 0, stream>>>(p, (uint32_t)cascade);
-                ctx->launches += 2;
+                ctx->launches++;
             }
         }
     }
