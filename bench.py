@@ -208,7 +208,7 @@ def run_ours(args):
     sky = scene.make_skybox(32)
     from lighthugger_b200 import sortlast
     n = scene.num_instances
-    first, count = sortlast.instance_range(n, rank, world)
+    (first, count), _ = sortlast.main_plan(n, rank, world, args.partition)
     end = first + count
     caps = sortlast.capacities(scene, world, args.shadow_split)
     ctx = make_context(scene, textures=tex, skybox=sky, caps=caps, flags=S.LH_CONFIG_WRITE_DRAW_COMMANDS | S.LH_CONFIG_PASS_TIMINGS,
@@ -218,10 +218,7 @@ def run_ours(args):
         dist.broadcast_object_list(ids, src=0)
         ctx.comm_init(rank, world, ids[0])
         ctx.comm_set_exchange(S.LH_EXCHANGE_NCCL if args.exchange == "nccl" else S.LH_EXCHANGE_PEER)
-        ctx.set_instance_range(first, count)
-        mask, sfirst, scount = sortlast.shadow_plan(n, rank, world, args.shadow_split)
-        ctx.set_shadow_cascade_mask(mask)
-        ctx.set_shadow_instance_range(sfirst, scount)
+        sortlast.apply(ctx, n, rank, world, args.shadow_split, args.partition)
     u = ctx.uniforms()
 
     def barrier():
@@ -335,7 +332,7 @@ def run_ours(args):
         "data": "synthetic",
         "config": {"workload": WORKLOADS[args.workload], "resolution": [W, H], "instances": n, "input_triangles": scene.total_triangles,
                    "candidate_meshlets": scene.total_meshlets, "l2": "flushed between timed frames (256 MB write)",
-                   "parallelism": (f"sort-last x{n_gpus}: instances split, {args.exchange} exchange, shadows split by {args.shadow_split}"
+                   "parallelism": (f"sort-last x{n_gpus}: instances split by {args.partition}, {args.exchange} exchange, shadows split by {args.shadow_split}"
                                    if n_gpus > 1 else "single GPU"), "texture_format": "BC7_SRGB",
                    "texture_size": args.tex_size},
         "culled_mtri_per_s": scene.total_triangles / (ms_per_step / 1e3) / 1e6,
@@ -375,6 +372,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"], help="multi-GPU: peer-memory kernels or whole-buffer NCCL")
     ap.add_argument("--shadow-split", default="instances", choices=["instances", "cascades"])
+    ap.add_argument("--partition", default="stripes", choices=["stripes", "range"], help="multi-GPU: how instances are shared out")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

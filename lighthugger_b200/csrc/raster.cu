@@ -93,14 +93,13 @@ struct Target {
             z = padd(z, 0.0f);                      // canonicalise -0
             if (!(z >= 0.0f && z < 1.0f)) return;   // 0 <= z <= w clip; LESS against the 1.0 clear
             uint32_t bits = __float_as_uint(z);
-            uint32_t* p = layer + (size_t)y * width + x;
-            if (bits < *p) atomicMin(p, bits);
+            // fire-and-forget reduction: no read-back, so a lane never waits on the L2 round trip of its own sample
+            atomicMin(layer + (size_t)y * width + x, bits);
         } else {
             z = fminf(fmaxf(z, 0.0f), 1.0f);
             if (!(z > 0.0f)) return;                // GREATER against the 0.0 clear
             unsigned long long key = ((unsigned long long)(~__float_as_uint(z)) << 32) | lo;
-            unsigned long long* p = vis + (size_t)y * width + x;
-            if (key < *p) atomicMin(p, key);
+            atomicMin(vis + (size_t)y * width + x, key);
         }
     }
 };
@@ -124,11 +123,13 @@ __device__ __forceinline__ bool alpha_discard(const AlphaTest& at, float w0, flo
 }
 
 // ---- warp-cooperative rasterisation of one snapped triangle inside a pixel rectangle ----
-template <bool SHADOW>
+// I: I in general; int when the triangle's sub-pixel extent is below 2^14 on both axes (every product and every
+// stepped edge value then stays below 2^31, so both instantiations compute the same integers)
+template <bool SHADOW, typename I>
 __device__ void raster_snapped_coop(SnapVert a, SnapVert b, SnapVert c, int cull, const Target<SHADOW>& tg, int rx0, int ry0, int rx1,
                                     int ry1, const AlphaTest& at, uint32_t lo) {
     const uint32_t lane = threadIdx.x & 31;
-    long long A2 = (long long)(b.x - a.x) * (c.y - a.y) - (long long)(b.y - a.y) * (c.x - a.x);
+    I A2 = (I)(b.x - a.x) * (c.y - a.y) - (I)(b.y - a.y) * (c.x - a.x);
     if (A2 == 0) return;
     bool front = A2 < 0;
     if (cull == CULL_BACK && !front) return;
@@ -144,10 +145,10 @@ __device__ void raster_snapped_coop(SnapVert a, SnapVert b, SnapVert c, int cull
     int px0 = max(rx0, (minx - 128 + 255) >> 8), px1 = min(rx1, (maxx - 128) >> 8);
     int py0 = max(ry0, (miny - 128 + 255) >> 8), py1 = min(ry1, (maxy - 128) >> 8);
     if (px0 > px1 || py0 > py1) return;
-    const long long e0x = (long long)c.x - b.x, e0y = (long long)c.y - b.y;
-    const long long e1x = (long long)a.x - c.x, e1y = (long long)a.y - c.y;
-    const long long e2x = (long long)b.x - a.x, e2y = (long long)b.y - a.y;
-    const long long bias0 = top_left(e0x, e0y) ? 0 : -1, bias1 = top_left(e1x, e1y) ? 0 : -1, bias2 = top_left(e2x, e2y) ? 0 : -1;
+    const I e0x = (I)c.x - b.x, e0y = (I)c.y - b.y;
+    const I e1x = (I)a.x - c.x, e1y = (I)a.y - c.y;
+    const I e2x = (I)b.x - a.x, e2y = (I)b.y - a.y;
+    const I bias0 = top_left(e0x, e0y) ? 0 : -1, bias1 = top_left(e1x, e1y) ? 0 : -1, bias2 = top_left(e2x, e2y) ? 0 : -1;
     const float fA = (float)A2;
     const float inv_area = pdiv(1.0f, fA);
     const float dz1 = psub(b.z, a.z), dz2 = psub(c.z, a.z);
@@ -155,24 +156,24 @@ __device__ void raster_snapped_coop(SnapVert a, SnapVert b, SnapVert c, int cull
     // The edge functions are affine in the pixel position, so everything below is additions: E_k at the centre of the
     // block's first pixel is carried from block to block (step_x per 8 pixels, step_y per 4 rows); the lane's own pixel
     // and the block corner where E_k is largest (for the trivial reject) are fixed offsets from it.
-    const long long cx0 = (long long)px0 * 256 + 128, cy0 = (long long)py0 * 256 + 128;
-    const long long dx0 = -e0y * 256, dx1 = -e1y * 256, dx2 = -e2y * 256;   // E_k(x + 1 pixel) - E_k(x)
-    const long long dy0 = e0x * 256, dy1 = e1x * 256, dy2 = e2x * 256;      // E_k(y + 1 pixel) - E_k(y)
-    long long row0 = e0x * (cy0 - b.y) - e0y * (cx0 - b.x) + bias0;          // top-left bias folded in: inside <=> all >= 0
-    long long row1 = e1x * (cy0 - c.y) - e1y * (cx0 - c.x) + bias1;
-    long long row2 = e2x * (cy0 - a.y) - e2y * (cx0 - a.x) + bias2;
-    const long long corner0 = (dx0 > 0 ? 7 * dx0 : 0) + (dy0 > 0 ? 3 * dy0 : 0);
-    const long long corner1 = (dx1 > 0 ? 7 * dx1 : 0) + (dy1 > 0 ? 3 * dy1 : 0);
-    const long long corner2 = (dx2 > 0 ? 7 * dx2 : 0) + (dy2 > 0 ? 3 * dy2 : 0);
+    const I cx0 = (I)px0 * 256 + 128, cy0 = (I)py0 * 256 + 128;
+    const I dx0 = -e0y * 256, dx1 = -e1y * 256, dx2 = -e2y * 256;   // E_k(x + 1 pixel) - E_k(x)
+    const I dy0 = e0x * 256, dy1 = e1x * 256, dy2 = e2x * 256;      // E_k(y + 1 pixel) - E_k(y)
+    I row0 = e0x * (cy0 - b.y) - e0y * (cx0 - b.x) + bias0;          // top-left bias folded in: inside <=> all >= 0
+    I row1 = e1x * (cy0 - c.y) - e1y * (cx0 - c.x) + bias1;
+    I row2 = e2x * (cy0 - a.y) - e2y * (cx0 - a.x) + bias2;
+    const I corner0 = (dx0 > 0 ? 7 * dx0 : 0) + (dy0 > 0 ? 3 * dy0 : 0);
+    const I corner1 = (dx1 > 0 ? 7 * dx1 : 0) + (dy1 > 0 ? 3 * dy1 : 0);
+    const I corner2 = (dx2 > 0 ? 7 * dx2 : 0) + (dy2 > 0 ? 3 * dy2 : 0);
     const int lx = (int)(lane & 7), ly = (int)(lane >> 3);
-    const long long mine0 = lx * dx0 + ly * dy0, mine1 = lx * dx1 + ly * dy1, mine2 = lx * dx2 + ly * dy2;
+    const I mine0 = lx * dx0 + ly * dy0, mine1 = lx * dx1 + ly * dy1, mine2 = lx * dx2 + ly * dy2;
     for (int by = 0; by < nby; by++) {
-        long long blk0 = row0, blk1 = row1, blk2 = row2;
+        I blk0 = row0, blk1 = row1, blk2 = row2;
         const int py = py0 + by * 4 + ly;
         for (int bx = 0; bx < nbx; bx++) {
             // trivial reject: the block corner where each (biased) edge function is largest is still outside
             const bool reject = ((blk0 + corner0) | (blk1 + corner1) | (blk2 + corner2)) < 0;
-            const long long w0b = blk0 + mine0, w1b = blk1 + mine1, w2b = blk2 + mine2;
+            const I w0b = blk0 + mine0, w1b = blk1 + mine1, w2b = blk2 + mine2;
             blk0 += 8 * dx0;
             blk1 += 8 * dx1;
             blk2 += 8 * dx2;
@@ -180,7 +181,7 @@ __device__ void raster_snapped_coop(SnapVert a, SnapVert b, SnapVert c, int cull
             const int px = px0 + bx * 8 + lx;
             if (px > px1 || py > py1) continue;
             if ((w0b | w1b | w2b) < 0) continue;
-            const long long w0 = w0b - bias0, w1 = w1b - bias1, w2 = w2b - bias2;
+            const I w0 = w0b - bias0, w1 = w1b - bias1, w2 = w2b - bias2;
             if (at.enabled && alpha_discard(at, (float)w0, (float)w1, (float)w2, fA, a, b, c)) continue;
             float z = padd(a.z, pmul(padd(pmul((float)w1, dz1), pmul((float)w2, dz2)), inv_area));
             tg.emit(px, py, z, lo);
@@ -967,7 +968,7 @@ struct DeferredTriangle {
     uint32_t lo;
     uint32_t rect_x, rect_y;     // x0 | x1 << 16, y0 | y1 << 16 (pixels); split: tile range instead
     uint16_t n;                  // vertices after clipping; 0: nothing to do
-    uint8_t cull, split;         // split: append one entry per tile of the rectangle instead of rasterising
+    uint8_t cull, split;         // split: append one entry per tile of the rectangle instead of rasterising; bit 1: 32-bit edge functions suffice
 };
 constexpr int kDeferredWarps = 4;
 
@@ -1042,7 +1043,16 @@ __global__ void __launch_bounds__(kDeferredWarps * 32) raster_deferred_kernel(co
                 d.rect_x = (uint32_t)rx0 | ((uint32_t)rx1 << 16);
                 d.rect_y = (uint32_t)ry0 | ((uint32_t)ry1 << 16);
                 d.cull = (uint8_t)(h.alpha ? CULL_NONE : (SHADOW ? CULL_FRONT : CULL_BACK));
-                d.split = split ? 1 : 0;
+                bool narrow = n != 0;   // sub-pixel extent of the (clipped) polygon below 2^14 on both axes
+                if (n != 0) {
+                    int minx = d.s[0].x, maxx = d.s[0].x, miny = d.s[0].y, maxy = d.s[0].y;
+                    for (int k = 1; k < n; k++) {
+                        minx = min(minx, d.s[k].x); maxx = max(maxx, d.s[k].x);
+                        miny = min(miny, d.s[k].y); maxy = max(maxy, d.s[k].y);
+                    }
+                    narrow = (long long)maxx - minx < kSmallMaxExtent && (long long)maxy - miny < kSmallMaxExtent;
+                }
+                d.split = (split ? 1 : 0) | (narrow ? 2 : 0);
                 d.tex = at.enabled ? at.tex : 0;
             }
         }
@@ -1054,7 +1064,7 @@ __global__ void __launch_bounds__(kDeferredWarps * 32) raster_deferred_kernel(co
             if (n == 0) continue;
             const int x0 = (int)(d.rect_x & 0xFFFFu), x1 = (int)(d.rect_x >> 16), y0 = (int)(d.rect_y & 0xFFFFu), y1 = (int)(d.rect_y >> 16);
             const uint32_t lo = d.lo;
-            if (d.split) {
+            if (d.split & 1) {
                 const uint32_t ntx = (uint32_t)(x1 - x0 + 1), ntiles = ntx * (uint32_t)(y1 - y0 + 1);
                 uint32_t at = 0;
                 if (lane == 0) at = atomicAdd(&P.pass->large_count, ntiles);
@@ -1070,8 +1080,13 @@ __global__ void __launch_bounds__(kDeferredWarps * 32) raster_deferred_kernel(co
                 continue;
             }
             const AlphaTest at{d.tex != 0, d.tex};
-            raster_snapped_coop<SHADOW>(d.s[0], d.s[1], d.s[2], (int)d.cull, tg, x0, y0, x1, y1, at, lo);
-            if (n == 4) raster_snapped_coop<SHADOW>(d.s[0], d.s[2], d.s[3], (int)d.cull, tg, x0, y0, x1, y1, at, lo);
+            if (d.split & 2) {
+                raster_snapped_coop<SHADOW, int>(d.s[0], d.s[1], d.s[2], (int)d.cull, tg, x0, y0, x1, y1, at, lo);
+                if (n == 4) raster_snapped_coop<SHADOW, int>(d.s[0], d.s[2], d.s[3], (int)d.cull, tg, x0, y0, x1, y1, at, lo);
+            } else {
+                raster_snapped_coop<SHADOW, long long>(d.s[0], d.s[1], d.s[2], (int)d.cull, tg, x0, y0, x1, y1, at, lo);
+                if (n == 4) raster_snapped_coop<SHADOW, long long>(d.s[0], d.s[2], d.s[3], (int)d.cull, tg, x0, y0, x1, y1, at, lo);
+            }
         }
         __syncwarp();
     }

@@ -63,7 +63,8 @@ def cuda_lib():
         lib.lh_set_shadow_cascade_mask.argtypes = [vp, u32]
         lib.lh_set_shadow_instance_range.argtypes = [vp, u32, u32]
         lib.lh_comm_set_exchange.argtypes = [vp, C.c_int]
-        lib.lh_set_instance_stripes.argtypes = [vp, C.c_int, u32, u32, u32]
+        if hasattr(lib, "lh_set_instance_stripes") or not os.environ.get("LH_CUDA_LIB"):   # an older A/B build may lack it
+            lib.lh_set_instance_stripes.argtypes = [vp, C.c_int, u32, u32, u32]
         lib.lh_comm_rows.argtypes = [vp, C.POINTER(u32), C.POINTER(u32)]
         lib.lh_frame_begin.argtypes = [vp, C.POINTER(S.LhUniforms)]
         for name in ("lh_reset", "lh_cull_instances", "lh_cull_meshlets", "lh_raster_visbuffer", "lh_composite",

@@ -35,22 +35,60 @@ def slot_offset(caps, rank):
     return rank * (caps.max_opaque_draws + caps.max_alpha_clip_draws)
 
 
-def shadow_plan(num_instances, rank, world, split="instances"):
-    """(cascade mask, first instance, instance count) of the shadow work of `rank`.  Over the ranks the (cascade,
-    instance) pairs are covered exactly once, so the uint32-min merge of the layers equals the single-GPU layers.
-      "instances": every rank draws all four cascades of its own instance range (even load whatever the cascade sizes);
+STRIPES_PER_RANK = 8   # interleaved screen stripes per GPU: narrow enough to even the load, wide enough to keep occluders together
+
+
+def main_plan(num_instances, rank, world, partition="stripes"):
+    """((first, count), (stripes, index, count)) of the main view of `rank`.
+      "range":   contiguous instance ranges [r*N/G, (r+1)*N/G) -- every GPU gets a sparse copy of the whole scene;
+      "stripes": all instances, filtered on the device by the screen stripe of their centre (lh_set_instance_stripes) --
+                 neighbours share a GPU, so a GPU's own geometry keeps occluding itself."""
+    if world == 1:
+        return (0, num_instances), (0, 0, 1)
+    if partition == "range":
+        return instance_range(num_instances, rank, world), (0, 0, 1)
+    if partition != "stripes":
+        raise ValueError(f"unknown partition {partition!r}")
+    return (0, num_instances), (STRIPES_PER_RANK * world, rank, world)
+
+
+def shadow_plan(num_instances, rank, world, split="instances", partition="range"):
+    """(cascade mask, (first instance, instance count), (stripes, index, count)) of the shadow work of `rank`.  Over the
+    ranks the (cascade, instance) pairs are covered exactly once, so the uint32-min merge of the layers equals the
+    single-GPU layers.
+      "instances": every rank draws all four cascades of its share of the instances (even load whatever the cascade sizes);
       "cascades":  one cascade per GPU over ALL instances (BASELINE config 3: 4 GPUs); 2 GPUs take two cascades each, and
-                   with more than 4 GPUs the ranks c, c + 4, ... split cascade c's instances between them."""
-    if split == "instances" or world == 1:
-        first, count = instance_range(num_instances, rank, world)
-        return 0xF, first, count
-    if split != "cascades":
+                   with more than 4 GPUs the ranks c, c + 4, ... split cascade c's instances between them.
+    A share of the instances is an index range or a set of light-space stripes (see main_plan)."""
+    if world == 1:
+        return 0xF, (0, num_instances), (0, 0, 1)
+    if split == "instances":
+        mask, index, members = 0xF, rank, world
+    elif split == "cascades":
+        groups = min(world, 4)                   # ranks with equal rank % groups share their cascades
+        mask = sum(1 << c for c in range(4) if c % groups == rank % groups)
+        group = [r for r in range(world) if r % groups == rank % groups]
+        index, members = group.index(rank), len(group)
+    else:
         raise ValueError(f"unknown shadow split {split!r}")
-    groups = min(world, 4)                       # ranks with equal rank % groups share their cascades
-    mask = sum(1 << c for c in range(4) if c % groups == rank % groups)
-    members = [r for r in range(world) if r % groups == rank % groups]
-    first, count = instance_range(num_instances, members.index(rank), len(members))
-    return mask, first, count
+    if members == 1:
+        return mask, (0, num_instances), (0, 0, 1)
+    if partition == "range":
+        return mask, instance_range(num_instances, index, members), (0, 0, 1)
+    if partition != "stripes":
+        raise ValueError(f"unknown partition {partition!r}")
+    return mask, (0, num_instances), (STRIPES_PER_RANK * members, index, members)
+
+
+def apply(ctx, num_instances, rank, world, split="instances", partition="stripes"):
+    """Configures a renderer.Context with the plan of `rank`."""
+    (first, count), (stripes, index, members) = main_plan(num_instances, rank, world, partition)
+    ctx.set_instance_range(first, count)
+    ctx.set_instance_stripes(0, stripes, index, members)
+    mask, (sfirst, scount), (sstripes, sindex, smembers) = shadow_plan(num_instances, rank, world, split, partition)
+    ctx.set_shadow_cascade_mask(mask)
+    ctx.set_shadow_instance_range(sfirst, scount)
+    ctx.set_instance_stripes(1, sstripes, sindex, smembers)
 
 
 def row_range(height, rank, world):

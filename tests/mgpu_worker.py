@@ -62,8 +62,12 @@ def main():
         one.close()
 
     failures = []
-    for exchange, ename in ((S.LH_EXCHANGE_PEER, "peer"), (S.LH_EXCHANGE_NCCL, "nccl")):
-        for split in ("instances", "cascades"):
+    for exchange, ename, split, partition in ((S.LH_EXCHANGE_PEER, "peer", "instances", "stripes"),
+                                              (S.LH_EXCHANGE_PEER, "peer", "cascades", "stripes"),
+                                              (S.LH_EXCHANGE_PEER, "peer", "instances", "range"),
+                                              (S.LH_EXCHANGE_NCCL, "nccl", "cascades", "range"),
+                                              (S.LH_EXCHANGE_NCCL, "nccl", "instances", "stripes")):
+        if True:
             caps = sortlast.capacities(sc, world, split)
             per_rank = caps.max_opaque_draws + caps.max_alpha_clip_draws
             ctx = make_context(sc, textures=tex, skybox=sky, caps=caps, device=local_rank)
@@ -71,11 +75,7 @@ def main():
             dist.broadcast_object_list(ids, src=0)
             ctx.comm_init(rank, world, ids[0])
             ctx.comm_set_exchange(exchange)
-            first, count = sortlast.instance_range(n, rank, world)
-            ctx.set_instance_range(first, count)
-            mask, sfirst, scount = sortlast.shadow_plan(n, rank, world, split)
-            ctx.set_shadow_cascade_mask(mask)
-            ctx.set_shadow_instance_range(sfirst, scount)
+            sortlast.apply(ctx, n, rank, world, split, partition)
             u = ctx.uniforms()
             for _ in range(2):   # the second frame reuses the peer mappings and every self-cleaning counter
                 ctx.render_frame_host(u)
@@ -89,7 +89,7 @@ def main():
             parts = [None] * world
             dist.all_gather_object(parts, mine)
             if rank == 0:
-                tag = f"{ename}/{split}"
+                tag = f"{ename}/{split}/{partition}"
                 tables = [p["table"] for p in parts]
                 if exchange == S.LH_EXCHANGE_PEER:
                     vis = np.concatenate([p["vis"] for p in parts])

@@ -50,7 +50,7 @@ def _worker(rank, world, port, out_dir):
         o.reduce_depth()
         for split in ("instances", "cascades"):
             o.generate_shadow_matrices()   # also resets the list counters (generate_shadow_matrices.glsl ends in reset_counters)
-            mask, sfirst, scount = sortlast.shadow_plan(sc.num_instances, rank, world, split)
+            mask, (sfirst, scount), _ = sortlast.shadow_plan(sc.num_instances, rank, world, split, "range")
             o.cfg.instance_first, o.cfg.instance_count = sfirst, scount
             o.shadow[:] = 1.0
             o.cull_instances_shadows()
@@ -112,13 +112,28 @@ def test_plan_tiles_instances_and_cascades():
             for split in ("instances", "cascades"):
                 cover = np.zeros((4, n), np.int32)
                 for r in range(world):
-                    mask, first, count = sortlast.shadow_plan(n, r, world, split)
+                    mask, (first, count), stripes = sortlast.shadow_plan(n, r, world, split, "range")
+                    assert stripes[0] == 0
                     for c in range(4):
                         if mask >> c & 1:
                             cover[c, first:first + count] += 1
                 assert np.all(cover == 1), (world, n, split)
         if world == 4:
-            assert [sortlast.shadow_plan(100, r, 4, "cascades") for r in range(4)] == [(1 << r, 0, 100) for r in range(4)]
+            assert [sortlast.shadow_plan(100, r, 4, "cascades")[:2] for r in range(4)] == [(1 << r, (0, 100)) for r in range(4)]
+        # stripe ownership: every rank looks at all instances; the (index, count) pairs tile the stripes' residues
+        for split in ("instances", "cascades"):
+            seen = {}
+            for r in range(world):
+                (first, count), (stripes, index, members) = sortlast.main_plan(1000, r, world, "stripes")
+                assert (first, count) == (0, 1000) and (world == 1 or (stripes % members == 0 and index == r and members == world))
+                mask, rng, (s2, i2, m2) = sortlast.shadow_plan(1000, r, world, split, "stripes")
+                assert rng == (0, 1000)
+                for c in range(4):
+                    if mask >> c & 1:
+                        seen.setdefault(c, []).append((i2, m2))
+            for c in range(4):
+                members = seen[c][0][1]
+                assert sorted(i for i, _ in seen[c]) == list(range(members)) and all(m == members for _, m in seen[c])
         for h in (1, 2, 1080, 2160, 4320, 37):
             rows = [sortlast.row_range(h, r, world) for r in range(world)]
             assert rows[0][0] == 0 and rows[-1][1] == h and all(rows[r][1] == rows[r + 1][0] for r in range(world - 1))
