@@ -2,6 +2,7 @@
 // textures, targets, the per-pass entry points in src/rendering.cpp order, and
 // readback.  There is no CPU fallback anywhere in this library.
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 
@@ -84,6 +85,7 @@ FrameParams make_params(LhContext* ctx, int cascade, int set, bool internal_list
     p.slot_offset = ctx->slot_offset;
     p.resolve_refs = ctx->gathered_refs ? (const LhMeshletReference*)ctx->gathered_refs : (const LhMeshletReference*)p.u.meshlet_references;
     p.scene = ctx->scene;
+    p.resolve_tmp = ctx->resolve_tmp;
     p.display = ctx->display;
     p.sky = ctx->sky_tex;
     p.lut = ctx->lut_tex;
@@ -138,6 +140,8 @@ int alloc_targets(LhContext* ctx, uint32_t w, uint32_t h) {
     cudaFree(ctx->scene);
     cudaFree(ctx->display);
     cudaFree(ctx->depth_plane);
+    cudaFree(ctx->resolve_tmp);
+    ctx->resolve_tmp = nullptr;
     ctx->vis = nullptr;
     ctx->scene = ctx->display = nullptr;
     ctx->depth_plane = nullptr;
@@ -190,7 +194,9 @@ int alloc_pass_scratch(LhContext* ctx, int set) {
         LH_CUDA(ctx, cudaMemset(sc.draw_calls, 0, 16));
         LH_CUDA(ctx, cudaMalloc(&sc.refs, (draws ? draws : 1) * sizeof(LhMeshletReference)));
         if (!ctx->side_streams[set - 1]) {
-            LH_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->side_streams[set - 1], cudaStreamNonBlocking));
+            int prio_least = 0, prio_greatest = 0;
+            cudaDeviceGetStreamPriorityRange(&prio_least, &prio_greatest);
+            LH_CUDA(ctx, cudaStreamCreateWithPriority(&ctx->side_streams[set - 1], cudaStreamNonBlocking, prio_greatest));
             LH_CUDA(ctx, cudaEventCreateWithFlags(&ctx->join_events[set - 1], cudaEventDisableTiming));
         }
         if (!ctx->fork_event) LH_CUDA(ctx, cudaEventCreateWithFlags(&ctx->fork_event, cudaEventDisableTiming));
@@ -271,6 +277,15 @@ int lh_context_create(const LhConfig* cfg, LhContext** out) {
     cudaDeviceProp prop;
     cudaGetDeviceProperties(&prop, cfg->device);
     ctx->num_sms = prop.multiProcessorCount;
+    if (const char* t = getenv("LH_TUNE")) {
+        unsigned v[4] = {ctx->tune.main_bands, ctx->tune.shadow_bands, ctx->tune.main_grid, ctx->tune.shadow_grid};
+        sscanf(t, "%u,%u,%u,%u", &v[0], &v[1], &v[2], &v[3]);
+        auto clamp = [](unsigned x, unsigned lo, unsigned hi) { return x < lo ? lo : (x > hi ? hi : x); };
+        ctx->tune.main_bands = clamp(v[0], 2, 8);
+        ctx->tune.shadow_bands = clamp(v[1], 2, 8);
+        ctx->tune.main_grid = clamp(v[2], 1, 64);
+        ctx->tune.shadow_grid = clamp(v[3], 1, 64);
+    }
     auto bail = [&](int rc) {
         g_create_error = ctx->error;
         lh_context_destroy(ctx);
@@ -281,7 +296,14 @@ int lh_context_create(const LhConfig* cfg, LhContext** out) {
         cudaError_t _e = (expr);                                               \
         if (_e != cudaSuccess) return bail(fail(ctx, LH_ERR_CUDA, #expr, _e)); \
     } while (0)
-    TRY(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+    // the context stream and the cascades' side streams carry the frame's critical path; the material phase of the
+    // resolve, which only fills the gaps beside the shadow passes, runs on a stream of the lowest priority
+    int prio_least = 0, prio_greatest = 0;
+    cudaDeviceGetStreamPriorityRange(&prio_least, &prio_greatest);
+    TRY(cudaStreamCreateWithPriority(&ctx->stream, cudaStreamNonBlocking, prio_greatest));
+    TRY(cudaStreamCreateWithPriority(&ctx->resolve_stream, cudaStreamNonBlocking, prio_least));
+    TRY(cudaEventCreateWithFlags(&ctx->vis_ready, cudaEventDisableTiming));
+    TRY(cudaEventCreateWithFlags(&ctx->material_done, cudaEventDisableTiming));
     int rc = alloc_targets(ctx, cfg->width, cfg->height);
     if (rc) return bail(rc);
     size_t shadow_bytes = (size_t)4 * cfg->shadowmap_size * cfg->shadowmap_size * 4;
@@ -329,6 +351,10 @@ int lh_context_destroy(LhContext* ctx) {
     cudaFree(ctx->scene);
     cudaFree(ctx->display);
     cudaFree(ctx->depth_plane);
+    cudaFree(ctx->resolve_tmp);
+    if (ctx->resolve_stream) cudaStreamDestroy(ctx->resolve_stream);
+    if (ctx->vis_ready) cudaEventDestroy(ctx->vis_ready);
+    if (ctx->material_done) cudaEventDestroy(ctx->material_done);
     cudaFree(ctx->shadow);
     cudaFree(ctx->state);
     cudaFree(ctx->instance_tiles);
@@ -698,6 +724,15 @@ int lh_render_frame(LhContext* ctx) {
     if ((rc = lh_cull_meshlets(ctx))) return rc;
     if ((rc = lh_raster_visbuffer(ctx))) return rc;
     if ((rc = lh_composite(ctx))) return rc;
+    // The resolve in two launches: its material phase needs the visibility buffer only and runs beside the depth and
+    // shadow passes; its shadow phase follows them.
+    if (!ctx->resolve_tmp) {
+        LH_CUDA(ctx, cudaMalloc(&ctx->resolve_tmp, (size_t)ctx->cfg.width * ctx->cfg.height * 40));
+    }
+    LH_CUDA(ctx, cudaEventRecord(ctx->vis_ready, ctx->stream));
+    LH_CUDA(ctx, cudaStreamWaitEvent(ctx->resolve_stream, ctx->vis_ready, 0));
+    launch_resolve(ctx, make_params(ctx), 1, ctx->resolve_stream);
+    LH_CUDA(ctx, cudaEventRecord(ctx->material_done, ctx->resolve_stream));
     if ((rc = lh_reduce_depth(ctx))) return rc;
     if ((rc = lh_generate_shadow_matrices(ctx))) return rc;
     if ((rc = lh_cull_instances_shadows(ctx))) return rc;
@@ -716,18 +751,25 @@ int lh_render_frame(LhContext* ctx) {
         for (int i = 0; i < n_others; i++)
             if ((rc = alloc_pass_scratch(ctx, 1 + i))) return rc;
         if (n_others) LH_CUDA(ctx, cudaEventRecord(ctx->fork_event, ctx->stream));
+        // the last cascade is the largest and the critical path: it is enqueued first, so that it does not wait for
+        // the host to enqueue the other three
+        if (last >= 0) enqueue_cascade(ctx, (uint32_t)last, 0, false, nullptr);
         for (int i = 0; i < n_others; i++) {
             cudaStream_t s = ctx->side_streams[i];
             LH_CUDA(ctx, cudaStreamWaitEvent(s, ctx->fork_event, 0));
             enqueue_cascade(ctx, (uint32_t)others[i], 1 + i, true, s);
             LH_CUDA(ctx, cudaEventRecord(ctx->join_events[i], s));
         }
-        if (last >= 0) enqueue_cascade(ctx, (uint32_t)last, 0, false, nullptr);
         for (int i = 0; i < n_others; i++) LH_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->join_events[i], 0));
         if ((rc = check_launch(ctx, "shadow cascades"))) return rc;
     }
     if ((rc = lh_shadow_exchange(ctx))) return rc;
-    if ((rc = lh_resolve(ctx))) return rc;
+    {
+        PassScope scope(ctx, LH_PASS_RENDER_GEOMETRY);   // what is left of the resolve on the critical path
+        LH_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->material_done, 0));
+        launch_resolve(ctx, make_params(ctx), 2);
+        if ((rc = check_launch(ctx, "resolve"))) return rc;
+    }
     // rank 0's frame is complete, and every table a peer reads may be rewritten, once all ranks have resolved their rows
     if (peer_exchange(ctx)) return frame_barrier(ctx);
     return LH_OK;

@@ -103,6 +103,7 @@ struct FrameParams {
     uint32_t shadowmap_size;
     uint32_t flags;
     uint32_t max_large;
+    uint32_t num_bands;                      // depth bands of the raster pass being launched (raster.cu)
     FrameState* state;
     unsigned long long* instance_tiles;      // [4][tiles] decoupled-lookback states
     // ---- the view being culled / rasterised (see PassState) ----
@@ -130,6 +131,7 @@ struct FrameParams {
     void* scene_remote;                      // rank 0's RGBA16F target mapped here (ranks != 0), else nullptr
     uint32_t* depth_pair;                    // {min depth bits, ~max depth bits} of this rank's rows, then of the frame
     void* scene;                             // RGBA16F target
+    void* resolve_tmp;                       // 40 B per pixel handed from the resolve's material phase to its shadow phase
     void* display;                           // BGRA8 target
     cudaTextureObject_t sky, lut;
     uint32_t resolve_y0, resolve_y1;         // screen rows this rank resolves
@@ -156,6 +158,9 @@ struct LhContext {
     uint32_t* shadow = nullptr;
     void* display = nullptr;     // BGRA8
     float* depth_plane = nullptr;
+    void* resolve_tmp = nullptr;           // allocated by the first lh_render_frame
+    cudaStream_t resolve_stream = nullptr; // the material phase of the resolve runs here, beside the shadow passes
+    cudaEvent_t vis_ready = nullptr, material_done = nullptr;
 
     // scratch
     lh::FrameState* state = nullptr;
@@ -223,6 +228,11 @@ struct LhContext {
     void* scene_remote = nullptr;
     uint32_t row0 = 0, row1 = 0;           // screen rows this rank composites and resolves
     int num_sms = 148;
+    // launch shapes of the rasteriser; defaults measured on B200 at BASELINE config 2.  Developer overrides:
+    // LH_TUNE="main_bands,shadow_bands,main_grid,shadow_grid" in the environment at context creation.
+    struct Tuning {
+        uint32_t main_bands = 4, shadow_bands = 6, main_grid = 16, shadow_grid = 3;
+    } tune;
 
     std::vector<void*> buffers;
 };
@@ -240,7 +250,8 @@ void launch_cull_meshlets(LhContext* ctx, const FrameParams& p, int cascade, cud
 void launch_raster(LhContext* ctx, const FrameParams& p, int cascade, cudaStream_t stream = nullptr);
 void launch_reduce_depth(LhContext* ctx, const FrameParams& p);
 void launch_shadow_matrices(LhContext* ctx, const FrameParams& p);
-void launch_resolve(LhContext* ctx, const FrameParams& p);
+// phase 0: the whole pass; 1: material (no shadow maps needed); 2: shadows + combination (resolve.cu)
+void launch_resolve(LhContext* ctx, const FrameParams& p, int phase = 0, cudaStream_t stream = nullptr);
 void launch_display_transform(LhContext* ctx, const FrameParams& p);
 void launch_extract_depth(LhContext* ctx, const FrameParams& p);
 void launch_gather_stats(LhContext* ctx, const FrameParams& p, LhFrameStats* dst_dev_or_pinned);

@@ -42,6 +42,7 @@ enum { FLAG_INSIDE = 1, FLAG_SNAPPED = 2 };
 
 // Per-warp scratch of the meshlet kernel: snapped vertices and the compacted list of triangles that cover a sample.
 // sx holds two sentinels instead of a flag byte: kVertOutside (behind the w - z >= 0 plane) and kVertNonFinite.
+constexpr int LH_FRONT_CHUNK_MAX = 8;
 struct WarpScratch {
     int sx[LH_MAX_MESHLET_UNIQUE_VERTICES];
     int sy[LH_MAX_MESHLET_UNIQUE_VERTICES];
@@ -51,9 +52,23 @@ struct WarpScratch {
     // centre is <= it.  min/max over a triangle's vertices (SIMD halfword ops) give its pixel rectangle directly.
     uint2 cover[LH_MAX_MESHLET_UNIQUE_VERTICES];
     uint8_t surv[128];
+    // what the pointer chase of a ticket's entries found (one lane per entry walks reference -> instance -> mesh info
+    // -> meshlet, so the chain's four dependent round trips are paid once per ticket, not once per meshlet)
+    struct alignas(16) Staged {
+        float T[16];
+        const uint16_t* positions;
+        const void* indices;
+        const uint8_t* micro;      // already offset by triangle_offset
+        const LhMeshInfo* mi;
+        uint32_t index_offset, counts_flags;   // triangle_count | index_count << 8 | MeshInfo.flags << 16
+        uint32_t local, pad;
+    } staged[LH_FRONT_CHUNK_MAX];
 };
 constexpr int kVertOutside = INT_MIN, kVertNonFinite = INT_MIN + 1;   // |snapped| <= 2^29, so neither can be a coordinate
-constexpr int kFrontChunk = 4;             // queue entries a warp takes per ticket
+#ifndef LH_FRONT_CHUNK
+#define LH_FRONT_CHUNK 4
+#endif
+constexpr int kFrontChunk = LH_FRONT_CHUNK;   // queue entries a warp takes per ticket
 constexpr int kMaxOcclusionBlocks = 16;    // early-out reads at most 16 blocks of 8x4 pixels (512 keys)
 
 struct SnapVert {
@@ -289,6 +304,59 @@ __device__ __forceinline__ void load_header(const FrameParams& P, uint32_t slot,
     h.base_color_texture = __ldg(&mi->base_color_texture_index);
 }
 
+// The pointer chase of load_header by ONE lane, parked in shared memory (WarpScratch::Staged)
+__device__ __forceinline__ void chase_header(const FrameParams& P, uint32_t slot, WarpScratch::Staged& st) {
+    const LhMeshletReference* refs = (const LhMeshletReference*)P.pass_refs;
+    const unsigned long long ref = __ldg((const unsigned long long*)(refs + slot));
+    const uint32_t instance_index = (uint32_t)ref, meshlet_index = (uint32_t)(ref >> 32) & 0xFFFFu;
+    const LhInstance* inst = (const LhInstance*)P.u.instances + instance_index;
+    const float4 c0 = __ldg((const float4*)&inst->transform), c1 = __ldg((const float4*)&inst->transform + 1);
+    const float4 c2 = __ldg((const float4*)&inst->transform + 2), c3 = __ldg((const float4*)&inst->transform + 3);
+    const LhMeshInfo* mi = (const LhMeshInfo*)__ldg((const unsigned long long*)&inst->mesh_info_address);
+    const unsigned long long positions = __ldg((const unsigned long long*)&mi->positions), indices = __ldg((const unsigned long long*)&mi->indices);
+    const unsigned long long micro = __ldg((const unsigned long long*)&mi->micro_indices), meshlets = __ldg((const unsigned long long*)&mi->meshlets);
+    const uint32_t flags = __ldg(&mi->flags);
+    const LhMeshlet* m = (const LhMeshlet*)meshlets + meshlet_index;
+    const unsigned long long tail = __ldg((const unsigned long long*)m + 6);  // index_offset | counts
+    const uint32_t triangle_offset = __ldg(&m->triangle_offset);
+    *(float4*)&st.T[0] = c0; *(float4*)&st.T[4] = c1; *(float4*)&st.T[8] = c2; *(float4*)&st.T[12] = c3;
+    st.positions = (const uint16_t*)positions;
+    st.indices = (const void*)indices;
+    st.micro = (const uint8_t*)micro + triangle_offset;
+    st.mi = mi;
+    st.index_offset = (uint32_t)tail;
+    st.counts_flags = ((uint32_t)(tail >> 32) & 0xFFFFu) | (flags << 16);
+    st.local = slot;
+}
+
+// ... and its retrieval by the whole warp (broadcast reads); the alpha-clip fields are fetched only where needed
+__device__ __forceinline__ void unstage_header(const WarpScratch::Staged& st, MeshletHeader& h) {
+#pragma unroll
+    for (int k = 0; k < 16; k++) h.T[k] = st.T[k];
+    h.positions = st.positions;
+    h.indices = st.indices;
+    h.micro = st.micro;
+    h.index_offset = st.index_offset;
+    const uint32_t cf = st.counts_flags;
+    h.tri_count = cf & 0xFFu;
+    h.vert_count = (cf >> 8) & 0xFFu;
+    const uint32_t flags = cf >> 16;
+    h.wide = (flags & LH_MESH_INFO_FLAGS_32_BIT_INDICES) != 0;
+    h.alpha = (flags & LH_MESH_INFO_FLAGS_ALPHA_CLIP) != 0;
+    h.uvs = nullptr;
+    h.tex_scale[0] = h.tex_scale[1] = h.tex_offset[0] = h.tex_offset[1] = 0.0f;
+    h.base_color_texture = LH_UNUSED_TEXTURE_INDEX;
+    if (h.alpha) {
+        const LhMeshInfo* mi = st.mi;
+        h.uvs = (const uint16_t*)__ldg((const unsigned long long*)&mi->uvs);
+        h.tex_scale[0] = __ldg(&mi->texture_scale[0]);
+        h.tex_scale[1] = __ldg(&mi->texture_scale[1]);
+        h.tex_offset[0] = __ldg(&mi->texture_offset[0]);
+        h.tex_offset[1] = __ldg(&mi->texture_offset[1]);
+        h.base_color_texture = __ldg(&mi->base_color_texture_index);
+    }
+}
+
 // What the early-outs need of one meshlet: the instance transform (3x3 + translation, columns packed) and the
 // meshlet's object-space bounding sphere.  Called by one lane per meshlet.
 __device__ __forceinline__ void load_bounds(const FrameParams& P, uint32_t slot, float T[12], float sphere[4]) {
@@ -364,13 +432,13 @@ struct MeshletBound {
     uint32_t key;              // depth key, smaller = nearer; kKeyEmpty: the rectangle holds no pixel centre
 };
 constexpr uint32_t kUntestable = 0xFFFFFFFFu, kKeyEmpty = 0xFFFFFFFFu;
-#ifndef LH_BANDS
-#define LH_BANDS 6
-#endif
-constexpr int kBands = LH_BANDS;
+constexpr int kMaxBands = 8;   // bands per view: FrameParams::num_bands (LhContext::Tuning), 2..8
 constexpr uint32_t kHistShift = 19, kHistBins = 1u << (32 - kHistShift);   // 8192 bins over the top bits of the depth key
 constexpr int kHizShift0 = 2, kHizShift1 = 4;   // hierarchical-Z levels: 4x4-pixel and 16x16-pixel tiles
-constexpr int kMaxHizTiles = 48;                // selection reads at most this many tiles of one level per meshlet
+#ifndef LH_MAX_HIZ_TILES
+#define LH_MAX_HIZ_TILES 48
+#endif
+constexpr int kMaxHizTiles = LH_MAX_HIZ_TILES;   // selection reads at most this many tiles of one level per meshlet
 
 // sigma_max(T) * r bounds |T (v - c)| for v in the object-space sphere (c, r).  Gershgorin on the Gram matrix and the
 // Frobenius norm are both valid for any matrix; for rotation * scale the first equals the reference's max column length.
@@ -498,15 +566,12 @@ __global__ void __launch_bounds__(1024) raster_bands_kernel(const __grid_constan
     if (tid == 1023) grand_total = partial[1023];
     __syncthreads();
     const uint32_t total = grand_total, before = partial[tid] - sum;
-#if LH_BANDS == 6
-    const float fractions[kBands - 1] = {0.02f, 0.07f, 0.17f, 0.35f, 0.60f};
-#elif LH_BANDS == 8
-    const float fractions[kBands - 1] = {0.01f, 0.03f, 0.07f, 0.14f, 0.26f, 0.42f, 0.65f};
-#elif LH_BANDS == 10
-    const float fractions[kBands - 1] = {0.01f, 0.025f, 0.05f, 0.09f, 0.15f, 0.24f, 0.36f, 0.52f, 0.72f};
-#elif LH_BANDS == 4
-    const float fractions[kBands - 1] = {0.03f, 0.12f, 0.40f};
-#endif
+    // cumulative count fractions at which the bands end, for each band count
+    const float tables[kMaxBands + 1][kMaxBands - 1] = {
+        {}, {}, {0.10f}, {0.04f, 0.25f}, {0.03f, 0.12f, 0.40f}, {0.025f, 0.09f, 0.25f, 0.55f}, {0.02f, 0.07f, 0.17f, 0.35f, 0.60f},
+        {0.015f, 0.05f, 0.11f, 0.22f, 0.40f, 0.65f}, {0.01f, 0.03f, 0.07f, 0.14f, 0.26f, 0.42f, 0.65f}};
+    const int kBands = (int)min(max(P.num_bands, 2u), (uint32_t)kMaxBands);
+    const float* fractions = tables[kBands];
     PassState* st = P.pass;
     if (tid == 0) {
         st->band_key[kBands - 1] = kKeyEmpty;   // the last band takes the rest (empty meshlets carry kKeyEmpty and are never selected)
@@ -703,7 +768,11 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, LH_RASTER_MIN_CTAS) raster_
         if (lane < n) {
             my_k = __ldg(P.raster_queue + ticket + lane);
             my_mb = __ldg((const uint4*)(bounds + my_k));
+            uint32_t slot, local;
+            work_to_slot(P, my_k, n_opaque, SHADOW, &slot, &local);
+            chase_header(P, slot, sv.staged[lane]);
         }
+        __syncwarp();
         uint32_t first[kFrontChunk];
 #pragma unroll
         for (int j = 0; j < kFrontChunk; j++) {
@@ -737,10 +806,9 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, LH_RASTER_MIN_CTAS) raster_
                     continue;
                 }
             }
-            uint32_t slot, local;
-            work_to_slot(P, k, n_opaque, SHADOW, &slot, &local);
+            const uint32_t local = sv.staged[j].local;
             MeshletHeader h;
-            load_header(P, slot, h);
+            unstage_header(sv.staged[j], h);
 
             const uint32_t nv = min(h.vert_count, (uint32_t)LH_MAX_MESHLET_UNIQUE_VERTICES);
             // cull modes: pipelines.cpp:10-25,255-315
@@ -1099,16 +1167,21 @@ __global__ void end_main_pass_kernel(const __grid_constant__ FrameParams P) {
 
 }  // namespace
 
-void launch_raster(LhContext* ctx, const FrameParams& p, int cascade, cudaStream_t stream) {
+void launch_raster(LhContext* ctx, const FrameParams& params, int cascade, cudaStream_t stream) {
     if (!stream) stream = ctx->stream;
-    const uint32_t grid = (uint32_t)ctx->num_sms * 8;
+    // The main view runs alone: many small CTAs even out its heavy near meshlets.  The cascades run side by side on
+    // four streams: grids of about one wave each let their kernels share the SMs instead of queueing behind one another.
+    const uint32_t bands = cascade < 0 ? ctx->tune.main_bands : ctx->tune.shadow_bands;
+    const uint32_t grid = (uint32_t)ctx->num_sms * (cascade < 0 ? ctx->tune.main_grid : ctx->tune.shadow_grid);
+    FrameParams p = params;
+    p.num_bands = bands;
     const bool timed = cascade < 0 && (ctx->cfg.flags & LH_CONFIG_PASS_TIMINGS) != 0;
     if (timed) cudaEventRecord(ctx->raster_kernel_a, stream);
     if (cascade < 0) raster_bounds_kernel<false><<<grid, 256, 0, stream>>>(p, 0);
     else raster_bounds_kernel<true><<<grid, 256, 0, stream>>>(p, (uint32_t)cascade);
     raster_bands_kernel<<<1, 1024, 0, stream>>>(p);   // also opens the pass: empty raster and deferred queues
     ctx->launches += 2;
-    for (uint32_t band = 0; band < (uint32_t)kBands; band++) {
+    for (uint32_t band = 0; band < bands; band++) {
         if (band != 0) {
             if (cascade < 0) raster_hiz_kernel<false><<<grid, 256, 0, stream>>>(p, 0);
             else raster_hiz_kernel<true><<<grid, 256, 0, stream>>>(p, (uint32_t)cascade);
@@ -1122,7 +1195,7 @@ void launch_raster(LhContext* ctx, const FrameParams& p, int cascade, cudaStream
         // The deferred queue is drained after the near bands (whose large triangles are the best occluders for the
         // bands that follow) and at the end; twice each time: the first launch splits, the second rasterises the pieces.
         // Each launch takes the entries appended before it began (finish_launch of the launch ahead of it).
-        if (band < 3 || band + 1 == (uint32_t)kBands) {
+        if (band < 3 || band + 1 == bands) {
             for (int round = 0; round < 2; round++) {
                 if (cascade < 0) raster_deferred_kernel<false><<<grid, kDeferredWarps * 32, 0, stream>>>(p, 0);
                 else raster_deferred_kernel<true><<<grid, kDeferredWarps * 32, 0, stream>>>(p, (uint32_t)cascade);

@@ -199,6 +199,14 @@ __device__ __forceinline__ unsigned long long owner_load(const LhMeshletReferenc
     return __ldcg((const unsigned long long*)p);
 }
 
+// PHASE 0: the whole pass.  The pass can also run in two launches, so that everything that does not need the shadow
+// maps overlaps the shadow passes (lh_render_frame):
+// PHASE 1 (material): visibility decode, attribute refetch, barycentrics, textures, BRDF -> per pixel the un-shadowed
+//          sun term, the ambient term, the world position and the alpha-clip flag (40 B in P.resolve_tmp); sky pixels
+//          are finished here;
+// PHASE 2 (shadow): cascade selection, 3x3 PCF, combination, RGBA16F store.
+// The combination is written with explicit roundings so that all phases produce the same bits.
+template <int PHASE>
 __global__ void __launch_bounds__(256) resolve_kernel(const __grid_constant__ FrameParams P) {
     const uint32_t W = P.u.window_size[0], H = P.u.window_size[1];
     // 32x8 pixels per CTA, one 8x4 block per warp
@@ -209,6 +217,12 @@ __global__ void __launch_bounds__(256) resolve_kernel(const __grid_constant__ Fr
     const size_t pixel = (size_t)y * W + x;
     const float ndc_x = (float)x / (float)W * 2.0f - 1.0f;  // pixel corner, render_geometry.comp:82-84
     const float ndc_y = (float)y / (float)H * 2.0f - 1.0f;
+    float4* tmp0 = (float4*)P.resolve_tmp;
+    float4* tmp1 = tmp0 + (size_t)W * H;
+    float2* tmp2 = (float2*)(tmp1 + (size_t)W * H);
+    F3 world, sun, ambient;
+    bool alpha;
+    if (PHASE != 2) {
     const unsigned long long key = P.vis[pixel];
     if (lh_vis_depth_bits(key) == 0u) {  // depth == 0: sky (:86-101)
         float4 un = mul4(&P.u.perspective_inverse.m[0][0], ndc_x, ndc_y, 0.0f, 1.0f);
@@ -216,6 +230,7 @@ __global__ void __launch_bounds__(256) resolve_kernel(const __grid_constant__ Fr
         float4 ray = mul4(&P.u.view_inverse.m[0][0], local.x, local.y, local.z, 0.0f);
         float4 s = P.sky ? texCubemapLod<float4>(P.sky, ray.x, ray.y, ray.z, 0.0f) : make_float4(0, 0, 0, 0);
         store_rgba16f(P.scene, P.scene_remote, pixel, s.x * 8.0f, s.y * 8.0f, s.z * 8.0f, 1.0f);
+        if (PHASE == 1) tmp2[pixel] = make_float2(0.0f, -1.0f);   // nothing left to do for this pixel
         return;
     }
     const uint32_t slot = lh_vis_slot(key), tri = lh_vis_tri(key);
@@ -242,7 +257,8 @@ __global__ void __launch_bounds__(256) resolve_kernel(const __grid_constant__ Fr
     const uint8_t* micro = (const uint8_t*)__ldg((const unsigned long long*)&mi->micro_indices);
     const LhMeshlet* m = (const LhMeshlet*)__ldg((const unsigned long long*)&mi->meshlets) + meshlet_index;
     const uint32_t flags = __ldg(&mi->flags);
-    const bool wide = (flags & LH_MESH_INFO_FLAGS_32_BIT_INDICES) != 0, alpha = (flags & LH_MESH_INFO_FLAGS_ALPHA_CLIP) != 0;
+    const bool wide = (flags & LH_MESH_INFO_FLAGS_32_BIT_INDICES) != 0;
+    alpha = (flags & LH_MESH_INFO_FLAGS_ALPHA_CLIP) != 0;
     const uint32_t index_offset = __ldg(&m->index_offset);
     micro += __ldg(&m->triangle_offset) + 3 * tri;
 
@@ -267,7 +283,7 @@ __global__ void __launch_bounds__(256) resolve_kernel(const __grid_constant__ Fr
     const Interp wx = interp1(bary, pos[0].x, pos[1].x, pos[2].x);
     const Interp wy = interp1(bary, pos[0].y, pos[1].y, pos[2].y);
     const Interp wz = interp1(bary, pos[0].z, pos[1].z, pos[2].z);
-    const F3 world{wx.value, wy.value, wz.value};
+    world = F3{wx.value, wy.value, wz.value};
     const Interp iu = interp1(bary, tu[0], tu[1], tu[2]), iv = interp1(bary, tv[0], tv[1], tv[2]);
     const float u = iu.value + __ldg(&mi->texture_offset[0]), v = iv.value + __ldg(&mi->texture_offset[1]);
     const float2 duv_dx = make_float2(iu.dx, iv.dx), duv_dy = make_float2(iu.dy, iv.dy);
@@ -284,28 +300,6 @@ __global__ void __launch_bounds__(256) resolve_kernel(const __grid_constant__ Fr
                               n9[2] * normal.x + n9[5] * normal.y + n9[8] * normal.z});
     }
     if (dot(cross(pos[1] - pos[0], pos[2] - pos[0]), view_vec) < 0.0f) normal = normal * -1.0f;
-
-    // cascade selection (:183-196) and 3x3 PCF (:200-226)
-    const LhMiscStorage* misc = (const LhMiscStorage*)P.u.misc_storage;
-    uint32_t cascade;
-    float4 sc = make_float4(0, 0, 0, 0);
-    for (cascade = 0; cascade < 4; cascade++) {
-        sc = mul4(&misc->uv_space_shadow_matrices[cascade].m[0][0], world.x, world.y, world.z, 1.0f);
-        if (fabsf(sc.x - 0.5f) < 0.5f && fabsf(sc.y - 0.5f) < 0.5f) break;
-    }
-    const float bias = alpha ? 0.000002f : 0.0f;
-    const float inv_w = 1.0f / sc.w;
-    sc.x *= inv_w; sc.y *= inv_w; sc.z *= inv_w;
-    const int sn = (int)P.shadowmap_size;
-    const uint32_t* layer = P.shadow + (size_t)min(cascade, 3u) * sn * sn;
-    float shadow_sum = 0.0f;
-#pragma unroll
-    for (int ox = -1; ox <= 1; ox++)
-#pragma unroll
-        for (int oy = -1; oy <= 1; oy++)
-            shadow_sum += sample_shadow(layer, sn, sc.x + (float)ox / 1024.0f, sc.y + (float)oy / 1024.0f, sc.z - bias);
-    shadow_sum *= (1.0f / 9.0f);
-    if (sc.z > 1.0f) shadow_sum = 1.0f;
 
     // material (:228-246)
     F3 base{1, 1, 1};
@@ -334,11 +328,50 @@ __global__ void __launch_bounds__(256) resolve_kernel(const __grid_constant__ Fr
         normal = normalize(t3 * (invmax * mn.x) + b3 * (invmax * mn.y) + normal * mn.z);
     }
     const float amb = 0.025f + 0.025f * normal.y;  // SH with sh[0] = sh[2] = 0.025 (:40-57)
-    const F3 sun = brdf(view_vec, F3{P.u.sun_dir[0], P.u.sun_dir[1], P.u.sun_dir[2]}, normal, roughness, metallic, base, alpha);
-    const float sun_intensity = kPi * shadow_sum;
-    const float dm = 1.0f - metallic;
-    store_rgba16f(P.scene, P.scene_remote, pixel, sun.x * sun_intensity + amb * dm * base.x, sun.y * sun_intensity + amb * dm * base.y,
-                  sun.z * sun_intensity + amb * dm * base.z, 1.0f);
+    sun = brdf(view_vec, F3{P.u.sun_dir[0], P.u.sun_dir[1], P.u.sun_dir[2]}, normal, roughness, metallic, base, alpha);
+    const float adm = __fmul_rn(amb, 1.0f - metallic);
+    ambient = F3{__fmul_rn(adm, base.x), __fmul_rn(adm, base.y), __fmul_rn(adm, base.z)};
+    if (PHASE == 1) {
+        tmp0[pixel] = make_float4(sun.x, sun.y, sun.z, world.x);
+        tmp1[pixel] = make_float4(ambient.x, ambient.y, ambient.z, world.y);
+        tmp2[pixel] = make_float2(world.z, alpha ? 1.0f : 0.0f);
+        return;
+    }
+    } else {   // PHASE 2: pick up what the material phase left
+        const float2 c = tmp2[pixel];
+        if (c.y < 0.0f) return;
+        const float4 a = tmp0[pixel], b = tmp1[pixel];
+        sun = F3{a.x, a.y, a.z};
+        ambient = F3{b.x, b.y, b.z};
+        world = F3{a.w, b.w, c.x};
+        alpha = c.y > 0.5f;
+    }
+
+    // cascade selection (:183-196) and 3x3 PCF (:200-226)
+    const LhMiscStorage* misc = (const LhMiscStorage*)P.u.misc_storage;
+    uint32_t cascade;
+    float4 sc = make_float4(0, 0, 0, 0);
+    for (cascade = 0; cascade < 4; cascade++) {
+        sc = mul4(&misc->uv_space_shadow_matrices[cascade].m[0][0], world.x, world.y, world.z, 1.0f);
+        if (fabsf(sc.x - 0.5f) < 0.5f && fabsf(sc.y - 0.5f) < 0.5f) break;
+    }
+    const float bias = alpha ? 0.000002f : 0.0f;
+    const float inv_w = 1.0f / sc.w;
+    sc.x *= inv_w; sc.y *= inv_w; sc.z *= inv_w;
+    const int sn = (int)P.shadowmap_size;
+    const uint32_t* layer = P.shadow + (size_t)min(cascade, 3u) * sn * sn;
+    float shadow_sum = 0.0f;
+#pragma unroll
+    for (int ox = -1; ox <= 1; ox++)
+#pragma unroll
+        for (int oy = -1; oy <= 1; oy++)
+            shadow_sum += sample_shadow(layer, sn, sc.x + (float)ox / 1024.0f, sc.y + (float)oy / 1024.0f, sc.z - bias);
+    shadow_sum *= (1.0f / 9.0f);
+    if (sc.z > 1.0f) shadow_sum = 1.0f;
+
+    const float sun_intensity = __fmul_rn(kPi, shadow_sum);
+    store_rgba16f(P.scene, P.scene_remote, pixel, __fmaf_rn(sun.x, sun_intensity, ambient.x), __fmaf_rn(sun.y, sun_intensity, ambient.y),
+                  __fmaf_rn(sun.z, sun_intensity, ambient.z), 1.0f);
 }
 
 // display_transform.comp:37-81: Tony McMapface LUT (48^3) + sRGB OETF -> BGRA8
@@ -368,11 +401,15 @@ __global__ void __launch_bounds__(256) display_transform_kernel(const __grid_con
 
 }  // namespace
 
-void launch_resolve(LhContext* ctx, const FrameParams& p) {
+void launch_resolve(LhContext* ctx, const FrameParams& p, int phase, cudaStream_t stream) {
     uint32_t W = p.u.window_size[0], rows = min(p.u.window_size[1], p.resolve_y1) - p.resolve_y0;
     if (!W || !rows) return;
+    if (!stream) stream = ctx->stream;
     dim3 grid((W + 31) / 32, (rows + 7) / 8);
-    resolve_kernel<<<grid, 256, 0, ctx->stream>>>(p); ctx->launches++;
+    if (phase == 0) resolve_kernel<0><<<grid, 256, 0, stream>>>(p);
+    else if (phase == 1) resolve_kernel<1><<<grid, 256, 0, stream>>>(p);
+    else resolve_kernel<2><<<grid, 256, 0, stream>>>(p);
+    ctx->launches++;
 }
 
 void launch_display_transform(LhContext* ctx, const FrameParams& p) {
