@@ -278,8 +278,9 @@ int lh_context_create(const LhConfig* cfg, LhContext** out) {
     cudaGetDeviceProperties(&prop, cfg->device);
     ctx->num_sms = prop.multiProcessorCount;
     if (const char* t = getenv("LH_TUNE")) {
-        unsigned v[4] = {ctx->tune.main_bands, ctx->tune.shadow_bands, ctx->tune.main_grid, ctx->tune.shadow_grid};
-        sscanf(t, "%u,%u,%u,%u", &v[0], &v[1], &v[2], &v[3]);
+        unsigned v[5] = {ctx->tune.main_bands, ctx->tune.shadow_bands, ctx->tune.main_grid, ctx->tune.shadow_grid, ctx->tune.resolve_low_priority};
+        sscanf(t, "%u,%u,%u,%u,%u", &v[0], &v[1], &v[2], &v[3], &v[4]);
+        ctx->tune.resolve_low_priority = v[4] != 0;
         auto clamp = [](unsigned x, unsigned lo, unsigned hi) { return x < lo ? lo : (x > hi ? hi : x); };
         ctx->tune.main_bands = clamp(v[0], 2, 8);
         ctx->tune.shadow_bands = clamp(v[1], 2, 8);
@@ -301,7 +302,7 @@ int lh_context_create(const LhConfig* cfg, LhContext** out) {
     int prio_least = 0, prio_greatest = 0;
     cudaDeviceGetStreamPriorityRange(&prio_least, &prio_greatest);
     TRY(cudaStreamCreateWithPriority(&ctx->stream, cudaStreamNonBlocking, prio_greatest));
-    TRY(cudaStreamCreateWithPriority(&ctx->resolve_stream, cudaStreamNonBlocking, prio_least));
+    TRY(cudaStreamCreateWithPriority(&ctx->resolve_stream, cudaStreamNonBlocking, ctx->tune.resolve_low_priority ? prio_least : prio_greatest));
     TRY(cudaEventCreateWithFlags(&ctx->vis_ready, cudaEventDisableTiming));
     TRY(cudaEventCreateWithFlags(&ctx->material_done, cudaEventDisableTiming));
     int rc = alloc_targets(ctx, cfg->width, cfg->height);

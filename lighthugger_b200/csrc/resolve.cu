@@ -150,6 +150,30 @@ __device__ __forceinline__ float sample_shadow(const uint32_t* layer, int n, flo
     return top + wy * (bot - top);
 }
 
+// The 3x3 PCF of render_geometry.comp:200-226 when the tap spacing (1/1024) is exactly one texel: the nine bilinear
+// compare taps share their fractional weights and touch a 4x4 texel neighbourhood, each texel with the summed weight
+// (1-w, 1, 1, w) per axis -- 16 loads instead of 36.  Returns the sum over the nine taps.
+__device__ __forceinline__ float pcf3x3_texel_spaced(const uint32_t* layer, int n, float u, float v, float ref) {
+    float x = u * (float)n - 0.5f, y = v * (float)n - 0.5f;
+    if (!(isfinite(x) && isfinite(y))) return 0.0f;
+    float fx = floorf(x), fy = floorf(y);
+    const float wx = x - fx, wy = y - fy;
+    fx = fminf(fmaxf(fx, -3.0f), (float)n + 2.0f);
+    fy = fminf(fmaxf(fy, -3.0f), (float)n + 2.0f);
+    const int bx = (int)fx - 1, by = (int)fy - 1;
+    const float wcol[4] = {1.0f - wx, 1.0f, 1.0f, wx}, wrow[4] = {1.0f - wy, 1.0f, 1.0f, wy};
+    float sum = 0.0f;
+#pragma unroll
+    for (int r = 0; r < 4; r++) {
+        const uint32_t* row = layer + (size_t)min(max(by + r, 0), n - 1) * n;
+        float acc = 0.0f;
+#pragma unroll
+        for (int c = 0; c < 4; c++) acc += ref < __uint_as_float(__ldg(row + min(max(bx + c, 0), n - 1))) ? wcol[c] : 0.0f;
+        sum += wrow[r] * acc;
+    }
+    return sum;
+}
+
 // textureGrad through repeat_sampler (render_geometry.comp:59-66, src/main.cpp:550-560).  Footprint per the Vulkan
 // specification's anisotropic model; every tap is one hardware bilinear fetch (BC decode + sRGB in the texture unit)
 // at an integer mip level.
@@ -361,11 +385,15 @@ __global__ void __launch_bounds__(256) resolve_kernel(const __grid_constant__ Fr
     const int sn = (int)P.shadowmap_size;
     const uint32_t* layer = P.shadow + (size_t)min(cascade, 3u) * sn * sn;
     float shadow_sum = 0.0f;
+    if (sn == 1024) {
+        shadow_sum = pcf3x3_texel_spaced(layer, sn, sc.x, sc.y, sc.z - bias);
+    } else {
 #pragma unroll
-    for (int ox = -1; ox <= 1; ox++)
+        for (int ox = -1; ox <= 1; ox++)
 #pragma unroll
-        for (int oy = -1; oy <= 1; oy++)
-            shadow_sum += sample_shadow(layer, sn, sc.x + (float)ox / 1024.0f, sc.y + (float)oy / 1024.0f, sc.z - bias);
+            for (int oy = -1; oy <= 1; oy++)
+                shadow_sum += sample_shadow(layer, sn, sc.x + (float)ox / 1024.0f, sc.y + (float)oy / 1024.0f, sc.z - bias);
+    }
     shadow_sum *= (1.0f / 9.0f);
     if (sc.z > 1.0f) shadow_sum = 1.0f;
 
