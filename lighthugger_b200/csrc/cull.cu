@@ -18,6 +18,7 @@
 // grid that takes tiles by ticket, finds the tile's instance window with two
 // binary searches and lets every thread finish its search inside that window.
 #include "lh_internal.cuh"
+#include "raster_bounds.cuh"
 
 namespace lh {
 
@@ -306,7 +307,11 @@ struct Survivor {
 
 template <bool SHADOWS>
 __global__ void __launch_bounds__(256) cull_meshlets_kernel(const __grid_constant__ FrameParams P, uint32_t cascade) {
-    __shared__ Survivor staged[2][kMeshletTile];  // [0] opaque, [1] alpha-clip, in ascending candidate order
+    // a tile has at most kMeshletTile survivors over both classes: the opaque ones are staged from the front (ascending
+    // candidate order), the alpha-clip ones from the back; each with the screen bound the rasteriser will want
+    __shared__ Survivor staged[kMeshletTile];
+    __shared__ uint4 staged_bound[kMeshletTile];
+    __shared__ BoundView bview;
     __shared__ uint32_t warp_counts[2][8];
     __shared__ uint32_t window[2];
     __shared__ uint32_t tile_ticket;
@@ -331,6 +336,8 @@ __global__ void __launch_bounds__(256) cull_meshlets_kernel(const __grid_constan
     PassState* ps = P.pass;
 
     if (tid == 0) planes = frustum_planes(P.u);
+    if (tid == 32) make_bound_view<SHADOWS>(P, cascade, bview);
+    uint32_t empty_bounds = 0;
     if (blockIdx.x == 0 && tid == 0) {
         // reset_buffers_b / _c: indirect size for the reference's 64-wide dispatch
         ((LhDispatchIndirectCommand*)P.u.dispatches)[LH_PER_MESHLET_DISPATCH] = LhDispatchIndirectCommand{dispatch_size((uint32_t)c64, 64), 1, 1};
@@ -365,6 +372,7 @@ __global__ void __launch_bounds__(256) cull_meshlets_kernel(const __grid_constan
             const uint32_t g = g0 + round * 256 + tid;
             uint32_t cls = 2;  // 0 opaque survivor, 1 alpha-clip survivor, 2 culled
             Survivor sv{0, 0};
+            uint4 bound = make_uint4(0u, 0u, 0u, 0u);
             if (g < g_end) {
                 // get_meshlet_reference, common/util.glsl:42-59
                 uint32_t vi = upper_bound_sum(values, win_lo, win_hi, g);
@@ -411,6 +419,14 @@ __global__ void __launch_bounds__(256) cull_meshlets_kernel(const __grid_constan
                     cls = alpha ? 1u : 0u;
                     sv.instance_index = r.index;
                     sv.meshlet_and_tris = local | (tri_count << 16);
+                    // the rasteriser's bound of this meshlet, and its depth key into the band histogram (aggregated over
+                    // the lanes that fall into the same bin: neighbouring meshlets mostly do)
+                    const MeshletBound mb = meshlet_bound<SHADOWS>(bview, Tl, mf + 7);
+                    bound = make_uint4(mb.rect_x, mb.rect_y, mb.edge, mb.key);
+                    const uint32_t bin = mb.key == kKeyEmpty ? kHistBins : mb.key >> kHistShift;
+                    if (mb.key == kKeyEmpty) empty_bounds++;
+                    const uint32_t peers = __match_any_sync(__activemask(), bin);
+                    if (bin < kHistBins && lane == (uint32_t)(__ffs(peers) - 1)) atomicAdd(P.depth_hist + bin, (uint32_t)__popc(peers));
                 }
             }
             // stable ranks inside the round, per class
@@ -432,7 +448,9 @@ __global__ void __launch_bounds__(256) cull_meshlets_kernel(const __grid_constan
             }
             if (cls < 2) {
                 uint32_t rank = base_count[cls] + before[cls] + __popc((cls ? b1 : b0) & ((1u << lane) - 1u));
-                staged[cls][rank] = sv;
+                const uint32_t at = cls ? kMeshletTile - 1u - rank : rank;
+                staged[at] = sv;
+                staged_bound[at] = bound;
             }
             base_count[0] += round_total[0];
             base_count[1] += round_total[1];
@@ -458,8 +476,12 @@ __global__ void __launch_bounds__(256) cull_meshlets_kernel(const __grid_constan
                     atomicOr(&st->overflow, cls ? (uint32_t)LH_OVERFLOW_ALPHA_CLIP : (uint32_t)LH_OVERFLOW_OPAQUE);
                     continue;
                 }
-                Survivor s = staged[cls][k];
+                const uint32_t at = cls ? kMeshletTile - 1u - k : k;
+                Survivor s = staged[at];
                 uint32_t draw_index = first_draw + n, slot = draw_index + P.pass_slot_base;
+                const uint4 bound = staged_bound[at];
+                ((uint4*)P.meshlet_bounds)[draw_index] = bound;
+                P.depth_keys[draw_index] = bound.w;
                 LhMeshletReference ref;
                 ref.instance_index = s.instance_index;
                 ref.meshlet_index = (uint16_t)(s.meshlet_and_tris & 0xFFFFu);
@@ -481,6 +503,10 @@ __global__ void __launch_bounds__(256) cull_meshlets_kernel(const __grid_constan
                 st->main_alpha_clip = n1;
             }
         }
+    }
+    if (P.flags & LH_CONFIG_PASS_TIMINGS) {
+        empty_bounds = __reduce_add_sync(0xFFFFFFFFu, empty_bounds);
+        if (lane == 0 && empty_bounds) atomicAdd(&st->skipped_empty[SHADOWS ? 1u + cascade : 0u], empty_bounds);
     }
     // self-cleaning: the last CTA out zeroes the tile states and the ticket
     __shared__ uint32_t last_out;

@@ -25,6 +25,7 @@
 // 64-bit edge functions.  Both paths evaluate identical integer coverage and
 // the identical depth expression, so the result is independent of the split.
 #include "lh_internal.cuh"
+#include "raster_bounds.cuh"
 
 namespace lh {
 
@@ -413,9 +414,10 @@ __device__ __forceinline__ void push_deferred(const FrameParams& P, uint32_t lo,
 // The reference's hardware rasteriser rejects hidden geometry early (hierarchical Z); a software rasteriser that
 // pushes 10^8 sub-pixel triangles through 64-bit atomics needs the same, and gets it at meshlet granularity:
 //
-//   raster_bounds_kernel   one lane per surviving meshlet: interval arithmetic through the view's matrix on the
-//                          meshlet's bounding sphere gives a conservative pixel rectangle, a conservative nearest
-//                          depth ("edge") and a depth key; stored as a 16-byte MeshletBound, keys histogrammed.
+//   (cull_meshlets_kernel) for every survivor, while its transform and sphere are in registers: interval arithmetic
+//                          through the view's matrix on the bounding sphere gives a conservative pixel rectangle, a
+//                          conservative nearest depth ("edge") and a depth key (raster_bounds.cuh); stored as a
+//                          16-byte MeshletBound next to the survivor's list entry, keys histogrammed.
 //   raster_bands_kernel    one CTA: histogram -> kBands key thresholds at fixed count fractions (nearest band small).
 //   raster_select_kernel   per band, nearest first: meshlets of the band whose rectangle holds a pixel centre and in
 //                          which some stored key is NOT already nearer than the edge depth are appended to a queue.
@@ -425,115 +427,6 @@ __device__ __forceinline__ void push_deferred(const FrameParams& P, uint32_t lo,
 //
 // Keys only ever decrease and a dropped meshlet could not have won any pixel, so the final buffer is bit-identical to
 // rasterising everything (tests compare it with the oracle, which does exactly that).
-
-struct MeshletBound {
-    uint32_t rect_x, rect_y;   // px0 | px1 << 16, py0 | py1 << 16; rect_x == kUntestable: rasterise without a test
-    uint32_t edge;             // main view: ~floatBits(nearest depth); cascade: floatBits(nearest depth)
-    uint32_t key;              // depth key, smaller = nearer; kKeyEmpty: the rectangle holds no pixel centre
-};
-constexpr uint32_t kUntestable = 0xFFFFFFFFu, kKeyEmpty = 0xFFFFFFFFu;
-constexpr int kMaxBands = 8;   // bands per view: FrameParams::num_bands (LhContext::Tuning), 2..8
-constexpr uint32_t kHistShift = 19, kHistBins = 1u << (32 - kHistShift);   // 8192 bins over the top bits of the depth key
-constexpr int kHizShift0 = 2, kHizShift1 = 4;   // hierarchical-Z levels: 4x4-pixel and 16x16-pixel tiles
-#ifndef LH_MAX_HIZ_TILES
-#define LH_MAX_HIZ_TILES 48
-#endif
-constexpr int kMaxHizTiles = LH_MAX_HIZ_TILES;   // selection reads at most this many tiles of one level per meshlet
-
-// sigma_max(T) * r bounds |T (v - c)| for v in the object-space sphere (c, r).  Gershgorin on the Gram matrix and the
-// Frobenius norm are both valid for any matrix; for rotation * scale the first equals the reference's max column length.
-// T here is the 3x3 part + translation of the instance transform, columns packed: T[0..2], T[3..5], T[6..8], T[9..11].
-__device__ __forceinline__ float sigma_max_bound(const float* T) {
-    const float c00 = T[0] * T[0] + T[1] * T[1] + T[2] * T[2], c11 = T[3] * T[3] + T[4] * T[4] + T[5] * T[5],
-                c22 = T[6] * T[6] + T[7] * T[7] + T[8] * T[8];
-    const float c01 = fabsf(T[0] * T[3] + T[1] * T[4] + T[2] * T[5]), c02 = fabsf(T[0] * T[6] + T[1] * T[7] + T[2] * T[8]),
-                c12 = fabsf(T[3] * T[6] + T[4] * T[7] + T[5] * T[8]);
-    const float gersh = fmaxf(fmaxf(c00 + c01 + c02, c11 + c01 + c12), c22 + c02 + c12);
-    return sqrtf(fminf(gersh, c00 + c11 + c22)) * 1.00001f;
-}
-
-template <bool SHADOW>
-__global__ void __launch_bounds__(256) raster_bounds_kernel(const __grid_constant__ FrameParams P, uint32_t cascade) {
-    const uint32_t* draw = (const uint32_t*)P.pass_draw_calls;
-    const uint32_t n_opaque = min(draw[0], P.max_opaque), n_alpha = min(draw[1], P.max_alpha);
-    const uint32_t total = n_opaque + n_alpha;
-    const int W = (int)(SHADOW ? P.shadowmap_size : P.u.window_size[0]), H = (int)(SHADOW ? P.shadowmap_size : P.u.window_size[1]);
-    const float half_w = (float)W * 0.5f, half_h = (float)H * 0.5f;
-    float Mreg[SHADOW ? 16 : 1];
-    if (SHADOW) {
-        const float* src = &((const LhMiscStorage*)P.u.misc_storage)->shadow_matrices[cascade].m[0][0];
-#pragma unroll
-        for (int k = 0; k < (SHADOW ? 16 : 1); k++) Mreg[k] = src[k];
-    }
-    const float* M = SHADOW ? Mreg : &P.u.combined_perspective_view.m[0][0];
-    // |row_k.xyz| of M
-    const float nrm_x = sqrtf(M[0] * M[0] + M[4] * M[4] + M[8] * M[8]), nrm_y = sqrtf(M[1] * M[1] + M[5] * M[5] + M[9] * M[9]);
-    const float nrm_z = sqrtf(M[2] * M[2] + M[6] * M[6] + M[10] * M[10]), nrm_w = sqrtf(M[3] * M[3] + M[7] * M[7] + M[11] * M[11]);
-    MeshletBound* bounds = (MeshletBound*)P.meshlet_bounds;
-    uint32_t empty = 0;
-    for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < total; k += gridDim.x * blockDim.x) {
-        uint32_t slot, local;
-        work_to_slot(P, k, n_opaque, SHADOW, &slot, &local);
-        float T[12], sphere[4];
-        load_bounds(P, slot, T, sphere);
-        MeshletBound mb{kUntestable, 0u, 0u, 0u};   // no usable bound: nearest band, rasterised without a test
-        const float R0 = sphere[3] * sigma_max_bound(T);
-        const float wx = T[0] * sphere[0] + T[3] * sphere[1] + T[6] * sphere[2] + T[9];
-        const float wy = T[1] * sphere[0] + T[4] * sphere[1] + T[7] * sphere[2] + T[10];
-        const float wz = T[2] * sphere[0] + T[5] * sphere[1] + T[8] * sphere[2] + T[11];
-        // radius padded for the rounding of the vertex transform itself (a few ulp of the terms' magnitude)
-        const float R = R0 * 1.0001f + 2e-6f * (fabsf(wx) + fabsf(wy) + fabsf(wz) + fabsf(T[9]) + fabsf(T[10]) + fabsf(T[11]));
-        const float ccx = M[0] * wx + M[4] * wy + M[8] * wz + M[12], ccy = M[1] * wx + M[5] * wy + M[9] * wz + M[13];
-        const float ccz = M[2] * wx + M[6] * wy + M[10] * wz + M[14], ccw = M[3] * wx + M[7] * wy + M[11] * wz + M[15];
-        const float ex = R * nrm_x, ey = R * nrm_y, ez = R * nrm_z, ew = R * nrm_w;
-        const float w_lo = ccw - ew, w_hi = ccw + ew;
-        if (w_lo > 1e-6f) {   // otherwise the sphere reaches the w = 0 plane: no bound
-            const float x_lo = ccx - ex, x_hi = ccx + ex, y_lo = ccy - ey, y_hi = ccy + ey;
-            const float nx_lo = x_lo / (x_lo >= 0.0f ? w_hi : w_lo), nx_hi = x_hi / (x_hi >= 0.0f ? w_lo : w_hi);
-            const float ny_lo = y_lo / (y_lo >= 0.0f ? w_hi : w_lo), ny_hi = y_hi / (y_hi >= 0.0f ? w_lo : w_hi);
-            float fx_lo = nx_lo * half_w + half_w, fx_hi = nx_hi * half_w + half_w;
-            float fy_lo = ny_lo * half_h + half_h, fy_hi = ny_hi * half_h + half_h;
-            // nearest depth the meshlet can produce: largest z/w for the reverse-Z view, smallest for a cascade
-            const float z_edge = SHADOW ? ccz - ez : ccz + ez;
-            float d_edge = SHADOW ? z_edge / (z_edge >= 0.0f ? w_hi : w_lo) : z_edge / (z_edge >= 0.0f ? w_lo : w_hi);
-            if (fabsf(fx_lo) + fabsf(fx_hi) + fabsf(fy_lo) + fabsf(fy_hi) + fabsf(d_edge) < 3.0e38f) {
-                fx_lo -= 0.125f + 1e-5f * fabsf(fx_lo); fx_hi += 0.125f + 1e-5f * fabsf(fx_hi);
-                fy_lo -= 0.125f + 1e-5f * fabsf(fy_lo); fy_hi += 0.125f + 1e-5f * fabsf(fy_hi);
-                const int px0 = max(0, (int)ceilf(fx_lo - 0.5f)), px1 = min(W - 1, (int)floorf(fx_hi - 0.5f));
-                const int py0 = max(0, (int)ceilf(fy_lo - 0.5f)), py1 = min(H - 1, (int)floorf(fy_hi - 0.5f));
-                // depth key, smaller = nearer.  Main view: float bits of the view distance of the nearest point (bins are
-                // logarithmic in distance); cascade: the nearest light-space depth in [0,1) as 31-bit fixed point (linear bins)
-                mb.key = SHADOW ? (uint32_t)(fminf(fmaxf(d_edge, 0.0f), 0.99999994f) * 2147483648.0f) : min(__float_as_uint(w_lo), 0x7F800000u);
-                if (px0 > px1 || py0 > py1) {
-                    mb.key = kKeyEmpty;   // no pixel centre inside the bound
-                    empty++;
-                } else {
-                    d_edge = SHADOW ? d_edge - (4e-5f * fabsf(d_edge) + 1e-7f) : d_edge + (4e-5f * fabsf(d_edge) + 1e-30f);
-                    const int ntx = (px1 >> kHizShift1) - (px0 >> kHizShift1) + 1, nty = (py1 >> kHizShift1) - (py0 >> kHizShift1) + 1;
-                    if (ntx * nty <= kMaxHizTiles && d_edge > 0.0f) {
-                        mb.rect_x = (uint32_t)px0 | ((uint32_t)px1 << 16);
-                        mb.rect_y = (uint32_t)py0 | ((uint32_t)py1 << 16);
-                        // main view: a fragment of depth d loses when floatBits(d) < ~hi(key) for the stored key, i.e.
-                        // hi(key) < ~floatBits(d); cascade: it loses when d >= stored depth (LESS test)
-                        mb.edge = SHADOW ? __float_as_uint(d_edge) : ~__float_as_uint(d_edge);
-                    }
-                }
-            }
-        }
-        *(uint4*)(bounds + k) = make_uint4(mb.rect_x, mb.rect_y, mb.edge, mb.key);
-        P.depth_keys[k] = mb.key;
-        // histogram, aggregated over the lanes that fall into the same bin (neighbouring meshlets mostly do; an
-        // un-aggregated add serialises on a handful of addresses)
-        const uint32_t bin = mb.key == kKeyEmpty ? kHistBins : mb.key >> kHistShift;
-        const uint32_t active = __activemask();
-        const uint32_t peers = __match_any_sync(active, bin);
-        if (bin < kHistBins && (threadIdx.x & 31u) == (uint32_t)(__ffs(peers) - 1)) atomicAdd(P.depth_hist + bin, (uint32_t)__popc(peers));
-    }
-    if (P.flags & LH_CONFIG_PASS_TIMINGS) {
-        empty = __reduce_add_sync(0xFFFFFFFFu, empty);
-        if ((threadIdx.x & 31) == 0 && empty) atomicAdd(&P.state->skipped_empty[SHADOW ? 1u + cascade : 0u], empty);
-    }
-}
 
 // One CTA of 1024 threads: scans the key histogram and writes the kBands upper key bounds (exclusive) at fixed
 // fractions of the meshlet count -- a small nearest band, so that the next bands already find most of the screen
@@ -654,7 +547,7 @@ __global__ void __launch_bounds__(256) raster_hiz_kernel(const __grid_constant__
 template <bool SHADOW>
 __global__ void __launch_bounds__(256) raster_select_kernel(const __grid_constant__ FrameParams P, uint32_t cascade, uint32_t band) {
     const uint32_t* draw = (const uint32_t*)P.pass_draw_calls;
-    const uint32_t total = min(draw[0], P.max_opaque) + min(draw[1], P.max_alpha);
+    const uint32_t n_opaque = min(draw[0], P.max_opaque), total = n_opaque + min(draw[1], P.max_alpha);
     const uint32_t lane = threadIdx.x & 31;
     const int W = (int)(SHADOW ? P.shadowmap_size : P.u.window_size[0]), H = (int)(SHADOW ? P.shadowmap_size : P.u.window_size[1]);
     const int TW0 = hiz_dim(W, kHizShift0), TH0 = hiz_dim(H, kHizShift0), TW1 = hiz_dim(W, kHizShift1);
@@ -665,9 +558,10 @@ __global__ void __launch_bounds__(256) raster_select_kernel(const __grid_constan
     uint32_t occluded = 0;
     const uint32_t stride = gridDim.x * blockDim.x;
     for (uint32_t base = blockIdx.x * blockDim.x + (threadIdx.x & ~31u); base < total; base += stride) {
-        const uint32_t k = base + lane;
+        // bounds and keys sit at the meshlets' list indices: the opaque draws from 0, the alpha-clip draws from max_opaque
+        const uint32_t k = base + lane < n_opaque ? base + lane : P.max_opaque + (base + lane - n_opaque);
         // the scan reads the 4-byte keys only; the 16-byte bound is fetched for the band's own meshlets
-        const uint32_t key = k < total ? __ldg(P.depth_keys + k) : kKeyEmpty;
+        const uint32_t key = base + lane < total ? __ldg(P.depth_keys + k) : kKeyEmpty;
         bool keep = key >= key_lo && key < key_hi;
         uint4 mb = make_uint4(kUntestable, 0u, 0u, kKeyEmpty);
         if (keep && band != 0) mb = __ldg((const uint4*)(bounds + k));
@@ -768,9 +662,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, LH_RASTER_MIN_CTAS) raster_
         if (lane < n) {
             my_k = __ldg(P.raster_queue + ticket + lane);
             my_mb = __ldg((const uint4*)(bounds + my_k));
-            uint32_t slot, local;
-            work_to_slot(P, my_k, n_opaque, SHADOW, &slot, &local);
-            chase_header(P, slot, sv.staged[lane]);
+            chase_header(P, my_k, sv.staged[lane]);   // the queue holds list indices
         }
         __syncwarp();
         uint32_t first[kFrontChunk];
@@ -1177,10 +1069,8 @@ void launch_raster(LhContext* ctx, const FrameParams& params, int cascade, cudaS
     p.num_bands = bands;
     const bool timed = cascade < 0 && (ctx->cfg.flags & LH_CONFIG_PASS_TIMINGS) != 0;
     if (timed) cudaEventRecord(ctx->raster_kernel_a, stream);
-    if (cascade < 0) raster_bounds_kernel<false><<<grid, 256, 0, stream>>>(p, 0);
-    else raster_bounds_kernel<true><<<grid, 256, 0, stream>>>(p, (uint32_t)cascade);
     raster_bands_kernel<<<1, 1024, 0, stream>>>(p);   // also opens the pass: empty raster and deferred queues
-    ctx->launches += 2;
+    ctx->launches++;
     for (uint32_t band = 0; band < bands; band++) {
         if (band != 0) {
             if (cascade < 0) raster_hiz_kernel<false><<<grid, 256, 0, stream>>>(p, 0);
