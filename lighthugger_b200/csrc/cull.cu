@@ -104,6 +104,16 @@ __device__ __forceinline__ V4 world_sphere(const float* T, const float* sphere) 
     return w;
 }
 
+// the same with the instance's scale max(|T[0].xyz|, |T[1].xyz|, |T[2].xyz|) already at hand (identical arithmetic)
+__device__ __forceinline__ float instance_scale(const float* T) {
+    return fmaxf(fmaxf(length3(V3{T[0], T[1], T[2]}), length3(V3{T[4], T[5], T[6]})), length3(V3{T[8], T[9], T[10]}));
+}
+__device__ __forceinline__ V4 world_sphere_scaled(const float* T, const float* sphere, float scale) {
+    V4 w = mat4_mul(T, sphere[0], sphere[1], sphere[2], 1.0f);
+    w.w = pmul(sphere[3], scale);
+    return w;
+}
+
 // cull_bounding_sphere, culling.glsl:1-46: true when culled
 __device__ __forceinline__ bool cull_sphere_main(const LhUniforms& u, const FrustumPlanes& f, V4 ws) {
     V4 v = mat4_mul(&u.initial_view.m[0][0], ws.x, ws.y, ws.z, 1.0f);
@@ -300,6 +310,18 @@ __device__ __forceinline__ uint32_t upper_bound_sum(const LhPrefixSumValue* valu
     return first;
 }
 
+// What the meshlet cull needs of one instance, staged once per tile: a tile of 1024 candidates spans only a few
+// instances (one or two at 1000 meshlets per instance), so the two dependent loads behind `values[]`, the transform,
+// its scale (three square roots) and the bound's sigma are fetched / computed per instance instead of per candidate.
+constexpr uint32_t kWindowMax = 8;
+struct alignas(16) WindowInstance {
+    float T[16];
+    float N[9];
+    float scale, sigma;
+    uint32_t index, sum, num_meshlets, flags;
+    unsigned long long meshlets;
+};
+
 struct Survivor {
     uint32_t instance_index;
     uint32_t meshlet_and_tris;  // meshlet_index | triangle_count << 16
@@ -312,6 +334,7 @@ __global__ void __launch_bounds__(256) cull_meshlets_kernel(const __grid_constan
     __shared__ Survivor staged[kMeshletTile];
     __shared__ uint4 staged_bound[kMeshletTile];
     __shared__ BoundView bview;
+    __shared__ WindowInstance win[kWindowMax];
     __shared__ uint32_t warp_counts[2][8];
     __shared__ uint32_t window[2];
     __shared__ uint32_t tile_ticket;
@@ -366,6 +389,26 @@ __global__ void __launch_bounds__(256) cull_meshlets_kernel(const __grid_constan
         if (tid < 2) window[tid] = upper_bound_sum(values, 0, n_values, tid == 0 ? g0 : g_end - 1);
         __syncthreads();
         const uint32_t win_lo = window[0], win_hi = min(window[1] + 1, n_values);
+        const uint32_t win_n = win_hi - win_lo;
+        const bool windowed = win_n <= kWindowMax;
+        if (windowed && tid < win_n) {
+            WindowInstance& wi = win[tid];
+            const LhPrefixSumValue r = values[win_lo + tid];
+            const LhInstance* inst = instances + r.index;
+#pragma unroll
+            for (int k = 0; k < 4; k++) *(float4*)&wi.T[4 * k] = __ldg((const float4*)&inst->transform + k);
+#pragma unroll
+            for (int k = 0; k < 9; k++) wi.N[k] = __ldg(&inst->normal_transform.m[0][0] + k);
+            const LhMeshInfo* mi = (const LhMeshInfo*)__ldg((const unsigned long long*)&inst->mesh_info_address);
+            wi.index = r.index;
+            wi.sum = r.sum;
+            wi.num_meshlets = __ldg(&mi->num_meshlets);
+            wi.flags = __ldg(&mi->flags);
+            wi.meshlets = __ldg((const unsigned long long*)&mi->meshlets);
+            wi.scale = instance_scale(wi.T);
+            wi.sigma = sigma_max_bound16(wi.T);
+        }
+        __syncthreads();
 
         uint32_t base_count[2] = {0, 0};
         for (uint32_t round = 0; round < kMeshletTile / 256; round++) {
@@ -375,36 +418,60 @@ __global__ void __launch_bounds__(256) cull_meshlets_kernel(const __grid_constan
             uint4 bound = make_uint4(0u, 0u, 0u, 0u);
             if (g < g_end) {
                 // get_meshlet_reference, common/util.glsl:42-59
-                uint32_t vi = upper_bound_sum(values, win_lo, win_hi, g);
-                LhPrefixSumValue r = values[vi];
-                const LhInstance* inst = instances + r.index;
-                const float* T = &inst->transform.m[0][0];
-                float Tl[16];
+                LhPrefixSumValue r;
+                float Tl[16], scale, sigma;
+                uint32_t nm, flags;
+                const LhMeshlet* meshlets;
+                const float* N;
+                if (windowed) {
+                    uint32_t w = 0;
+                    while (w + 1 < win_n && g >= win[w].sum) w++;   // the first instance whose inclusive sum exceeds g
+                    const WindowInstance& wi = win[w];
+                    r.index = wi.index;
+                    r.sum = wi.sum;
 #pragma unroll
-                for (int k = 0; k < 4; k++) {
-                    float4 c = __ldg((const float4*)T + k);
-                    Tl[4 * k] = c.x; Tl[4 * k + 1] = c.y; Tl[4 * k + 2] = c.z; Tl[4 * k + 3] = c.w;
+                    for (int k = 0; k < 16; k++) Tl[k] = wi.T[k];
+                    scale = wi.scale;
+                    sigma = wi.sigma;
+                    nm = wi.num_meshlets;
+                    flags = wi.flags;
+                    meshlets = (const LhMeshlet*)wi.meshlets;
+                    N = wi.N;
+                } else {
+                    const uint32_t vi = upper_bound_sum(values, win_lo, win_hi, g);
+                    r = values[vi];
+                    const LhInstance* inst = instances + r.index;
+#pragma unroll
+                    for (int k = 0; k < 4; k++) {
+                        float4 c = __ldg((const float4*)&inst->transform + k);
+                        Tl[4 * k] = c.x; Tl[4 * k + 1] = c.y; Tl[4 * k + 2] = c.z; Tl[4 * k + 3] = c.w;
+                    }
+                    const LhMeshInfo* mi = (const LhMeshInfo*)__ldg((const unsigned long long*)&inst->mesh_info_address);
+                    nm = __ldg(&mi->num_meshlets);
+                    flags = __ldg(&mi->flags);
+                    meshlets = (const LhMeshlet*)__ldg((const unsigned long long*)&mi->meshlets);
+                    scale = instance_scale(Tl);
+                    sigma = -1.0f;
+                    N = &inst->normal_transform.m[0][0];
                 }
-                const LhMeshInfo* mi = (const LhMeshInfo*)__ldg((const unsigned long long*)&inst->mesh_info_address);
-                uint32_t nm = __ldg(&mi->num_meshlets);
-                uint32_t local = (g - (r.sum - nm)) & 0xFFFFu;
-                bool alpha = (__ldg(&mi->flags) & LH_MESH_INFO_FLAGS_ALPHA_CLIP) != 0;
-                const LhMeshlet* m = (const LhMeshlet*)__ldg((const unsigned long long*)&mi->meshlets) + local;
+                const uint32_t local = (g - (r.sum - nm)) & 0xFFFFu;
+                const bool alpha = (flags & LH_MESH_INFO_FLAGS_ALPHA_CLIP) != 0;
+                const LhMeshlet* m = meshlets + local;
                 // 56-byte meshlet as seven 8-byte loads
                 unsigned long long raw[7];
 #pragma unroll
                 for (int k = 0; k < 7; k++) raw[k] = __ldg((const unsigned long long*)m + k);
                 const float* mf = (const float*)raw;  // cone_apex[3] cone_axis[3] cutoff sphere[4]
                 const uint32_t tri_count = ((const uint8_t*)raw)[52];
-                V4 ws = world_sphere(Tl, mf + 7);
+                V4 ws = world_sphere_scaled(Tl, mf + 7, scale);
                 bool culled;
                 if (SHADOWS) culled = cull_sphere_shadows(misc, ws, cascade);
                 else culled = cull_sphere_main(P.u, planes, ws);
                 if (!culled && !alpha) {
-                    float N[9];
+                    float Nl[9];
 #pragma unroll
-                    for (int k = 0; k < 9; k++) N[k] = __ldg(&inst->normal_transform.m[0][0] + k);
-                    V3 axis = normalize3(mat3_mul(N, mf[3], mf[4], mf[5]));
+                    for (int k = 0; k < 9; k++) Nl[k] = N[k];
+                    V3 axis = normalize3(mat3_mul(Nl, mf[3], mf[4], mf[5]));
                     if (SHADOWS) {
                         // cull_cone_orthographic, culling.glsl:147-151
                         culled = dot3(V3{P.u.sun_dir[0], P.u.sun_dir[1], P.u.sun_dir[2]}, axis) >= mf[6];
@@ -421,7 +488,7 @@ __global__ void __launch_bounds__(256) cull_meshlets_kernel(const __grid_constan
                     sv.meshlet_and_tris = local | (tri_count << 16);
                     // the rasteriser's bound of this meshlet, and its depth key into the band histogram (aggregated over
                     // the lanes that fall into the same bin: neighbouring meshlets mostly do)
-                    const MeshletBound mb = meshlet_bound<SHADOWS>(bview, Tl, mf + 7);
+                    const MeshletBound mb = meshlet_bound<SHADOWS>(bview, Tl, mf + 7, sigma);
                     bound = make_uint4(mb.rect_x, mb.rect_y, mb.edge, mb.key);
                     const uint32_t bin = mb.key == kKeyEmpty ? kHistBins : mb.key >> kHistShift;
                     if (mb.key == kKeyEmpty) empty_bounds++;

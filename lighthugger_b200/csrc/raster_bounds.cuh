@@ -57,14 +57,20 @@ __device__ __forceinline__ float sigma_max_bound(const float* T) {
 // T16: the instance transform (column-major 4x4); sphere: the meshlet's object-space bounding sphere.
 // Interval arithmetic through T and the view's matrix: a conservative pixel rectangle, the nearest depth the meshlet
 // can produce ("edge") and a depth key.
+__device__ __forceinline__ float sigma_max_bound16(const float* T16) {
+    const float T[9] = {T16[0], T16[1], T16[2], T16[4], T16[5], T16[6], T16[8], T16[9], T16[10]};
+    return sigma_max_bound(T);
+}
+
+// sigma: sigma_max_bound of T16's 3x3 part (a per-instance value the caller may have at hand), or a negative number
 template <bool SHADOW>
-__device__ __forceinline__ MeshletBound meshlet_bound(const BoundView& bv, const float* T16, const float* sphere) {
+__device__ __forceinline__ MeshletBound meshlet_bound(const BoundView& bv, const float* T16, const float* sphere, float sigma = -1.0f) {
     const float* M = bv.M;
     const int W = bv.W, H = bv.H;
     const float half_w = (float)W * 0.5f, half_h = (float)H * 0.5f;
     const float T[12] = {T16[0], T16[1], T16[2], T16[4], T16[5], T16[6], T16[8], T16[9], T16[10], T16[12], T16[13], T16[14]};
     MeshletBound mb{kUntestable, 0u, 0u, 0u};   // no usable bound: nearest band, rasterised without a test
-    const float R0 = sphere[3] * sigma_max_bound(T);
+    const float R0 = sphere[3] * (sigma >= 0.0f ? sigma : sigma_max_bound(T));
     const float wx = T[0] * sphere[0] + T[3] * sphere[1] + T[6] * sphere[2] + T[9];
     const float wy = T[1] * sphere[0] + T[4] * sphere[1] + T[7] * sphere[2] + T[10];
     const float wz = T[2] * sphere[0] + T[5] * sphere[1] + T[8] * sphere[2] + T[11];
