@@ -295,32 +295,48 @@ def run_ours(args):
     inst_here = end - first
     avg_tris = scene.total_triangles / max(1, scene.total_meshlets)
     survivors = stats.num_opaque + stats.num_alpha_clip
+    # meshlets that reach the vertex phase of the main view's raster kernel: survivors of the cull minus the early-outs
+    rasterised = max(0, survivors - int(stats.meshlets_skipped_no_sample[0]) - int(stats.meshlets_skipped_occluded[0]))
     y0, y1 = ctx.comm_rows()           # rows rank 0 composites and resolves (the whole frame on one GPU)
     px_here = (y1 - y0) * W
     peer = n_gpus > 1 and args.exchange == "peer"
     alg = {
         "cull_instances": 112 * inst_here + 8 * stats.num_visible_instances,
-        "cull_meshlets": 56 * stats.num_candidate_meshlets + (8 + 16) * survivors + 8 * stats.num_visible_instances,
+        # 56 B per candidate; per survivor the 8 B reference, the 16 B draw command, and the rasteriser's 16 B bound + 4 B key
+        "cull_meshlets": 56 * stats.num_candidate_meshlets + (8 + 16 + 16 + 4) * survivors + 8 * stats.num_visible_instances,
         # peer exchange: the composite kernel reads this rank's rows of every rank's keys and writes them once, with
         # the depth bounds folded in (the depth pass is then an 8-byte all-reduce)
         "composite": 8 * px_here * (n_gpus + 1) if peer else (2 * 8 * px * (n_gpus - 1) // n_gpus if n_gpus > 1 else 0),
         "depth_reduction": 0 if peer else 8 * px,
-        "render_geometry": 16 * px_here,
+        # the shadow phase of the resolve (what is left on the critical path): 40 B of material results in, 8 B colour out
+        "render_geometry": (40 + 8) * px_here,
         # raster geometry fetch per rasterised meshlet: 56 + 3 tri + 2 idx + 6 pos per vertex + 64 B of instance transform
-        "raster_meshlets_kernel": survivors * (56 + 3 * avg_tris + (2 + 6) * 64 + 64),
+        "raster_meshlets_kernel": rasterised * (56 + 3 * avg_tris + (2 + 6) * 64 + 64),
     }
     passes = {}
     for k, b in alg.items():
         ms = med.get(k, 0.0)
         if ms > 0 and b > 0:
             passes[k] = {"ms": round(ms, 4), "alg_bytes": int(b), "gbs": round(b / ms / 1e6, 1), "frac": round(b / ms / 1e6 / peak, 4)}
-    kernel_share = {k: round(v / med["frame"], 4) for k, v in med.items() if k not in ("frame",) and med["frame"] > 0}
+    kernel_share = {k: round(v / med["frame"], 4) for k, v in med.items() if k not in ("frame", "raster_meshlets_kernel_launches") and med["frame"] > 0}
     dom = "raster_meshlets_kernel"
+    n_launch = max(1, int(round(med.get("raster_meshlets_kernel_launches", 1))))
+    traffic = None
+    try:   # per-launch DRAM bytes of the same kernel from the committed `ncu --set full` capture (profiles/)
+        with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
+            traffic = json.load(f).get("raster_meshlets_kernel<main view>", {}).get("dram_bytes_per_launch")
+    except Exception:
+        pass
     roofline = {
-        "bound": "hbm", "kernel": "raster_meshlets_kernel<main view> (one warp per meshlet)",
+        "bound": "hbm", "kernel": "raster_meshlets_kernel<main view> (one warp per meshlet; one launch per depth band)",
+        "launches_per_step": n_launch,
+        "avg_launch_ms": round(med.get(dom, 0.0) / n_launch, 4),
+        "alg_bytes_per_launch": int(alg[dom] / n_launch),
         "achieved": passes.get(dom, {}).get("gbs"), "peak": peak, "unit": "GB/s", "frac": passes.get(dom, {}).get("frac"),
-        "traffic": None, "peak_source": peak_src,
-        "note": "dominant kernel by time; it is issue/L2-atomic bound, not HBM bound (see DESIGN.md); HBM-bound passes under 'passes'",
+        "traffic": traffic, "peak_source": peak_src,
+        "note": ("dominant kernel by time (the cascades run the same kernel on side streams); it is instruction-issue / L2-latency "
+                 "bound, not HBM bound: its working set (mesh data, 66 MB key buffer) lives in L2 (see DESIGN.md); the HBM-bound "
+                 "passes are under 'passes'"),
     }
     cpu = None
     if n_gpus == 1 and not args.no_cpu_baseline:
@@ -343,6 +359,9 @@ def run_ours(args):
                   "meshlets_skipped_occluded": list(stats.meshlets_skipped_occluded),
                   "shadow_rasterised_meshlets": [int(a) + int(b) for a, b in zip(stats.shadow_opaque, stats.shadow_alpha_clip)]},
         "pass_ms": {k: round(v, 4) for k, v in med.items()},
+        "pass_notes": ("render_geometry is the resolve's shadow phase (critical path); its material phase (resolve_kernel<1>) runs on a "
+                       "low-priority stream beside the depth and shadow passes; shadowmaps is the span of the four cascades on four "
+                       "concurrent streams; raster_meshlets_kernel sums the main view's launches of that kernel"),
         "pass_share": kernel_share,
         "passes": passes,
         "roofline": roofline,

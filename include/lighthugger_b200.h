@@ -123,7 +123,8 @@ enum {
 typedef struct LhPassTimes {
     float ms[LH_PASS_COUNT];
     float frame_ms;                /* first pass start -> last pass end */
-    float raster_meshlets_kernel_ms; /* the main-view one-warp-per-meshlet raster kernel alone */
+    float raster_meshlets_kernel_ms; /* the main view's launches of the one-warp-per-meshlet raster kernel, summed */
+    uint32_t raster_meshlets_kernel_launches; /* how many launches that was (one per depth band) */
 } LhPassTimes;
 
 enum {

@@ -118,7 +118,8 @@ class LhFrameStats(C.Structure):
 
 
 class LhPassTimes(C.Structure):
-    _fields_ = [("ms", f32 * LH_PASS_COUNT), ("frame_ms", f32), ("raster_meshlets_kernel_ms", f32)]
+    _fields_ = [("ms", f32 * LH_PASS_COUNT), ("frame_ms", f32), ("raster_meshlets_kernel_ms", f32),
+                ("raster_meshlets_kernel_launches", u32)]
 
 
 # ---- include/lh_scene.h ----

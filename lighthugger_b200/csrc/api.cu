@@ -325,8 +325,10 @@ int lh_context_create(const LhConfig* cfg, LhContext** out) {
     }
     TRY(cudaEventCreate(&ctx->timer_a));
     TRY(cudaEventCreate(&ctx->timer_b));
-    TRY(cudaEventCreate(&ctx->raster_kernel_a));
-    TRY(cudaEventCreate(&ctx->raster_kernel_b));
+    for (int i = 0; i < 8; i++) {
+        TRY(cudaEventCreate(&ctx->raster_band_a[i]));
+        TRY(cudaEventCreate(&ctx->raster_band_b[i]));
+    }
     rc = ensure_instance_tiles(ctx, cfg->max_instances);
     if (rc) return bail(rc);
 #undef TRY
@@ -377,8 +379,10 @@ int lh_context_destroy(LhContext* ctx) {
     }
     if (ctx->timer_a) cudaEventDestroy(ctx->timer_a);
     if (ctx->timer_b) cudaEventDestroy(ctx->timer_b);
-    if (ctx->raster_kernel_a) cudaEventDestroy(ctx->raster_kernel_a);
-    if (ctx->raster_kernel_b) cudaEventDestroy(ctx->raster_kernel_b);
+    for (int i = 0; i < 8; i++) {
+        if (ctx->raster_band_a[i]) cudaEventDestroy(ctx->raster_band_a[i]);
+        if (ctx->raster_band_b[i]) cudaEventDestroy(ctx->raster_band_b[i]);
+    }
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
     return LH_OK;
@@ -615,7 +619,7 @@ int lh_frame_begin(LhContext* ctx, const LhUniforms* u) {
     ctx->uniforms = *u;
     ctx->have_uniforms = true;
     for (int i = 0; i < LH_PASS_COUNT; i++) ctx->pass_recorded[i] = false;
-    ctx->raster_kernel_recorded = false;
+    ctx->raster_bands_recorded = 0;
     if (int rc = ensure_peer_maps(ctx)) return rc;
     return ensure_instance_tiles(ctx, u->num_instances);
 }
@@ -863,7 +867,12 @@ int lh_get_timings(LhContext* ctx, LhPassTimes* out) {
         last = i;
     }
     if (first >= 0) cudaEventElapsedTime(&out->frame_ms, ctx->pass_start[first], ctx->pass_stop[last]);
-    if (ctx->raster_kernel_recorded) cudaEventElapsedTime(&out->raster_meshlets_kernel_ms, ctx->raster_kernel_a, ctx->raster_kernel_b);
+    out->raster_meshlets_kernel_launches = ctx->raster_bands_recorded;
+    for (uint32_t i = 0; i < ctx->raster_bands_recorded; i++) {   // sum over the main view's launches of the kernel
+        float ms = 0.0f;
+        cudaEventElapsedTime(&ms, ctx->raster_band_a[i], ctx->raster_band_b[i]);
+        out->raster_meshlets_kernel_ms += ms;
+    }
     return LH_OK;
 }
 

@@ -204,8 +204,8 @@ struct LhContext {
     cudaEvent_t pass_start[LH_PASS_COUNT] = {}, pass_stop[LH_PASS_COUNT] = {};
     bool pass_recorded[LH_PASS_COUNT] = {};
     cudaEvent_t timer_a = nullptr, timer_b = nullptr;
-    cudaEvent_t raster_kernel_a = nullptr, raster_kernel_b = nullptr;
-    bool raster_kernel_recorded = false;
+    cudaEvent_t raster_band_a[8] = {}, raster_band_b[8] = {};   // around each main-view raster_meshlets_kernel launch
+    uint32_t raster_bands_recorded = 0;
     uint64_t launches = 0;
 
     // multi-GPU

@@ -358,26 +358,6 @@ __device__ __forceinline__ void unstage_header(const WarpScratch::Staged& st, Me
     }
 }
 
-// What the early-outs need of one meshlet: the instance transform (3x3 + translation, columns packed) and the
-// meshlet's object-space bounding sphere.  Called by one lane per meshlet.
-__device__ __forceinline__ void load_bounds(const FrameParams& P, uint32_t slot, float T[12], float sphere[4]) {
-    const LhMeshletReference* refs = (const LhMeshletReference*)P.pass_refs;
-    const unsigned long long ref = __ldg((const unsigned long long*)(refs + slot));
-    const LhInstance* inst = (const LhInstance*)P.u.instances + (uint32_t)ref;
-#pragma unroll
-    for (int k = 0; k < 4; k++) {
-        const float4 c = __ldg((const float4*)&inst->transform + k);
-        T[3 * k] = c.x; T[3 * k + 1] = c.y; T[3 * k + 2] = c.z;
-    }
-    const LhMeshInfo* mi = (const LhMeshInfo*)__ldg((const unsigned long long*)&inst->mesh_info_address);
-    const LhMeshlet* m = (const LhMeshlet*)__ldg((const unsigned long long*)&mi->meshlets) + ((uint32_t)(ref >> 32) & 0xFFFFu);
-    const unsigned long long q3 = __ldg((const unsigned long long*)m + 3), q4 = __ldg((const unsigned long long*)m + 4);
-    sphere[0] = __uint_as_float((uint32_t)(q3 >> 32));
-    sphere[1] = __uint_as_float((uint32_t)q4);
-    sphere[2] = __uint_as_float((uint32_t)(q4 >> 32));
-    sphere[3] = __ldg(&m->bounding_sphere[3]);
-}
-
 __device__ __forceinline__ uint32_t load_vertex_index(const MeshletHeader& h, uint32_t v) {
     return h.wide ? __ldg((const uint32_t*)h.indices + h.index_offset + v) : (uint32_t)__ldg((const uint16_t*)h.indices + h.index_offset + v);
 }
@@ -389,14 +369,6 @@ __device__ __forceinline__ AlphaTest make_alpha_test(const FrameParams& P, const
         at.enabled = at.tex != 0;
     }
     return at;
-}
-
-// work item k of the view -> index into the view's meshlet-reference list (P.pass_refs); the alpha-clip draws start at
-// max_opaque (ALPHA_CLIP_DRAWS_OFFSET).  slot and local are the same index: the list pointer already carries the section.
-__device__ __forceinline__ void work_to_slot(const FrameParams& P, uint32_t k, uint32_t n_opaque, bool shadow, uint32_t* slot, uint32_t* local) {
-    bool alpha = k >= n_opaque;
-    *local = alpha ? P.max_opaque + (k - n_opaque) : k;
-    *slot = *local;
 }
 
 __device__ __forceinline__ void push_deferred(const FrameParams& P, uint32_t lo, uint32_t tile) {
@@ -556,34 +528,56 @@ __global__ void __launch_bounds__(256) raster_select_kernel(const __grid_constan
     const uint32_t key_lo = band ? P.pass->band_key[band - 1] : 0u, key_hi = P.pass->band_key[band];
     const MeshletBound* bounds = (const MeshletBound*)P.meshlet_bounds;
     uint32_t occluded = 0;
-    const uint32_t stride = gridDim.x * blockDim.x;
-    for (uint32_t base = blockIdx.x * blockDim.x + (threadIdx.x & ~31u); base < total; base += stride) {
+    // A lane takes FOUR consecutive entries per round: their keys arrive in one 16-byte load where the list index allows
+    // it, and the warp claims queue space for all 128 entries of the round with one atomic.
+    const uint32_t stride = gridDim.x * blockDim.x * 4u;
+    for (uint32_t base = (blockIdx.x * blockDim.x + (threadIdx.x & ~31u)) * 4u; base < total; base += stride) {
+        const uint32_t e0 = base + lane * 4u;
         // bounds and keys sit at the meshlets' list indices: the opaque draws from 0, the alpha-clip draws from max_opaque
-        const uint32_t k = base + lane < n_opaque ? base + lane : P.max_opaque + (base + lane - n_opaque);
-        // the scan reads the 4-byte keys only; the 16-byte bound is fetched for the band's own meshlets
-        const uint32_t key = base + lane < total ? __ldg(P.depth_keys + k) : kKeyEmpty;
-        bool keep = key >= key_lo && key < key_hi;
-        uint4 mb = make_uint4(kUntestable, 0u, 0u, kKeyEmpty);
-        if (keep && band != 0) mb = __ldg((const uint4*)(bounds + k));
-        if (keep && band != 0 && mb.x != kUntestable) {
-            const int px0 = (int)(mb.x & 0xFFFFu), px1 = (int)(mb.x >> 16), py0 = (int)(mb.y & 0xFFFFu), py1 = (int)(mb.y >> 16);
-            const bool fine = ((px1 >> kHizShift0) - (px0 >> kHizShift0) + 1) * ((py1 >> kHizShift0) - (py0 >> kHizShift0) + 1) <= kMaxHizTiles;
-            const int shift = fine ? kHizShift0 : kHizShift1, TW = fine ? TW0 : TW1;
-            const uint32_t* level = fine ? level0 : level1;
-            uint32_t worst = 0;   // main view: largest stored key high word; cascade: largest stored depth
-            for (int ty = py0 >> shift; ty <= (py1 >> shift); ty++)
-                for (int tx = px0 >> shift; tx <= (px1 >> shift); tx++) worst = max(worst, __ldcg(level + (size_t)ty * TW + tx));
-            if (SHADOW ? mb.z >= worst : worst < mb.z) {
-                keep = false;
-                occluded++;
-            }
+        uint32_t k[4], key[4];
+#pragma unroll
+        for (int j = 0; j < 4; j++) k[j] = e0 + j < n_opaque ? e0 + j : P.max_opaque + (e0 + j - n_opaque);
+        if (e0 + 3 < total && k[3] == k[0] + 3 && (k[0] & 3u) == 0) {
+            const uint4 q = __ldg((const uint4*)(P.depth_keys + k[0]));
+            key[0] = q.x; key[1] = q.y; key[2] = q.z; key[3] = q.w;
+        } else {
+#pragma unroll
+            for (int j = 0; j < 4; j++) key[j] = e0 + j < total ? __ldg(P.depth_keys + k[j]) : kKeyEmpty;
         }
-        const uint32_t ballot = __ballot_sync(0xFFFFFFFFu, keep);
-        if (ballot) {
+        uint32_t ballots[4], round_count = 0;
+        bool keep[4];
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            // the scan reads the 4-byte keys only; the 16-byte bound is fetched for the band's own meshlets
+            keep[j] = key[j] >= key_lo && key[j] < key_hi;
+            if (keep[j] && band != 0) {
+                const uint4 mb = __ldg((const uint4*)(bounds + k[j]));
+                if (mb.x != kUntestable) {
+                    const int px0 = (int)(mb.x & 0xFFFFu), px1 = (int)(mb.x >> 16), py0 = (int)(mb.y & 0xFFFFu), py1 = (int)(mb.y >> 16);
+                    const bool fine = ((px1 >> kHizShift0) - (px0 >> kHizShift0) + 1) * ((py1 >> kHizShift0) - (py0 >> kHizShift0) + 1) <= kMaxHizTiles;
+                    const int shift = fine ? kHizShift0 : kHizShift1, TW = fine ? TW0 : TW1;
+                    const uint32_t* level = fine ? level0 : level1;
+                    uint32_t worst = 0;   // main view: largest stored key high word; cascade: largest stored depth
+                    for (int ty = py0 >> shift; ty <= (py1 >> shift); ty++)
+                        for (int tx = px0 >> shift; tx <= (px1 >> shift); tx++) worst = max(worst, __ldcg(level + (size_t)ty * TW + tx));
+                    if (SHADOW ? mb.z >= worst : worst < mb.z) {
+                        keep[j] = false;
+                        occluded++;
+                    }
+                }
+            }
+            ballots[j] = __ballot_sync(0xFFFFFFFFu, keep[j]);
+            round_count += __popc(ballots[j]);
+        }
+        if (round_count) {
             uint32_t at = 0;
-            if (lane == 0) at = atomicAdd(&P.pass->queue_count, (uint32_t)__popc(ballot));
+            if (lane == 0) at = atomicAdd(&P.pass->queue_count, round_count);
             at = __shfl_sync(0xFFFFFFFFu, at, 0);
-            if (keep) P.raster_queue[at + __popc(ballot & ((1u << lane) - 1u))] = k;
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                if (keep[j]) P.raster_queue[at + __popc(ballots[j] & ((1u << lane) - 1u))] = k[j];
+                at += __popc(ballots[j]);
+            }
         }
     }
     if (P.flags & LH_CONFIG_PASS_TIMINGS) {
@@ -618,8 +612,6 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, LH_RASTER_MIN_CTAS) raster_
     __shared__ WarpScratch scratch_all[kWarpsPerCta];
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     WarpScratch& sv = scratch_all[warp];
-    const uint32_t* draw = (const uint32_t*)P.pass_draw_calls;
-    const uint32_t n_opaque = min(draw[0], P.max_opaque);   // drawIndirectCount clamps to maxDrawCount
     // band b owns the queue entries appended by its selection: [band_mark[b], queue_count); nothing appends while
     // this kernel runs, and the mark it leaves for band b + 1 is read by that band's launch only
     const uint32_t band_first = P.pass->band_mark[band], band_end = P.pass->queue_count;
@@ -1068,7 +1060,6 @@ void launch_raster(LhContext* ctx, const FrameParams& params, int cascade, cudaS
     FrameParams p = params;
     p.num_bands = bands;
     const bool timed = cascade < 0 && (ctx->cfg.flags & LH_CONFIG_PASS_TIMINGS) != 0;
-    if (timed) cudaEventRecord(ctx->raster_kernel_a, stream);
     raster_bands_kernel<<<1, 1024, 0, stream>>>(p);   // also opens the pass: empty raster and deferred queues
     ctx->launches++;
     for (uint32_t band = 0; band < bands; band++) {
@@ -1079,23 +1070,25 @@ void launch_raster(LhContext* ctx, const FrameParams& params, int cascade, cudaS
         }
         if (cascade < 0) raster_select_kernel<false><<<grid, 256, 0, stream>>>(p, 0, band);
         else raster_select_kernel<true><<<grid, 256, 0, stream>>>(p, (uint32_t)cascade, band);
+        if (timed) cudaEventRecord(ctx->raster_band_a[band], stream);
         if (cascade < 0) raster_meshlets_kernel<false><<<grid, kWarpsPerCta * 32, 0, stream>>>(p, 0, band);
         else raster_meshlets_kernel<true><<<grid, kWarpsPerCta * 32, 0, stream>>>(p, (uint32_t)cascade, band);
+        if (timed) {
+            cudaEventRecord(ctx->raster_band_b[band], stream);
+            ctx->raster_bands_recorded = band + 1;
+        }
         ctx->launches += 2;
         // The deferred queue is drained after the near bands (whose large triangles are the best occluders for the
         // bands that follow) and at the end; twice each time: the first launch splits, the second rasterises the pieces.
         // Each launch takes the entries appended before it began (finish_launch of the launch ahead of it).
-        if (band < 3 || band + 1 == bands) {
+        // (a cascade defers next to nothing: one drain at the end)
+        if ((cascade < 0 && band < 3) || band + 1 == bands) {
             for (int round = 0; round < 2; round++) {
                 if (cascade < 0) raster_deferred_kernel<false><<<grid, kDeferredWarps * 32, 0, stream>>>(p, 0);
                 else raster_deferred_kernel<true><<<grid, kDeferredWarps * 32, 0, stream>>>(p, (uint32_t)cascade);
                 ctx->launches++;
             }
         }
-    }
-    if (timed) {
-        cudaEventRecord(ctx->raster_kernel_b, stream);
-        ctx->raster_kernel_recorded = true;
     }
     if (cascade < 0) {
         end_main_pass_kernel<<<1, 32, 0, stream>>>(p); ctx->launches++;

@@ -236,7 +236,8 @@ class Context:
         t = S.LhPassTimes()
         self._check(self.lib.lh_get_timings(self.handle, C.byref(t)))
         return {n: float(t.ms[i]) for i, n in enumerate(S.LH_PASS_NAMES)} | {
-            "frame": float(t.frame_ms), "raster_meshlets_kernel": float(t.raster_meshlets_kernel_ms)}
+            "frame": float(t.frame_ms), "raster_meshlets_kernel": float(t.raster_meshlets_kernel_ms),
+                "raster_meshlets_kernel_launches": int(t.raster_meshlets_kernel_launches)}
 
     def launch_count(self):
         n = C.c_uint64()
