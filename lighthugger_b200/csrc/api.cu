@@ -278,14 +278,15 @@ int lh_context_create(const LhConfig* cfg, LhContext** out) {
     cudaGetDeviceProperties(&prop, cfg->device);
     ctx->num_sms = prop.multiProcessorCount;
     if (const char* t = getenv("LH_TUNE")) {
-        unsigned v[5] = {ctx->tune.main_bands, ctx->tune.shadow_bands, ctx->tune.main_grid, ctx->tune.shadow_grid, ctx->tune.resolve_low_priority};
-        sscanf(t, "%u,%u,%u,%u,%u", &v[0], &v[1], &v[2], &v[3], &v[4]);
+        unsigned v[6] = {ctx->tune.main_bands, ctx->tune.shadow_bands, ctx->tune.main_grid, ctx->tune.shadow_grid, ctx->tune.resolve_low_priority, ctx->tune.select_grid};
+        sscanf(t, "%u,%u,%u,%u,%u,%u", &v[0], &v[1], &v[2], &v[3], &v[4], &v[5]);
         ctx->tune.resolve_low_priority = v[4] != 0;
         auto clamp = [](unsigned x, unsigned lo, unsigned hi) { return x < lo ? lo : (x > hi ? hi : x); };
         ctx->tune.main_bands = clamp(v[0], 2, 8);
         ctx->tune.shadow_bands = clamp(v[1], 2, 8);
         ctx->tune.main_grid = clamp(v[2], 1, 64);
         ctx->tune.shadow_grid = clamp(v[3], 1, 64);
+        ctx->tune.select_grid = clamp(v[5], 1, 64);
     }
     auto bail = [&](int rc) {
         g_create_error = ctx->error;

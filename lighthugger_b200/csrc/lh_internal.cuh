@@ -229,9 +229,9 @@ struct LhContext {
     uint32_t row0 = 0, row1 = 0;           // screen rows this rank composites and resolves
     int num_sms = 148;
     // launch shapes of the rasteriser; defaults measured on B200 at BASELINE config 2.  Developer overrides:
-    // LH_TUNE="main_bands,shadow_bands,main_grid,shadow_grid,resolve_low_priority" in the environment at context creation.
+    // LH_TUNE="main_bands,shadow_bands,main_grid,shadow_grid,resolve_low_priority,select_grid" in the environment at context creation.
     struct Tuning {
-        uint32_t main_bands = 4, shadow_bands = 6, main_grid = 16, shadow_grid = 3, resolve_low_priority = 1;
+        uint32_t main_bands = 4, shadow_bands = 6, main_grid = 16, shadow_grid = 3, resolve_low_priority = 1, select_grid = 16;
     } tune;
 
     std::vector<void*> buffers;

@@ -528,56 +528,34 @@ __global__ void __launch_bounds__(256) raster_select_kernel(const __grid_constan
     const uint32_t key_lo = band ? P.pass->band_key[band - 1] : 0u, key_hi = P.pass->band_key[band];
     const MeshletBound* bounds = (const MeshletBound*)P.meshlet_bounds;
     uint32_t occluded = 0;
-    // A lane takes FOUR consecutive entries per round: their keys arrive in one 16-byte load where the list index allows
-    // it, and the warp claims queue space for all 128 entries of the round with one atomic.
-    const uint32_t stride = gridDim.x * blockDim.x * 4u;
-    for (uint32_t base = (blockIdx.x * blockDim.x + (threadIdx.x & ~31u)) * 4u; base < total; base += stride) {
-        const uint32_t e0 = base + lane * 4u;
+    const uint32_t stride = gridDim.x * blockDim.x;
+    for (uint32_t base = blockIdx.x * blockDim.x + (threadIdx.x & ~31u); base < total; base += stride) {
         // bounds and keys sit at the meshlets' list indices: the opaque draws from 0, the alpha-clip draws from max_opaque
-        uint32_t k[4], key[4];
-#pragma unroll
-        for (int j = 0; j < 4; j++) k[j] = e0 + j < n_opaque ? e0 + j : P.max_opaque + (e0 + j - n_opaque);
-        if (e0 + 3 < total && k[3] == k[0] + 3 && (k[0] & 3u) == 0) {
-            const uint4 q = __ldg((const uint4*)(P.depth_keys + k[0]));
-            key[0] = q.x; key[1] = q.y; key[2] = q.z; key[3] = q.w;
-        } else {
-#pragma unroll
-            for (int j = 0; j < 4; j++) key[j] = e0 + j < total ? __ldg(P.depth_keys + k[j]) : kKeyEmpty;
-        }
-        uint32_t ballots[4], round_count = 0;
-        bool keep[4];
-#pragma unroll
-        for (int j = 0; j < 4; j++) {
-            // the scan reads the 4-byte keys only; the 16-byte bound is fetched for the band's own meshlets
-            keep[j] = key[j] >= key_lo && key[j] < key_hi;
-            if (keep[j] && band != 0) {
-                const uint4 mb = __ldg((const uint4*)(bounds + k[j]));
-                if (mb.x != kUntestable) {
-                    const int px0 = (int)(mb.x & 0xFFFFu), px1 = (int)(mb.x >> 16), py0 = (int)(mb.y & 0xFFFFu), py1 = (int)(mb.y >> 16);
-                    const bool fine = ((px1 >> kHizShift0) - (px0 >> kHizShift0) + 1) * ((py1 >> kHizShift0) - (py0 >> kHizShift0) + 1) <= kMaxHizTiles;
-                    const int shift = fine ? kHizShift0 : kHizShift1, TW = fine ? TW0 : TW1;
-                    const uint32_t* level = fine ? level0 : level1;
-                    uint32_t worst = 0;   // main view: largest stored key high word; cascade: largest stored depth
-                    for (int ty = py0 >> shift; ty <= (py1 >> shift); ty++)
-                        for (int tx = px0 >> shift; tx <= (px1 >> shift); tx++) worst = max(worst, __ldcg(level + (size_t)ty * TW + tx));
-                    if (SHADOW ? mb.z >= worst : worst < mb.z) {
-                        keep[j] = false;
-                        occluded++;
-                    }
-                }
+        const uint32_t k = base + lane < n_opaque ? base + lane : P.max_opaque + (base + lane - n_opaque);
+        // the scan reads the 4-byte keys only; the 16-byte bound is fetched for the band's own meshlets
+        const uint32_t key = base + lane < total ? __ldg(P.depth_keys + k) : kKeyEmpty;
+        bool keep = key >= key_lo && key < key_hi;
+        uint4 mb = make_uint4(kUntestable, 0u, 0u, kKeyEmpty);
+        if (keep && band != 0) mb = __ldg((const uint4*)(bounds + k));
+        if (keep && band != 0 && mb.x != kUntestable) {
+            const int px0 = (int)(mb.x & 0xFFFFu), px1 = (int)(mb.x >> 16), py0 = (int)(mb.y & 0xFFFFu), py1 = (int)(mb.y >> 16);
+            const bool fine = ((px1 >> kHizShift0) - (px0 >> kHizShift0) + 1) * ((py1 >> kHizShift0) - (py0 >> kHizShift0) + 1) <= kMaxHizTiles;
+            const int shift = fine ? kHizShift0 : kHizShift1, TW = fine ? TW0 : TW1;
+            const uint32_t* level = fine ? level0 : level1;
+            uint32_t worst = 0;   // main view: largest stored key high word; cascade: largest stored depth
+            for (int ty = py0 >> shift; ty <= (py1 >> shift); ty++)
+                for (int tx = px0 >> shift; tx <= (px1 >> shift); tx++) worst = max(worst, __ldcg(level + (size_t)ty * TW + tx));
+            if (SHADOW ? mb.z >= worst : worst < mb.z) {
+                keep = false;
+                occluded++;
             }
-            ballots[j] = __ballot_sync(0xFFFFFFFFu, keep[j]);
-            round_count += __popc(ballots[j]);
         }
-        if (round_count) {
+        const uint32_t ballot = __ballot_sync(0xFFFFFFFFu, keep);
+        if (ballot) {
             uint32_t at = 0;
-            if (lane == 0) at = atomicAdd(&P.pass->queue_count, round_count);
+            if (lane == 0) at = atomicAdd(&P.pass->queue_count, (uint32_t)__popc(ballot));
             at = __shfl_sync(0xFFFFFFFFu, at, 0);
-#pragma unroll
-            for (int j = 0; j < 4; j++) {
-                if (keep[j]) P.raster_queue[at + __popc(ballots[j] & ((1u << lane) - 1u))] = k[j];
-                at += __popc(ballots[j]);
-            }
+            if (keep) P.raster_queue[at + __popc(ballot & ((1u << lane) - 1u))] = k;
         }
     }
     if (P.flags & LH_CONFIG_PASS_TIMINGS) {
@@ -1057,6 +1035,7 @@ void launch_raster(LhContext* ctx, const FrameParams& params, int cascade, cudaS
     // four streams: grids of about one wave each let their kernels share the SMs instead of queueing behind one another.
     const uint32_t bands = cascade < 0 ? ctx->tune.main_bands : ctx->tune.shadow_bands;
     const uint32_t grid = (uint32_t)ctx->num_sms * (cascade < 0 ? ctx->tune.main_grid : ctx->tune.shadow_grid);
+    const uint32_t select_grid = (uint32_t)ctx->num_sms * ctx->tune.select_grid;
     FrameParams p = params;
     p.num_bands = bands;
     const bool timed = cascade < 0 && (ctx->cfg.flags & LH_CONFIG_PASS_TIMINGS) != 0;
@@ -1068,8 +1047,9 @@ void launch_raster(LhContext* ctx, const FrameParams& params, int cascade, cudaS
             else raster_hiz_kernel<true><<<grid, 256, 0, stream>>>(p, (uint32_t)cascade);
             ctx->launches++;
         }
-        if (cascade < 0) raster_select_kernel<false><<<grid, 256, 0, stream>>>(p, 0, band);
-        else raster_select_kernel<true><<<grid, 256, 0, stream>>>(p, (uint32_t)cascade, band);
+        // selection is a chain of dependent L2 round trips per entry (key -> bound -> tiles): many light CTAs
+        if (cascade < 0) raster_select_kernel<false><<<select_grid, 256, 0, stream>>>(p, 0, band);
+        else raster_select_kernel<true><<<select_grid, 256, 0, stream>>>(p, (uint32_t)cascade, band);
         if (timed) cudaEventRecord(ctx->raster_band_a[band], stream);
         if (cascade < 0) raster_meshlets_kernel<false><<<grid, kWarpsPerCta * 32, 0, stream>>>(p, 0, band);
         else raster_meshlets_kernel<true><<<grid, kWarpsPerCta * 32, 0, stream>>>(p, (uint32_t)cascade, band);
