@@ -178,7 +178,7 @@ int alloc_pass_scratch(LhContext* ctx, int set) {
     LH_CUDA(ctx, cudaMemset(sc.pass, 0, sizeof(PassState)));
     LH_CUDA(ctx, cudaMalloc(&sc.meshlet_tiles, ctx->meshlet_tile_count * 8));
     LH_CUDA(ctx, cudaMemset(sc.meshlet_tiles, 0, ctx->meshlet_tile_count * 8));
-    LH_CUDA(ctx, cudaMalloc(&sc.large_queue, (size_t)(ctx->cfg.max_large_triangles ? ctx->cfg.max_large_triangles : 1) * 8));
+    LH_CUDA(ctx, cudaMalloc(&sc.large_queue, (size_t)(ctx->cfg.max_large_triangles ? ctx->cfg.max_large_triangles : 1) * 8 * 2));   // deferred + split queue
     LH_CUDA(ctx, cudaMalloc(&sc.meshlet_bounds, (draws ? draws : 1) * 16));
     LH_CUDA(ctx, cudaMalloc(&sc.raster_queue, (draws ? draws : 1) * 4));
     LH_CUDA(ctx, cudaMalloc(&sc.depth_keys, (draws ? draws : 1) * 4));
@@ -303,6 +303,9 @@ int lh_context_create(const LhConfig* cfg, LhContext** out) {
     int prio_least = 0, prio_greatest = 0;
     cudaDeviceGetStreamPriorityRange(&prio_least, &prio_greatest);
     TRY(cudaStreamCreateWithPriority(&ctx->stream, cudaStreamNonBlocking, prio_greatest));
+    TRY(cudaStreamCreateWithPriority(&ctx->deferred_stream, cudaStreamNonBlocking, prio_greatest));
+    for (int i = 0; i < 8; i++) TRY(cudaEventCreateWithFlags(&ctx->band_done[i], cudaEventDisableTiming));
+    TRY(cudaEventCreateWithFlags(&ctx->drains_done, cudaEventDisableTiming));
     TRY(cudaStreamCreateWithPriority(&ctx->resolve_stream, cudaStreamNonBlocking, ctx->tune.resolve_low_priority ? prio_least : prio_greatest));
     TRY(cudaEventCreateWithFlags(&ctx->vis_ready, cudaEventDisableTiming));
     TRY(cudaEventCreateWithFlags(&ctx->material_done, cudaEventDisableTiming));
@@ -357,6 +360,10 @@ int lh_context_destroy(LhContext* ctx) {
     cudaFree(ctx->depth_plane);
     cudaFree(ctx->resolve_tmp);
     if (ctx->resolve_stream) cudaStreamDestroy(ctx->resolve_stream);
+    if (ctx->deferred_stream) cudaStreamDestroy(ctx->deferred_stream);
+    for (int i = 0; i < 8; i++)
+        if (ctx->band_done[i]) cudaEventDestroy(ctx->band_done[i]);
+    if (ctx->drains_done) cudaEventDestroy(ctx->drains_done);
     if (ctx->vis_ready) cudaEventDestroy(ctx->vis_ready);
     if (ctx->material_done) cudaEventDestroy(ctx->material_done);
     cudaFree(ctx->shadow);

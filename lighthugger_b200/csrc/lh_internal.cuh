@@ -78,8 +78,14 @@ struct FrameState {
 // can be in flight at the same time has its own, with its own scratch buffers, so cascades can run on separate streams.
 struct PassState {
     uint32_t cull_ticket, cull_done;   // meshlet cull: next tile, CTAs finished (self-cleaning)
-    uint32_t large_count;              // entries in the deferred-triangle queue
-    uint32_t deferred_begin, deferred_end;   // queue range the current deferred launch processes
+    // Deferred triangles.  Raster launches append to the deferred queue, the first round of a drain appends the
+    // per-tile pieces of the triangles it splits to the split queue (the second half of the same allocation), the
+    // second round rasterises those.  Ranges are handed over by index, written once by the last CTA of the producing
+    // launch, so a drain may run on its own stream beside the next band.
+    uint32_t large_count, split_count;
+    uint32_t drain_end[9];             // [b + 1]: large_count when band b's rasterisation finished; [0] = 0
+    uint32_t split_end[9];             // [d + 1]: split_count when drain d's first round finished; [0] = 0
+    uint32_t cta_done_deferred;        // CTAs of the running deferred launch that have finished (self-cleaning)
     uint32_t queue_count;              // entries appended to the raster queue so far
     uint32_t band_mark[9];             // queue_count when band b's rasterisation began: band b owns [band_mark[b], band_mark[b+1])
     uint32_t band_ticket[8];           // next unclaimed entry of band b's range, relative to band_mark[b]
@@ -182,6 +188,8 @@ struct LhContext {
         void* refs = nullptr;
     } scratch[4];
     size_t meshlet_tile_count = 0;
+    cudaStream_t deferred_stream = nullptr;   // the main view's deferred-triangle drains run here, beside the next band
+    cudaEvent_t band_done[8] = {}, drains_done = nullptr;
     cudaStream_t side_streams[3] = {};
     cudaEvent_t fork_event = nullptr, join_events[3] = {};
     void* l2_flush = nullptr;

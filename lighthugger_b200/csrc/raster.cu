@@ -443,9 +443,9 @@ __global__ void __launch_bounds__(1024) raster_bands_kernel(const __grid_constan
         st->queue_count = 0;
         st->band_mark[0] = 0;
         // a raster pass begins: empty deferred queue
-        st->large_count = 0;
-        st->deferred_begin = st->deferred_end = 0;
-        st->cta_done = 0;
+        st->large_count = st->split_count = 0;
+        st->drain_end[0] = st->split_end[0] = 0;
+        st->cta_done = st->cta_done_deferred = 0;
     }
     if (tid < 8) st->band_ticket[tid] = 0;
     for (int b = 0; b < kBands - 1; b++) {
@@ -564,21 +564,20 @@ __global__ void __launch_bounds__(256) raster_select_kernel(const __grid_constan
     }
 }
 
-// What the last CTA of a raster or deferred launch to finish does: the deferred entries appended so far become the
-// range of the next deferred launch.  consumed: this launch was a deferred one and has processed its range.
-__device__ __forceinline__ void finish_launch(const FrameParams& P, bool consumed) {
+// What the last CTA of a launch to finish does: it publishes how far the queue the launch appended to has grown
+// (raster launch of band b: drain_end[b + 1]; first round of drain d: split_end[d + 1]).  Each slot is written once and
+// read only by launches ordered after this one, whatever else runs beside them.
+__device__ __forceinline__ void publish_queue_end(uint32_t* done_counter, const uint32_t* count, uint32_t* slot, uint32_t cap) {
     __shared__ bool last;
     __syncthreads();
     if (threadIdx.x == 0) {
         __threadfence();
-        last = atomicAdd(&P.pass->cta_done, 1u) == gridDim.x - 1u;
+        last = atomicAdd(done_counter, 1u) == gridDim.x - 1u;
     }
     __syncthreads();
     if (last && threadIdx.x == 0) {
-        PassState* st = P.pass;
-        st->cta_done = 0;
-        if (consumed) st->deferred_begin = st->deferred_end;
-        st->deferred_end = min(*(volatile uint32_t*)&st->large_count, P.max_large);
+        *done_counter = 0;
+        *slot = min(*(volatile const uint32_t*)count, cap);
     }
 }
 
@@ -882,7 +881,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, LH_RASTER_MIN_CTAS) raster_
             if (skipped_empty) atomicAdd(&P.state->skipped_empty[pass], skipped_empty);
         }
     }
-    finish_launch(P, false);
+    publish_queue_end(&P.pass->cta_done, &P.pass->large_count, &P.pass->drain_end[band + 1], P.max_large);
 }
 
 // ---- the deferred queue: large and near-plane-crossing triangles, one warp per entry ----
@@ -903,11 +902,16 @@ struct DeferredTriangle {
 constexpr int kDeferredWarps = 4;
 
 template <bool SHADOW>
-__global__ void __launch_bounds__(kDeferredWarps * 32) raster_deferred_kernel(const __grid_constant__ FrameParams P, uint32_t cascade) {
+__global__ void __launch_bounds__(kDeferredWarps * 32) raster_deferred_kernel(const __grid_constant__ FrameParams P, uint32_t cascade, uint32_t round, uint32_t from, uint32_t to, uint32_t drain) {
     __shared__ DeferredTriangle parked_all[kDeferredWarps][32];
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     DeferredTriangle* parked = parked_all[warp];
-    const uint32_t range_begin = P.pass->deferred_begin, range_end = P.pass->deferred_end;
+    // round 0: the deferred queue's entries appended by the bands from .. to - 1 (drain_end[from] .. drain_end[to]);
+    // round 1: the split queue's entries appended by round 0 of the same drain
+    const uint32_t range_begin = round == 0 ? P.pass->drain_end[from] : P.pass->split_end[drain];
+    const uint32_t range_end = round == 0 ? P.pass->drain_end[to] : P.pass->split_end[drain + 1];
+    const uint32_t* queue = round == 0 ? P.large_queue : P.large_queue + 2 * (size_t)P.max_large;
+    uint32_t* split_queue = P.large_queue + 2 * (size_t)P.max_large;
     Target<SHADOW> tg;
     tg.vis = P.vis;
     tg.layer = SHADOW ? P.shadow + (size_t)cascade * P.shadowmap_size * P.shadowmap_size : nullptr;
@@ -922,7 +926,7 @@ __global__ void __launch_bounds__(kDeferredWarps * 32) raster_deferred_kernel(co
             d.n = 0;
             const uint32_t e = base + lane;
             if (e < range_end) {
-                const uint32_t lo = P.large_queue[2 * (size_t)e], tile = P.large_queue[2 * (size_t)e + 1];
+                const uint32_t lo = queue[2 * (size_t)e], tile = queue[2 * (size_t)e + 1];
                 const uint32_t local = (lo >> LH_VIS_TRI_BITS) - P.slot_offset, t = lo & LH_VIS_TRI_MASK;
                 MeshletHeader h;
                 load_header(P, local, h);
@@ -997,12 +1001,12 @@ __global__ void __launch_bounds__(kDeferredWarps * 32) raster_deferred_kernel(co
             if (d.split & 1) {
                 const uint32_t ntx = (uint32_t)(x1 - x0 + 1), ntiles = ntx * (uint32_t)(y1 - y0 + 1);
                 uint32_t at = 0;
-                if (lane == 0) at = atomicAdd(&P.pass->large_count, ntiles);
+                if (lane == 0) at = atomicAdd(&P.pass->split_count, ntiles);
                 at = __shfl_sync(0xFFFFFFFFu, at, 0);
                 for (uint32_t k = lane; k < ntiles; k += 32) {
                     if (at + k < P.max_large) {
-                        P.large_queue[2 * (size_t)(at + k)] = lo;
-                        P.large_queue[2 * (size_t)(at + k) + 1] = ((uint32_t)x0 + k % ntx) | (((uint32_t)y0 + k / ntx) << 16);
+                        split_queue[2 * (size_t)(at + k)] = lo;
+                        split_queue[2 * (size_t)(at + k) + 1] = ((uint32_t)x0 + k % ntx) | (((uint32_t)y0 + k / ntx) << 16);
                     } else {
                         atomicOr(&P.state->overflow, (uint32_t)LH_OVERFLOW_LARGE_TRIANGLES);
                     }
@@ -1020,11 +1024,11 @@ __global__ void __launch_bounds__(kDeferredWarps * 32) raster_deferred_kernel(co
         }
         __syncwarp();
     }
-    finish_launch(P, true);
+    if (round == 0) publish_queue_end(&P.pass->cta_done_deferred, &P.pass->split_count, &P.pass->split_end[drain + 1], P.max_large);
 }
 
 __global__ void end_main_pass_kernel(const __grid_constant__ FrameParams P) {
-    if (threadIdx.x == 0 && blockIdx.x == 0) P.state->main_large_count = P.pass->large_count;
+    if (threadIdx.x == 0 && blockIdx.x == 0) P.state->main_large_count = P.pass->large_count + P.pass->split_count;
 }
 
 }  // namespace
@@ -1036,6 +1040,8 @@ void launch_raster(LhContext* ctx, const FrameParams& params, int cascade, cudaS
     const uint32_t bands = cascade < 0 ? ctx->tune.main_bands : ctx->tune.shadow_bands;
     const uint32_t grid = (uint32_t)ctx->num_sms * (cascade < 0 ? ctx->tune.main_grid : ctx->tune.shadow_grid);
     const uint32_t select_grid = (uint32_t)ctx->num_sms * ctx->tune.select_grid;
+    const uint32_t deferred_grid = (uint32_t)ctx->num_sms * (cascade < 0 ? 8u : ctx->tune.shadow_grid);
+    uint32_t drained_to = 0, drain = 0;
     FrameParams p = params;
     p.num_bands = bands;
     const bool timed = cascade < 0 && (ctx->cfg.flags & LH_CONFIG_PASS_TIMINGS) != 0;
@@ -1059,16 +1065,29 @@ void launch_raster(LhContext* ctx, const FrameParams& params, int cascade, cudaS
         }
         ctx->launches += 2;
         // The deferred queue is drained after the near bands (whose large triangles are the best occluders for the
-        // bands that follow) and at the end; twice each time: the first launch splits, the second rasterises the pieces.
-        // Each launch takes the entries appended before it began (finish_launch of the launch ahead of it).
-        // (a cascade defers next to nothing: one drain at the end)
+        // bands that follow) and at the end; each drain is two launches: the first splits and rasterises, the second
+        // rasterises the pieces.  The main view's drains run on their own stream BESIDE the next band's passes (the
+        // hierarchical Z stays valid when keys arrive late: stored values only get nearer); a cascade defers next to
+        // nothing and drains once, at the end, on its own stream.
         if ((cascade < 0 && band < 3) || band + 1 == bands) {
-            for (int round = 0; round < 2; round++) {
-                if (cascade < 0) raster_deferred_kernel<false><<<grid, kDeferredWarps * 32, 0, stream>>>(p, 0);
-                else raster_deferred_kernel<true><<<grid, kDeferredWarps * 32, 0, stream>>>(p, (uint32_t)cascade);
+            cudaStream_t ds = stream;
+            if (cascade < 0) {
+                ds = ctx->deferred_stream;
+                cudaEventRecord(ctx->band_done[band], stream);
+                cudaStreamWaitEvent(ds, ctx->band_done[band], 0);
+            }
+            for (uint32_t round = 0; round < 2; round++) {
+                if (cascade < 0) raster_deferred_kernel<false><<<deferred_grid, kDeferredWarps * 32, 0, ds>>>(p, 0, round, drained_to, band + 1, drain);
+                else raster_deferred_kernel<true><<<deferred_grid, kDeferredWarps * 32, 0, ds>>>(p, (uint32_t)cascade, round, drained_to, band + 1, drain);
                 ctx->launches++;
             }
+            drained_to = band + 1;
+            drain++;
         }
+    }
+    if (cascade < 0) {   // the drains join the main view before anything reads the finished buffer
+        cudaEventRecord(ctx->drains_done, ctx->deferred_stream);
+        cudaStreamWaitEvent(stream, ctx->drains_done, 0);
     }
     if (cascade < 0) {
         end_main_pass_kernel<<<1, 32, 0, stream>>>(p); ctx->launches++;
