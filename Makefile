@@ -39,7 +39,7 @@ $(LIBDIR)/liblighthugger_b200.so: $(CUDA_OBJS)
 
 $(LIBDIR)/liblh_host.so: $(HOST_SRCS) $(HOST_HDRS)
 	@mkdir -p $(LIBDIR)
-	$(CXX) $(CXXFLAGS) -shared -o $@ $(HOST_SRCS) $(LDFLAGS_SO)
+	$(CXX) $(CXXFLAGS) -shared -o $@ $(HOST_SRCS) $(LDFLAGS_SO) -ldl
 
 oracle/liblh_oracle.so: $(ORACLE_SRCS) $(ORACLE_HDRS)
 	$(CXX) $(CXXFLAGS) -fvisibility=default -pthread -shared -o $@ $(ORACLE_SRCS) $(LDFLAGS_SO)

@@ -267,3 +267,60 @@ def test_sort_last_partition_on_one_gpu():
     want = np.stack([rw[sw[cov], 0], rw[sw[cov], 1], tw[cov]], 1)
     assert np.array_equal(got[cov], want)
     whole.close()
+
+
+def test_sort_last_stripes_on_one_gpu():
+    # screen-stripe ownership (lh_set_instance_stripes): three contexts own interleaved stripes of the main view and of
+    # the cascades; the min of their key buffers and of their shadow layers is the whole frame's
+    sc = Scene.preset("tiny")
+    whole = make_context(sc)
+    whole.render_frame_host(whole.uniforms())
+    vw = whole.target(S.LH_TARGET_VIS64)
+    sw = whole.target(S.LH_TARGET_SHADOW).view(np.uint32)
+    rw = whole.meshlet_references(0, whole.stats().num_opaque)
+    dw, slot_w, tri_w = vis_fields(vw)
+    parts, acc, visible = [], np.full_like(vw, S.LH_VIS_CLEAR), 0
+    members = 3
+    for index in range(members):
+        c = make_context(sc)
+        c.set_instance_stripes(0, 4 * members, index, members)
+        c.set_instance_stripes(1, 4 * members, index, members)
+        c.render_frame_host(c.uniforms())
+        # the cascade matrices come from this context's own depth bounds, so only the main view is compared here; the
+        # cascades' partition is checked below with the whole frame's depth bounds
+        v = c.target(S.LH_TARGET_VIS64)
+        acc = np.minimum(acc, v)
+        st = c.stats()
+        visible += st.num_visible_instances
+        parts.append((v, c.meshlet_references(0, st.num_opaque)))
+        c.close()
+    assert visible == whole.stats().num_visible_instances, "the stripes do not partition the visible instances"
+    da, _, _ = vis_fields(acc)
+    assert np.array_equal(dw, da)
+    cov = dw != 0
+    got = np.zeros((acc.size, 3), np.int64) - 1
+    for v, refs in parts:
+        d, s, t = vis_fields(v)
+        win = (v == acc) & (d != 0)
+        got[win, 0], got[win, 1], got[win, 2] = refs[s[win], 0], refs[s[win], 1], t[win]
+    want = np.stack([rw[slot_w[cov], 0], rw[slot_w[cov], 1], tri_w[cov]], 1)
+    assert np.array_equal(got[cov], want)
+    # cascades: pass by pass with the whole frame's visibility buffer, so that every context derives the same matrices
+    layers = np.full_like(sw, 0x3F800000)
+    shadow_visible = np.zeros(4, np.int64)
+    for index in range(members):
+        c = make_context(sc)
+        c.set_instance_stripes(1, 4 * members, index, members)   # main view whole, cascades striped
+        c.frame_begin(c.uniforms())
+        c.reset(); c.cull_instances(); c.cull_meshlets(); c.raster_visbuffer(); c.reduce_depth()
+        c.generate_shadow_matrices(); c.cull_instances_shadows()
+        for k in range(4):
+            c.shadow_cascade(k)
+        c.sync()
+        st = c.stats()
+        shadow_visible += np.array(list(st.shadow_visible_instances), np.int64)
+        layers = np.minimum(layers, c.target(S.LH_TARGET_SHADOW).view(np.uint32))
+        c.close()
+    assert np.array_equal(shadow_visible, np.array(list(whole.stats().shadow_visible_instances), np.int64))
+    assert np.array_equal(layers, sw)
+    whole.close()

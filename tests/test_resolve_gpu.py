@@ -88,3 +88,57 @@ def test_display_transform_runs():
     want = np.rint(np.clip(display(scene[:, :3]), 0, 1) * 255)
     assert np.abs(want[:, ::-1] - bgra[:, :3]).max() <= 1
     ctx.close()
+
+
+def test_textures_from_dds_and_ktx2_files_render_like_direct_uploads():
+    # the preset's BC7 mip chains wrapped into DDS (DX10) and KTX2 + Zstandard containers, parsed by
+    # lh_image_parse / lh_image_decode and handed to lh_texture_create, must give the frame the direct upload gives
+    import test_image_files as F
+    from lighthugger_b200 import image_files as IF
+    sc = Scene.preset("tiny")
+    tex = Textures(sc, 32)
+    direct = make_context(sc, textures=tex)
+    direct.render_frame_host(direct.uniforms())
+    want = direct.target(S.LH_TARGET_SCENE_RGBA16F).view(np.uint16).copy()
+    direct.close()
+    files = make_context(sc)
+    for i, (blocks, levels, _) in enumerate(tex.entries):
+        if i % 2 == 0:
+            data = F.dds_file(F.DXGI["BC7_UNORM"], tex.size, tex.size, levels, blocks)   # UNORM on disk, sRGB when sampled
+        else:
+            sizes = F.level_bytes(tex.size, tex.size, levels, 8, True)
+            cuts = np.cumsum([0] + sizes)
+            chain = [blocks[cuts[l]:cuts[l + 1]].tobytes() for l in range(levels)]
+            data = F.ktx2_file(F.VK["BC7_SRGB"], tex.size, tex.size, levels, chain, scheme=2, stored=[F._zstd_compress(c) for c in chain])
+        assert IF.upload(files, data) == ("texture", i)
+    files.render_frame_host(files.uniforms())
+    got = files.target(S.LH_TARGET_SCENE_RGBA16F).view(np.uint16)
+    assert np.array_equal(got, want)
+    files.close()
+
+
+def test_display_lut_and_skybox_from_rgb9e5_dds():
+    import test_image_files as F
+    from lighthugger_b200 import image_files as IF
+    sc = Scene.preset("tiny")
+    n = 48   # the size display_transform.comp's texel-centre mapping (encoded * 47/48 + 0.5/48) is written for
+    # an identity table and a constant sky, written as R9G9B9E5 texels (exponent 15: mantissa / 512)
+    g = np.arange(n, dtype=np.uint32) * 511 // (n - 1)
+    b, gg, r = np.meshgrid(g, g, g, indexing="ij")
+    lut = (r | (gg << 9) | (b << 18) | (15 << 27)).astype(np.uint32).reshape(-1)
+    sky = np.full(6 * 4 * 4, 128 | (128 << 9) | (256 << 18) | (15 << 27), np.uint32)
+    ctx = make_context(sc)
+    assert IF.upload(ctx, F.dds_file(F.DXGI["RGB9E5"], n, n, 1, lut.tobytes(), depth=n, dimension=4)) == ("lut", n)
+    assert IF.upload(ctx, F.dds_file(F.DXGI["RGB9E5"], 4, 4, 1, sky.tobytes(), cubemap=True)) == ("skybox", 4)
+    ctx.render_frame_host(ctx.uniforms())
+    ctx.display_transform(); ctx.sync()
+    scene = ctx.target(S.LH_TARGET_SCENE_RGBA16F).astype(np.float32).reshape(-1, 4)
+    depth, _, _ = vis_fields(ctx.target(S.LH_TARGET_VIS64))
+    skyp = depth == 0
+    assert skyp.any() and np.allclose(scene[skyp, :3], np.array([0.25, 0.25, 0.5]) * 8, rtol=1e-3)   # skybox * 2^3 (render_geometry.comp:86-101)
+    # the table maps encoded c/(1+c) to itself (trilinear between exact grid points), so the result is the OETF of it
+    bgra = ctx.target(S.LH_TARGET_DISPLAY_BGRA8).reshape(-1, 4)
+    enc = np.clip(scene[:, :3], 0, None) / (1 + np.clip(scene[:, :3], 0, None))
+    want = np.rint(np.clip(np.where(enc <= 0.0031308, 12.92 * enc, 1.055 * np.power(enc, 1 / 2.4) - 0.055), 0, 1) * 255)
+    assert np.abs(want[:, ::-1] - bgra[:, :3]).max() <= 3
+    ctx.close()
