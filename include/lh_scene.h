@@ -159,6 +159,18 @@ LH_HOST_API int lh_host_upload(void* user, uint64_t addr, const void* src, uint6
 LH_HOST_API int lh_host_free(void* user, uint64_t addr);
 
 /* stand-alone pieces, exported for tests against oracle/_ref */
+/* ---- the reference's meshlet cache (src/resources/fs_cache.h:3-25, src/resources/mesh_loading.cpp:602-649) ----
+ * Three raw blobs per primitive under <dir>/<std::hash of "<name> meshlets" | "<name> indices" | "<name> micro indices">:
+ * the Meshlet records, the per-meshlet vertex indices (u16 / u32) and the micro-indices.  which: 0, 1, 2 in that order. */
+typedef struct LhMeshletBlobs LhMeshletBlobs;
+LH_HOST_API int lh_meshlet_cache_path(const char* dir, const char* primitive_name, int which, char* out, uint64_t out_bytes);
+LH_HOST_API int lh_meshlet_cache_store(const char* dir, const char* primitive_name, const LhMeshView* mesh);
+/* 0: hit (*out owns the blobs); 1: miss (build and store); < 0: unreadable or inconsistent blobs */
+LH_HOST_API int lh_meshlet_cache_load(const char* dir, const char* primitive_name, uint32_t index_bytes, LhMeshletBlobs** out);
+/* fills the meshlet / index / micro-index fields (and num_triangles) of a view; the vertex streams are the caller's */
+LH_HOST_API int lh_meshlet_blobs_view(const LhMeshletBlobs* blobs, uint32_t index_bytes, LhMeshView* view);
+LH_HOST_API void lh_meshlet_blobs_free(LhMeshletBlobs* blobs);
+
 LH_HOST_API void lh_compute_bounding_sphere(float result[4], const float* points, uint64_t count);
 LH_HOST_API void lh_compute_meshlet_bounds(const uint32_t* meshlet_vertices, const uint8_t* meshlet_triangles,
                                            uint32_t triangle_count, const float* positions /* xyz */,
