@@ -77,6 +77,13 @@ struct SnapVert {
     float z, w, u, v;
 };
 
+// (sat16(hi) << 16) | (sat16(lo) & 0xFFFF)
+__device__ __forceinline__ uint32_t pack_sat_s16(int hi, int lo) {
+    uint32_t d;
+    asm("cvt.pack.sat.s16.s32 %0, %1, %2;" : "=r"(d) : "r"(hi), "r"(lo));
+    return d;
+}
+
 // project_snap of the pinned model: false when the vertex is not finite
 __device__ __forceinline__ bool project_snap(float cx, float cy, float cz, float cw, float half_w, float half_h, int* sx, int* sy, float* z) {
     // x / 1.0f == x exactly: an orthographic (cascade) matrix yields w == 1 and skips the three IEEE divisions
@@ -419,18 +426,28 @@ __global__ void __launch_bounds__(1024) raster_bands_kernel(const __grid_constan
 #pragma unroll
         for (uint32_t j = 0; j < kPer; j++) sum += local[j];
     }
-    partial[tid] = sum;
-    __syncthreads();
-    // inclusive scan of the 1024 partials (Hillis-Steele)
-    for (uint32_t o = 1; o < 1024; o <<= 1) {
-        const uint32_t v = tid >= o ? partial[tid - o] : 0u;
-        __syncthreads();
-        partial[tid] += v;
-        __syncthreads();
+    // inclusive scan of the 1024 partials: shuffles inside each warp, then the 32 warp totals by warp 0
+    const uint32_t lane = tid & 31, warp = tid >> 5;
+    uint32_t incl = sum;
+#pragma unroll
+    for (uint32_t o = 1; o < 32; o <<= 1) {
+        const uint32_t v = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+        if (lane >= o) incl += v;
     }
-    if (tid == 1023) grand_total = partial[1023];
+    if (lane == 31) partial[warp] = incl;
     __syncthreads();
-    const uint32_t total = grand_total, before = partial[tid] - sum;
+    if (warp == 0) {
+        uint32_t w = partial[lane];
+#pragma unroll
+        for (uint32_t o = 1; o < 32; o <<= 1) {
+            const uint32_t v = __shfl_up_sync(0xFFFFFFFFu, w, o);
+            if (lane >= o) w += v;
+        }
+        partial[32 + lane] = w;   // inclusive totals of the warps
+        if (lane == 31) grand_total = w;
+    }
+    __syncthreads();
+    const uint32_t total = grand_total, before = incl - sum + (warp ? partial[32 + warp - 1] : 0u);
     // cumulative count fractions at which the bands end, for each band count
     const float tables[kMaxBands + 1][kMaxBands - 1] = {
         {}, {}, {0.10f}, {0.04f, 0.25f}, {0.03f, 0.12f, 0.40f}, {0.025f, 0.09f, 0.25f, 0.55f}, {0.02f, 0.07f, 0.17f, 0.35f, 0.60f},
@@ -611,6 +628,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, LH_RASTER_MIN_CTAS) raster_
         for (int k = 0; k < (SHADOW ? 16 : 1); k++) Mreg[k] = src[k];
     }
     const float* M = SHADOW ? Mreg : &P.u.combined_perspective_view.m[0][0];
+    const bool affine = SHADOW && Mreg[SHADOW ? 3 : 0] == 0.0f && Mreg[SHADOW ? 7 : 0] == 0.0f && Mreg[SHADOW ? 11 : 0] == 0.0f && Mreg[SHADOW ? 15 : 0] == 1.0f;
     const MeshletBound* bounds = (const MeshletBound*)P.meshlet_bounds;
     uint32_t tris_done = 0, skipped_occluded = 0, skipped_empty = 0;
 
@@ -685,7 +703,17 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, LH_RASTER_MIN_CTAS) raster_
                 const uint16_t* p = h.positions + 3 * (size_t)idx;
                 const float px = (float)__ldg(p), py = (float)__ldg(p + 1), pz = (float)__ldg(p + 2);
                 const V4 world = mat4_mul(h.T, px, py, pz, 1.0f);
-                const V4 clip = mat4_mul(M, world.x, world.y, world.z, 1.0f);
+                V4 clip;
+                if (SHADOW && affine) {
+                    // a cascade matrix ends in the row (0, 0, 0, 1): w is exactly 1 for every finite position, and a
+                    // non-finite one makes x, y and z non-finite too, so the vertex is classified the same without w
+                    clip.x = padd(padd(pmul(M[0], world.x), pmul(M[4], world.y)), padd(pmul(M[8], world.z), M[12]));
+                    clip.y = padd(padd(pmul(M[1], world.x), pmul(M[5], world.y)), padd(pmul(M[9], world.z), M[13]));
+                    clip.z = padd(padd(pmul(M[2], world.x), pmul(M[6], world.y)), padd(pmul(M[10], world.z), M[14]));
+                    clip.w = 1.0f;
+                } else {
+                    clip = mat4_mul(M, world.x, world.y, world.z, 1.0f);
+                }
                 int sx = kVertOutside, sy = 0;
                 float z = 0.0f;
                 if (SHADOW || psub(clip.w, clip.z) >= 0.0f) {
@@ -695,11 +723,8 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, LH_RASTER_MIN_CTAS) raster_
                 sv.sy[v] = sy;
                 sv.z[v] = z;
                 if (h.alpha) sv.w[v] = clip.w;
-                {
-                    const int fx = min(max((sx + 127) >> 8, -32768), 32767), fy = min(max((sy + 127) >> 8, -32768), 32767);
-                    const int lx = min(max((sx - 128) >> 8, -32768), 32767), ly = min(max((sy - 128) >> 8, -32768), 32767);
-                    sv.cover[v] = make_uint2(((uint32_t)fx & 0xFFFFu) | ((uint32_t)fy << 16), ((uint32_t)lx & 0xFFFFu) | ((uint32_t)ly << 16));
-                }
+                // first / last pixel per axis, saturated to int16 and packed (x low, y high) in one instruction each
+                sv.cover[v] = make_uint2(pack_sat_s16((sy + 127) >> 8, (sx + 127) >> 8), pack_sat_s16((sy - 128) >> 8, (sx - 128) >> 8));
                 if (sx == kVertOutside || sx == kVertNonFinite || !(z >= 0.0f)) {
                     special = true;
                 } else {

@@ -187,24 +187,40 @@ __device__ __forceinline__ float4 sample_trilinear(cudaTextureObject_t t, float 
     }
     return a;
 }
-__device__ float4 sample_texture_grad(cudaTextureObject_t t, uint4 dims, float u, float v, float2 ddx, float2 ddy) {
-    const float w = (float)dims.x, h = (float)dims.y, max_level = (float)(dims.z - 1u);
+// The footprint depends on the texture's size and the uv derivatives only, so the material's three textures (same size
+// in practice) share one: probes == 0 stands for the degenerate case (a single trilinear fetch at lod 0).
+struct Footprint {
+    float lod, max_level;
+    float2 major;
+    int probes;
+};
+__device__ __forceinline__ Footprint texture_footprint(uint4 dims, float2 ddx, float2 ddy) {
+    Footprint f;
+    const float w = (float)dims.x, h = (float)dims.y;
+    f.max_level = (float)(dims.z - 1u);
     const float ax0 = ddx.x * w, ax1 = ddx.y * h, ay0 = ddy.x * w, ay1 = ddy.y * h;
     const float px = sqrtf(ax0 * ax0 + ax1 * ax1), py = sqrtf(ay0 * ay0 + ay1 * ay1);
     const float pmax = fmaxf(px, py), pmin = fminf(px, py);
-    if (!(pmax > 0.0f) || !isfinite(pmax)) return sample_trilinear(t, u, v, 0.0f, max_level);
+    f.probes = 0;
+    f.lod = 0.0f;
+    f.major = make_float2(0.0f, 0.0f);
+    if (!(pmax > 0.0f) || !isfinite(pmax)) return f;
     float n = pmin > 0.0f ? fminf(ceilf(pmax / pmin), 16.0f) : 16.0f;
     if (pmax <= 1.0f) n = 1.0f;  // magnification: a single bilinear probe
-    const float lod = log2f(pmax / n);
-    const int probes = (int)n;
-    const float2 major = px >= py ? ddx : ddy;
+    f.lod = log2f(pmax / n);
+    f.probes = (int)n;
+    f.major = px >= py ? ddx : ddy;
+    return f;
+}
+__device__ float4 sample_texture_footprint(cudaTextureObject_t t, const Footprint& f, float u, float v) {
+    if (f.probes == 0) return sample_trilinear(t, u, v, 0.0f, f.max_level);
     float4 acc = make_float4(0, 0, 0, 0);
-    for (int i = 0; i < probes; i++) {
-        const float o = ((float)i + 0.5f) / (float)probes - 0.5f;
-        const float4 s = sample_trilinear(t, u + o * major.x, v + o * major.y, lod, max_level);
+    for (int i = 0; i < f.probes; i++) {
+        const float o = ((float)i + 0.5f) / (float)f.probes - 0.5f;
+        const float4 s = sample_trilinear(t, u + o * f.major.x, v + o * f.major.y, f.lod, f.max_level);
         acc.x += s.x; acc.y += s.y; acc.z += s.z; acc.w += s.w;
     }
-    const float inv = 1.0f / (float)probes;
+    const float inv = 1.0f / (float)f.probes;
     return make_float4(acc.x * inv, acc.y * inv, acc.z * inv, acc.w * inv);
 }
 
@@ -330,18 +346,30 @@ __global__ void __launch_bounds__(256) resolve_kernel(const __grid_constant__ Fr
     float roughness = 1.0f, metallic = 1.0f;
     const uint32_t t_base = __ldg(&mi->base_color_texture_index), t_mr = __ldg(&mi->metallic_roughness_texture_index);
     const uint32_t t_nrm = __ldg(&mi->normal_texture_index);
+    uint4 fp_dims = make_uint4(0u, 0u, 0u, 0u);   // the size the current footprint was laid out for
+    Footprint fp{};
+    auto footprint_for = [&](uint32_t slot) {
+        const uint4 dims = __ldg(&P.tex_dims[slot]);
+        if (dims.x != fp_dims.x || dims.y != fp_dims.y || dims.z != fp_dims.z) {
+            fp = texture_footprint(dims, duv_dx, duv_dy);
+            fp_dims = dims;
+        }
+    };
     if (t_base < LH_MAX_TEXTURES && P.textures[t_base]) {
-        float4 s = sample_texture_grad(P.textures[t_base], __ldg(&P.tex_dims[t_base]), u, v, duv_dx, duv_dy);
+        footprint_for(t_base);
+        float4 s = sample_texture_footprint(P.textures[t_base], fp, u, v);
         base = F3{s.x, s.y, s.z};
     }
     base = F3{base.x * __ldg(&mi->base_color_factor[0]), base.y * __ldg(&mi->base_color_factor[1]), base.z * __ldg(&mi->base_color_factor[2])};
     if (t_mr < LH_MAX_TEXTURES && P.textures[t_mr]) {
-        float4 s = sample_texture_grad(P.textures[t_mr], __ldg(&P.tex_dims[t_mr]), u, v, duv_dx, duv_dy);
+        footprint_for(t_mr);
+        float4 s = sample_texture_footprint(P.textures[t_mr], fp, u, v);
         roughness = s.y;
         metallic = s.z;
     }
     if (t_nrm != LH_UNUSED_TEXTURE_INDEX && t_nrm < LH_MAX_TEXTURES && P.textures[t_nrm]) {
-        float4 s = sample_texture_grad(P.textures[t_nrm], __ldg(&P.tex_dims[t_nrm]), u, v, duv_dx, duv_dy);
+        footprint_for(t_nrm);
+        float4 s = sample_texture_footprint(P.textures[t_nrm], fp, u, v);
         F3 mn{s.x * (255.0f / 127.0f) - 128.0f / 127.0f, s.y * (255.0f / 127.0f) - 128.0f / 127.0f, s.z * (255.0f / 127.0f) - 128.0f / 127.0f};
         // compute_cotangent_frame (:25-38)
         F3 pdx{wx.dx, wy.dx, wz.dx}, pdy{wx.dy, wy.dy, wz.dy};
