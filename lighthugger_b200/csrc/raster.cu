@@ -35,7 +35,10 @@ constexpr int kWarpsPerCta = 8;
 constexpr uint32_t kTileW = 128, kTileH = 32;   // deferred-triangle screen tile
 constexpr uint32_t kWholeTriangle = 0xFFFFFFFFu;
 constexpr int kSmallMaxSpan = 32;               // small path: pixel bbox < 32 on each axis ...
-constexpr int kSmallMaxArea = 64;               // ... and at most this many pixel tests
+#ifndef LH_SMALL_MAX_AREA
+#define LH_SMALL_MAX_AREA 128
+#endif
+constexpr int kSmallMaxArea = LH_SMALL_MAX_AREA;   // ... and at most this many pixel tests (swept on B200: 16..1024)
 constexpr int kSmallMaxExtent = 1 << 14;        // ... and sub-pixel extent < 2^14 (32-bit edge functions stay exact)
 
 enum { CULL_NONE = 0, CULL_BACK = 1, CULL_FRONT = 2 };
