@@ -277,6 +277,10 @@ int lh_context_create(const LhConfig* cfg, LhContext** out) {
     cudaDeviceProp prop;
     cudaGetDeviceProperties(&prop, cfg->device);
     ctx->num_sms = prop.multiProcessorCount;
+    if (const char* t = getenv("LH_TUNE_FRACTIONS")) {
+        float* f = ctx->tune.main_fractions;
+        sscanf(t, "%f,%f,%f,%f,%f,%f,%f", &f[0], &f[1], &f[2], &f[3], &f[4], &f[5], &f[6]);
+    }
     if (const char* t = getenv("LH_TUNE")) {
         unsigned v[6] = {ctx->tune.main_bands, ctx->tune.shadow_bands, ctx->tune.main_grid, ctx->tune.shadow_grid, ctx->tune.resolve_low_priority, ctx->tune.select_grid};
         sscanf(t, "%u,%u,%u,%u,%u,%u", &v[0], &v[1], &v[2], &v[3], &v[4], &v[5]);

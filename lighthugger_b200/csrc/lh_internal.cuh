@@ -110,6 +110,7 @@ struct FrameParams {
     uint32_t flags;
     uint32_t max_large;
     uint32_t num_bands;                      // depth bands of the raster pass being launched (raster.cu)
+    float band_fractions[7];                 // cumulative meshlet-count fractions at which its bands end; [0] == 0: built-in table
     FrameState* state;
     unsigned long long* instance_tiles;      // [4][tiles] decoupled-lookback states
     // ---- the view being culled / rasterised (see PassState) ----
@@ -239,6 +240,7 @@ struct LhContext {
     // launch shapes of the rasteriser; defaults measured on B200 at BASELINE config 2.  Developer overrides:
     // LH_TUNE="main_bands,shadow_bands,main_grid,shadow_grid,resolve_low_priority,select_grid" in the environment at context creation.
     struct Tuning {
+        float main_fractions[7] = {0, 0, 0, 0, 0, 0, 0};   // LH_TUNE_FRACTIONS="f0,f1,..." (main view)
         uint32_t main_bands = 4, shadow_bands = 6, main_grid = 16, shadow_grid = 3, resolve_low_priority = 1, select_grid = 16;
     } tune;
 

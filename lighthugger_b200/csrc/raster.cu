@@ -453,10 +453,10 @@ __global__ void __launch_bounds__(1024) raster_bands_kernel(const __grid_constan
     const uint32_t total = grand_total, before = incl - sum + (warp ? partial[32 + warp - 1] : 0u);
     // cumulative count fractions at which the bands end, for each band count
     const float tables[kMaxBands + 1][kMaxBands - 1] = {
-        {}, {}, {0.10f}, {0.04f, 0.25f}, {0.03f, 0.12f, 0.40f}, {0.025f, 0.09f, 0.25f, 0.55f}, {0.02f, 0.07f, 0.17f, 0.35f, 0.60f},
+        {}, {}, {0.10f}, {0.04f, 0.25f}, {0.02f, 0.08f, 0.30f}, {0.025f, 0.09f, 0.25f, 0.55f}, {0.02f, 0.07f, 0.17f, 0.35f, 0.60f},
         {0.015f, 0.05f, 0.11f, 0.22f, 0.40f, 0.65f}, {0.01f, 0.03f, 0.07f, 0.14f, 0.26f, 0.42f, 0.65f}};
     const int kBands = (int)min(max(P.num_bands, 2u), (uint32_t)kMaxBands);
-    const float* fractions = tables[kBands];
+    const float* fractions = P.band_fractions[0] > 0.0f ? P.band_fractions : tables[kBands];
     PassState* st = P.pass;
     if (tid == 0) {
         st->band_key[kBands - 1] = kKeyEmpty;   // the last band takes the rest (empty meshlets carry kKeyEmpty and are never selected)
@@ -1072,6 +1072,7 @@ void launch_raster(LhContext* ctx, const FrameParams& params, int cascade, cudaS
     uint32_t drained_to = 0, drain = 0;
     FrameParams p = params;
     p.num_bands = bands;
+    for (int i = 0; i < 7; i++) p.band_fractions[i] = cascade < 0 ? ctx->tune.main_fractions[i] : 0.0f;
     const bool timed = cascade < 0 && (ctx->cfg.flags & LH_CONFIG_PASS_TIMINGS) != 0;
     raster_bands_kernel<<<1, 1024, 0, stream>>>(p);   // also opens the pass: empty raster and deferred queues
     ctx->launches++;
