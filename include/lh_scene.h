@@ -159,6 +159,28 @@ LH_HOST_API int lh_host_upload(void* user, uint64_t addr, const void* src, uint6
 LH_HOST_API int lh_host_free(void* user, uint64_t addr);
 
 /* stand-alone pieces, exported for tests against oracle/_ref */
+/* ---- glTF ingestion: one KHR_mesh_quantization primitive as the reference reads it
+ * (src/resources/mesh_loading.cpp:400-597): POSITION u16 x3 padded to 8 bytes, NORMAL i8 x3 padded to 4, TEXCOORD_0
+ * u16 x2, a u16 / u32 triangle list; the material's texture slots, KHR_texture_transform scale / offset (already
+ * divided by 65535 for normalised uvs, :555-557), MASK -> LH_MESH_INFO_FLAGS_ALPHA_CLIP and the base colour factor.
+ * Compacts the streams to 3 components (copy_quantized_positions / _normals), builds meshlets + bounds and the mesh
+ * bounding sphere from the raw integer positions, and takes 32-bit indices from index_bytes as the reference does. ---- */
+typedef struct LhIndexedMesh {
+    const void* positions;  uint32_t position_stride;   /* >= 6 */
+    const void* normals;    uint32_t normal_stride;     /* >= 3 */
+    const void* uvs;        uint32_t uv_stride;         /* >= 4 */
+    uint64_t num_vertices;
+    const void* indices;    uint64_t num_indices;  uint32_t index_bytes;   /* 2 or 4; num_indices % 3 == 0 */
+    uint32_t flags;                                      /* LH_MESH_INFO_FLAGS_ALPHA_CLIP or 0 */
+    float texture_scale[2], texture_offset[2];
+    uint16_t base_color_texture_index, metallic_roughness_texture_index, normal_texture_index, _pad;
+    float base_color_factor[3];
+} LhIndexedMesh;
+LH_HOST_API int lh_scene_add_mesh_indexed(LhScene* scene, const LhIndexedMesh* mesh);        /* returns mesh id or <0 */
+/* an instance with the node's matrix as it is (column-major; the quantisation is already part of a glTF node's
+ * scale / translation): Instance(transform, mesh_info) of src/main.cpp:433-440 */
+LH_HOST_API int lh_scene_add_instance_matrix(LhScene* scene, int mesh, const float transform[16]);
+
 /* ---- the reference's meshlet cache (src/resources/fs_cache.h:3-25, src/resources/mesh_loading.cpp:602-649) ----
  * Three raw blobs per primitive under <dir>/<std::hash of "<name> meshlets" | "<name> indices" | "<name> micro indices">:
  * the Meshlet records, the per-meshlet vertex indices (u16 / u32) and the micro-indices.  which: 0, 1, 2 in that order. */

@@ -388,6 +388,68 @@ int lh_scene_add_mesh(LhScene* scene, const LhMeshDesc* desc) {
     return (int)scene->meshes.size() - 1;
 }
 
+int lh_scene_add_mesh_indexed(LhScene* scene, const LhIndexedMesh* d) {
+    if (!scene || !d || !d->positions || !d->normals || !d->uvs || !d->indices) return -1;
+    if (d->position_stride < 6 || d->normal_stride < 3 || d->uv_stride < 4 || (d->index_bytes != 2 && d->index_bytes != 4)) return -1;
+    if (d->num_vertices == 0 || d->num_indices % 3 != 0) return -1;
+    const size_t nv = (size_t)d->num_vertices;
+    auto mesh = std::make_unique<Mesh>();
+    mesh->positions.resize(nv * 3);
+    mesh->normals.resize(nv * 3);
+    mesh->uvs.resize(nv * 2);
+    std::vector<float> raw(nv * 3);
+    for (size_t i = 0; i < nv; i++) {
+        uint16_t p[3], uv[2];
+        int8_t n[3];
+        memcpy(p, (const uint8_t*)d->positions + i * d->position_stride, 6);
+        memcpy(n, (const uint8_t*)d->normals + i * d->normal_stride, 3);
+        memcpy(uv, (const uint8_t*)d->uvs + i * d->uv_stride, 4);
+        for (int a = 0; a < 3; a++) {
+            mesh->positions[3 * i + a] = p[a];
+            raw[3 * i + a] = (float)p[a];   // meshlets and bounds are built on the raw integers (mesh_loading.cpp:584-597)
+            mesh->normals[3 * i + a] = n[a];
+        }
+        mesh->uvs[2 * i] = uv[0];
+        mesh->uvs[2 * i + 1] = uv[1];
+    }
+    std::vector<uint32_t> tris((size_t)d->num_indices);
+    for (size_t i = 0; i < tris.size(); i++) {
+        tris[i] = d->index_bytes == 4 ? ((const uint32_t*)d->indices)[i] : (uint32_t)((const uint16_t*)d->indices)[i];
+        if (tris[i] >= nv) return -3;   // an index past the vertex streams
+    }
+    mesh->num_triangles = tris.size() / 3;
+    build_meshlets(*mesh, tris, raw, nv);
+    if (d->index_bytes == 4 && !mesh->wide_indices) {   // the index width follows the accessor (mesh_loading.cpp:455-462)
+        mesh->idx32.assign(mesh->idx16.begin(), mesh->idx16.end());
+        mesh->idx16.clear();
+        mesh->wide_indices = true;
+    }
+    if (mesh->meshlets.size() > 65535) return -2;  // 16-bit meshlet index cap (mesh_loading.cpp:710-713)
+    LhMeshInfo& info = mesh->info;
+    memset(&info, 0, sizeof(info));
+    info.num_meshlets = (uint16_t)mesh->meshlets.size();
+    info.flags = (uint8_t)((mesh->wide_indices ? LH_MESH_INFO_FLAGS_32_BIT_INDICES : 0u) | (d->flags & LH_MESH_INFO_FLAGS_ALPHA_CLIP));
+    bounding_sphere(info.bounding_sphere, raw.data(), nv);
+    for (int a = 0; a < 2; a++) {
+        info.texture_scale[a] = d->texture_scale[a];
+        info.texture_offset[a] = d->texture_offset[a];
+    }
+    info.base_color_texture_index = d->base_color_texture_index;
+    info.metallic_roughness_texture_index = d->metallic_roughness_texture_index;
+    info.normal_texture_index = d->normal_texture_index;
+    for (int a = 0; a < 3; a++) info.base_color_factor[a] = d->base_color_factor[a];
+    scene->meshes.push_back(std::move(mesh));
+    return (int)scene->meshes.size() - 1;
+}
+
+int lh_scene_add_instance_matrix(LhScene* scene, int mesh, const float transform[16]) {
+    if (!scene || !transform || mesh < 0 || mesh >= (int)scene->meshes.size()) return -1;
+    LhMat4 m;
+    memcpy(&m, transform, sizeof(m));
+    scene->instances.push_back({mesh, m});
+    return 0;
+}
+
 int lh_scene_add_mesh_raw(LhScene* scene, const LhMeshView* v) {
     if (!scene || !v) return -1;
     auto mesh = std::make_unique<Mesh>();

@@ -142,3 +142,32 @@ def test_display_lut_and_skybox_from_rgb9e5_dds():
     want = np.rint(np.clip(np.where(enc <= 0.0031308, 12.92 * enc, 1.055 * np.power(enc, 1 / 2.4) - 0.055), 0, 1) * 255)
     assert np.abs(want[:, ::-1] - bgra[:, :3]).max() <= 3
     ctx.close()
+
+
+def test_gltf_scene_renders_like_the_directly_built_scene(tmp_path):
+    # .gltf + .bin + .dds / .ktx2 files -> lighthugger_b200.gltf.load + image_files.upload -> the same frame
+    # as the scene assembled from the same arrays and textures through the host library
+    import gltf_fixture
+    import test_image_files as F
+    from lighthugger_b200 import gltf as G, image_files as IF
+    donor = Scene.preset("tiny")
+    tex = Textures(donor, 32)
+    files = []
+    for i in range(3):
+        blocks, levels, _ = tex.entries[i]
+        files.append((f"tex{i}.dds", F.dds_file(F.DXGI["BC7_SRGB"], tex.size, tex.size, levels, blocks)))
+    path, expected = gltf_fixture.build(str(tmp_path), files)
+    loaded, images = G.load(path)
+    gltf_fixture.look_at_instances(loaded)
+    frames = []
+    for scene in (loaded, expected):
+        ctx = make_context(scene)
+        for i, image in enumerate(images):
+            assert IF.upload(ctx, open(image, "rb").read()) == ("texture", i)
+        st = ctx.render_frame_host(ctx.uniforms())
+        assert st.num_visible_instances == 3 and st.num_opaque > 0 and st.num_alpha_clip > 0
+        frames.append((ctx.target(S.LH_TARGET_VIS64).copy(), ctx.target(S.LH_TARGET_SCENE_RGBA16F).view(np.uint16).copy()))
+        ctx.close()
+    assert np.array_equal(frames[0][0], frames[1][0]) and np.array_equal(frames[0][1], frames[1][1])
+    depth, _, _ = vis_fields(frames[0][0])
+    assert np.count_nonzero(depth) > 0.02 * depth.size
