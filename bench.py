@@ -207,6 +207,8 @@ def run_ours(args):
     tex = scene_textures(scene, args.tex_size)
     sky = scene.make_skybox(32)
     from lighthugger_b200 import sortlast
+    if args.stripes_per_rank > 0:
+        sortlast.STRIPES_PER_RANK = args.stripes_per_rank
     n = scene.num_instances
     (first, count), _ = sortlast.main_plan(n, rank, world, args.partition)
     end = first + count
@@ -392,6 +394,7 @@ def main():
     ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"], help="multi-GPU: peer-memory kernels or whole-buffer NCCL")
     ap.add_argument("--shadow-split", default="instances", choices=["instances", "cascades"])
     ap.add_argument("--partition", default="stripes", choices=["stripes", "range"], help="multi-GPU: how instances are shared out")
+    ap.add_argument("--stripes-per-rank", type=int, default=0, help="multi-GPU: interleaved screen stripes per GPU (0: sortlast.STRIPES_PER_RANK)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

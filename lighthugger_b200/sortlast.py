@@ -35,7 +35,7 @@ def slot_offset(caps, rank):
     return rank * (caps.max_opaque_draws + caps.max_alpha_clip_draws)
 
 
-STRIPES_PER_RANK = 8   # interleaved screen stripes per GPU: narrow enough to even the load, wide enough to keep occluders together
+STRIPES_PER_RANK = 2   # interleaved screen stripes per GPU: wide stripes keep occluders together (measured on 2 x B200 at C2: 1 -> 299, 2 -> 321, 3 -> 318, 4 -> 310, 8 -> 294, 16 -> 276, 32 -> 266 frames/s)
 
 
 def main_plan(num_instances, rank, world, partition="stripes"):
