@@ -200,7 +200,7 @@ LH_API int lh_reset(LhContext* ctx);                    /* reset_buffers_a, rend
 LH_API int lh_cull_instances(LhContext* ctx);           /* cull_instances.comp:7-27, rendering.cpp:139-147 */
 LH_API int lh_cull_meshlets(LhContext* ctx);            /* reset_buffers_b + write_draw_calls.comp:7-57, rendering.cpp:156-183 */
 LH_API int lh_raster_visbuffer(LhContext* ctx);         /* rasterization.glsl:38-97 + fixed function incl. the depth clear 0.0, rendering.cpp:195-266 */
-LH_API int lh_composite(LhContext* ctx);                /* new: sort-last u64-min over NCCL; no-op without lh_comm_init */
+LH_API int lh_composite(LhContext* ctx);                /* new: sort-last u64-min composite (peer-memory kernel or NCCL, lh_comm_set_exchange); no-op without lh_comm_init */
 LH_API int lh_reduce_depth(LhContext* ctx);             /* compute/read_depth.glsl:22-83, rendering.cpp:289-300 */
 LH_API int lh_generate_shadow_matrices(LhContext* ctx); /* compute/generate_shadow_matrices.glsl:15-110, rendering.cpp:302 */
 LH_API int lh_cull_instances_shadows(LhContext* ctx);   /* cull_instances.comp:31-56, rendering.cpp:304-312 */

@@ -124,7 +124,7 @@ struct FrameParams {
     uint32_t* raster_queue;                  // indices of the meshlets selected for rasterisation, band after band
     uint32_t* depth_keys;                    // the bounds' depth keys on their own (4 B per meshlet): what band selection scans
     uint32_t* depth_hist;                    // 8192 bins of the depth-key histogram (self-cleaning)
-    uint32_t* hiz;                           // farthest stored value per 8x8-pixel tile of the current raster target
+    uint32_t* hiz;                           // two hierarchical-Z levels of the current raster target: farthest stored value per 4x4- and per 16x16-pixel tile
     unsigned long long* vis;
     uint32_t* shadow;                        // 4 layers of float bits
     const cudaTextureObject_t* textures;
