@@ -155,3 +155,37 @@ def test_reference_lut_file_when_present():
     texels = data.view(np.uint32)
     assert texels.size == int(g["texel_count"]) and np.bitwise_xor.reduce(texels) == g["xor_all"]
     assert int(texels.astype(np.uint64).sum()) == int(g["sum_all"])
+
+
+def test_parser_survives_mutated_files_under_address_sanitizer(tmp_path):
+    # the host library's parser + decoder compiled with -fsanitize=address,undefined and driven by a mutation fuzzer
+    # (tests/native/fuzz_image_files.cpp): malformed input must come back as an error code, never as an out-of-bounds access
+    import shutil
+    import subprocess
+    cxx = shutil.which("g++")
+    if cxx is None:
+        pytest.skip("no C++ compiler")
+    exe = str(tmp_path / "fuzz_image_files")
+    build = subprocess.run([cxx, "-std=c++20", "-O1", "-g", "-fsanitize=address,undefined", "-fno-sanitize-recover=all", "-I", os.path.join(ROOT, "include"),
+                            os.path.join(ROOT, "tests", "native", "fuzz_image_files.cpp"), os.path.join(ROOT, "lighthugger_b200", "host", "image_files.cpp"),
+                            "-o", exe, "-ldl"], capture_output=True, text=True)
+    if build.returncode != 0 and "sanitize" in build.stderr:
+        pytest.skip("the sanitizer runtimes are not installed")
+    assert build.returncode == 0, build.stderr[-2000:]
+    rng = np.random.default_rng(3)
+    sizes = level_bytes(32, 16, 6, 8, True)
+    seeds = {
+        "bc7.dds": dds_file(DXGI["BC7_SRGB"], 32, 16, 6, rng.integers(0, 256, sum(sizes), dtype=np.uint8)),
+        "cube.dds": dds_file(DXGI["RGB9E5"], 4, 4, 1, bytes(6 * 16 * 4), cubemap=True),
+        "lut.dds": dds_file(DXGI["RGB9E5"], 4, 4, 1, bytes(64 * 4), depth=4, dimension=4),
+        "plain.ktx2": ktx2_file(VK["BC7_SRGB"], 32, 16, 6, [bytes(s) for s in sizes]),
+        "zstd.ktx2": ktx2_file(VK["BC7_SRGB"], 32, 16, 6, [bytes(s) for s in sizes], scheme=2, stored=[_zstd_compress(bytes(s)) for s in sizes]),
+    }
+    paths = []
+    for name, data in seeds.items():
+        p = str(tmp_path / name)
+        open(p, "wb").write(data)
+        paths.append(p)
+    run = subprocess.run([exe, "3000"] + paths, capture_output=True, text=True, timeout=300,
+                         env=dict(os.environ, ASAN_OPTIONS="detect_leaks=0"))
+    assert run.returncode == 0 and "fuzz ok" in run.stdout, (run.stdout + run.stderr)[-3000:]
