@@ -27,7 +27,8 @@ class LhoConfig(C.Structure):
 def oracle_lib():
     global _lib
     if _lib is None:
-        path = os.path.join(ROOT, "oracle", "liblh_oracle.so")
+        # LH_ORACLE_LIB: a differently built oracle (the sanitizer test builds one with -fsanitize=address,undefined)
+        path = os.environ.get("LH_ORACLE_LIB") or os.path.join(ROOT, "oracle", "liblh_oracle.so")
         if not os.path.exists(path):
             raise RuntimeError(f"{path} is missing: run `make oracle`")
         lib = C.CDLL(path)

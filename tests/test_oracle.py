@@ -1,6 +1,7 @@
 """The oracle checked against independent restatements and the domain's own
 properties (the reference ships no golden vectors for this path: SURVEY.md 8c)."""
 import ctypes as C
+import os
 
 import numpy as np
 import pytest
@@ -202,3 +203,34 @@ def test_resolve_is_finite_and_sky_where_empty():
     assert np.isfinite(col).all() and (col[:, 3] == 1).all() and (col[:, :3] >= 0).all()
     depth, _, _ = vis_fields(o.vis)
     assert (depth == 0).any() and (depth != 0).any()
+
+
+def test_oracle_frame_is_clean_under_address_and_ub_sanitizers(tmp_path):
+    # the oracle is the checker of every parity test: one whole frame of it (all passes, textures, skybox) runs here in
+    # a build with -fsanitize=address,undefined ("host -fsanitize=address,undefined for the oracle")
+    import glob
+    import shutil
+    import subprocess
+    import sys
+    cxx = shutil.which("g++")
+    if cxx is None:
+        pytest.skip("no C++ compiler")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    lib = str(tmp_path / "liblh_oracle_asan.so")
+    build = subprocess.run([cxx, "-O1", "-g", "-std=c++20", "-fPIC", "-ffp-contract=off", "-fsanitize=address,undefined", "-fno-sanitize-recover=all",
+                            "-I", os.path.join(root, "include"), "-fvisibility=default", "-pthread", "-shared", "-o", lib] +
+                           sorted(glob.glob(os.path.join(root, "oracle", "*.cpp"))), capture_output=True, text=True)
+    runtimes = [subprocess.run([cxx, f"-print-file-name={n}"], capture_output=True, text=True).stdout.strip() for n in ("libasan.so", "libubsan.so")]
+    if build.returncode != 0 and "sanitize" in build.stderr or not all(os.path.isabs(r) and os.path.exists(r) for r in runtimes):
+        pytest.skip("the sanitizer runtimes are not installed")
+    assert build.returncode == 0, build.stderr[-2000:]
+    script = ("import sys; sys.path[:0] = [%r, %r]\\n"
+              "from lighthugger_b200.scene import Scene\\n"
+              "from helpers import Textures, make_oracle\\n"
+              "sc = Scene.preset('tiny'); tex = Textures(sc, 32)\\n"
+              "o = make_oracle(sc, textures=tex, skybox=sc.make_skybox(8)); o.render_frame(resolve=True)\\n"
+              "print('covered', int((o.vis != 0xFFFFFFFFFFFFFFFF).sum()))\\n") % (root, os.path.join(root, "tests"))
+    env = dict(os.environ, LD_PRELOAD=" ".join(runtimes), ASAN_OPTIONS="detect_leaks=0", LH_ORACLE_LIB=lib)
+    run = subprocess.run([sys.executable, "-c", script.replace("\\n", "\n")], capture_output=True, text=True, timeout=600, env=env)
+    assert run.returncode == 0 and "covered" in run.stdout, (run.stdout + run.stderr)[-3000:]
+    assert int(run.stdout.split("covered")[1].split()[0]) > 1000
