@@ -22,11 +22,12 @@ NVCCFLAGS := -gencode arch=compute_100a,code=sm_100a -O3 -std=c++20 -lineinfo \
 LDFLAGS_SO := -Wl,--exclude-libs,ALL
 CXXFLAGS := -O2 -std=c++20 -fPIC -fvisibility=hidden -ffp-contract=off -Iinclude -Wall -Wextra -Wno-unused-parameter
 
-all: cuda host oracle ref
+all: cuda host oracle ref examples
 
 cuda: $(LIBDIR)/liblighthugger_b200.so
 host: $(LIBDIR)/liblh_host.so
 oracle: oracle/liblh_oracle.so
+examples: lighthugger_b200/bin/lh_frame_loop
 
 CUDA_OBJS := $(patsubst lighthugger_b200/csrc/%.cu,build/%.o,$(CUDA_SRCS))
 build/%.o: lighthugger_b200/csrc/%.cu $(CUDA_HDRS)
@@ -40,6 +41,11 @@ $(LIBDIR)/liblighthugger_b200.so: $(CUDA_OBJS)
 $(LIBDIR)/liblh_host.so: $(HOST_SRCS) $(HOST_HDRS)
 	@mkdir -p $(LIBDIR)
 	$(CXX) $(CXXFLAGS) -shared -o $@ $(HOST_SRCS) $(LDFLAGS_SO) -ldl
+
+# a C++20 host on top of the two C ABIs, the counterpart of the reference's main() frame loop
+lighthugger_b200/bin/lh_frame_loop: examples/frame_loop.cpp $(LIBDIR)/liblighthugger_b200.so $(LIBDIR)/liblh_host.so $(HOST_HDRS)
+	@mkdir -p lighthugger_b200/bin
+	$(CXX) -O2 -std=c++20 -Iinclude -Wall -Wextra -o $@ examples/frame_loop.cpp -L$(LIBDIR) -llighthugger_b200 -llh_host -Wl,-rpath,'$$ORIGIN/../lib'
 
 oracle/liblh_oracle.so: $(ORACLE_SRCS) $(ORACLE_HDRS)
 	$(CXX) $(CXXFLAGS) -fvisibility=default -pthread -shared -o $@ $(ORACLE_SRCS) $(LDFLAGS_SO)
@@ -59,6 +65,6 @@ oracle/_ref/libref_sceneprep.so: oracle/ref_shim/ref_exports.cpp oracle/ref_shim
 	    oracle/ref_shim/ref_exports.cpp $(REF_MESHOPT)/clusterizer.cpp $(REF_MESHOPT)/allocator.cpp $(LDFLAGS_SO)
 
 clean:
-	rm -f $(LIBDIR)/*.so oracle/*.so oracle/_ref/*.so
+	rm -f $(LIBDIR)/*.so oracle/*.so oracle/_ref/*.so lighthugger_b200/bin/lh_frame_loop
 
-.PHONY: all cuda host oracle ref clean
+.PHONY: all cuda host oracle ref examples clean

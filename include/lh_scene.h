@@ -158,7 +158,6 @@ LH_HOST_API int lh_host_alloc(void* user, uint64_t bytes, uint64_t* addr);
 LH_HOST_API int lh_host_upload(void* user, uint64_t addr, const void* src, uint64_t bytes);
 LH_HOST_API int lh_host_free(void* user, uint64_t addr);
 
-/* stand-alone pieces, exported for tests against oracle/_ref */
 /* ---- glTF ingestion: one KHR_mesh_quantization primitive as the reference reads it
  * (src/resources/mesh_loading.cpp:400-597): POSITION u16 x3 padded to 8 bytes, NORMAL i8 x3 padded to 4, TEXCOORD_0
  * u16 x2, a u16 / u32 triangle list; the material's texture slots, KHR_texture_transform scale / offset (already
@@ -193,6 +192,7 @@ LH_HOST_API int lh_meshlet_cache_load(const char* dir, const char* primitive_nam
 LH_HOST_API int lh_meshlet_blobs_view(const LhMeshletBlobs* blobs, uint32_t index_bytes, LhMeshView* view);
 LH_HOST_API void lh_meshlet_blobs_free(LhMeshletBlobs* blobs);
 
+/* stand-alone pieces, exported for tests against oracle/_ref */
 LH_HOST_API void lh_compute_bounding_sphere(float result[4], const float* points, uint64_t count);
 LH_HOST_API void lh_compute_meshlet_bounds(const uint32_t* meshlet_vertices, const uint8_t* meshlet_triangles,
                                            uint32_t triangle_count, const float* positions /* xyz */,
