@@ -21,7 +21,8 @@ def capacities(scene, world, split="instances"):
         return scene.default_capacities()
     per_rank = -(-scene.total_meshlets // world)
     alpha = max(1024, per_rank // 8)
-    opaque = per_rank + 1024
+    # twice the even share where the slot field allows it: stripes do not split the meshlets evenly
+    opaque = max(per_rank + 1024, min(2 * per_rank + 1024, S.LH_VIS_MAX_SLOTS // world - alpha))
     if split == "cascades":
         opaque = max(opaque, min(scene.total_meshlets + 1024, S.LH_VIS_MAX_SLOTS // world - alpha))
     caps = S.LhCapacities(max_instances=scene.num_instances, max_opaque_draws=opaque, max_alpha_clip_draws=alpha)
