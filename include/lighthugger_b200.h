@@ -241,7 +241,10 @@ LH_API int lh_comm_info(LhContext* ctx, int* rank, int* nranks);
  * pulls those rows of every peer's key buffer through peer memory, takes the uint64 min and folds the depth min/max
  * in; the resolve reads the winners' MeshletReference from the owning rank's table through peer memory and stores
  * its rows of lit colour into rank 0's frame.  LH_EXCHANGE_NCCL: ncclAllReduce(uint64, min) of whole buffers and an
- * all-gather of the reference tables; every rank then holds and resolves the whole frame. */
+ * all-gather of the reference tables; every rank then holds and resolves the whole frame.
+ * LH_EXCHANGE_PEER maps whole allocations: LhUniforms.meshlet_references must be an address lh_buffer_alloc returned
+ * (not an offset into a larger buffer), and ranks must move that buffer, resize their targets or destroy their
+ * communicator together. */
 enum { LH_EXCHANGE_PEER = 0, LH_EXCHANGE_NCCL = 1 };
 LH_API int lh_comm_set_exchange(LhContext* ctx, int mode);
 LH_API int lh_comm_rows(LhContext* ctx, uint32_t* y0, uint32_t* y1);   /* rows this rank composites and resolves */
