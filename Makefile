@@ -55,7 +55,7 @@ oracle/liblh_oracle.so: $(ORACLE_SRCS) $(ORACLE_HDRS)
 REF_GLM := $(REF)/external/VulkanMemoryAllocator-Hpp/Vulkan-Hpp/glm
 REF_MESHOPT := $(REF)/external/meshoptimizer/src
 ref:
-	@if [ -d $(REF)/src ]; then $(MAKE) --no-print-directory oracle/_ref/libref_sceneprep.so; \
+	@if [ -d $(REF)/src ]; then $(MAKE) --no-print-directory oracle/_ref/libref_sceneprep.so oracle/_ref/libref_shaders.so; \
 	 else echo "no $(REF): keeping prebuilt oracle/_ref"; fi
 
 oracle/_ref/libref_sceneprep.so: oracle/ref_shim/ref_exports.cpp oracle/ref_shim/ref_pch.h
@@ -63,6 +63,23 @@ oracle/_ref/libref_sceneprep.so: oracle/ref_shim/ref_exports.cpp oracle/ref_shim
 	$(CXX) -O2 -std=c++20 -fPIC -fvisibility=hidden -w -shared -o $@ \
 	    -include oracle/ref_shim/ref_pch.h -Ioracle/ref_shim -I$(REF)/src -I$(REF_GLM) -I$(REF_MESHOPT) \
 	    oracle/ref_shim/ref_exports.cpp $(REF_MESHOPT)/clusterizer.cpp $(REF_MESHOPT)/allocator.cpp $(LDFLAGS_SO)
+
+# The reference's GLSL (every compute entry point of the path, the vertex shaders and the function files they include)
+# compiled as C++ against its own glm and its own shared_cpu_gpu.h: glsl_filter.py drops what is not C++ (layout
+# declarations, #extension) into oracle/_ref/gen/, ref_shaders.cpp includes the result.  This pins the oracle.
+REF_SHADERS := common/prefix_sum.glsl common/util.glsl common/culling.glsl common/matrices.glsl common/vbuffer.glsl \
+               common/pbr.glsl common/debug.glsl cull_instances.comp write_draw_calls.comp rasterization.glsl \
+               render_geometry.comp display_transform.comp compute/reset_buffers.glsl compute/generate_shadow_matrices.glsl \
+               compute/read_depth.glsl
+REF_SHADERS_GEN := $(addprefix oracle/_ref/gen/,$(REF_SHADERS))
+oracle/_ref/gen/%: $(REF)/src/shaders/% oracle/ref_shim/glsl_filter.py
+	@mkdir -p $(dir $@)
+	python oracle/ref_shim/glsl_filter.py $< $@
+
+oracle/_ref/libref_shaders.so: oracle/ref_shim/ref_shaders.cpp oracle/ref_shim/glsl_shim.h $(REF_SHADERS_GEN) oracle/liblh_oracle.so
+	$(CXX) -O2 -std=gnu++20 -fPIC -fvisibility=hidden -ffp-contract=off -w -shared -o $@ \
+	    -Ioracle/ref_shim -Ioracle/_ref -Ioracle -Iinclude -I$(REF)/src -I$(REF_GLM) oracle/ref_shim/ref_shaders.cpp \
+	    -Loracle -llh_oracle -Wl,-rpath,'$$ORIGIN/..' $(LDFLAGS_SO)
 
 clean:
 	rm -f $(LIBDIR)/*.so oracle/*.so oracle/_ref/*.so lighthugger_b200/bin/lh_frame_loop

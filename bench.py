@@ -359,6 +359,7 @@ def run_ours(args):
                   "rasterised_triangles_nonempty": int(stats.rasterized_triangles),
                   "meshlets_skipped_no_sample": list(stats.meshlets_skipped_no_sample),
                   "meshlets_skipped_occluded": list(stats.meshlets_skipped_occluded),
+                  "meshlets_queued": list(stats.meshlets_queued),
                   "shadow_rasterised_meshlets": [int(a) + int(b) for a, b in zip(stats.shadow_opaque, stats.shadow_alpha_clip)]},
         "pass_ms": {k: round(v, 4) for k, v in med.items()},
         "pass_notes": ("render_geometry is the resolve's shadow phase (critical path); its material phase (resolve_kernel<1>) runs on a "

@@ -82,6 +82,10 @@ LH_HOST_API int lh_scene_mesh_view(const LhScene* scene, int mesh, LhMeshView* o
 LH_HOST_API int lh_scene_place_instances(LhScene* scene, uint32_t count, uint64_t seed,
                                          const float extent[3], float scale_min, float scale_max,
                                          const int32_t* mesh_ids, uint32_t num_mesh_ids);
+/* the same with uniformly random rotations and a different scale per axis (parity tests: general transforms) */
+LH_HOST_API int lh_scene_place_instances_general(LhScene* scene, uint32_t count, uint64_t seed,
+                                                 const float extent[3], float scale_min, float scale_max,
+                                                 const int32_t* mesh_ids, uint32_t num_mesh_ids);
 LH_HOST_API int lh_scene_add_instance(LhScene* scene, int mesh, const float translation[3],
                                       const float rotation_quat_xyzw[4], float scale);
 LH_HOST_API uint32_t lh_scene_num_instances(const LhScene* scene);

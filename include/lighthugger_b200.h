@@ -95,6 +95,8 @@ typedef struct LhFrameStats {
     /* rasteriser early-outs, [0] main view, [1..4] cascades (counted only with LH_CONFIG_PASS_TIMINGS) */
     uint32_t meshlets_skipped_no_sample[5]; /* the meshlet's bound holds no pixel centre */
     uint32_t meshlets_skipped_occluded[5];  /* every key already stored in the bound is nearer */
+    uint32_t meshlets_queued[5];            /* meshlets the band selection handed to the raster kernel */
+    uint32_t _pad1;
 } LhFrameStats;
 
 enum {

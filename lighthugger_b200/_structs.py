@@ -86,6 +86,8 @@ LH_TARGET_VIS64, LH_TARGET_DEPTH, LH_TARGET_SCENE_RGBA16F, LH_TARGET_SHADOW, LH_
 LH_TEXTURE_RGBA8_SRGB, LH_TEXTURE_RGBA8_UNORM, LH_TEXTURE_BC7_SRGB, LH_TEXTURE_BC1_SRGB = range(4)
 LH_ERR_CAPACITY = -4
 LH_EXCHANGE_PEER, LH_EXCHANGE_NCCL = 0, 1
+# the reference's compile-time capacities (shared_cpu_gpu.h:119-125,159): LhConfig / LhCapacities defaults
+LH_MAX_INSTANCES, LH_MAX_OPAQUE_DRAWS, LH_MAX_ALPHA_CLIP_DRAWS = 1024, 200000, 200000
 LH_VIS_CLEAR = 0xFFFFFFFFFFFFFFFF
 LH_VIS_TRI_BITS = 7
 LH_VIS_MAX_SLOTS = 1 << 25
@@ -114,6 +116,7 @@ class LhFrameStats(C.Structure):
         ("shadow_candidate_meshlets", u32 * 4), ("shadow_opaque", u32 * 4), ("shadow_alpha_clip", u32 * 4),
         ("num_large_triangles", u32), ("overflow", u32), ("rasterized_triangles", u64),
         ("meshlets_skipped_no_sample", u32 * 5), ("meshlets_skipped_occluded", u32 * 5),
+        ("meshlets_queued", u32 * 5), ("_pad1", u32),
     ]
 
 

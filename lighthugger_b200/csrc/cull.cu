@@ -177,7 +177,7 @@ __global__ void reset_kernel(const __grid_constant__ FrameParams P) {
     s->main_large_count = 0;
     s->main_visible = s->main_candidates = s->main_opaque = s->main_alpha_clip = 0;
     s->rasterized_triangles = 0ull;
-    for (int c = 0; c < 5; c++) s->skipped_empty[c] = s->skipped_occluded[c] = 0;
+    for (int c = 0; c < 5; c++) s->skipped_empty[c] = s->skipped_occluded[c] = s->queued[c] = 0;
     for (int c = 0; c < 4; c++) {
         s->shadow_opaque[c] = 0;
         s->shadow_alpha_clip[c] = 0;

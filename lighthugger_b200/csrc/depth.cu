@@ -184,6 +184,7 @@ __global__ void extract_depth_kernel(const unsigned long long* vis, float* depth
 __global__ void gather_stats_kernel(const __grid_constant__ FrameParams P, LhFrameStats* out) {
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
     LhFrameStats s;
+    s._pad1 = 0;
     const FrameState* st = P.state;
     const LhMiscStorage* misc = (const LhMiscStorage*)P.u.misc_storage;
     s.num_visible_instances = st->main_visible;
@@ -204,6 +205,7 @@ __global__ void gather_stats_kernel(const __grid_constant__ FrameParams P, LhFra
     for (int c = 0; c < 5; c++) {
         s.meshlets_skipped_no_sample[c] = st->skipped_empty[c];
         s.meshlets_skipped_occluded[c] = st->skipped_occluded[c];
+        s.meshlets_queued[c] = st->queued[c];
     }
     *out = s;
 }

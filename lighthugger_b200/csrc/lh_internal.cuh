@@ -52,9 +52,11 @@ __device__ __forceinline__ V3 mat3_mul(const float* m, float x, float y, float z
 }
 __device__ __forceinline__ float dot3(V3 a, V3 b) { return padd(padd(pmul(a.x, b.x), pmul(a.y, b.y)), pmul(a.z, b.z)); }
 __device__ __forceinline__ float length3(V3 a) { return psqrt(dot3(a, a)); }
+// glm's normalize (what the reference's GLSL compiles to against its own glm, and one IEEE division instead of three):
+// v * inversesqrt(dot(v, v)), inversesqrt(x) = 1 / sqrt(x)
 __device__ __forceinline__ V3 normalize3(V3 a) {
-    float l = length3(a);
-    return V3{pdiv(a.x, l), pdiv(a.y, l), pdiv(a.z, l)};
+    const float inv = pdiv(1.0f, length3(a));
+    return V3{pmul(a.x, inv), pmul(a.y, inv), pmul(a.z, inv)};
 }
 __device__ __forceinline__ V3 cross3(V3 a, V3 b) {
     return V3{psub(pmul(a.y, b.z), pmul(b.y, a.z)), psub(pmul(a.z, b.x), pmul(b.z, a.x)), psub(pmul(a.x, b.y), pmul(b.x, a.y))};
@@ -71,7 +73,7 @@ struct FrameState {
     uint32_t shadow_candidates[4];
     uint32_t done[4];              // instance cull: CTAs finished per sector (self-cleaning of the tile states)
     unsigned long long rasterized_triangles;
-    uint32_t skipped_empty[5], skipped_occluded[5];   // meshlets dropped by the rasteriser's early-outs: [0] main view, [1..4] cascades (stats)
+    uint32_t skipped_empty[5], skipped_occluded[5], queued[5];   // meshlets dropped by the rasteriser's early-outs: [0] main view, [1..4] cascades (stats)
 };
 
 // Work counters of one view (the main view or one cascade) through meshlet cull and rasterisation.  Each view that

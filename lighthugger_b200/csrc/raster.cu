@@ -612,7 +612,10 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, LH_RASTER_MIN_CTAS) raster_
     // band b owns the queue entries appended by its selection: [band_mark[b], queue_count); nothing appends while
     // this kernel runs, and the mark it leaves for band b + 1 is read by that band's launch only
     const uint32_t band_first = P.pass->band_mark[band], band_end = P.pass->queue_count;
-    if (blockIdx.x == 0 && threadIdx.x == 0) P.pass->band_mark[band + 1] = band_end;
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        P.pass->band_mark[band + 1] = band_end;
+        if (P.flags & LH_CONFIG_PASS_TIMINGS) atomicAdd(&P.state->queued[SHADOW ? 1u + cascade : 0u], band_end - band_first);
+    }
 
     Target<SHADOW> tg;
     tg.vis = P.vis;

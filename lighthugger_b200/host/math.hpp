@@ -22,9 +22,9 @@ inline Vec3 cross(Vec3 a, Vec3 b) {
     return {a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x};
 }
 inline float length(Vec3 a) { return std::sqrt(dot(a, a)); }
-inline Vec3 normalize(Vec3 a) {
-    float l = length(a);
-    return {a.x / l, a.y / l, a.z / l};
+inline Vec3 normalize(Vec3 a) {   // glm's: v * inversesqrt(dot(v, v)) (the reference host builds its view matrix with glm::lookAt)
+    float inv = 1.0f / std::sqrt(dot(a, a));
+    return {a.x * inv, a.y * inv, a.z * inv};
 }
 
 inline LhMat4 identity4() {

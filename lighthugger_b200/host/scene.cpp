@@ -532,6 +532,35 @@ int lh_scene_place_instances(LhScene* scene, uint32_t count, uint64_t seed, cons
     return 0;
 }
 
+// Uniformly random rotations (unit quaternions) and a different scale per axis: here mat3(inverse(T)) differs from the
+// inverse transpose, which exercises the reference's untransposed normal transform (shared_cpu_gpu.h:92-97,
+// culling.glsl:141) where it is NOT the correct normal matrix (SURVEY 8d "random rotation").  The reference's own scenes
+// never rotate (mesh_loading.cpp:8-49), so this placement is for parity tests; the bench scenes keep half-turns.
+int lh_scene_place_instances_general(LhScene* scene, uint32_t count, uint64_t seed, const float extent[3], float smin,
+                                     float smax, const int32_t* mesh_ids, uint32_t num_mesh_ids) {
+    if (!scene || !mesh_ids || num_mesh_ids == 0) return -1;
+    uint32_t first = (uint32_t)scene->instances.size();
+    for (uint32_t k = 0; k < count; k++) {
+        uint64_t c = (uint64_t)(first + k) * 16;
+        int mesh = mesh_ids[(first + k) % num_mesh_ids];
+        if (mesh < 0 || mesh >= (int)scene->meshes.size()) return -1;
+        const Mesh& m = *scene->meshes[mesh];
+        float t[3], s[3];
+        for (int a = 0; a < 3; a++) t[a] = (u01(seed, c + a) * 2.0f - 1.0f) * extent[a];
+        for (int a = 0; a < 3; a++) s[a] = smin + (smax - smin) * u01(seed, c + 3 + a);
+        // Shoemake: a uniformly distributed unit quaternion from three uniforms
+        const float two_pi = 6.28318530717958647692f;
+        float u1 = u01(seed, c + 6), u2 = u01(seed, c + 7), u3 = u01(seed, c + 8);
+        float a = std::sqrt(1.0f - u1), b = std::sqrt(u1);
+        float q[4] = {a * std::sin(two_pi * u2), a * std::cos(two_pi * u2), b * std::sin(two_pi * u3), b * std::cos(two_pi * u3)};
+        LhMat4 dequant = mul(translation({m.dq_offset[0], m.dq_offset[1], m.dq_offset[2]}),
+                             scaling({m.dq_scale[0], m.dq_scale[1], m.dq_scale[2]}));
+        LhMat4 trs = mul(translation({t[0], t[1], t[2]}), mul(rotation(q), scaling({s[0], s[1], s[2]})));
+        scene->instances.push_back({mesh, mul(trs, dequant)});
+    }
+    return 0;
+}
+
 uint32_t lh_scene_num_instances(const LhScene* scene) { return scene ? (uint32_t)scene->instances.size() : 0; }
 
 uint64_t lh_scene_total_triangles(const LhScene* scene) {

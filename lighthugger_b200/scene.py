@@ -28,6 +28,7 @@ def host_lib():
         lib.lh_scene_mesh_view.argtypes = [vp, C.c_int, C.POINTER(S.LhMeshView)]
         lib.lh_scene_place_instances.argtypes = [vp, u32, u64, C.POINTER(C.c_float), C.c_float, C.c_float,
                                                  C.POINTER(C.c_int32), u32]
+        lib.lh_scene_place_instances_general.argtypes = lib.lh_scene_place_instances.argtypes
         lib.lh_scene_add_instance.argtypes = [vp, C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_float), C.c_float]
         lib.lh_scene_num_instances.argtypes = [vp]
         lib.lh_scene_num_instances.restype = u32
@@ -145,10 +146,12 @@ class Scene:
             "info": v.info,
         }
 
-    def place_instances(self, count, extent, scale=(0.5, 2.0), mesh_ids=(0,), seed=0x5EED0001):
+    def place_instances(self, count, extent, scale=(0.5, 2.0), mesh_ids=(0,), seed=0x5EED0001, general=False):
+        """general: uniformly random rotations and per-axis scales instead of half-turns and uniform scales."""
         ext = (C.c_float * 3)(*extent)
         ids = (C.c_int32 * len(mesh_ids))(*mesh_ids)
-        rc = self.lib.lh_scene_place_instances(self.handle, count, seed, ext, scale[0], scale[1], ids, len(mesh_ids))
+        fn = self.lib.lh_scene_place_instances_general if general else self.lib.lh_scene_place_instances
+        rc = fn(self.handle, count, seed, ext, scale[0], scale[1], ids, len(mesh_ids))
         if rc != 0:
             raise RuntimeError(f"lh_scene_place_instances failed: {rc}")
 

@@ -106,7 +106,7 @@ bool cull_bounding_sphere_shadows(const LhUniforms* u, const LhInstance* inst, c
 }
 
 // cull_cone_perspective, common/culling.glsl:137-145 (axis is normalised twice)
-static bool cull_cone_perspective(const LhUniforms* u, const LhInstance* inst, const LhMeshlet* m) {
+bool cull_cone_perspective(const LhUniforms* u, const LhInstance* inst, const LhMeshlet* m) {
     V4 apex = mat4_mul(inst->transform, V4{m->cone_apex[0], m->cone_apex[1], m->cone_apex[2], 1.0f});
     V3 axis = normalize3(mat3_mul(inst->normal_transform, V3{m->cone_axis[0], m->cone_axis[1], m->cone_axis[2]}));
     V3 to = normalize3(V3{apex.x - u->camera_pos[0], apex.y - u->camera_pos[1], apex.z - u->camera_pos[2]});
@@ -114,7 +114,7 @@ static bool cull_cone_perspective(const LhUniforms* u, const LhInstance* inst, c
 }
 
 // cull_cone_orthographic, common/culling.glsl:147-151
-static bool cull_cone_orthographic(const LhUniforms* u, const LhInstance* inst, const LhMeshlet* m) {
+bool cull_cone_orthographic(const LhUniforms* u, const LhInstance* inst, const LhMeshlet* m) {
     V3 axis = normalize3(mat3_mul(inst->normal_transform, V3{m->cone_axis[0], m->cone_axis[1], m->cone_axis[2]}));
     return dot3(V3{u->sun_dir[0], u->sun_dir[1], u->sun_dir[2]}, axis) >= m->cone_cutoff;
 }
@@ -519,6 +519,14 @@ void lho_composite_min(uint64_t* dst, const uint64_t* src, uint64_t count) {
 
 // pow(x, p) for x > 0 evaluated with a fixed sequence of IEEE double
 // operations (no libm), so the device reproduces it bit for bit.
+// single decisions on caller-supplied inputs: compared with the reference's GLSL on random inputs (tests/test_ref_shaders.py)
+int lho_test_cull_sphere(const LhUniforms* u, const LhInstance* inst, const float sphere[4]) { return lho::cull_bounding_sphere(u, inst, sphere) ? 1 : 0; }
+int lho_test_cull_sphere_shadows(const LhUniforms* u, const LhInstance* inst, const float sphere[4], uint32_t cascade) {
+    return lho::cull_bounding_sphere_shadows(u, inst, sphere, cascade) ? 1 : 0;
+}
+int lho_test_cull_cone_perspective(const LhUniforms* u, const LhInstance* inst, const LhMeshlet* m) { return lho::cull_cone_perspective(u, inst, m) ? 1 : 0; }
+int lho_test_cull_cone_orthographic(const LhUniforms* u, const LhInstance* inst, const LhMeshlet* m) { return lho::cull_cone_orthographic(u, inst, m) ? 1 : 0; }
+
 float lho_pinned_powf(float xf, float pf) {
     if (!(xf > 0.0f)) return xf == 0.0f ? 0.0f : NAN;
     double x = (double)xf;

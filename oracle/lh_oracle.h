@@ -22,7 +22,7 @@
  * SURVEY.md 8c): IEEE-754 binary32, round-to-nearest-even, no FMA contraction
  * (build with -ffp-contract=off), mat4*vec4 = (c0*x + c1*y) + (c2*z + c3*w),
  * mat3*vec3 = (c0*x + c1*y) + c2*z, dot = (ax*bx + ay*by) + az*bz,
- * length = sqrt(dot(v,v)), normalize(v) = v / length(v) (true division),
+ * length = sqrt(dot(v,v)), normalize(v) = v * (1 / length(v)) (glm's, detail/func_geometric.inl:82-91),
  * appends in ascending invocation order.
  */
 #ifndef LH_ORACLE_H
@@ -84,6 +84,12 @@ int lho_render_frame(const LhUniforms* u, const LhoConfig* cfg, uint64_t* vis, f
 
 /* sort-last composite: dst[i] = min(dst[i], src[i]) (new) */
 void lho_composite_min(uint64_t* dst, const uint64_t* src, uint64_t count);
+
+/* single culling decisions (1 = culled) on caller-supplied inputs, for the random-input comparison with the reference's GLSL */
+int lho_test_cull_sphere(const LhUniforms* u, const LhInstance* inst, const float sphere[4]);
+int lho_test_cull_sphere_shadows(const LhUniforms* u, const LhInstance* inst, const float sphere[4], uint32_t cascade);
+int lho_test_cull_cone_perspective(const LhUniforms* u, const LhInstance* inst, const LhMeshlet* m);
+int lho_test_cull_cone_orthographic(const LhUniforms* u, const LhInstance* inst, const LhMeshlet* m);
 
 /* pinned pow used by generate_shadow_matrices (double arithmetic, identical op sequence on host and device) */
 float lho_pinned_powf(float x, float p);

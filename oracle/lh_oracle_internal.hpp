@@ -59,9 +59,10 @@ inline V3 mat3_mul(const LhMat3& m, V3 v) {
 }
 inline float dot3(V3 a, V3 b) { return (a.x * b.x + a.y * b.y) + a.z * b.z; }
 inline float length3(V3 a) { return sqrtf(dot3(a, a)); }
+// glm's normalize (detail/func_geometric.inl:82-91): v * inversesqrt(dot(v, v)) with inversesqrt(x) = 1 / sqrt(x)
 inline V3 normalize3(V3 a) {
-    float l = length3(a);
-    return V3{a.x / l, a.y / l, a.z / l};
+    float inv = 1.0f / sqrtf(dot3(a, a));
+    return V3{a.x * inv, a.y * inv, a.z * inv};
 }
 inline V3 cross3(V3 a, V3 b) {
     return V3{a.y * b.z - b.y * a.z, a.z * b.x - b.z * a.x, a.x * b.y - b.x * a.y};

@@ -1,5 +1,7 @@
 """Shared test plumbing: builds a scene once, binds it for the oracle (host
 memory) and for the CUDA layer (device memory), with identical textures."""
+import os
+
 import numpy as np
 
 from lighthugger_b200 import _structs as S
@@ -94,6 +96,42 @@ def make_context(scene, textures=None, skybox=None, caps=None, flags=None, width
     if skybox is not None:
         ctx.create_skybox(int(round((skybox.size // 24) ** 0.5)), skybox)
     return ctx
+
+
+def golden_torus_scene(count=48, extent=(9.0, 4.0, 6.0), general=False):
+    """A scene whose mesh was meshletised by the REFERENCE's build_meshlets (tests/golden/torus_32x16_ref.npz)."""
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "torus_32x16_ref.npz"))
+    sc = Scene()
+    arrs = {k: np.ascontiguousarray(g[k]) for k in ("positions", "normals", "uvs", "indices", "micro_indices", "meshlets")}
+    v = S.LhMeshView()
+    v.positions, v.num_vertices = arrs["positions"].ctypes.data, len(arrs["positions"])
+    v.normals, v.uvs = arrs["normals"].ctypes.data, arrs["uvs"].ctypes.data
+    v.indices, v.num_indices, v.index_bytes = arrs["indices"].ctypes.data, len(arrs["indices"]), 2
+    v.micro_indices, v.micro_indices_bytes = arrs["micro_indices"].ctypes.data, len(arrs["micro_indices"])
+    v.meshlets, v.num_meshlets = arrs["meshlets"].ctypes.data, len(arrs["meshlets"])
+    v.num_triangles = len(g["triangles"]) // 3
+    v.info.bounding_sphere[:] = [float(x) for x in g["bounding_sphere"]]
+    v.info.texture_scale[:] = (1 / 65535.0, 1 / 65535.0)
+    v.info.base_color_texture_index = v.info.metallic_roughness_texture_index = v.info.normal_texture_index = 0xFFFF
+    v.info.base_color_factor[:] = (0.8, 0.7, 0.6)
+    v.dequant_scale[:] = [float(g["dequant_scale"])] * 3
+    v.dequant_offset[:] = [float(x) for x in g["dequant_offset"]]
+    sc.add_mesh_raw(v, keep=list(arrs.values()))
+    sc.place_instances(count, extent, general=general)
+    sc.camera.position[:] = (0.0, 0.0, -extent[2] * 1.3)
+    sc.camera.yaw = np.pi / 2
+    sc.width, sc.height = 320, 200
+    return sc
+
+
+def rotated_scene(count=96):
+    """General transforms: uniformly random rotations and a different scale per axis (the reference's untransposed
+    normal transform is then NOT the inverse transpose), over reference-meshletised tori and a procedural sphere."""
+    sc = golden_torus_scene(0, general=True)
+    sphere = sc.add_mesh(S.LH_MESH_SPHERE, 24, 12, base_color=(0.5, 0.8, 0.6))
+    sc.place_instances(count, (8.0, 4.0, 6.0), scale=(0.4, 2.2), mesh_ids=(0, 0, sphere), general=True)
+    sc.camera.position[:] = (0.0, 1.0, -15.0)
+    return sc
 
 
 def vis_fields(vis):

@@ -6,7 +6,7 @@ import pytest
 
 from lighthugger_b200 import _structs as S
 from lighthugger_b200.scene import Scene
-from helpers import Textures, make_context, make_oracle, vis_fields
+from helpers import Textures, golden_torus_scene, make_context, make_oracle, rotated_scene, vis_fields
 
 pytestmark = pytest.mark.gpu
 
@@ -16,33 +16,6 @@ def build(name, tex_size=32, **kw):
     tex = Textures(sc, tex_size) if sc.num_texture_sets else None
     sky = sc.make_skybox(8)
     return sc, tex, sky
-
-
-def golden_torus_scene(count=48, extent=(9.0, 4.0, 6.0)):
-    """A scene whose mesh was meshletised by the REFERENCE's build_meshlets (tests/golden/torus_32x16_ref.npz)."""
-    import os
-    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "torus_32x16_ref.npz"))
-    sc = Scene()
-    arrs = {k: np.ascontiguousarray(g[k]) for k in ("positions", "normals", "uvs", "indices", "micro_indices", "meshlets")}
-    v = S.LhMeshView()
-    v.positions, v.num_vertices = arrs["positions"].ctypes.data, len(arrs["positions"])
-    v.normals, v.uvs = arrs["normals"].ctypes.data, arrs["uvs"].ctypes.data
-    v.indices, v.num_indices, v.index_bytes = arrs["indices"].ctypes.data, len(arrs["indices"]), 2
-    v.micro_indices, v.micro_indices_bytes = arrs["micro_indices"].ctypes.data, len(arrs["micro_indices"])
-    v.meshlets, v.num_meshlets = arrs["meshlets"].ctypes.data, len(arrs["meshlets"])
-    v.num_triangles = len(g["triangles"]) // 3
-    v.info.bounding_sphere[:] = [float(x) for x in g["bounding_sphere"]]
-    v.info.texture_scale[:] = (1 / 65535.0, 1 / 65535.0)
-    v.info.base_color_texture_index = v.info.metallic_roughness_texture_index = v.info.normal_texture_index = 0xFFFF
-    v.info.base_color_factor[:] = (0.8, 0.7, 0.6)
-    v.dequant_scale[:] = [float(g["dequant_scale"])] * 3
-    v.dequant_offset[:] = [float(x) for x in g["dequant_offset"]]
-    sc.add_mesh_raw(v, keep=list(arrs.values()))
-    sc.place_instances(count, extent)
-    sc.camera.position[:] = (0.0, 0.0, -extent[2] * 1.3)
-    sc.camera.yaw = np.pi / 2
-    sc.width, sc.height = 320, 200
-    return sc
 
 
 def run_cull(o, ctx, u):
