@@ -71,7 +71,10 @@ REF_SHADERS := common/prefix_sum.glsl common/util.glsl common/culling.glsl commo
                common/pbr.glsl common/debug.glsl cull_instances.comp write_draw_calls.comp rasterization.glsl \
                render_geometry.comp display_transform.comp compute/reset_buffers.glsl compute/generate_shadow_matrices.glsl \
                compute/read_depth.glsl
-REF_SHADERS_GEN := $(addprefix oracle/_ref/gen/,$(REF_SHADERS))
+REF_SHADERS_GEN := $(addprefix oracle/_ref/gen/,$(REF_SHADERS)) oracle/_ref/gen/shared_cpu_gpu.h
+oracle/_ref/gen/shared_cpu_gpu.h: $(REF)/src/shared_cpu_gpu.h oracle/ref_shim/glsl_filter.py
+	@mkdir -p $(dir $@)
+	python oracle/ref_shim/glsl_filter.py $< $@
 oracle/_ref/gen/%: $(REF)/src/shaders/% oracle/ref_shim/glsl_filter.py
 	@mkdir -p $(dir $@)
 	python oracle/ref_shim/glsl_filter.py $< $@

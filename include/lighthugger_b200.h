@@ -249,6 +249,10 @@ LH_API int lh_comm_info(LhContext* ctx, int* rank, int* nranks);
  * communicator together. */
 enum { LH_EXCHANGE_PEER = 0, LH_EXCHANGE_NCCL = 1 };
 LH_API int lh_comm_set_exchange(LhContext* ctx, int mode);
+/* Collective (LH_EXCHANGE_PEER): every rank drops its mappings of its peers' buffers and waits for the others to have done
+ * so; call it on all ranks before moving LhUniforms.meshlet_references to another buffer.  lh_targets_resize does the
+ * same internally (ranks resize together); the next lh_frame_begin maps the current buffers again. */
+LH_API int lh_comm_remap(LhContext* ctx);
 LH_API int lh_comm_rows(LhContext* ctx, uint32_t* y0, uint32_t* y1);   /* rows this rank composites and resolves */
 
 #ifdef __cplusplus

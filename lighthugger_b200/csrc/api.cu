@@ -6,6 +6,8 @@
 #include <cstring>
 #include <new>
 
+#include <nvtx3/nvToolsExt.h>
+
 #include "lh_internal.cuh"
 
 using namespace lh;
@@ -63,7 +65,7 @@ FrameParams make_params(LhContext* ctx, int cascade, int set, bool internal_list
     p.meshlet_tiles = sc.meshlet_tiles;
     p.large_queue = sc.large_queue;
     p.meshlet_bounds = sc.meshlet_bounds;
-    p.raster_queue = sc.raster_queue;
+    p.raster_records = sc.raster_records;
     p.depth_keys = sc.depth_keys;
     p.depth_hist = sc.depth_hist;
     p.hiz = sc.hiz;
@@ -109,10 +111,18 @@ FrameParams make_params(LhContext* ctx, int cascade, int set, bool internal_list
 
 namespace {
 
+// NVTX ranges named like the reference's Tracy zones (src/rendering.cpp:42,140,172,198,290,305,326,463,492), so a
+// timeline of this layer reads like one of the reference; passes the reference has no zone for get descriptive names
+const char* const kPassZone[LH_PASS_COUNT] = {
+    "reset buffers", "cull instances", "cull meshlets and write draw calls", "visbuffer rendering", "composite (sort-last)",
+    "depth reduction", "generate shadow matrices", "cull instances for shadows", "shadowmap rasterization", "render geometry",
+    "display transform"};
+
 struct PassScope {
     LhContext* ctx;
     int pass;
     PassScope(LhContext* c, int p) : ctx(c), pass(p) {
+        nvtxRangePushA(kPassZone[pass]);
         if (ctx->cfg.flags & LH_CONFIG_PASS_TIMINGS) cudaEventRecord(ctx->pass_start[pass], ctx->stream);
     }
     ~PassScope() {
@@ -120,7 +130,12 @@ struct PassScope {
             cudaEventRecord(ctx->pass_stop[pass], ctx->stream);
             ctx->pass_recorded[pass] = true;
         }
+        nvtxRangePop();
     }
+};
+struct ZoneScope {   // a range without a timed pass behind it
+    explicit ZoneScope(const char* name) { nvtxRangePushA(name); }
+    ~ZoneScope() { nvtxRangePop(); }
 };
 
 int check_launch(LhContext* ctx, const char* what) {
@@ -180,7 +195,7 @@ int alloc_pass_scratch(LhContext* ctx, int set) {
     LH_CUDA(ctx, cudaMemset(sc.meshlet_tiles, 0, ctx->meshlet_tile_count * 8));
     LH_CUDA(ctx, cudaMalloc(&sc.large_queue, (size_t)(ctx->cfg.max_large_triangles ? ctx->cfg.max_large_triangles : 1) * 8 * 2));   // deferred + split queue
     LH_CUDA(ctx, cudaMalloc(&sc.meshlet_bounds, (draws ? draws : 1) * 16));
-    LH_CUDA(ctx, cudaMalloc(&sc.raster_queue, (draws ? draws : 1) * 4));
+    LH_CUDA(ctx, cudaMalloc(&sc.raster_records, (draws ? draws : 1) * 64));
     LH_CUDA(ctx, cudaMalloc(&sc.depth_keys, (draws ? draws : 1) * 4));
     LH_CUDA(ctx, cudaMalloc(&sc.depth_hist, 8192 * 4));
     LH_CUDA(ctx, cudaMemset(sc.depth_hist, 0, 8192 * 4));
@@ -207,7 +222,7 @@ int alloc_pass_scratch(LhContext* ctx, int set) {
 void free_pass_scratch(LhContext* ctx) {
     for (auto& sc : ctx->scratch) {
         cudaFree(sc.pass); cudaFree(sc.meshlet_tiles); cudaFree(sc.large_queue); cudaFree(sc.meshlet_bounds);
-        cudaFree(sc.raster_queue); cudaFree(sc.depth_keys); cudaFree(sc.depth_hist); cudaFree(sc.hiz); cudaFree(sc.draw_calls); cudaFree(sc.refs);
+        cudaFree(sc.raster_records); cudaFree(sc.depth_keys); cudaFree(sc.depth_hist); cudaFree(sc.hiz); cudaFree(sc.draw_calls); cudaFree(sc.refs);
         sc = LhContext::PassScratch{};
     }
 }
@@ -282,9 +297,10 @@ int lh_context_create(const LhConfig* cfg, LhContext** out) {
         sscanf(t, "%f,%f,%f,%f,%f,%f,%f", &f[0], &f[1], &f[2], &f[3], &f[4], &f[5], &f[6]);
     }
     if (const char* t = getenv("LH_TUNE")) {
-        unsigned v[6] = {ctx->tune.main_bands, ctx->tune.shadow_bands, ctx->tune.main_grid, ctx->tune.shadow_grid, ctx->tune.resolve_low_priority, ctx->tune.select_grid};
-        sscanf(t, "%u,%u,%u,%u,%u,%u", &v[0], &v[1], &v[2], &v[3], &v[4], &v[5]);
+        unsigned v[7] = {ctx->tune.main_bands, ctx->tune.shadow_bands, ctx->tune.main_grid, ctx->tune.shadow_grid, ctx->tune.resolve_low_priority, ctx->tune.select_grid, ctx->tune.resolve_split};
+        sscanf(t, "%u,%u,%u,%u,%u,%u,%u", &v[0], &v[1], &v[2], &v[3], &v[4], &v[5], &v[6]);
         ctx->tune.resolve_low_priority = v[4] != 0;
+        ctx->tune.resolve_split = v[6] != 0;
         auto clamp = [](unsigned x, unsigned lo, unsigned hi) { return x < lo ? lo : (x > hi ? hi : x); };
         ctx->tune.main_bands = clamp(v[0], 2, 8);
         ctx->tune.shadow_bands = clamp(v[1], 2, 8);
@@ -445,6 +461,7 @@ int lh_download(LhContext* ctx, uint64_t dev_addr, void* dst, uint64_t bytes) {
 int lh_texture_create(LhContext* ctx, int format, uint32_t width, uint32_t height, uint32_t mip_levels, const void* data,
                       uint64_t bytes, uint16_t* slot_out) {
     if (!ctx || !data || !slot_out || !width || !height || !mip_levels) return LH_ERR_INVALID_ARGUMENT;
+    if (width > 65536u || height > 65536u || mip_levels > 17u) return fail(ctx, LH_ERR_INVALID_ARGUMENT, "texture dimensions out of range");
     uint32_t slot = 0;
     while (slot < LH_MAX_TEXTURES && ctx->tex_host[slot]) slot++;
     if (slot == LH_MAX_TEXTURES) return fail(ctx, LH_ERR_CAPACITY, "all 512 bindless texture slots are in use");
@@ -589,7 +606,11 @@ int lh_set_display_lut(LhContext* ctx, uint32_t size, const float* rgb) {
 int lh_targets_resize(LhContext* ctx, uint32_t width, uint32_t height) {
     if (!ctx) return LH_ERR_INVALID_ARGUMENT;
     cudaStreamSynchronize(ctx->stream);
-    return alloc_targets(ctx, width, height);
+    // sort-last ranks resize together: unmap -> barrier -> reallocate, and the row slices follow the new height
+    if (int rc = peer_release_collective(ctx)) return rc;
+    if (int rc = alloc_targets(ctx, width, height)) return rc;
+    comm_update_rows(ctx);
+    return LH_OK;
 }
 
 int lh_set_instance_range(LhContext* ctx, uint32_t first, uint32_t count) {
@@ -705,6 +726,7 @@ int lh_cull_instances_shadows(LhContext* ctx) {
 
 // reset_buffers_c + write_draw_calls_shadows + the layer clear + the depth-only raster of one cascade
 static void enqueue_cascade(LhContext* ctx, uint32_t cascade, int set, bool internal_lists, cudaStream_t stream) {
+    ZoneScope zone("shadowmap inner");
     FrameParams p = make_params(ctx, (int)cascade, set, internal_lists);
     if (internal_lists) p.flags &= ~(uint32_t)LH_CONFIG_WRITE_DRAW_COMMANDS;
     launch_cull_meshlets(ctx, p, (int)cascade, stream);
@@ -735,6 +757,7 @@ int lh_display_transform(LhContext* ctx) {
 }
 
 int lh_render_frame(LhContext* ctx) {
+    ZoneScope zone("render");
     int rc;
     if ((rc = lh_reset(ctx))) return rc;
     if ((rc = lh_cull_instances(ctx))) return rc;
@@ -743,13 +766,14 @@ int lh_render_frame(LhContext* ctx) {
     if ((rc = lh_composite(ctx))) return rc;
     // The resolve in two launches: its material phase needs the visibility buffer only and runs beside the depth and
     // shadow passes; its shadow phase follows them.
-    if (!ctx->resolve_tmp) {
-        LH_CUDA(ctx, cudaMalloc(&ctx->resolve_tmp, (size_t)ctx->cfg.width * ctx->cfg.height * 40));
+    const bool split = ctx->tune.resolve_split;
+    if (split) {
+        if (!ctx->resolve_tmp) LH_CUDA(ctx, cudaMalloc(&ctx->resolve_tmp, (size_t)ctx->cfg.width * ctx->cfg.height * 40));
+        LH_CUDA(ctx, cudaEventRecord(ctx->vis_ready, ctx->stream));
+        LH_CUDA(ctx, cudaStreamWaitEvent(ctx->resolve_stream, ctx->vis_ready, 0));
+        launch_resolve(ctx, make_params(ctx), 1, ctx->resolve_stream);
+        LH_CUDA(ctx, cudaEventRecord(ctx->material_done, ctx->resolve_stream));
     }
-    LH_CUDA(ctx, cudaEventRecord(ctx->vis_ready, ctx->stream));
-    LH_CUDA(ctx, cudaStreamWaitEvent(ctx->resolve_stream, ctx->vis_ready, 0));
-    launch_resolve(ctx, make_params(ctx), 1, ctx->resolve_stream);
-    LH_CUDA(ctx, cudaEventRecord(ctx->material_done, ctx->resolve_stream));
     if ((rc = lh_reduce_depth(ctx))) return rc;
     if ((rc = lh_generate_shadow_matrices(ctx))) return rc;
     if ((rc = lh_cull_instances_shadows(ctx))) return rc;
@@ -783,8 +807,8 @@ int lh_render_frame(LhContext* ctx) {
     if ((rc = lh_shadow_exchange(ctx))) return rc;
     {
         PassScope scope(ctx, LH_PASS_RENDER_GEOMETRY);   // what is left of the resolve on the critical path
-        LH_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->material_done, 0));
-        launch_resolve(ctx, make_params(ctx), 2);
+        if (split) LH_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->material_done, 0));
+        launch_resolve(ctx, make_params(ctx), split ? 2 : 0);
         if ((rc = check_launch(ctx, "resolve"))) return rc;
     }
     // rank 0's frame is complete, and every table a peer reads may be rewritten, once all ranks have resolved their rows
@@ -794,8 +818,15 @@ int lh_render_frame(LhContext* ctx) {
 
 int lh_frame_sync(LhContext* ctx) {
     if (!ctx) return LH_ERR_INVALID_ARGUMENT;
+    // the frame's overflow word rides along (4 bytes into pinned memory), so a list that outgrew its LhConfig capacity is
+    // an error here too, not only in lh_get_frame_stats
+    ctx->pinned_stats->overflow = 0;
+    LH_CUDA(ctx, cudaMemcpyAsync(&ctx->pinned_stats->overflow, &ctx->state->overflow, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
     LH_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    return check_launch(ctx, "frame");
+    if (int rc = check_launch(ctx, "frame")) return rc;
+    if (ctx->have_uniforms && ctx->pinned_stats->overflow)
+        return fail(ctx, LH_ERR_CAPACITY, "a list overflowed its LhConfig capacity (see LhFrameStats.overflow)");
+    return LH_OK;
 }
 
 int lh_get_frame_stats(LhContext* ctx, LhFrameStats* out) {

@@ -85,6 +85,14 @@ int nccl_fail(LhContext* ctx, const char* what, ncclResult_t r) {
     return fail(ctx, LH_ERR_NCCL, msg.c_str());
 }
 
+void close_peer_handles(LhContext* ctx, LhContext::PeerMap& m) {
+    for (size_t q = 0; q < m.ptrs.size(); q++)
+        if ((int)q != ctx->rank && m.ptrs[q]) cudaIpcCloseMemHandle(m.ptrs[q]);
+    m.ptrs.clear();
+    cudaFree(m.table_dev);
+    m.table_dev = nullptr;
+}
+
 // Maps `local` (a cudaMalloc allocation of this rank) on every peer and the peers' counterparts here.  Collective:
 // every rank must call it with its own counterpart at the same point of the stream.
 int peer_map(LhContext* ctx, void* local, LhContext::PeerMap** out) {
@@ -114,25 +122,34 @@ int peer_map(LhContext* ctx, void* local, LhContext::PeerMap** out) {
         }
         cudaError_t e = cudaIpcOpenMemHandle(&m.ptrs[q], all[q], cudaIpcMemLazyEnablePeerAccess);
         if (e != cudaSuccess) {
-            for (int k = 0; k < q; k++)
-                if (k != ctx->rank && m.ptrs[k]) cudaIpcCloseMemHandle(m.ptrs[k]);
+            close_peer_handles(ctx, m);
             return fail(ctx, LH_ERR_CUDA, "cudaIpcOpenMemHandle (peer buffer; LH_EXCHANGE_NCCL does not need peer memory)", e);
         }
     }
-    LH_CUDA(ctx, cudaMalloc(&m.table_dev, sizeof(void*) * (size_t)n));
-    LH_CUDA(ctx, cudaMemcpy(m.table_dev, m.ptrs.data(), sizeof(void*) * (size_t)n, cudaMemcpyHostToDevice));
+    cudaError_t e = cudaMalloc(&m.table_dev, sizeof(void*) * (size_t)n);
+    if (e == cudaSuccess) e = cudaMemcpy(m.table_dev, m.ptrs.data(), sizeof(void*) * (size_t)n, cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) {
+        close_peer_handles(ctx, m);
+        return fail(ctx, LH_ERR_CUDA, "peer pointer table", e);
+    }
     ctx->peer_maps.push_back(std::move(m));
     *out = &ctx->peer_maps.back();
     return LH_OK;
 }
 
 void peer_unmap_all(LhContext* ctx) {
-    for (auto& m : ctx->peer_maps) {
-        for (size_t q = 0; q < m.ptrs.size(); q++)
-            if ((int)q != ctx->rank && m.ptrs[q]) cudaIpcCloseMemHandle(m.ptrs[q]);
-        cudaFree(m.table_dev);
-    }
+    for (auto& m : ctx->peer_maps) close_peer_handles(ctx, m);
     ctx->peer_maps.clear();
+    ctx->peer_vis_dev = ctx->peer_refs_dev = nullptr;
+    ctx->scene_remote = nullptr;
+    ctx->mapped_refs = 0;
+}
+
+// screen rows of this rank: even row counts so that a slice is a whole number of 16-byte key pairs
+void update_rows(LhContext* ctx) {
+    const uint32_t H = ctx->cfg.height, n = (uint32_t)ctx->nranks, per = ((H + n - 1) / n + 1) & ~1u;
+    ctx->row0 = per * (uint32_t)ctx->rank < H ? per * (uint32_t)ctx->rank : H;
+    ctx->row1 = ctx->row0 + per < H ? ctx->row0 + per : H;
 }
 
 // A collective on 4 bytes: nothing after it on any rank's stream starts before everything ahead of it on every rank's
@@ -200,11 +217,18 @@ int ensure_peer_maps(LhContext* ctx) {
     ctx->peer_vis_dev = ctx->peer_refs_dev = nullptr;
     ctx->scene_remote = nullptr;
     if (!peer_exchange(ctx)) return LH_OK;
+    // The handle exchange is a collective, so WHETHER it runs must not depend on rank-local state such as the address
+    // cudaMalloc happened to return: buffers are mapped once after lh_comm_init / lh_targets_resize / lh_comm_remap (all
+    // of which every rank calls together and which drop every mapping), and a host that moves its MeshletReference
+    // buffer in between is told so instead of deadlocking its peers.
+    if (ctx->mapped_refs && ctx->mapped_refs != ctx->uniforms.meshlet_references)
+        return fail(ctx, LH_ERR_NOT_READY, "LhUniforms.meshlet_references moved while peers map the old buffer: call lh_comm_remap on every rank");
     LhContext::PeerMap* m = nullptr;
     if (int rc = peer_map(ctx, ctx->vis, &m)) return rc;
     ctx->peer_vis_dev = m->table_dev;
     if (int rc = peer_map(ctx, (void*)(uintptr_t)ctx->uniforms.meshlet_references, &m)) return rc;
     ctx->peer_refs_dev = m->table_dev;
+    ctx->mapped_refs = ctx->uniforms.meshlet_references;
     if (int rc = peer_map(ctx, ctx->scene, &m)) return rc;
     ctx->scene_remote = ctx->rank == 0 ? nullptr : m->ptrs[0];
     return LH_OK;
@@ -235,6 +259,21 @@ int reduce_depth_exchange(LhContext* ctx) {
 
 int frame_barrier(LhContext* ctx) { return stream_barrier(ctx); }
 
+// Collective: every rank drops its mappings of everybody's buffers; when it returns no rank maps any peer buffer any
+// more, so targets may be freed / reallocated and the MeshletReference buffer moved.
+int peer_release_collective(LhContext* ctx) {
+    if (!ctx->nccl_comm || ctx->nranks <= 1) return LH_OK;
+    LH_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    peer_unmap_all(ctx);
+    if (int rc = stream_barrier(ctx)) return rc;
+    LH_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return LH_OK;
+}
+
+void comm_update_rows(LhContext* ctx) {
+    if (ctx->nccl_comm) update_rows(ctx);
+}
+
 int composite_allreduce_min(LhContext* ctx) {
     ncclComm_t comm = (ncclComm_t)ctx->nccl_comm;
     const size_t pixels = (size_t)ctx->cfg.width * ctx->cfg.height;
@@ -242,6 +281,11 @@ int composite_allreduce_min(LhContext* ctx) {
     if (r != ncclSuccess) return nccl_fail(ctx, "ncclAllReduce(vis, uint64, min)", r);
     // every rank needs the (instance, meshlet) of any slot that can win a pixel it resolves
     const void* local_refs = (const void*)(uintptr_t)ctx->uniforms.meshlet_references;
+    if (!ctx->gathered_refs) {   // lh_comm_set_exchange before lh_comm_init, or a re-initialised communicator
+        const size_t bytes = (size_t)ctx->slots_per_rank * ctx->nranks * sizeof(LhMeshletReference);
+        LH_CUDA(ctx, cudaMalloc(&ctx->gathered_refs, bytes));
+        LH_CUDA(ctx, cudaMemsetAsync(ctx->gathered_refs, 0, bytes, ctx->stream));
+    }
     r = g_nccl.AllGather(local_refs, ctx->gathered_refs, (size_t)ctx->slots_per_rank * sizeof(LhMeshletReference), ncclUint8, comm, ctx->stream);
     if (r != ncclSuccess) return nccl_fail(ctx, "ncclAllGather(meshlet references)", r);
     return LH_OK;
@@ -268,6 +312,7 @@ int lh_comm_init(LhContext* ctx, int rank, int nranks, const void* id128) {
     if (per_rank * nranks > LH_VIS_MAX_SLOTS)
         return fail(ctx, LH_ERR_INVALID_ARGUMENT, "nranks * (max_opaque_draws + max_alpha_clip_draws) exceeds the 25-bit slot field");
     cudaSetDevice(ctx->device);
+    if (ctx->nccl_comm) lh_comm_destroy(ctx);   // a second init replaces the communicator (and everything sized by the old one)
     ncclUniqueId id;
     memcpy(&id, id128, sizeof(id));
     ncclComm_t comm = nullptr;
@@ -282,10 +327,7 @@ int lh_comm_init(LhContext* ctx, int rank, int nranks, const void* id128) {
     ctx->comm_scratch = nullptr;
     LH_CUDA(ctx, cudaMalloc(&ctx->comm_scratch, 64 + 64 * (size_t)nranks));
     LH_CUDA(ctx, cudaMemset(ctx->comm_scratch, 0, 64 + 64 * (size_t)nranks));
-    // screen rows of this rank: even row counts so that a slice is a whole number of 16-byte key pairs
-    const uint32_t H = ctx->cfg.height, per = ((H + nranks - 1) / nranks + 1) & ~1u;
-    ctx->row0 = per * rank < H ? per * rank : H;
-    ctx->row1 = ctx->row0 + per < H ? ctx->row0 + per : H;
+    update_rows(ctx);
     return LH_OK;
 }
 
@@ -311,8 +353,9 @@ int lh_comm_rows(LhContext* ctx, uint32_t* y0, uint32_t* y1) {
 int lh_comm_destroy(LhContext* ctx) {
     if (!ctx) return LH_ERR_INVALID_ARGUMENT;
     if (ctx->nccl_comm && g_nccl.CommDestroy) {
-        cudaStreamSynchronize(ctx->stream);
-        peer_unmap_all(ctx);
+        // unmap -> barrier -> destroy: no rank frees a buffer a peer still maps (ranks destroy their communicators together)
+        if (peer_exchange(ctx) && !ctx->peer_maps.empty()) peer_release_collective(ctx);
+        else cudaStreamSynchronize(ctx->stream);
         g_nccl.CommDestroy((ncclComm_t)ctx->nccl_comm);
     }
     cudaFree(ctx->comm_scratch);
@@ -324,6 +367,11 @@ int lh_comm_destroy(LhContext* ctx) {
     ctx->nranks = 1;
     ctx->slot_offset = 0;
     return LH_OK;
+}
+
+int lh_comm_remap(LhContext* ctx) {
+    if (!ctx) return LH_ERR_INVALID_ARGUMENT;
+    return peer_release_collective(ctx);   // the next lh_frame_begin maps the current buffers again (collectively)
 }
 
 int lh_comm_info(LhContext* ctx, int* rank, int* nranks) {

@@ -363,7 +363,10 @@ __global__ void __launch_bounds__(256) cull_meshlets_kernel(const __grid_constan
     uint32_t empty_bounds = 0;
     if (blockIdx.x == 0 && tid == 0) {
         // reset_buffers_b / _c: indirect size for the reference's 64-wide dispatch
-        ((LhDispatchIndirectCommand*)P.u.dispatches)[LH_PER_MESHLET_DISPATCH] = LhDispatchIndirectCommand{dispatch_size((uint32_t)c64, 64), 1, 1};
+        // (a cascade that runs concurrently on a side stream with internal lists leaves the host-visible slot alone, so
+        // what is left there is the last cascade's, as in the reference)
+        if (P.pass_draw_calls == P.u.draw_calls)
+            ((LhDispatchIndirectCommand*)P.u.dispatches)[LH_PER_MESHLET_DISPATCH] = LhDispatchIndirectCommand{dispatch_size((uint32_t)c64, 64), 1, 1};
         if (num_tiles == 0) {
             draw[0] = 0;
             draw[1] = 0;

@@ -123,7 +123,7 @@ struct FrameParams {
     unsigned long long* meshlet_tiles;       // decoupled-lookback states of the meshlet cull
     uint32_t* large_queue;
     void* meshlet_bounds;                    // 16 B per surviving meshlet of the current raster pass (raster.cu MeshletBound)
-    uint32_t* raster_queue;                  // indices of the meshlets selected for rasterisation, band after band
+    void* raster_records;                    // 64 B per meshlet selected for rasterisation, band after band (raster.cu RasterRecord)
     uint32_t* depth_keys;                    // the bounds' depth keys on their own (4 B per meshlet): what band selection scans
     uint32_t* depth_hist;                    // 8192 bins of the depth-key histogram (self-cleaning)
     uint32_t* hiz;                           // two hierarchical-Z levels of the current raster target: farthest stored value per 4x4- and per 16x16-pixel tile
@@ -183,7 +183,7 @@ struct LhContext {
         unsigned long long* meshlet_tiles = nullptr;
         uint32_t* large_queue = nullptr;
         void* meshlet_bounds = nullptr;
-        uint32_t* raster_queue = nullptr;
+        void* raster_records = nullptr;
         uint32_t* depth_keys = nullptr;
         uint32_t* depth_hist = nullptr;
         uint32_t* hiz = nullptr;
@@ -237,13 +237,14 @@ struct LhContext {
     void** peer_vis_dev = nullptr;         // device tables of the current frame (owned by peer_maps)
     void** peer_refs_dev = nullptr;
     void* scene_remote = nullptr;
+    uint64_t mapped_refs = 0;              // the MeshletReference buffer the peers currently map (0: none)
     uint32_t row0 = 0, row1 = 0;           // screen rows this rank composites and resolves
     int num_sms = 148;
     // launch shapes of the rasteriser; defaults measured on B200 at BASELINE config 2.  Developer overrides:
-    // LH_TUNE="main_bands,shadow_bands,main_grid,shadow_grid,resolve_low_priority,select_grid" in the environment at context creation.
+    // LH_TUNE="main_bands,shadow_bands,main_grid,shadow_grid,resolve_low_priority,select_grid,resolve_split" in the environment at context creation.
     struct Tuning {
         float main_fractions[7] = {0, 0, 0, 0, 0, 0, 0};   // LH_TUNE_FRACTIONS="f0,f1,..." (main view)
-        uint32_t main_bands = 4, shadow_bands = 6, main_grid = 16, shadow_grid = 3, resolve_low_priority = 1, select_grid = 16;
+        uint32_t main_bands = 4, shadow_bands = 6, main_grid = 16, shadow_grid = 3, resolve_low_priority = 1, select_grid = 16, resolve_split = 1;
     } tune;
 
     std::vector<void*> buffers;
@@ -275,6 +276,8 @@ int reduce_depth_exchange(LhContext* ctx);   // ... the frame's depth bounds fro
 int frame_barrier(LhContext* ctx);           // every rank has finished its part of the frame
 bool peer_exchange(const LhContext* ctx);    // multi-GPU and LH_EXCHANGE_PEER
 int ensure_peer_maps(LhContext* ctx);        // maps what the frame needs of the peers (collective the first time)
+int peer_release_collective(LhContext* ctx); // every rank unmaps everything, then a barrier: buffers may now be freed / moved
+void comm_update_rows(LhContext* ctx);       // row slices follow the target height
 extern "C" int lh_shadow_exchange(LhContext* ctx);
 
 }  // namespace lh

@@ -44,10 +44,42 @@ constexpr int kSmallMaxExtent = 1 << 14;        // ... and sub-pixel extent < 2^
 enum { CULL_NONE = 0, CULL_BACK = 1, CULL_FRONT = 2 };
 enum { FLAG_INSIDE = 1, FLAG_SNAPPED = 2 };
 
-// Per-warp scratch of the meshlet kernel: snapped vertices and the compacted list of triangles that cover a sample.
+// What the band selection hands to the raster kernel about one queued meshlet (64 bytes): the end of the pointer
+// chain reference -> instance -> mesh info -> meshlet, walked once by the selection's lane (one lane per meshlet, so
+// the chain's dependent round trips hide behind the other lanes' work), and the meshlet's bound.  The raster kernel
+// then never chases a pointer: it pulls records, and through them the meshlet's micro-indices, vertex indices and
+// instance transform, into shared memory with bulk-asynchronous copies (cp.async.bulk + mbarrier) ahead of use.
+struct alignas(16) RasterRecord {
+    const uint16_t* positions;
+    const uint8_t* indices;        // byte address of the meshlet's first vertex index (u16 or u32)
+    const uint8_t* micro;          // the meshlet's first micro-index
+    const LhMeshInfo* mi;
+    const LhInstance* instance;    // 16-byte aligned; the transform is its first 64 bytes
+    uint32_t counts_flags;         // triangle_count | index_count << 8 | MeshInfo.flags << 16
+    uint32_t local;                // list index of the meshlet (its slot minus the view's slot base)
+    uint32_t rect_x, rect_y, edge; // MeshletBound
+    uint32_t pad;
+};
+static_assert(sizeof(RasterRecord) == 64, "records are moved in 16-byte units");
+
+#ifndef LH_CHUNK
+#define LH_CHUNK 2
+#endif
+constexpr int kChunk = LH_CHUNK;   // queue entries per ticket
+constexpr int kRecSlots = 3;       // record ring: processing / staging its streams / in flight
+constexpr int kAuxSlots = 2;       // stream ring: processing / in flight
+// a meshlet's micro-indices (<= 124 triangles x 3 bytes) and vertex indices (<= 64 x 4 bytes) start at any byte: the
+// copies are the enclosing 16-byte-aligned ranges
+constexpr int kMicroBuf = (15 + 3 * (int)LH_MAX_MESHLET_TRIANGLES + 15) & ~15;           // 400
+constexpr int kIndexBuf = (15 + 4 * (int)LH_MAX_MESHLET_UNIQUE_VERTICES + 15) & ~15;     // 272
+
+// Per-warp scratch of the meshlet kernel.
 // sx holds two sentinels instead of a flag byte: kVertOutside (behind the w - z >= 0 plane) and kVertNonFinite.
-constexpr int LH_FRONT_CHUNK_MAX = 8;
-struct WarpScratch {
+struct alignas(16) WarpScratch {
+    RasterRecord rec[kRecSlots][kChunk];
+    float T[kAuxSlots][kChunk][16];
+    uint8_t micro[kAuxSlots][kChunk][kMicroBuf];
+    uint8_t index[kAuxSlots][kChunk][kIndexBuf];
     int sx[LH_MAX_MESHLET_UNIQUE_VERTICES];
     int sy[LH_MAX_MESHLET_UNIQUE_VERTICES];
     float z[LH_MAX_MESHLET_UNIQUE_VERTICES];
@@ -56,24 +88,39 @@ struct WarpScratch {
     // centre is <= it.  min/max over a triangle's vertices (SIMD halfword ops) give its pixel rectangle directly.
     uint2 cover[LH_MAX_MESHLET_UNIQUE_VERTICES];
     uint8_t surv[128];
-    // what the pointer chase of a ticket's entries found (one lane per entry walks reference -> instance -> mesh info
-    // -> meshlet, so the chain's four dependent round trips are paid once per ticket, not once per meshlet)
-    struct alignas(16) Staged {
-        float T[16];
-        const uint16_t* positions;
-        const void* indices;
-        const uint8_t* micro;      // already offset by triangle_offset
-        const LhMeshInfo* mi;
-        uint32_t index_offset, counts_flags;   // triangle_count | index_count << 8 | MeshInfo.flags << 16
-        uint32_t local, pad;
-    } staged[LH_FRONT_CHUNK_MAX];
+    unsigned long long rec_bar[kRecSlots], aux_bar[kAuxSlots];   // mbarriers: records / streams of a ring slot have landed
 };
 constexpr int kVertOutside = INT_MIN, kVertNonFinite = INT_MIN + 1;   // |snapped| <= 2^29, so neither can be a coordinate
-#ifndef LH_FRONT_CHUNK
-#define LH_FRONT_CHUNK 4
-#endif
-constexpr int kFrontChunk = LH_FRONT_CHUNK;   // queue entries a warp takes per ticket
 constexpr int kMaxOcclusionBlocks = 16;    // early-out reads at most 16 blocks of 8x4 pixels (512 keys)
+
+// ---- bulk-asynchronous copies global -> shared, completion counted in bytes on an mbarrier ----
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(void* bar, uint32_t arrivals) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(arrivals) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(void* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(void* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(void* bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "LH_MBAR_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra LH_MBAR_DONE;\n"
+        "bra LH_MBAR_WAIT;\n"
+        "LH_MBAR_DONE:\n"
+        "}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+// dst, src and bytes are multiples of 16
+__device__ __forceinline__ void bulk_copy_g2s(void* dst, const void* src, uint32_t bytes, void* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)), "l"(src),
+                 "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
 
 struct SnapVert {
     int x, y;
@@ -315,14 +362,12 @@ __device__ __forceinline__ void load_header(const FrameParams& P, uint32_t slot,
     h.base_color_texture = __ldg(&mi->base_color_texture_index);
 }
 
-// The pointer chase of load_header by ONE lane, parked in shared memory (WarpScratch::Staged)
-__device__ __forceinline__ void chase_header(const FrameParams& P, uint32_t slot, WarpScratch::Staged& st) {
+// The pointer chase of load_header by ONE lane of the selection, left as a RasterRecord for the raster kernel
+__device__ __forceinline__ void make_record(const FrameParams& P, uint32_t k, uint4 mb, RasterRecord* out) {
     const LhMeshletReference* refs = (const LhMeshletReference*)P.pass_refs;
-    const unsigned long long ref = __ldg((const unsigned long long*)(refs + slot));
+    const unsigned long long ref = __ldg((const unsigned long long*)(refs + k));
     const uint32_t instance_index = (uint32_t)ref, meshlet_index = (uint32_t)(ref >> 32) & 0xFFFFu;
     const LhInstance* inst = (const LhInstance*)P.u.instances + instance_index;
-    const float4 c0 = __ldg((const float4*)&inst->transform), c1 = __ldg((const float4*)&inst->transform + 1);
-    const float4 c2 = __ldg((const float4*)&inst->transform + 2), c3 = __ldg((const float4*)&inst->transform + 3);
     const LhMeshInfo* mi = (const LhMeshInfo*)__ldg((const unsigned long long*)&inst->mesh_info_address);
     const unsigned long long positions = __ldg((const unsigned long long*)&mi->positions), indices = __ldg((const unsigned long long*)&mi->indices);
     const unsigned long long micro = __ldg((const unsigned long long*)&mi->micro_indices), meshlets = __ldg((const unsigned long long*)&mi->meshlets);
@@ -330,52 +375,24 @@ __device__ __forceinline__ void chase_header(const FrameParams& P, uint32_t slot
     const LhMeshlet* m = (const LhMeshlet*)meshlets + meshlet_index;
     const unsigned long long tail = __ldg((const unsigned long long*)m + 6);  // index_offset | counts
     const uint32_t triangle_offset = __ldg(&m->triangle_offset);
-    *(float4*)&st.T[0] = c0; *(float4*)&st.T[4] = c1; *(float4*)&st.T[8] = c2; *(float4*)&st.T[12] = c3;
-    st.positions = (const uint16_t*)positions;
-    st.indices = (const void*)indices;
-    st.micro = (const uint8_t*)micro + triangle_offset;
-    st.mi = mi;
-    st.index_offset = (uint32_t)tail;
-    st.counts_flags = ((uint32_t)(tail >> 32) & 0xFFFFu) | (flags << 16);
-    st.local = slot;
-}
-
-// ... and its retrieval by the whole warp (broadcast reads); the alpha-clip fields are fetched only where needed
-__device__ __forceinline__ void unstage_header(const WarpScratch::Staged& st, MeshletHeader& h) {
-#pragma unroll
-    for (int k = 0; k < 16; k++) h.T[k] = st.T[k];
-    h.positions = st.positions;
-    h.indices = st.indices;
-    h.micro = st.micro;
-    h.index_offset = st.index_offset;
-    const uint32_t cf = st.counts_flags;
-    h.tri_count = cf & 0xFFu;
-    h.vert_count = (cf >> 8) & 0xFFu;
-    const uint32_t flags = cf >> 16;
-    h.wide = (flags & LH_MESH_INFO_FLAGS_32_BIT_INDICES) != 0;
-    h.alpha = (flags & LH_MESH_INFO_FLAGS_ALPHA_CLIP) != 0;
-    h.uvs = nullptr;
-    h.tex_scale[0] = h.tex_scale[1] = h.tex_offset[0] = h.tex_offset[1] = 0.0f;
-    h.base_color_texture = LH_UNUSED_TEXTURE_INDEX;
-    if (h.alpha) {
-        const LhMeshInfo* mi = st.mi;
-        h.uvs = (const uint16_t*)__ldg((const unsigned long long*)&mi->uvs);
-        h.tex_scale[0] = __ldg(&mi->texture_scale[0]);
-        h.tex_scale[1] = __ldg(&mi->texture_scale[1]);
-        h.tex_offset[0] = __ldg(&mi->texture_offset[0]);
-        h.tex_offset[1] = __ldg(&mi->texture_offset[1]);
-        h.base_color_texture = __ldg(&mi->base_color_texture_index);
-    }
+    const unsigned long long first_index = indices + (unsigned long long)(uint32_t)tail * ((flags & LH_MESH_INFO_FLAGS_32_BIT_INDICES) ? 4u : 2u);
+    uint4* dst = (uint4*)out;
+    dst[0] = make_uint4((uint32_t)positions, (uint32_t)(positions >> 32), (uint32_t)first_index, (uint32_t)(first_index >> 32));
+    const unsigned long long micro_first = micro + triangle_offset, mi_bits = (unsigned long long)(uintptr_t)mi;
+    dst[1] = make_uint4((uint32_t)micro_first, (uint32_t)(micro_first >> 32), (uint32_t)mi_bits, (uint32_t)(mi_bits >> 32));
+    const unsigned long long inst_bits = (unsigned long long)(uintptr_t)inst;
+    dst[2] = make_uint4((uint32_t)inst_bits, (uint32_t)(inst_bits >> 32), ((uint32_t)(tail >> 32) & 0xFFFFu) | (flags << 16), k);
+    dst[3] = make_uint4(mb.x, mb.y, mb.z, 0u);
 }
 
 __device__ __forceinline__ uint32_t load_vertex_index(const MeshletHeader& h, uint32_t v) {
     return h.wide ? __ldg((const uint32_t*)h.indices + h.index_offset + v) : (uint32_t)__ldg((const uint16_t*)h.indices + h.index_offset + v);
 }
 
-__device__ __forceinline__ AlphaTest make_alpha_test(const FrameParams& P, const MeshletHeader& h) {
+__device__ __forceinline__ AlphaTest make_alpha_test(const FrameParams& P, bool alpha, uint32_t base_color_texture) {
     AlphaTest at{false, 0};
-    if (h.alpha && h.base_color_texture < LH_MAX_TEXTURES) {
-        at.tex = P.textures[h.base_color_texture];
+    if (alpha && base_color_texture < LH_MAX_TEXTURES) {
+        at.tex = P.textures[base_color_texture];
         at.enabled = at.tex != 0;
     }
     return at;
@@ -556,7 +573,7 @@ __global__ void __launch_bounds__(256) raster_select_kernel(const __grid_constan
         const uint32_t key = base + lane < total ? __ldg(P.depth_keys + k) : kKeyEmpty;
         bool keep = key >= key_lo && key < key_hi;
         uint4 mb = make_uint4(kUntestable, 0u, 0u, kKeyEmpty);
-        if (keep && band != 0) mb = __ldg((const uint4*)(bounds + k));
+        if (keep) mb = __ldg((const uint4*)(bounds + k));
         if (keep && band != 0 && mb.x != kUntestable) {
             const int px0 = (int)(mb.x & 0xFFFFu), px1 = (int)(mb.x >> 16), py0 = (int)(mb.y & 0xFFFFu), py1 = (int)(mb.y >> 16);
             const bool fine = ((px1 >> kHizShift0) - (px0 >> kHizShift0) + 1) * ((py1 >> kHizShift0) - (py0 >> kHizShift0) + 1) <= kMaxHizTiles;
@@ -575,7 +592,7 @@ __global__ void __launch_bounds__(256) raster_select_kernel(const __grid_constan
             uint32_t at = 0;
             if (lane == 0) at = atomicAdd(&P.pass->queue_count, (uint32_t)__popc(ballot));
             at = __shfl_sync(0xFFFFFFFFu, at, 0);
-            if (keep) P.raster_queue[at + __popc(ballot & ((1u << lane) - 1u))] = k;
+            if (keep) make_record(P, k, mb, (RasterRecord*)P.raster_records + at + __popc(ballot & ((1u << lane) - 1u)));
         }
     }
     if (P.flags & LH_CONFIG_PASS_TIMINGS) {
@@ -604,9 +621,286 @@ __device__ __forceinline__ void publish_queue_end(uint32_t* done_counter, const 
 #ifndef LH_RASTER_MIN_CTAS
 #define LH_RASTER_MIN_CTAS 4
 #endif
+
+struct RasterCounters {
+    uint32_t tris_done = 0, skipped_occluded = 0, skipped_empty = 0;
+};
+
+// One queued meshlet by one warp.  rec: its record; T, micro, index: its staged instance transform, micro-indices and
+// vertex indices (shared memory; micro / index point at the meshlet's first byte inside the staged 16-byte-aligned
+// ranges); first_keys: the lane's stored key under the first 8x4 block of the bound, prefetched a chunk ago;
+// M: the view's matrix (main view: the kernel parameter, i.e. constant-bank operands; cascade: shared memory).
+template <bool SHADOW, bool ALPHA>
+__device__ __forceinline__ void raster_one_meshlet(const FrameParams& P, const Target<SHADOW>& tg, WarpScratch& sv, const RasterRecord& rec,
+                                                   const float* T, const uint8_t* micro, const uint8_t* index, uint32_t first_keys, const float* M,
+                                                   bool affine, RasterCounters& cnt) {
+    const uint32_t lane = threadIdx.x & 31;
+    const int W = (int)tg.width, H = (int)tg.height;
+    // ---- (0) re-test against the keys stored since the selection (the band's own meshlets occlude one another) ----
+    {
+        const uint4 mb = *(const uint4*)&rec.rect_x;   // rect_x, rect_y, edge, pad
+        const int px0 = (int)(mb.x & 0xFFFFu), px1 = (int)(mb.x >> 16), py0 = (int)(mb.y & 0xFFFFu), py1 = (int)(mb.y >> 16);
+        if (mb.x != kUntestable && (((px1 - px0) >> 3) + 1) * (((py1 - py0) >> 2) + 1) <= kMaxOcclusionBlocks) {
+            uint32_t worst = first_keys;
+            if (px1 - px0 >= 8 || py1 - py0 >= 4) {   // more than the prefetched block
+                for (int y = py0 + (int)(lane >> 3); y <= py1; y += 4) {
+                    const uint32_t* row = SHADOW ? tg.layer + (size_t)y * W : (const uint32_t*)tg.vis + 2 * (size_t)y * W + 1;
+                    for (int x = px0 + (int)(lane & 7); x <= px1; x += 8) worst = max(worst, __ldcg(row + (SHADOW ? x : 2 * x)));
+                }
+            }
+            worst = __reduce_max_sync(0xFFFFFFFFu, worst);
+            if (SHADOW ? mb.z >= worst : worst < mb.z) {
+                cnt.skipped_occluded++;
+                return;
+            }
+        }
+    }
+    const uint32_t cf = rec.counts_flags;
+    // more triangles / vertices than a meshlet may have (MAX_MESHLET_TRIANGLES, MAX_MESHLET_UNIQUE_VERTICES) are cut off
+    const uint32_t tri_count = min(cf & 0xFFu, (uint32_t)LH_MAX_MESHLET_TRIANGLES);
+    const uint32_t nv = min((cf >> 8) & 0xFFu, (uint32_t)LH_MAX_MESHLET_UNIQUE_VERTICES);
+    const bool wide = (cf >> 16) & LH_MESH_INFO_FLAGS_32_BIT_INDICES;
+    constexpr bool alpha = ALPHA;   // MESH_INFO_FLAGS_ALPHA_CLIP: the caller branches once per meshlet, so the opaque path carries none of its state
+    const float half_w = pmul((float)tg.width, 0.5f), half_h = pmul((float)tg.height, 0.5f);
+
+    // ---- (1) vertex phase: load_vertex_data + calculate_world_pos + matrix * (world, 1) ----
+    int vminx = INT_MAX, vmaxx = INT_MIN, vminy = INT_MAX, vmaxy = INT_MIN;
+    uint32_t vnear = SHADOW ? 0xFFFFFFFFu : 0u;   // bits of the nearest vertex depth (depths are >= 0, so bits order like values)
+    bool special = false;                          // some vertex is behind the near plane, non-finite or of negative depth
+    {
+        const uint16_t* positions = rec.positions;
+        // the instance transform from shared memory: live for this phase only
+        float Tl[16];
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const float4 c = *(const float4*)(T + 4 * k);
+            Tl[4 * k] = c.x; Tl[4 * k + 1] = c.y; Tl[4 * k + 2] = c.z; Tl[4 * k + 3] = c.w;
+        }
+        for (uint32_t v = lane; v < nv; v += 32) {
+            const uint32_t idx = wide ? *(const uint32_t*)(index + 4 * v) : (uint32_t)*(const uint16_t*)(index + 2 * v);
+            const uint16_t* p = positions + 3 * (size_t)idx;
+            const float px = (float)__ldg(p), py = (float)__ldg(p + 1), pz = (float)__ldg(p + 2);
+            const V4 world = mat4_mul(Tl, px, py, pz, 1.0f);
+            V4 clip;
+            if (SHADOW && affine) {
+                // a cascade matrix ends in the row (0, 0, 0, 1): w is exactly 1 for every finite position, and a
+                // non-finite one makes x, y and z non-finite too, so the vertex is classified the same without w
+                clip.x = padd(padd(pmul(M[0], world.x), pmul(M[4], world.y)), padd(pmul(M[8], world.z), M[12]));
+                clip.y = padd(padd(pmul(M[1], world.x), pmul(M[5], world.y)), padd(pmul(M[9], world.z), M[13]));
+                clip.z = padd(padd(pmul(M[2], world.x), pmul(M[6], world.y)), padd(pmul(M[10], world.z), M[14]));
+                clip.w = 1.0f;
+            } else {
+                clip = mat4_mul(M, world.x, world.y, world.z, 1.0f);
+            }
+            int sx = kVertOutside, sy = 0;
+            float z = 0.0f;
+            if (SHADOW || psub(clip.w, clip.z) >= 0.0f) {
+                if (!project_snap(clip.x, clip.y, clip.z, clip.w, half_w, half_h, &sx, &sy, &z)) sx = kVertNonFinite;
+            }
+            sv.sx[v] = sx;
+            sv.sy[v] = sy;
+            sv.z[v] = z;
+            if (alpha) sv.w[v] = clip.w;
+            // first / last pixel per axis, saturated to int16 and packed (x low, y high) in one instruction each
+            sv.cover[v] = make_uint2(pack_sat_s16((sy + 127) >> 8, (sx + 127) >> 8), pack_sat_s16((sy - 128) >> 8, (sx - 128) >> 8));
+            if (sx == kVertOutside || sx == kVertNonFinite || !(z >= 0.0f)) {
+                special = true;
+            } else {
+                vminx = min(vminx, sx); vmaxx = max(vmaxx, sx);
+                vminy = min(vminy, sy); vmaxy = max(vmaxy, sy);
+                vnear = SHADOW ? min(vnear, __float_as_uint(z)) : max(vnear, __float_as_uint(z));
+            }
+        }
+    }
+    __syncwarp();
+
+    // ---- (1b) the same two early-outs with the exact vertex bounds: every triangle lies inside the vertices'
+    // rectangle, and (screen-linear depth) no fragment is nearer than the nearest vertex ----
+    const bool any_special = __any_sync(0xFFFFFFFFu, special);
+    if (!any_special) {
+        vminx = __reduce_min_sync(0xFFFFFFFFu, vminx); vmaxx = __reduce_max_sync(0xFFFFFFFFu, vmaxx);
+        vminy = __reduce_min_sync(0xFFFFFFFFu, vminy); vmaxy = __reduce_max_sync(0xFFFFFFFFu, vmaxy);
+        const int bx0 = max(0, (vminx - 128 + 255) >> 8), bx1 = min(W - 1, (vmaxx - 128) >> 8);
+        const int by0 = max(0, (vminy - 128 + 255) >> 8), by1 = min(H - 1, (vmaxy - 128) >> 8);
+        if (bx0 > bx1 || by0 > by1) {   // no pixel centre inside
+            cnt.skipped_empty++;
+            return;
+        }
+        if (bx1 - bx0 < 8 && by1 - by0 < 4) {   // one 8x4 block: test the stored keys against the nearest vertex depth
+            vnear = SHADOW ? __reduce_min_sync(0xFFFFFFFFu, vnear) : __reduce_max_sync(0xFFFFFFFFu, vnear);
+            const float zn = __uint_as_float(vnear);
+            // the interpolated depth can leave the vertices' range by rounding only: pad by a few ulp
+            const float d = SHADOW ? zn - (4e-6f * zn + 1e-30f) : zn + (4e-6f * zn + 1e-30f);
+            const int x = bx0 + (int)(lane & 7), y = by0 + (int)(lane >> 3);
+            uint32_t worst = 0;
+            if (x <= bx1 && y <= by1) {
+                const size_t at = (size_t)y * W + x;
+                worst = SHADOW ? __ldcg(tg.layer + at) : __ldcg((const uint32_t*)tg.vis + 2 * at + 1);
+            }
+            worst = __reduce_max_sync(0xFFFFFFFFu, worst);
+            if (d > 0.0f && (SHADOW ? __float_as_uint(d) >= worst : worst < ~__float_as_uint(d))) {
+                cnt.skipped_occluded++;
+                return;
+            }
+        }
+    }
+
+    // cull modes: pipelines.cpp:10-25,255-315
+    const int cull = alpha ? CULL_NONE : (SHADOW ? CULL_FRONT : CULL_BACK);
+    const uint32_t lo_base = (P.slot_offset + rec.local) << LH_VIS_TRI_BITS;
+
+    // ---- (2) triangle cull phase ----
+    uint32_t n_surv = 0;
+    const uint32_t screen_max = (uint32_t)(W - 1) | ((uint32_t)(H - 1) << 16);
+    for (uint32_t t0 = 0; t0 < tri_count; t0 += 32) {
+        const uint32_t t = t0 + lane;
+        bool keep = false;
+        if (t < tri_count) {
+            const uint32_t i0 = micro[3 * t], i1 = micro[3 * t + 1], i2 = micro[3 * t + 2];
+            if (max(i0, max(i1, i2)) < nv) {
+                const uint32_t lo = lo_base | t;
+                // facing test and routing of a triangle whose pixel rectangle [px0,px1] x [py0,py1] is not empty
+                auto covered = [&](int px0, int px1, int py0, int py1) {
+                    const int ax = sv.sx[i0], bx = sv.sx[i1], cx = sv.sx[i2], ay = sv.sy[i0], by = sv.sy[i1], cy = sv.sy[i2];
+                    const int minx = min(ax, min(bx, cx)), maxx = max(ax, max(bx, cx));
+                    const int miny = min(ay, min(by, cy)), maxy = max(ay, max(by, cy));
+                    cnt.tris_done++;
+                    // exact in 32 bits when the sub-pixel extent is < 2^14 (every product < 2^28)
+                    const bool small_extent = (maxx - minx) < kSmallMaxExtent && (maxy - miny) < kSmallMaxExtent;
+                    const long long A2 = small_extent
+                                             ? (long long)((bx - ax) * (cy - ay) - (by - ay) * (cx - ax))
+                                             : (long long)(bx - ax) * (cy - ay) - (long long)(by - ay) * (cx - ax);
+                    const bool front = A2 < 0;
+                    if (A2 == 0 || (cull == CULL_BACK && !front) || (cull == CULL_FRONT && front)) return;
+                    const int spanx = px1 - px0 + 1, spany = py1 - py0 + 1;
+                    if (small_extent && spanx <= kSmallMaxSpan && spany <= kSmallMaxSpan && spanx * spany <= kSmallMaxArea) {
+                        keep = true;
+                    } else {
+                        // large footprint: one queue entry per 128x32 screen tile the bounding box touches
+                        const uint32_t tx0 = (uint32_t)px0 / kTileW, tx1 = (uint32_t)px1 / kTileW;
+                        const uint32_t ty0 = (uint32_t)py0 / kTileH, ty1 = (uint32_t)py1 / kTileH;
+                        if ((tx1 - tx0 + 1) * (ty1 - ty0 + 1) > 2) {
+                            push_deferred(P, lo, kWholeTriangle);   // split by the deferred kernel, a warp per triangle
+                        } else {
+                            for (uint32_t ty = ty0; ty <= ty1; ty++)
+                                for (uint32_t tx = tx0; tx <= tx1; tx++) push_deferred(P, lo, tx | (ty << 16));
+                        }
+                    }
+                };
+                if (!any_special) {
+                    // the common case: every vertex is in front of the near plane and finite.  Rectangle by
+                    // halfword min/max of the per-vertex pixel bounds; most triangles end here (no sample inside).
+                    const uint2 c0 = sv.cover[i0], c1 = sv.cover[i1], c2 = sv.cover[i2];
+                    const uint32_t first = __vmaxs2(__vmins2(__vmins2(c0.x, c1.x), c2.x), 0u);
+                    const uint32_t last = __vmins2(__vmaxs2(__vmaxs2(c0.y, c1.y), c2.y), screen_max);
+                    if (__vcmpgts2(first, last) == 0u)
+                        covered((int)(first & 0xFFFFu), (int)(last & 0xFFFFu), (int)(first >> 16), (int)(last >> 16));
+                } else {
+                    const int ax = sv.sx[i0], bx = sv.sx[i1], cx = sv.sx[i2];
+                    const int n_out = (ax == kVertOutside) + (bx == kVertOutside) + (cx == kVertOutside);
+                    if (n_out == 0) {
+                        if (ax != kVertNonFinite && bx != kVertNonFinite && cx != kVertNonFinite) {
+                            const int ay = sv.sy[i0], by = sv.sy[i1], cy = sv.sy[i2];
+                            const int minx = min(ax, min(bx, cx)), maxx = max(ax, max(bx, cx));
+                            const int miny = min(ay, min(by, cy)), maxy = max(ay, max(by, cy));
+                            const int px0 = max(0, (minx - 128 + 255) >> 8), px1 = min(W - 1, (maxx - 128) >> 8);
+                            const int py0 = max(0, (miny - 128 + 255) >> 8), py1 = min(H - 1, (maxy - 128) >> 8);
+                            if (px0 <= px1 && py0 <= py1) covered(px0, px1, py0, py1);
+                        }
+                    } else if (n_out < 3) {
+                        push_deferred(P, lo, kWholeTriangle);   // crosses the near plane: generic path
+                    }
+                }
+            }
+        }
+        const uint32_t ballot = __ballot_sync(0xFFFFFFFFu, keep);
+        if (keep) sv.surv[n_surv + __popc(ballot & ((1u << lane) - 1u))] = (uint8_t)t;
+        n_surv += __popc(ballot);
+    }
+    __syncwarp();
+    if (n_surv == 0) return;
+
+    // ---- (3) raster phase over the compacted survivors ----
+    AlphaTest at{false, 0};
+    const uint16_t* uvs = nullptr;
+    float tex_scale[2] = {0.0f, 0.0f}, tex_offset[2] = {0.0f, 0.0f};
+    if (ALPHA) {
+        const LhMeshInfo* mi = rec.mi;
+        at = make_alpha_test(P, true, __ldg(&mi->base_color_texture_index));
+        uvs = (const uint16_t*)__ldg((const unsigned long long*)&mi->uvs);
+        tex_scale[0] = __ldg(&mi->texture_scale[0]);
+        tex_scale[1] = __ldg(&mi->texture_scale[1]);
+        tex_offset[0] = __ldg(&mi->texture_offset[0]);
+        tex_offset[1] = __ldg(&mi->texture_offset[1]);
+    }
+    for (uint32_t s = lane; s < n_surv; s += 32) {
+        const uint32_t t = sv.surv[s];
+        const uint32_t lo = lo_base | t;
+        uint32_t ia = micro[3 * t], ib = micro[3 * t + 1], ic = micro[3 * t + 2];
+        int ax = sv.sx[ia], ay = sv.sy[ia], bx = sv.sx[ib], by = sv.sy[ib], cx = sv.sx[ic], cy = sv.sy[ic];
+        const int minx = min(ax, min(bx, cx)), maxx = max(ax, max(bx, cx));
+        const int miny = min(ay, min(by, cy)), maxy = max(ay, max(by, cy));
+        const int px0 = max(0, (minx - 128 + 255) >> 8), px1 = min(W - 1, (maxx - 128) >> 8);
+        const int py0 = max(0, (miny - 128 + 255) >> 8), py1 = min(H - 1, (maxy - 128) >> 8);
+        int A2 = (bx - ax) * (cy - ay) - (by - ay) * (cx - ax);
+        float az = sv.z[ia], bz = sv.z[ib], cz = sv.z[ic];
+        if (A2 < 0) {
+            int t0 = bx; bx = cx; cx = t0;
+            t0 = by; by = cy; cy = t0;
+            float tz = bz; bz = cz; cz = tz;
+            const uint32_t ti = ib; ib = ic; ic = ti;
+            A2 = -A2;
+        }
+        const int e0x = cx - bx, e0y = cy - by, e1x = ax - cx, e1y = ay - cy, e2x = bx - ax, e2y = by - ay;
+        const int bias0 = top_left(e0x, e0y) ? 0 : -1, bias1 = top_left(e1x, e1y) ? 0 : -1, bias2 = top_left(e2x, e2y) ? 0 : -1;
+        const float fA = (float)A2;
+        const float inv_area = pdiv(1.0f, fA);
+        const float dz1 = psub(bz, az), dz2 = psub(cz, az);
+        const int ccx = px0 * 256 + 128, ccy = py0 * 256 + 128;
+        int w0_row = e0x * (ccy - by) - e0y * (ccx - bx);
+        int w1_row = e1x * (ccy - cy) - e1y * (ccx - cx);
+        int w2_row = e2x * (ccy - ay) - e2y * (ccx - ax);
+        SnapVert A, B, C;
+        if (ALPHA && at.enabled) {
+            // perspective-correct uv needs the clip w and the vertex uvs
+            const uint32_t ids[3] = {ia, ib, ic};
+            SnapVert* out[3] = {&A, &B, &C};
+            for (int q = 0; q < 3; q++) {
+                const uint32_t idx = wide ? *(const uint32_t*)(index + 4 * ids[q]) : (uint32_t)*(const uint16_t*)(index + 2 * ids[q]);
+                out[q]->w = sv.w[ids[q]];
+                out[q]->u = padd(pmul((float)__ldg(uvs + 2 * (size_t)idx), tex_scale[0]), tex_offset[0]);
+                out[q]->v = padd(pmul((float)__ldg(uvs + 2 * (size_t)idx + 1), tex_scale[1]), tex_offset[1]);
+            }
+        }
+        for (int py = py0; py <= py1; py++) {
+            int w0 = w0_row, w1 = w1_row, w2 = w2_row;
+            for (int px = px0; px <= px1; px++) {
+                if (((w0 + bias0) | (w1 + bias1) | (w2 + bias2)) >= 0) {
+                    if (!(ALPHA && at.enabled && alpha_discard(at, (float)w0, (float)w1, (float)w2, fA, A, B, C))) {
+                        float z = padd(az, pmul(padd(pmul((float)w1, dz1), pmul((float)w2, dz2)), inv_area));
+                        tg.emit(px, py, z, lo);
+                    }
+                }
+                w0 -= e0y * 256;
+                w1 -= e1y * 256;
+                w2 -= e2y * 256;
+            }
+            w0_row += e0x * 256;
+            w1_row += e1x * 256;
+            w2_row += e2x * 256;
+        }
+    }
+}
+
+// One warp per queued meshlet.  The front end is a software pipeline of bulk-asynchronous copies, three chunks deep:
+// while chunk i is rasterised, the micro-indices, vertex indices and instance transforms of chunk i + 1 are landing in
+// shared memory (their addresses came with that chunk's records, which landed during chunk i - 1), the records of
+// chunk i + 2 are landing, and the ticket of chunk i + 3 is on its way back from L2.  Nothing in the loop waits on a
+// dependent global load except the vertex positions (gathered through the staged indices).
 template <bool SHADOW>
 __global__ void __launch_bounds__(kWarpsPerCta * 32, LH_RASTER_MIN_CTAS) raster_meshlets_kernel(const __grid_constant__ FrameParams P, uint32_t cascade, uint32_t band) {
     __shared__ WarpScratch scratch_all[kWarpsPerCta];
+    __shared__ float cascade_matrix[16];
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     WarpScratch& sv = scratch_all[warp];
     // band b owns the queue entries appended by its selection: [band_mark[b], queue_count); nothing appends while
@@ -616,300 +910,124 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, LH_RASTER_MIN_CTAS) raster_
         P.pass->band_mark[band + 1] = band_end;
         if (P.flags & LH_CONFIG_PASS_TIMINGS) atomicAdd(&P.state->queued[SHADOW ? 1u + cascade : 0u], band_end - band_first);
     }
+    if (lane == 0) {
+        for (int s = 0; s < kRecSlots; s++) mbar_init(&sv.rec_bar[s], 1);
+        for (int s = 0; s < kAuxSlots; s++) mbar_init(&sv.aux_bar[s], kChunk);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    // The main view multiplies by the kernel parameter itself (constant-bank operands, no registers); a cascade's
+    // matrix was generated on the device: it is read from shared memory where it is used.
+    if (SHADOW && threadIdx.x < 16) cascade_matrix[threadIdx.x] = (&((const LhMiscStorage*)P.u.misc_storage)->shadow_matrices[cascade].m[0][0])[threadIdx.x];
+    __syncthreads();
 
     Target<SHADOW> tg;
     tg.vis = P.vis;
     tg.layer = SHADOW ? P.shadow + (size_t)cascade * P.shadowmap_size * P.shadowmap_size : nullptr;
     tg.width = SHADOW ? P.shadowmap_size : P.u.window_size[0];
     tg.height = SHADOW ? P.shadowmap_size : P.u.window_size[1];
-    const float half_w = pmul((float)tg.width, 0.5f), half_h = pmul((float)tg.height, 0.5f);
-    const int W = (int)tg.width, H = (int)tg.height;
+    const int W = (int)tg.width;
+    const float* M = SHADOW ? cascade_matrix : &P.u.combined_perspective_view.m[0][0];
+    const bool affine = SHADOW && cascade_matrix[3] == 0.0f && cascade_matrix[7] == 0.0f && cascade_matrix[11] == 0.0f && cascade_matrix[15] == 1.0f;
+    const RasterRecord* records = (const RasterRecord*)P.raster_records;
+    RasterCounters cnt;
 
-    // The main view multiplies by the kernel parameter itself (constant-bank operands, no registers); a cascade's
-    // matrix was generated on the device and is held in registers.
-    float Mreg[SHADOW ? 16 : 1];
-    if (SHADOW) {
-        const float* src = &((const LhMiscStorage*)P.u.misc_storage)->shadow_matrices[cascade].m[0][0];
-#pragma unroll
-        for (int k = 0; k < (SHADOW ? 16 : 1); k++) Mreg[k] = src[k];
-    }
-    const float* M = SHADOW ? Mreg : &P.u.combined_perspective_view.m[0][0];
-    const bool affine = SHADOW && Mreg[SHADOW ? 3 : 0] == 0.0f && Mreg[SHADOW ? 7 : 0] == 0.0f && Mreg[SHADOW ? 11 : 0] == 0.0f && Mreg[SHADOW ? 15 : 0] == 1.0f;
-    const MeshletBound* bounds = (const MeshletBound*)P.meshlet_bounds;
-    uint32_t tris_done = 0, skipped_occluded = 0, skipped_empty = 0;
-
-    // A warp takes up to kFrontChunk queue entries per ticket (one when the band is small, so that every warp gets
-    // work and a heavy near meshlet does not serialise its neighbours): the entries, their bounds and the first 8x4
-    // block of every rectangle are fetched before any entry is processed, so the dependent round trips
-    // ticket -> queue -> bounds -> stored keys are paid once per chunk instead of once per meshlet.
+    // kChunk entries per ticket; one when the band is small, so that every warp gets work and a heavy near meshlet does
+    // not serialise its neighbours
     const uint32_t band_count = band_end - band_first;
-    const uint32_t chunk = max(1u, min((uint32_t)kFrontChunk, band_count / (gridDim.x * kWarpsPerCta * 8u)));
-    for (;;) {
-        uint32_t ticket = 0;
-        if (lane == 0) ticket = band_first + atomicAdd(&P.pass->band_ticket[band], chunk);
-        ticket = __shfl_sync(0xFFFFFFFFu, ticket, 0);
-        if (ticket >= band_end) break;
-        const uint32_t n = min(chunk, band_end - ticket);
-        uint32_t my_k = 0;
-        uint4 my_mb = make_uint4(kUntestable, 0u, 0u, 0u);
-        if (lane < n) {
-            my_k = __ldg(P.raster_queue + ticket + lane);
-            my_mb = __ldg((const uint4*)(bounds + my_k));
-            chase_header(P, my_k, sv.staged[lane]);   // the queue holds list indices
+    const uint32_t chunk = max(1u, min((uint32_t)kChunk, band_count / (gridDim.x * kWarpsPerCta * 8u)));
+    // lane 0 holds a ticket from the moment it is taken; everybody learns it (one shuffle) when it is first needed
+    auto take_ticket = [&]() -> uint32_t { return lane == 0 ? band_first + atomicAdd(&P.pass->band_ticket[band], chunk) : 0u; };
+    auto entries = [&](uint32_t first) -> uint32_t { return first < band_end ? min(chunk, band_end - first) : 0u; };
+    auto issue_records = [&](uint32_t slot, uint32_t first, uint32_t n) {
+        if (lane == 0 && n) {
+            mbar_arrive_expect_tx(&sv.rec_bar[slot], n * (uint32_t)sizeof(RasterRecord));
+            bulk_copy_g2s(&sv.rec[slot][0], records + first, n * (uint32_t)sizeof(RasterRecord), &sv.rec_bar[slot]);
         }
-        __syncwarp();
-        uint32_t first[kFrontChunk];
+    };
+    // lane j < n stages entry j's streams: the 16-byte-aligned ranges around its micro-indices and vertex indices, and
+    // the instance transform; every lane prefetches the stored keys under the first 8x4 block of each bound
+    auto issue_streams = [&](uint32_t aux, uint32_t slot, uint32_t n, uint32_t* first_keys) {
+        if (lane < (uint32_t)kChunk) {
+            if (lane < n) {
+                const RasterRecord& r = sv.rec[slot][lane];
+                const uint32_t cf = r.counts_flags;
+                const uint32_t tris = min(cf & 0xFFu, (uint32_t)LH_MAX_MESHLET_TRIANGLES), verts = min((cf >> 8) & 0xFFu, (uint32_t)LH_MAX_MESHLET_UNIQUE_VERTICES);
+                const uintptr_t m = (uintptr_t)r.micro, x = (uintptr_t)r.indices;
+                const uint32_t m_bytes = tris ? (uint32_t)(((m & 15u) + 3u * tris + 15u) & ~15u) : 0u;
+                const uint32_t x_bytes = verts ? (uint32_t)(((x & 15u) + (((cf >> 16) & LH_MESH_INFO_FLAGS_32_BIT_INDICES) ? 4u : 2u) * verts + 15u) & ~15u) : 0u;
+                mbar_arrive_expect_tx(&sv.aux_bar[aux], m_bytes + x_bytes + 64u);
+                bulk_copy_g2s(&sv.T[aux][lane][0], r.instance, 64u, &sv.aux_bar[aux]);
+                if (m_bytes) bulk_copy_g2s(&sv.micro[aux][lane][0], (const void*)(m & ~(uintptr_t)15), m_bytes, &sv.aux_bar[aux]);
+                if (x_bytes) bulk_copy_g2s(&sv.index[aux][lane][0], (const void*)(x & ~(uintptr_t)15), x_bytes, &sv.aux_bar[aux]);
+            } else {
+                mbar_arrive(&sv.aux_bar[aux]);
+            }
+        }
 #pragma unroll
-        for (int j = 0; j < kFrontChunk; j++) {
-            first[j] = 0;
-            const uint32_t rx = __shfl_sync(0xFFFFFFFFu, my_mb.x, j), ry = __shfl_sync(0xFFFFFFFFu, my_mb.y, j);
-            const int x = (int)(rx & 0xFFFFu) + (int)(lane & 7), y = (int)(ry & 0xFFFFu) + (int)(lane >> 3);
-            if ((uint32_t)j < n && rx != kUntestable && x <= (int)(rx >> 16) && y <= (int)(ry >> 16)) {
-                const size_t at = (size_t)y * W + x;
-                first[j] = SHADOW ? __ldcg(tg.layer + at) : __ldcg((const uint32_t*)tg.vis + 2 * at + 1);
+        for (int j = 0; j < kChunk; j++) {
+            first_keys[j] = 0;
+            if ((uint32_t)j < n) {
+                const uint32_t rx = sv.rec[slot][j].rect_x, ry = sv.rec[slot][j].rect_y;
+                const int x = (int)(rx & 0xFFFFu) + (int)(lane & 7), y = (int)(ry & 0xFFFFu) + (int)(lane >> 3);
+                if (rx != kUntestable && x <= (int)(rx >> 16) && y <= (int)(ry >> 16)) {
+                    const size_t at = (size_t)y * W + x;
+                    first_keys[j] = SHADOW ? __ldcg(tg.layer + at) : __ldcg((const uint32_t*)tg.vis + 2 * at + 1);
+                }
             }
         }
+    };
+
+    // ---- prologue: chunk 0's records and streams, chunk 1's records, chunk 2's ticket ----
+    uint32_t t_cur = __shfl_sync(0xFFFFFFFFu, take_ticket(), 0);
+    uint32_t n_cur = entries(t_cur);
+    issue_records(0, t_cur, n_cur);
+    uint32_t t_next = __shfl_sync(0xFFFFFFFFu, take_ticket(), 0);
+    uint32_t n_next = entries(t_next);
+    uint32_t keys_cur[kChunk], keys_next[kChunk];
+    if (n_cur) {
+        mbar_wait(&sv.rec_bar[0], 0);
+        issue_streams(0, 0, n_cur, keys_cur);
+    }
+    issue_records(1, t_next, n_next);
+    uint32_t t_after = take_ticket();   // lane 0 only, until it is needed
+
+    for (uint32_t i = 0; n_cur != 0; i++) {
+        const uint32_t slot = i % kRecSlots, aux = i % kAuxSlots;
+        // ---- advance the pipeline: chunk i + 1's streams, chunk i + 2's records, chunk i + 3's ticket ----
+        if (n_next) {
+            mbar_wait(&sv.rec_bar[(i + 1) % kRecSlots], ((i + 1) / kRecSlots) & 1u);
+            issue_streams((i + 1) % kAuxSlots, (i + 1) % kRecSlots, n_next, keys_next);
+        }
+        const uint32_t t_after_all = __shfl_sync(0xFFFFFFFFu, t_after, 0);
+        const uint32_t n_after = entries(t_after_all);
+        issue_records((i + 2) % kRecSlots, t_after_all, n_after);
+        t_after = take_ticket();
+        // ---- chunk i ----
+        mbar_wait(&sv.aux_bar[aux], (i / kAuxSlots) & 1u);
 #pragma unroll
-        for (int j = 0; j < kFrontChunk; j++) {
-            if ((uint32_t)j >= n) break;
-            const uint32_t k = __shfl_sync(0xFFFFFFFFu, my_k, j);
-            // ---- (0) re-test against the keys stored since the selection (the band's own meshlets occlude one another) ----
-            const uint4 mb = make_uint4(__shfl_sync(0xFFFFFFFFu, my_mb.x, j), __shfl_sync(0xFFFFFFFFu, my_mb.y, j),
-                                        __shfl_sync(0xFFFFFFFFu, my_mb.z, j), 0u);
-            const int px0 = (int)(mb.x & 0xFFFFu), px1 = (int)(mb.x >> 16), py0 = (int)(mb.y & 0xFFFFu), py1 = (int)(mb.y >> 16);
-            if (mb.x != kUntestable && (((px1 - px0) >> 3) + 1) * (((py1 - py0) >> 2) + 1) <= kMaxOcclusionBlocks) {
-                uint32_t worst = first[j];
-                if (px1 - px0 >= 8 || py1 - py0 >= 4) {   // more than the prefetched block
-                    for (int y = py0 + (int)(lane >> 3); y <= py1; y += 4) {
-                        const uint32_t* row = SHADOW ? tg.layer + (size_t)y * W : (const uint32_t*)tg.vis + 2 * (size_t)y * W + 1;
-                        for (int x = px0 + (int)(lane & 7); x <= px1; x += 8) worst = max(worst, __ldcg(row + (SHADOW ? x : 2 * x)));
-                    }
-                }
-                worst = __reduce_max_sync(0xFFFFFFFFu, worst);
-                if (SHADOW ? mb.z >= worst : worst < mb.z) {
-                    skipped_occluded++;
-                    continue;
-                }
-            }
-            const uint32_t local = sv.staged[j].local;
-            MeshletHeader h;
-            unstage_header(sv.staged[j], h);
-
-            const uint32_t nv = min(h.vert_count, (uint32_t)LH_MAX_MESHLET_UNIQUE_VERTICES);
-            // cull modes: pipelines.cpp:10-25,255-315
-            const int cull = h.alpha ? CULL_NONE : (SHADOW ? CULL_FRONT : CULL_BACK);
-            const AlphaTest at = make_alpha_test(P, h);
-
-            // ---- (1) vertex phase: load_vertex_data + calculate_world_pos + matrix * (world, 1) ----
-            int vminx = INT_MAX, vmaxx = INT_MIN, vminy = INT_MAX, vmaxy = INT_MIN;
-            uint32_t vnear = SHADOW ? 0xFFFFFFFFu : 0u;   // bits of the nearest vertex depth (depths are >= 0, so bits order like values)
-            bool special = false;                          // some vertex is behind the near plane, non-finite or of negative depth
-            for (uint32_t v = lane; v < nv; v += 32) {
-                const uint32_t idx = load_vertex_index(h, v);
-                const uint16_t* p = h.positions + 3 * (size_t)idx;
-                const float px = (float)__ldg(p), py = (float)__ldg(p + 1), pz = (float)__ldg(p + 2);
-                const V4 world = mat4_mul(h.T, px, py, pz, 1.0f);
-                V4 clip;
-                if (SHADOW && affine) {
-                    // a cascade matrix ends in the row (0, 0, 0, 1): w is exactly 1 for every finite position, and a
-                    // non-finite one makes x, y and z non-finite too, so the vertex is classified the same without w
-                    clip.x = padd(padd(pmul(M[0], world.x), pmul(M[4], world.y)), padd(pmul(M[8], world.z), M[12]));
-                    clip.y = padd(padd(pmul(M[1], world.x), pmul(M[5], world.y)), padd(pmul(M[9], world.z), M[13]));
-                    clip.z = padd(padd(pmul(M[2], world.x), pmul(M[6], world.y)), padd(pmul(M[10], world.z), M[14]));
-                    clip.w = 1.0f;
-                } else {
-                    clip = mat4_mul(M, world.x, world.y, world.z, 1.0f);
-                }
-                int sx = kVertOutside, sy = 0;
-                float z = 0.0f;
-                if (SHADOW || psub(clip.w, clip.z) >= 0.0f) {
-                    if (!project_snap(clip.x, clip.y, clip.z, clip.w, half_w, half_h, &sx, &sy, &z)) sx = kVertNonFinite;
-                }
-                sv.sx[v] = sx;
-                sv.sy[v] = sy;
-                sv.z[v] = z;
-                if (h.alpha) sv.w[v] = clip.w;
-                // first / last pixel per axis, saturated to int16 and packed (x low, y high) in one instruction each
-                sv.cover[v] = make_uint2(pack_sat_s16((sy + 127) >> 8, (sx + 127) >> 8), pack_sat_s16((sy - 128) >> 8, (sx - 128) >> 8));
-                if (sx == kVertOutside || sx == kVertNonFinite || !(z >= 0.0f)) {
-                    special = true;
-                } else {
-                    vminx = min(vminx, sx); vmaxx = max(vmaxx, sx);
-                    vminy = min(vminy, sy); vmaxy = max(vmaxy, sy);
-                    vnear = SHADOW ? min(vnear, __float_as_uint(z)) : max(vnear, __float_as_uint(z));
-                }
-            }
-            __syncwarp();
-
-            // ---- (1b) the same two early-outs with the exact vertex bounds: every triangle lies inside the vertices'
-            // rectangle, and (screen-linear depth) no fragment is nearer than the nearest vertex ----
-            const bool any_special = __any_sync(0xFFFFFFFFu, special);
-            if (!any_special) {
-                vminx = __reduce_min_sync(0xFFFFFFFFu, vminx); vmaxx = __reduce_max_sync(0xFFFFFFFFu, vmaxx);
-                vminy = __reduce_min_sync(0xFFFFFFFFu, vminy); vmaxy = __reduce_max_sync(0xFFFFFFFFu, vmaxy);
-                const int bx0 = max(0, (vminx - 128 + 255) >> 8), bx1 = min(W - 1, (vmaxx - 128) >> 8);
-                const int by0 = max(0, (vminy - 128 + 255) >> 8), by1 = min(H - 1, (vmaxy - 128) >> 8);
-                if (bx0 > bx1 || by0 > by1) {   // no pixel centre inside
-                    skipped_empty++;
-                    continue;
-                }
-                if (bx1 - bx0 < 8 && by1 - by0 < 4) {   // one 8x4 block: test the stored keys against the nearest vertex depth
-                    vnear = SHADOW ? __reduce_min_sync(0xFFFFFFFFu, vnear) : __reduce_max_sync(0xFFFFFFFFu, vnear);
-                    const float zn = __uint_as_float(vnear);
-                    // the interpolated depth can leave the vertices' range by rounding only: pad by a few ulp
-                    const float d = SHADOW ? zn - (4e-6f * zn + 1e-30f) : zn + (4e-6f * zn + 1e-30f);
-                    const int x = bx0 + (int)(lane & 7), y = by0 + (int)(lane >> 3);
-                    uint32_t worst = 0;
-                    if (x <= bx1 && y <= by1) {
-                        const size_t at = (size_t)y * W + x;
-                        worst = SHADOW ? __ldcg(tg.layer + at) : __ldcg((const uint32_t*)tg.vis + 2 * at + 1);
-                    }
-                    worst = __reduce_max_sync(0xFFFFFFFFu, worst);
-                    if (d > 0.0f && (SHADOW ? __float_as_uint(d) >= worst : worst < ~__float_as_uint(d))) {
-                        skipped_occluded++;
-                        continue;
-                    }
-                }
-            }
-
-            // ---- (2) triangle cull phase ----
-            uint32_t n_surv = 0;
-            const uint32_t screen_max = (uint32_t)(W - 1) | ((uint32_t)(H - 1) << 16);
-            for (uint32_t t0 = 0; t0 < h.tri_count; t0 += 32) {
-                const uint32_t t = t0 + lane;
-                bool keep = false;
-                if (t < h.tri_count) {
-                    const uint32_t i0 = __ldg(h.micro + 3 * t), i1 = __ldg(h.micro + 3 * t + 1), i2 = __ldg(h.micro + 3 * t + 2);
-                    if (max(i0, max(i1, i2)) < nv) {
-                        const uint32_t lo = ((P.slot_offset + local) << LH_VIS_TRI_BITS) | t;
-                        // facing test and routing of a triangle whose pixel rectangle [px0,px1] x [py0,py1] is not empty
-                        auto covered = [&](int px0, int px1, int py0, int py1) {
-                            const int ax = sv.sx[i0], bx = sv.sx[i1], cx = sv.sx[i2], ay = sv.sy[i0], by = sv.sy[i1], cy = sv.sy[i2];
-                            const int minx = min(ax, min(bx, cx)), maxx = max(ax, max(bx, cx));
-                            const int miny = min(ay, min(by, cy)), maxy = max(ay, max(by, cy));
-                            tris_done++;
-                            // exact in 32 bits when the sub-pixel extent is < 2^14 (every product < 2^28)
-                            const bool small_extent = (maxx - minx) < kSmallMaxExtent && (maxy - miny) < kSmallMaxExtent;
-                            const long long A2 = small_extent
-                                                     ? (long long)((bx - ax) * (cy - ay) - (by - ay) * (cx - ax))
-                                                     : (long long)(bx - ax) * (cy - ay) - (long long)(by - ay) * (cx - ax);
-                            const bool front = A2 < 0;
-                            if (A2 == 0 || (cull == CULL_BACK && !front) || (cull == CULL_FRONT && front)) return;
-                            const int spanx = px1 - px0 + 1, spany = py1 - py0 + 1;
-                            if (small_extent && spanx <= kSmallMaxSpan && spany <= kSmallMaxSpan && spanx * spany <= kSmallMaxArea) {
-                                keep = true;
-                            } else {
-                                // large footprint: one queue entry per 128x32 screen tile the bounding box touches
-                                const uint32_t tx0 = (uint32_t)px0 / kTileW, tx1 = (uint32_t)px1 / kTileW;
-                                const uint32_t ty0 = (uint32_t)py0 / kTileH, ty1 = (uint32_t)py1 / kTileH;
-                                if ((tx1 - tx0 + 1) * (ty1 - ty0 + 1) > 2) {
-                                    push_deferred(P, lo, kWholeTriangle);   // split by the deferred kernel, a warp per triangle
-                                } else {
-                                    for (uint32_t ty = ty0; ty <= ty1; ty++)
-                                        for (uint32_t tx = tx0; tx <= tx1; tx++) push_deferred(P, lo, tx | (ty << 16));
-                                }
-                            }
-                        };
-                        if (!any_special) {
-                            // the common case: every vertex is in front of the near plane and finite.  Rectangle by
-                            // halfword min/max of the per-vertex pixel bounds; most triangles end here (no sample inside).
-                            const uint2 c0 = sv.cover[i0], c1 = sv.cover[i1], c2 = sv.cover[i2];
-                            const uint32_t first = __vmaxs2(__vmins2(__vmins2(c0.x, c1.x), c2.x), 0u);
-                            const uint32_t last = __vmins2(__vmaxs2(__vmaxs2(c0.y, c1.y), c2.y), screen_max);
-                            if (__vcmpgts2(first, last) == 0u)
-                                covered((int)(first & 0xFFFFu), (int)(last & 0xFFFFu), (int)(first >> 16), (int)(last >> 16));
-                        } else {
-                            const int ax = sv.sx[i0], bx = sv.sx[i1], cx = sv.sx[i2];
-                            const int n_out = (ax == kVertOutside) + (bx == kVertOutside) + (cx == kVertOutside);
-                            if (n_out == 0) {
-                                if (ax != kVertNonFinite && bx != kVertNonFinite && cx != kVertNonFinite) {
-                                    const int ay = sv.sy[i0], by = sv.sy[i1], cy = sv.sy[i2];
-                                    const int minx = min(ax, min(bx, cx)), maxx = max(ax, max(bx, cx));
-                                    const int miny = min(ay, min(by, cy)), maxy = max(ay, max(by, cy));
-                                    const int px0 = max(0, (minx - 128 + 255) >> 8), px1 = min(W - 1, (maxx - 128) >> 8);
-                                    const int py0 = max(0, (miny - 128 + 255) >> 8), py1 = min(H - 1, (maxy - 128) >> 8);
-                                    if (px0 <= px1 && py0 <= py1) covered(px0, px1, py0, py1);
-                                }
-                            } else if (n_out < 3) {
-                                push_deferred(P, lo, kWholeTriangle);   // crosses the near plane: generic path
-                            }
-                        }
-                    }
-                }
-                const uint32_t ballot = __ballot_sync(0xFFFFFFFFu, keep);
-                if (keep) sv.surv[n_surv + __popc(ballot & ((1u << lane) - 1u))] = (uint8_t)t;
-                n_surv += __popc(ballot);
-            }
-            __syncwarp();
-
-            // ---- (3) raster phase over the compacted survivors ----
-            for (uint32_t s = lane; s < n_surv; s += 32) {
-                const uint32_t t = sv.surv[s];
-                const uint32_t lo = ((P.slot_offset + local) << LH_VIS_TRI_BITS) | t;
-                uint32_t ia = __ldg(h.micro + 3 * t), ib = __ldg(h.micro + 3 * t + 1), ic = __ldg(h.micro + 3 * t + 2);
-                int ax = sv.sx[ia], ay = sv.sy[ia], bx = sv.sx[ib], by = sv.sy[ib], cx = sv.sx[ic], cy = sv.sy[ic];
-                const int minx = min(ax, min(bx, cx)), maxx = max(ax, max(bx, cx));
-                const int miny = min(ay, min(by, cy)), maxy = max(ay, max(by, cy));
-                const int px0 = max(0, (minx - 128 + 255) >> 8), px1 = min(W - 1, (maxx - 128) >> 8);
-                const int py0 = max(0, (miny - 128 + 255) >> 8), py1 = min(H - 1, (maxy - 128) >> 8);
-                int A2 = (bx - ax) * (cy - ay) - (by - ay) * (cx - ax);
-                float az = sv.z[ia], bz = sv.z[ib], cz = sv.z[ic];
-                if (A2 < 0) {
-                    int t0 = bx; bx = cx; cx = t0;
-                    t0 = by; by = cy; cy = t0;
-                    float tz = bz; bz = cz; cz = tz;
-                    const uint32_t ti = ib; ib = ic; ic = ti;
-                    A2 = -A2;
-                }
-                const int e0x = cx - bx, e0y = cy - by, e1x = ax - cx, e1y = ay - cy, e2x = bx - ax, e2y = by - ay;
-                const int bias0 = top_left(e0x, e0y) ? 0 : -1, bias1 = top_left(e1x, e1y) ? 0 : -1, bias2 = top_left(e2x, e2y) ? 0 : -1;
-                const float fA = (float)A2;
-                const float inv_area = pdiv(1.0f, fA);
-                const float dz1 = psub(bz, az), dz2 = psub(cz, az);
-                const int ccx = px0 * 256 + 128, ccy = py0 * 256 + 128;
-                int w0_row = e0x * (ccy - by) - e0y * (ccx - bx);
-                int w1_row = e1x * (ccy - cy) - e1y * (ccx - cx);
-                int w2_row = e2x * (ccy - ay) - e2y * (ccx - ax);
-                SnapVert A, B, C;
-                if (at.enabled) {
-                    // perspective-correct uv needs the clip w and the vertex uvs
-                    const uint32_t ids[3] = {ia, ib, ic};
-                    SnapVert* out[3] = {&A, &B, &C};
-                    for (int q = 0; q < 3; q++) {
-                        const uint32_t idx = load_vertex_index(h, ids[q]);
-                        out[q]->w = sv.w[ids[q]];
-                        out[q]->u = padd(pmul((float)__ldg(h.uvs + 2 * (size_t)idx), h.tex_scale[0]), h.tex_offset[0]);
-                        out[q]->v = padd(pmul((float)__ldg(h.uvs + 2 * (size_t)idx + 1), h.tex_scale[1]), h.tex_offset[1]);
-                    }
-                }
-                for (int py = py0; py <= py1; py++) {
-                    int w0 = w0_row, w1 = w1_row, w2 = w2_row;
-                    for (int px = px0; px <= px1; px++) {
-                        if (((w0 + bias0) | (w1 + bias1) | (w2 + bias2)) >= 0) {
-                            if (!(at.enabled && alpha_discard(at, (float)w0, (float)w1, (float)w2, fA, A, B, C))) {
-                                float z = padd(az, pmul(padd(pmul((float)w1, dz1), pmul((float)w2, dz2)), inv_area));
-                                tg.emit(px, py, z, lo);
-                            }
-                        }
-                        w0 -= e0y * 256;
-                        w1 -= e1y * 256;
-                        w2 -= e2y * 256;
-                    }
-                    w0_row += e0x * 256;
-                    w1_row += e1x * 256;
-                    w2_row += e2x * 256;
-                }
-            }
+        for (int j = 0; j < kChunk; j++) {
+            if ((uint32_t)j >= n_cur) break;
+            const RasterRecord& rec = sv.rec[slot][j];
+            const uint8_t* micro = &sv.micro[aux][j][0] + ((uintptr_t)rec.micro & 15u);
+            const uint8_t* index = &sv.index[aux][j][0] + ((uintptr_t)rec.indices & 15u);
+            if ((rec.counts_flags >> 16) & LH_MESH_INFO_FLAGS_ALPHA_CLIP)
+                raster_one_meshlet<SHADOW, true>(P, tg, sv, rec, &sv.T[aux][j][0], micro, index, keys_cur[j], M, affine, cnt);
+            else
+                raster_one_meshlet<SHADOW, false>(P, tg, sv, rec, &sv.T[aux][j][0], micro, index, keys_cur[j], M, affine, cnt);
             __syncwarp();
         }
+        n_cur = n_next;
+        n_next = n_after;
+#pragma unroll
+        for (int j = 0; j < kChunk; j++) keys_cur[j] = keys_next[j];
     }
     if (P.flags & LH_CONFIG_PASS_TIMINGS) {
-        tris_done = __reduce_add_sync(0xFFFFFFFFu, tris_done);
+        const uint32_t tris_done = __reduce_add_sync(0xFFFFFFFFu, cnt.tris_done);
         if (lane == 0) {
             const uint32_t pass = SHADOW ? 1u + cascade : 0u;
             if (tris_done && !SHADOW) atomicAdd(&P.state->rasterized_triangles, (unsigned long long)tris_done);
-            if (skipped_occluded) atomicAdd(&P.state->skipped_occluded[pass], skipped_occluded);
-            if (skipped_empty) atomicAdd(&P.state->skipped_empty[pass], skipped_empty);
+            if (cnt.skipped_occluded) atomicAdd(&P.state->skipped_occluded[pass], cnt.skipped_occluded);
+            if (cnt.skipped_empty) atomicAdd(&P.state->skipped_empty[pass], cnt.skipped_empty);
         }
     }
     publish_queue_end(&P.pass->cta_done, &P.pass->large_count, &P.pass->drain_end[band + 1], P.max_large);
@@ -961,7 +1079,7 @@ __global__ void __launch_bounds__(kDeferredWarps * 32) raster_deferred_kernel(co
                 const uint32_t local = (lo >> LH_VIS_TRI_BITS) - P.slot_offset, t = lo & LH_VIS_TRI_MASK;
                 MeshletHeader h;
                 load_header(P, local, h);
-                const AlphaTest at = make_alpha_test(P, h);
+                const AlphaTest at = make_alpha_test(P, h.alpha, h.base_color_texture);
                 ClipVert v[3];
                 for (int q = 0; q < 3; q++) {
                     const uint32_t mi = __ldg(h.micro + 3 * t + q);

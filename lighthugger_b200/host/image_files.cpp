@@ -38,6 +38,7 @@ constexpr uint32_t kDdsCaps2Cubemap = 0x200;
 constexpr uint32_t kDxgiR9G9B9E5 = 67, kDxgiBc1Unorm = 71, kDxgiBc1UnormSrgb = 72, kDxgiBc7Unorm = 98, kDxgiBc7UnormSrgb = 99;
 constexpr uint32_t kDxgiRgba8Unorm = 28, kDxgiRgba8UnormSrgb = 29;
 constexpr uint32_t kD3d10Texture2d = 3, kD3d10Texture3d = 4;
+constexpr uint32_t kMaxDimension = 65536;   // per axis; larger headers are rejected before any size arithmetic
 
 bool dxgi_format(uint32_t dxgi, LhImageInfo* info) {
     switch (dxgi) {
@@ -72,6 +73,8 @@ int parse_dds(Reader& r, LhImageInfo* info) {
     else if (dimension == kD3d10Texture3d) info->dimension = 3;
     else return LH_IMAGE_ERR_FORMAT;
     if (info->width == 0 || info->height == 0 || info->levels > LH_IMAGE_MAX_LEVELS) return LH_IMAGE_ERR_FORMAT;
+    // dimensions a GPU can bind; also keeps the 64-bit size products below from wrapping (four 32-bit header fields)
+    if (info->width > kMaxDimension || info->height > kMaxDimension || info->depth > kMaxDimension || info->faces > 6) return LH_IMAGE_ERR_FORMAT;
     uint64_t offset = data_offset;
     for (uint32_t l = 0; l < info->levels; l++) {
         LhImageLevel& level = info->levels_info[l];
@@ -133,6 +136,7 @@ int parse_ktx2(Reader& r, LhImageInfo* info) {
     info->dimension = info->depth > 1 ? 3 : 2;
     if (info->width == 0 || info->levels > LH_IMAGE_MAX_LEVELS || (info->faces != 1 && info->faces != 6)) return LH_IMAGE_ERR_FORMAT;
     if (r.size < kKtx2Levels + 24ull * info->levels) return LH_IMAGE_ERR_TRUNCATED;
+    if (info->width > kMaxDimension || info->height > kMaxDimension || info->depth > kMaxDimension || info->faces > 6) return LH_IMAGE_ERR_FORMAT;
     for (uint32_t l = 0; l < info->levels; l++) {
         LhImageLevel& level = info->levels_info[l];
         level.offset = r.at<uint64_t>(kKtx2Levels + 24ull * l);

@@ -84,6 +84,8 @@ int lh_meshlet_cache_load(const char* dir, const char* primitive_name, uint32_t 
         memcpy(&m, blobs->meshlets.data() + i * sizeof(LhMeshlet), sizeof(m));
         sane = m.triangle_count <= LH_MAX_MESHLET_TRIANGLES && m.index_count <= LH_MAX_MESHLET_UNIQUE_VERTICES &&
                (uint64_t)m.index_offset + m.index_count <= n_idx && (uint64_t)m.triangle_offset + 3ull * m.triangle_count <= blobs->micro.size();
+        // every micro index names one of the meshlet's own vertices (the kernels index per-meshlet arrays with them)
+        for (uint32_t k = 0; sane && k < 3u * m.triangle_count; k++) sane = blobs->micro[m.triangle_offset + k] < m.index_count;
     }
     if (!sane) {
         delete blobs;

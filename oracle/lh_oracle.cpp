@@ -527,6 +527,21 @@ int lho_test_cull_sphere_shadows(const LhUniforms* u, const LhInstance* inst, co
 int lho_test_cull_cone_perspective(const LhUniforms* u, const LhInstance* inst, const LhMeshlet* m) { return lho::cull_cone_perspective(u, inst, m) ? 1 : 0; }
 int lho_test_cull_cone_orthographic(const LhUniforms* u, const LhInstance* inst, const LhMeshlet* m) { return lho::cull_cone_orthographic(u, inst, m) ? 1 : 0; }
 
+// clip-space positions the oracle's rasteriser starts from for the draw in `slot`: 3 * triangle_count vertices in draw
+// order (what the reference's vertex shader sees as gl_VertexIndex).  cascade < 0: the main view.  Returns the count.
+uint32_t lho_test_clip_positions(const LhUniforms* u, int cascade, uint32_t slot, float* out) {
+    const LhMeshletReference* refs = (const LhMeshletReference*)(uintptr_t)u->meshlet_references;
+    const LhInstance* inst = (const LhInstance*)(uintptr_t)u->instances + refs[slot].instance_index;
+    const LhMeshInfo* mi = (const LhMeshInfo*)(uintptr_t)inst->mesh_info_address;
+    const LhMeshlet* m = (const LhMeshlet*)(uintptr_t)mi->meshlets + refs[slot].meshlet_index;
+    const LhMiscStorage* misc = (const LhMiscStorage*)(uintptr_t)u->misc_storage;
+    lho::V4 clip[256];
+    lho::transform_meshlet_vertices(inst, mi, m, cascade < 0 ? u->combined_perspective_view : misc->shadow_matrices[cascade], clip, nullptr);
+    const uint8_t* micro = (const uint8_t*)(uintptr_t)mi->micro_indices + m->triangle_offset;
+    for (uint32_t k = 0; k < 3u * m->triangle_count; k++) memcpy(out + 4 * k, &clip[micro[k]], 16);
+    return 3u * m->triangle_count;
+}
+
 float lho_pinned_powf(float xf, float pf) {
     if (!(xf > 0.0f)) return xf == 0.0f ? 0.0f : NAN;
     double x = (double)xf;

@@ -91,6 +91,8 @@ int lho_test_cull_sphere_shadows(const LhUniforms* u, const LhInstance* inst, co
 int lho_test_cull_cone_perspective(const LhUniforms* u, const LhInstance* inst, const LhMeshlet* m);
 int lho_test_cull_cone_orthographic(const LhUniforms* u, const LhInstance* inst, const LhMeshlet* m);
 
+uint32_t lho_test_clip_positions(const LhUniforms* u, int cascade, uint32_t slot, float* out_xyzw);
+
 /* pinned pow used by generate_shadow_matrices (double arithmetic, identical op sequence on host and device) */
 float lho_pinned_powf(float x, float p);
 

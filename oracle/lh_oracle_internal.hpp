@@ -82,6 +82,13 @@ void transform_meshlet_vertices(const LhInstance* inst, const LhMeshInfo* mi, co
 // bilinear, level `lod` (clamped), repeat addressing; returns linear RGBA
 void sample_texture_lod(const LhoTexture& t, float u, float v, float lod, float out[4]);
 
+// textureGrad through repeat_sampler (trilinear, anisotropy 16), textureLod(samplerCube, ., 0), and one tap of
+// sampler2DArrayShadow + shadowmap_comparison_sampler; also what the reference's GLSL is given as its texture unit
+// when it runs on the host (oracle/ref_shim/)
+void sample_texture_grad(const LhoTexture& t, const float uv[2], const float dx[2], const float dy[2], float out[4]);
+void sample_skybox(const LhoConfig* cfg, V3 d, float out[3]);
+float sample_shadow(const float* layer, uint32_t n, float u, float v, float ref);
+
 struct AlphaTest {
     bool enabled;
     const LhoTexture* texture;

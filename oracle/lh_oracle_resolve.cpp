@@ -26,6 +26,12 @@ static float srgb_to_linear(uint8_t v) {
     return table[v];
 }
 
+// Sub-texel precision of the bilinear weights: 8 bits, round to nearest.  Vulkan leaves it implementation-defined
+// (VkPhysicalDeviceLimits::subTexelPrecisionBits); the model pins what the B200 texture unit does, measured with
+// tools/texfilter_probe.cu: the weight of the right-hand texel is round(frac * 256) / 256 (257 distinct values, steps
+// at (k + 0.5) / 256).  Applied wherever the device filters in the texture unit: material textures, skybox, display LUT.
+static inline float snap_subtexel(float x) { return floorf(x * 256.0f + 0.5f) * (1.0f / 256.0f); }
+
 static void fetch_texel(const LhoTexture& t, uint32_t level, int x, int y, float out[4]) {
     uint32_t w = std::max(1u, t.width >> level), h = std::max(1u, t.height >> level);
     const uint8_t* base = t.rgba8;
@@ -39,7 +45,7 @@ static void fetch_texel(const LhoTexture& t, uint32_t level, int x, int y, float
 
 static void sample_bilinear_level(const LhoTexture& t, float u, float v, uint32_t level, float out[4]) {
     uint32_t w = std::max(1u, t.width >> level), h = std::max(1u, t.height >> level);
-    float x = u * (float)w - 0.5f, y = v * (float)h - 0.5f;
+    float x = snap_subtexel(u * (float)w - 0.5f), y = snap_subtexel(v * (float)h - 0.5f);
     float fx = floorf(x), fy = floorf(y);
     float ax = x - fx, ay = y - fy;
     int x0 = (int)fx, y0 = (int)fy;
@@ -74,7 +80,7 @@ void sample_texture_lod(const LhoTexture& t, float u, float v, float lod, float 
 // textureGrad with the reference's repeat_sampler: trilinear, anisotropy 16.
 // The Vulkan spec's anisotropic model: N = min(ceil(Pmax/Pmin), 16) probes
 // along the major axis, lod = log2(Pmax / N).
-static void sample_texture_grad(const LhoTexture& t, const float uv[2], const float dx[2], const float dy[2], float out[4]) {
+void sample_texture_grad(const LhoTexture& t, const float uv[2], const float dx[2], const float dy[2], float out[4]) {
     float w = (float)t.width, h = (float)t.height;
     float ax[2] = {dx[0] * w, dx[1] * h}, ay[2] = {dy[0] * w, dy[1] * h};
     float px = sqrtf(ax[0] * ax[0] + ax[1] * ax[1]), py = sqrtf(ay[0] * ay[0] + ay[1] * ay[1]);
@@ -99,7 +105,7 @@ static void sample_texture_grad(const LhoTexture& t, const float uv[2], const fl
 }
 
 // textureLod(samplerCube, ray, 0): bilinear inside the selected face
-static void sample_skybox(const LhoConfig* cfg, V3 d, float out[3]) {
+void sample_skybox(const LhoConfig* cfg, V3 d, float out[3]) {
     if (!cfg->skybox || cfg->skybox_size == 0) {
         out[0] = out[1] = out[2] = 0.0f;
         return;
@@ -116,7 +122,7 @@ static void sample_skybox(const LhoConfig* cfg, V3 d, float out[3]) {
     }
     uint32_t n = cfg->skybox_size;
     float u = 0.5f * (sc / ma + 1.0f), v = 0.5f * (tc / ma + 1.0f);
-    float x = u * (float)n - 0.5f, y = v * (float)n - 0.5f;
+    float x = snap_subtexel(u * (float)n - 0.5f), y = snap_subtexel(v * (float)n - 0.5f);
     float fx = floorf(x), fy = floorf(y), wx = x - fx, wy = y - fy;
     auto tex = [&](int xi, int yi, int c) {
         xi = std::min(std::max(xi, 0), (int)n - 1);
@@ -132,7 +138,7 @@ static void sample_skybox(const LhoConfig* cfg, V3 d, float out[3]) {
 
 // sampler2DArrayShadow + shadowmap_comparison_sampler (src/main.cpp:569-581):
 // 4 texels, each compared `ref < texel`, bilinearly weighted, clamp to edge.
-static float sample_shadow(const float* layer, uint32_t n, float u, float v, float ref) {
+float sample_shadow(const float* layer, uint32_t n, float u, float v, float ref) {
     float x = u * (float)n - 0.5f, y = v * (float)n - 0.5f;
     float fx = floorf(x), fy = floorf(y), wx = x - fx, wy = y - fy;
     auto cmp = [&](int xi, int yi) {

@@ -20,7 +20,18 @@
 #include <glm/gtc/type_precision.hpp>
 #undef _MSC_EXTENSIONS
 
-#include <shared_cpu_gpu.h>   // the reference's own header, C++ side (-I$(REF)/src); brings `using namespace glm`
+// The reference's own src/shared_cpu_gpu.h, GLSL side (through the filter, which only drops its #include of
+// hlsl4glsl.glsl): the structs are then plain aggregates, as GLSL sees them (the C++ side gives Instance a constructor
+// and no default one, which GLSL code such as `VertexData vertex_data;` cannot live with).  Layouts are identical
+// (tests/test_ref_shaders.py compares the sizes with the C++ side's).
+using namespace glm;
+#define GLSL 1
+#include "gen/shared_cpu_gpu.h"
+#undef GLSL
+
+#include <functional>
+#include "lh_oracle.h"
+#include "lh_oracle_internal.hpp"   // the samplers that stand in for the texture unit
 
 namespace glm {
 // ---- swizzle proxies in generic functions: forward to the vector they stand for ----
@@ -32,10 +43,6 @@ SHIM_UNARY(length)
 SHIM_UNARY(normalize)
 SHIM_UNARY(abs)
 #undef SHIM_UNARY
-SHIM_SWZ inline vec<N, T, Q> operator-(SHIM_SWZ_T const& s, T b) { return s() - b; }
-SHIM_SWZ inline vec<N, T, Q> operator+(SHIM_SWZ_T const& s, T b) { return s() + b; }
-SHIM_SWZ inline vec<N, T, Q> operator*(SHIM_SWZ_T const& s, T b) { return s() * b; }
-SHIM_SWZ inline vec<N, T, Q> operator/(SHIM_SWZ_T const& s, T b) { return s() / b; }
 #undef SHIM_SWZ
 #undef SHIM_SWZ_T
 
@@ -149,8 +156,131 @@ template <class T>
 inline T atomicMin(T& mem, T v) { T old = mem; mem = v < old ? v : old; return old; }
 template <class T>
 inline T atomicMax(T& mem, T v) { T old = mem; mem = v > old ? v : old; return old; }
+inline uint64_t clockARB() { return 0; }
+template <class T>
+inline T nonuniformEXT(T v) { return v; }
+inline void shim_discard() {}
 inline uint32_t subgroupMin(uint32_t v) { return v; }
 inline uint32_t subgroupMax(uint32_t v) { return v; }
 inline bool subgroupElect() { return true; }
+
+
+// ---- descriptors (src/shaders/common/bindings.glsl:7-25): what the texture unit of a device would do is done by the
+// ---- oracle's samplers (oracle/lh_oracle_internal.hpp); the reference's GLSL decides WHAT is sampled and how it is used
+struct ShimFrame {
+    const LhoConfig* cfg = nullptr;       // textures + skybox
+    const uint64_t* vis = nullptr;        // packed keys: depth = ~hi32, lo = slot << 7 | triangle
+    const float* shadow = nullptr;        // 4 layers
+    uint32_t width = 0, height = 0, shadow_size = 0;
+    float* scene_out = nullptr;           // rw_scene_referred_framebuffer (RGBA32F)
+    const float* scene_in = nullptr;      // scene_referred_framebuffer
+    const float* lut = nullptr;           // display_transform_lut: size^3 RGB32F
+    uint32_t lut_size = 0;
+    float* swapchain_out = nullptr;       // swapchain_image (RGBA32F, before the UNORM conversion)
+};
+inline thread_local ShimFrame shim_frame;
+
+struct sampler { int id; };
+inline const sampler clamp_sampler{0}, repeat_sampler{1}, shadowmap_comparison_sampler{2};
+struct texture2D { int id; uint32_t index; };          // id 0: textures[index], 1: depth_buffer, 2: scene_referred_framebuffer
+struct utexture2D { int id; };
+struct texture2DArray { int id; };
+struct texture3D { int id; };
+struct textureCube { int id; };
+struct image2D { int id; };                            // 0: rw_scene_referred_framebuffer, 1: swapchain_image
+struct TextureTable { texture2D operator[](uint32_t i) const { return texture2D{0, i}; } };
+inline const TextureTable textures;
+inline const texture2D scene_referred_framebuffer{2, 0}, depth_buffer{1, 0};
+inline const utexture2D visibility_buffer{0};
+inline const texture2DArray shadowmap{0};
+inline const texture3D display_transform_lut{0};
+inline const textureCube skybox{0};
+inline const image2D rw_scene_referred_framebuffer{0}, swapchain_image{1};
+struct sampler2D { texture2D t; sampler s; sampler2D(texture2D t_, sampler s_) : t(t_), s(s_) {} };
+struct sampler2DArray { sampler2DArray(texture2DArray, sampler) {} };
+struct sampler2DArrayShadow { sampler2DArrayShadow(texture2DArray, sampler) {} };
+struct sampler3D { sampler3D(texture3D, sampler) {} };
+struct samplerCube { samplerCube(textureCube, sampler) {} };
+
+inline float shim_depth_at(int x, int y) {   // D32F: the float whose bits are ~hi32 of the key (0 where nothing was drawn)
+    const uint64_t key = shim_frame.vis[(size_t)y * shim_frame.width + x];
+    return uintBitsToFloat(~(uint32_t)(key >> 32));
+}
+inline vec4 texelFetch(texture2D t, ivec2 c, int) {
+    if (t.id == 1) return vec4(shim_depth_at(c.x, c.y), 0, 0, 0);
+    const float* p = shim_frame.scene_in + ((size_t)c.y * shim_frame.width + c.x) * 4;
+    return vec4(p[0], p[1], p[2], p[3]);
+}
+inline uvec4 texelFetch(utexture2D, ivec2 c, int) {   // R32_UINT: triangle << 24 | slot (util.glsl:18-20)
+    const uint32_t lo = (uint32_t)shim_frame.vis[(size_t)c.y * shim_frame.width + c.x];
+    return uvec4(((lo & 0x7Fu) << 24) | (lo >> 7), 0, 0, 0);
+}
+// textureGather(depth_buffer + clamp_sampler): texels (i0,j1), (i1,j1), (i1,j0), (i0,j0) around the sample position
+inline vec4 textureGather(sampler2D, vec2 uv) {
+    const int W = (int)shim_frame.width, H = (int)shim_frame.height;
+    const float x = uv.x * (float)W - 0.5f, y = uv.y * (float)H - 0.5f;
+    auto cx = [&](int v) { return v < 0 ? 0 : (v > W - 1 ? W - 1 : v); };
+    auto cy = [&](int v) { return v < 0 ? 0 : (v > H - 1 ? H - 1 : v); };
+    const int i0 = (int)std::floor(x), j0 = (int)std::floor(y);
+    return vec4(shim_depth_at(cx(i0), cy(j0 + 1)), shim_depth_at(cx(i0 + 1), cy(j0 + 1)), shim_depth_at(cx(i0 + 1), cy(j0)), shim_depth_at(cx(i0), cy(j0)));
+}
+inline vec4 textureGrad(sampler2D s, vec2 uv, vec2 dx, vec2 dy) {
+    const LhoConfig* cfg = shim_frame.cfg;
+    if (!cfg || !cfg->textures || s.t.index >= cfg->num_textures) return vec4(1, 1, 1, 1);   // an unbound slot (the oracle's convention)
+    float out[4];
+    lho::sample_texture_grad(cfg->textures[s.t.index], &uv.x, &dx.x, &dy.x, out);
+    return vec4(out[0], out[1], out[2], out[3]);
+}
+inline vec4 textureLod(samplerCube, vec3 dir, float) {
+    float out[3];
+    lho::sample_skybox(shim_frame.cfg, lho::V3{dir.x, dir.y, dir.z}, out);
+    return vec4(out[0], out[1], out[2], 1.0f);
+}
+inline float texture(sampler2DArrayShadow, vec4 c) {   // (u, v, layer, reference depth); the layer index is clamped
+    const uint32_t n = shim_frame.shadow_size;
+    int layer = (int)std::floor(c.z + 0.5f);
+    layer = layer < 0 ? 0 : (layer > 3 ? 3 : layer);
+    return lho::sample_shadow(shim_frame.shadow + (size_t)layer * n * n, n, c.x, c.y, c.w);
+}
+inline vec4 textureLod(sampler2DArray, vec3 c, float) {   // display_transform's debug overlay: nearest layer, bilinear, clamp
+    const uint32_t n = shim_frame.shadow_size;
+    int layer = (int)std::floor(c.z + 0.5f);
+    layer = layer < 0 ? 0 : (layer > 3 ? 3 : layer);
+    const float* L = shim_frame.shadow + (size_t)layer * n * n;
+    const float x = c.x * (float)n - 0.5f, y = c.y * (float)n - 0.5f, fx = std::floor(x), fy = std::floor(y), wx = x - fx, wy = y - fy;
+    auto at = [&](int xi, int yi) { xi = xi < 0 ? 0 : (xi > (int)n - 1 ? (int)n - 1 : xi); yi = yi < 0 ? 0 : (yi > (int)n - 1 ? (int)n - 1 : yi); return L[(size_t)yi * n + xi]; };
+    const float top = at((int)fx, (int)fy) + wx * (at((int)fx + 1, (int)fy) - at((int)fx, (int)fy));
+    const float bot = at((int)fx, (int)fy + 1) + wx * (at((int)fx + 1, (int)fy + 1) - at((int)fx, (int)fy + 1));
+    return vec4(top + wy * (bot - top));
+}
+// textureLod(display_transform_lut + clamp_sampler): trilinear, clamp to edge
+inline vec4 textureLod(sampler3D, vec3 uvw, float) {
+    const int n = (int)shim_frame.lut_size;
+    const float* L = shim_frame.lut;
+    float f[3];
+    int i0[3], i1[3];
+    for (int a = 0; a < 3; a++) {
+        const float x = uvw[a] * (float)n - 0.5f, fl = std::floor(x);
+        f[a] = x - fl;
+        const int i = (int)fl;
+        i0[a] = i < 0 ? 0 : (i > n - 1 ? n - 1 : i);
+        i1[a] = i + 1 < 0 ? 0 : (i + 1 > n - 1 ? n - 1 : i + 1);
+    }
+    vec3 r(0.0f);
+    for (int c = 0; c < 3; c++) {
+        auto at = [&](int x, int y, int z) { return L[(((size_t)z * n + y) * n + x) * 3 + c]; };
+        const float x00 = at(i0[0], i0[1], i0[2]) + f[0] * (at(i1[0], i0[1], i0[2]) - at(i0[0], i0[1], i0[2]));
+        const float x10 = at(i0[0], i1[1], i0[2]) + f[0] * (at(i1[0], i1[1], i0[2]) - at(i0[0], i1[1], i0[2]));
+        const float x01 = at(i0[0], i0[1], i1[2]) + f[0] * (at(i1[0], i0[1], i1[2]) - at(i0[0], i0[1], i1[2]));
+        const float x11 = at(i0[0], i1[1], i1[2]) + f[0] * (at(i1[0], i1[1], i1[2]) - at(i0[0], i1[1], i1[2]));
+        const float y0 = x00 + f[1] * (x10 - x00), y1 = x01 + f[1] * (x11 - x01);
+        r[c] = y0 + f[2] * (y1 - y0);
+    }
+    return vec4(r, 1.0f);
+}
+inline void imageStore(image2D img, ivec2 c, vec4 v) {
+    float* dst = (img.id == 0 ? shim_frame.scene_out : shim_frame.swapchain_out) + ((size_t)c.y * shim_frame.width + c.x) * 4;
+    dst[0] = v.x; dst[1] = v.y; dst[2] = v.z; dst[3] = v.w;
+}
 
 }  // namespace refsh

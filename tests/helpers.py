@@ -139,3 +139,29 @@ def vis_fields(vis):
     depth = (~(vis >> np.uint64(32))).astype(np.uint32)
     lo = (vis & np.uint64(0xFFFFFFFF)).astype(np.uint32)
     return depth, lo >> 7, lo & 0x7F
+
+
+def display(c):
+    """The display transfer the colour tolerance is stated after: Reinhard-style compression, then the sRGB OETF."""
+    c = np.clip(np.asarray(c, np.float64), 0, None)
+    c = c / (1 + c)
+    return np.where(c <= 0.0031308, 12.92 * c, 1.055 * np.power(c, 1 / 2.4) - 0.055)
+
+
+# SURVEY 8c: |delta| <= 2/255 per channel after the display transfer on >= 99.9 % of pixels, <= 8/255 on the rest
+COLOR_FRAC_TOL, COLOR_TIGHT, COLOR_LOOSE = 0.001, 2 / 255, 8 / 255
+
+
+def compare_color(ctx, o, frac_tol=COLOR_FRAC_TOL, tight=COLOR_TIGHT, loose=COLOR_LOOSE, ignore=None):
+    """Lit colour of the CUDA frame against the oracle's.  ignore: pixel indices whose visibility differs (alpha-clip
+    raster tie pixels), which shade a different triangle by construction."""
+    got = ctx.target(S.LH_TARGET_SCENE_RGBA16F).astype(np.float32).reshape(-1, 4)
+    want = o.color.reshape(-1, 4)
+    assert np.isfinite(got).all() and (got[:, 3] == 1).all()
+    d = np.abs(display(got[:, :3]) - display(want[:, :3])).max(axis=1)
+    if ignore is not None and len(ignore):
+        d[ignore] = 0.0
+    bad = np.count_nonzero(d > tight) / len(d)
+    assert bad <= frac_tol, f"{bad:.4%} of pixels differ by more than {tight * 255:.0f}/255 (max {d.max() * 255:.2f}/255)"
+    assert d.max() <= loose, f"maximum error {d.max() * 255:.2f}/255 exceeds {loose * 255:.0f}/255"
+    return bad, float(d.max())

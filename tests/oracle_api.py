@@ -110,10 +110,16 @@ class Oracle:
         return self._call("lho_resolve", self.vis.ctypes.data, self.shadow.ctypes.data, self.color.ctypes.data)
 
     def render_frame(self, resolve=True):
+        """Steps 1-11 of rendering.cpp, pass by pass (so the main view's draw counts can be noted before the cascades
+        reuse the counters)."""
+        self.reset(); self.cull_instances(); self.cull_meshlets()
+        self.main_draw_counts = self.draw_counts()
+        self.raster_visbuffer(); self.reduce_depth(); self.generate_shadow_matrices(); self.cull_instances_shadows()
+        for c in range(4):
+            self.shadow_cascade(c)
         if resolve:
-            self.color = np.zeros(self.width * self.height * 4, np.float32)
-        return self._call("lho_render_frame", self.vis.ctypes.data, self.shadow.ctypes.data,
-                          self.color.ctypes.data if resolve else None)
+            self.resolve()
+        return 0
 
     # ---- views into the host-bound pipeline buffers ----
     def sector(self, cascade=0):

@@ -194,3 +194,104 @@ def test_cull_functions_match_the_reference_on_random_inputs():
             kept[k] += want[k] == 0
     assert flips.sum() == 0, f"decisions differing from the reference's GLSL: {flips.tolist()} of {N}"
     assert np.all(kept > N // 100) and np.all(kept < N - N // 100), f"both outcomes must be exercised: kept {kept.tolist()}"
+
+
+# ---- stage 2: vertex shaders, depth reduction, lighting resolve ----
+
+def _stage2_lib():
+    from oracle_api import LhoConfig
+    lib = ref_lib()
+    K = C.POINTER(LhoConfig)
+    fp = C.POINTER(C.c_float)
+    lib.ref_sh_vertex.argtypes = [U, C.c_int, C.c_uint32, C.c_uint32, fp]
+    lib.ref_sh_vertex.restype = C.c_uint32
+    lib.ref_sh_vertex_alpha_clip.argtypes = [U, C.c_int, C.c_uint32, C.c_uint32, fp, fp]
+    lib.ref_sh_vertex_alpha_clip.restype = C.c_uint32
+    lib.ref_sh_read_depth.argtypes = [U, K, C.c_void_p]
+    lib.ref_sh_read_depth.restype = None
+    lib.ref_sh_render_geometry.argtypes = [U, K, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32]
+    lib.ref_sh_render_geometry.restype = None
+    return lib
+
+
+@pytest.mark.parametrize("preset", ["tiny", "rotated", "c4small"])
+def test_vertex_shaders_match_the_oracle_vertex_transform(preset):
+    """gl_Position of the reference's vertex shaders (rasterization.glsl:12-50,101-135) for every vertex of a sample of the
+    surviving meshlets, main view and one cascade, against the clip positions the oracle's rasteriser starts from."""
+    from oracle_api import oracle_lib
+    lib, orc = _stage2_lib(), oracle_lib()
+    orc.lho_test_clip_positions.argtypes = [U, C.c_int, C.c_uint32, C.POINTER(C.c_float)]
+    orc.lho_test_clip_positions.restype = C.c_uint32
+    sc, kw = _scene(preset)
+    o = make_oracle(sc, caps=reference_caps(), **kw)
+    o.reset(); o.cull_instances(); o.cull_meshlets()
+    o.raster_visbuffer(); o.reduce_depth(); o.generate_shadow_matrices(); o.cull_instances_shadows()
+    n_main = o.draw_counts()
+    checked = 0
+    pos = (C.c_float * 4)()
+    uv = (C.c_float * 2)()
+    buf = (C.c_float * (4 * 3 * 255))()
+    rng = np.random.default_rng(7)
+
+    def check(cascade, first_slot, n_op, n_al):
+        nonlocal checked
+        slots = [first_slot + int(s) for s in rng.choice(n_op, min(n_op, 60), replace=False)] if n_op else []
+        slots += [first_slot + o.cfg.max_opaque_draws + int(s) for s in rng.choice(n_al, min(n_al, 30), replace=False)] if n_al else []
+        for slot in slots:
+            nverts = orc.lho_test_clip_positions(C.byref(o.u), cascade, slot, buf)   # 3 * triangle_count positions, draw order
+            want = np.frombuffer(buf, np.float32, 4 * nverts).reshape(-1, 4)
+            alpha = slot - first_slot >= o.cfg.max_opaque_draws
+            for v in range(nverts):
+                if alpha:
+                    packed = lib.ref_sh_vertex_alpha_clip(C.byref(o.u), cascade, slot, v, pos, uv)
+                else:
+                    packed = lib.ref_sh_vertex(C.byref(o.u), cascade, slot, v, pos)
+                assert np.array_equal(np.frombuffer(pos, np.uint32), want[v].view(np.uint32)), (cascade, slot, v)
+                if cascade < 0:
+                    assert packed == ((v // 3) << 24 | slot)          # pack(), util.glsl:18-20
+                checked += 1
+
+    check(-1, 0, *n_main)
+    section = o.cfg.max_opaque_draws + o.cfg.max_alpha_clip_draws
+    o.shadow_cascade(2)
+    check(2, section, *o.draw_counts())
+    assert checked > 3000
+
+
+@pytest.mark.parametrize("preset", ["tiny", "rotated"])
+def test_depth_reduction_matches_the_reference_shader(preset):
+    lib = _stage2_lib()
+    sc, kw = _scene(preset)
+    o = make_oracle(sc, caps=reference_caps(), **kw)
+    o.reset(); o.cull_instances(); o.cull_meshlets(); o.raster_visbuffer()
+    o.reduce_depth()
+    want = (o.misc().min_depth, o.misc().max_depth)
+    o.reset()                                                      # min = 0xFFFFFFFF, max = 0 again
+    lib.ref_sh_read_depth(C.byref(o.u), C.byref(o.cfg), o.vis.ctypes.data)   # compute/read_depth.glsl:22-83
+    assert (o.misc().min_depth, o.misc().max_depth) == want and want[1] != 0
+
+
+@pytest.mark.parametrize("preset", ["tiny", "rotated", "c4small"])
+def test_lighting_resolve_matches_the_reference_shader(preset):
+    """render_geometry.comp main() -- the reference's own text, incl. vbuffer.glsl and pbr.glsl -- against the oracle's
+    restatement on every pixel.  Both sample through the same texture functions, so what is compared is everything the
+    shader computes around them: attribute refetch, barycentrics and derivatives, normals, cascade selection, PCF,
+    BRDF.  The restatement reorders a few float operations, hence a tolerance -- three orders of magnitude below the one
+    the CUDA resolve is held to."""
+    from helpers import Textures
+    lib = _stage2_lib()
+    sc, kw = _scene(preset)
+    tex = Textures(sc, 32) if sc.num_texture_sets else None
+    sky = sc.make_skybox(8)
+    o = make_oracle(sc, textures=tex, skybox=sky, caps=reference_caps(), **kw)
+    o.render_frame(resolve=True)
+    ref = np.zeros_like(o.color)
+    lib.ref_sh_render_geometry(C.byref(o.u), C.byref(o.cfg), o.vis.ctypes.data, o.shadow.ctypes.data, ref.ctypes.data, 0, o.height)
+    a, b = o.color.reshape(-1, 4), ref.reshape(-1, 4)
+    assert np.isfinite(b).all() and (b[:, 3] == 1).all()
+    geometry = (o.vis != S.LH_VIS_CLEAR)
+    assert geometry.any() and (~geometry).any()
+    assert np.array_equal(a[~geometry], b[~geometry])                  # sky pixels: identical operations
+    err = np.abs(a[:, :3] - b[:, :3]).max(axis=1) / (1e-3 + np.abs(b[:, :3]).max(axis=1))
+    assert np.quantile(err, 0.999) < 1e-4, f"99.9th percentile relative error {np.quantile(err, 0.999):.2e}"
+    assert err.max() < 2e-2, f"max relative error {err.max():.2e}"

@@ -9,26 +9,9 @@ import pytest
 
 from lighthugger_b200 import _structs as S
 from lighthugger_b200.scene import Scene
-from helpers import Textures, make_context, make_oracle, vis_fields
+from helpers import Textures, compare_color, display, make_context, make_oracle, vis_fields
 
 pytestmark = pytest.mark.gpu
-
-
-def display(c):
-    c = np.clip(np.asarray(c, np.float64), 0, None)
-    c = c / (1 + c)
-    return np.where(c <= 0.0031308, 12.92 * c, 1.055 * np.power(c, 1 / 2.4) - 0.055)
-
-
-def compare_color(ctx, o, frac_tol=0.002, tight=2 / 255, loose=12 / 255):
-    got = ctx.target(S.LH_TARGET_SCENE_RGBA16F).astype(np.float32).reshape(-1, 4)
-    want = o.color.reshape(-1, 4)
-    assert np.isfinite(got).all() and (got[:, 3] == 1).all()
-    d = np.abs(display(got[:, :3]) - display(want[:, :3])).max(axis=1)
-    bad = np.count_nonzero(d > tight) / len(d)
-    assert bad <= frac_tol, f"{bad:.4%} of pixels differ by more than 2/255 (max {d.max():.4f})"
-    assert d.max() <= loose, f"maximum error {d.max():.4f} exceeds 12/255"
-    return bad, float(d.max())
 
 
 @pytest.mark.parametrize("name,bc7", [("tiny", True), ("tiny", False)])
