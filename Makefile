@@ -38,9 +38,18 @@ $(LIBDIR)/liblighthugger_b200.so: $(CUDA_OBJS)
 	@mkdir -p $(LIBDIR)
 	$(NVCC) -shared -o $@ $(CUDA_OBJS) -lcudart_static -ldl -lrt -lpthread
 
+# Scene preparation meshletises with the reference's vendored meshoptimizer (north star; src/resources/meshlets.cpp),
+# compiled from where the reference keeps it; without /root/reference the built-in greedy builder is the fallback.
+REF_MESHOPT_SRCS := $(wildcard $(REF)/external/meshoptimizer/src/clusterizer.cpp $(REF)/external/meshoptimizer/src/allocator.cpp)
+ifneq ($(words $(REF_MESHOPT_SRCS)),2)
+REF_MESHOPT_SRCS :=
+HOST_MESHOPT_FLAGS :=
+else
+HOST_MESHOPT_FLAGS := -DLH_HAVE_MESHOPTIMIZER -I$(REF)/external/meshoptimizer/src
+endif
 $(LIBDIR)/liblh_host.so: $(HOST_SRCS) $(HOST_HDRS)
 	@mkdir -p $(LIBDIR)
-	$(CXX) $(CXXFLAGS) -shared -o $@ $(HOST_SRCS) $(LDFLAGS_SO) -ldl
+	$(CXX) $(CXXFLAGS) $(HOST_MESHOPT_FLAGS) -shared -o $@ $(HOST_SRCS) $(REF_MESHOPT_SRCS) $(LDFLAGS_SO) -ldl
 
 # a C++20 host on top of the two C ABIs, the counterpart of the reference's main() frame loop
 lighthugger_b200/bin/lh_frame_loop: examples/frame_loop.cpp $(LIBDIR)/liblighthugger_b200.so $(LIBDIR)/liblh_host.so $(HOST_HDRS)

@@ -119,6 +119,13 @@ typedef struct LhPresetInfo {
     uint32_t alpha_cutout_set;  /* texture set whose base colour carries alpha cut-outs (or 0xFFFFFFFF) */
     LhCamera camera;
 } LhPresetInfo;
+/* 1 when meshlets are built by the reference's vendored meshoptimizer (meshopt_buildMeshlets, 64 / 124 / 0.25, as
+ * src/resources/meshlets.cpp:10-57), 0 when the built-in greedy fallback is in use (library built without
+ * /root/reference, or LH_MESHLET_BUILDER=greedy in the environment) */
+LH_HOST_API int lh_host_has_meshoptimizer(void);
+/* the triangle list (3 vertex indices per triangle, in the order handed to the meshlet builder) of a mesh built by
+ * lh_scene_add_mesh / lh_scene_add_mesh_indexed; returns the index count (call with out NULL to query) */
+LH_HOST_API uint64_t lh_scene_mesh_triangles(const LhScene* scene, int mesh, uint32_t* out);
 LH_HOST_API int lh_scene_build_preset(LhScene* scene, int preset, uint32_t instance_count, uint64_t seed, LhPresetInfo* out);
 
 /* procedural textures: RGBA8 with a full box-filtered mip chain, tightly

@@ -63,11 +63,20 @@ struct alignas(16) RasterRecord {
 static_assert(sizeof(RasterRecord) == 64, "records are moved in 16-byte units");
 
 #ifndef LH_CHUNK
-#define LH_CHUNK 2
+#define LH_CHUNK 4
 #endif
-constexpr int kChunk = LH_CHUNK;   // queue entries per ticket
-constexpr int kRecSlots = 3;       // record ring: processing / staging its streams / in flight
-constexpr int kAuxSlots = 2;       // stream ring: processing / in flight
+constexpr int kChunk = LH_CHUNK;   // queue entries a warp takes per ticket
+// LH_STAGE_STREAMS: the chunk's micro-indices, vertex indices and instance transforms are copied to shared memory
+// (cp.async, 16 bytes per lane) as soon as its records have landed, instead of being fetched where they are used
+#ifndef LH_STAGE_STREAMS
+#define LH_STAGE_STREAMS 1
+#endif
+// LH_RECORD_BULK: the chunk's records arrive by ONE bulk-asynchronous copy (cp.async.bulk + mbarrier, issued by an
+// elected lane) instead of four 16-byte loads + stores by each of the chunk's lanes
+#ifndef LH_RECORD_BULK
+#define LH_RECORD_BULK 0
+#endif
+constexpr bool kStageStreams = LH_STAGE_STREAMS != 0, kRecordBulk = LH_RECORD_BULK != 0;
 // a meshlet's micro-indices (<= 124 triangles x 3 bytes) and vertex indices (<= 64 x 4 bytes) start at any byte: the
 // copies are the enclosing 16-byte-aligned ranges
 constexpr int kMicroBuf = (15 + 3 * (int)LH_MAX_MESHLET_TRIANGLES + 15) & ~15;           // 400
@@ -76,10 +85,10 @@ constexpr int kIndexBuf = (15 + 4 * (int)LH_MAX_MESHLET_UNIQUE_VERTICES + 15) & 
 // Per-warp scratch of the meshlet kernel.
 // sx holds two sentinels instead of a flag byte: kVertOutside (behind the w - z >= 0 plane) and kVertNonFinite.
 struct alignas(16) WarpScratch {
-    RasterRecord rec[kRecSlots][kChunk];
-    float T[kAuxSlots][kChunk][16];
-    uint8_t micro[kAuxSlots][kChunk][kMicroBuf];
-    uint8_t index[kAuxSlots][kChunk][kIndexBuf];
+    RasterRecord rec[kChunk];
+    float T[kStageStreams ? kChunk : 1][16];
+    uint8_t micro[kStageStreams ? kChunk : 1][kMicroBuf];
+    uint8_t index[kStageStreams ? kChunk : 1][kIndexBuf];
     int sx[LH_MAX_MESHLET_UNIQUE_VERTICES];
     int sy[LH_MAX_MESHLET_UNIQUE_VERTICES];
     float z[LH_MAX_MESHLET_UNIQUE_VERTICES];
@@ -88,7 +97,7 @@ struct alignas(16) WarpScratch {
     // centre is <= it.  min/max over a triangle's vertices (SIMD halfword ops) give its pixel rectangle directly.
     uint2 cover[LH_MAX_MESHLET_UNIQUE_VERTICES];
     uint8_t surv[128];
-    unsigned long long rec_bar[kRecSlots], aux_bar[kAuxSlots];   // mbarriers: records / streams of a ring slot have landed
+    unsigned long long rec_bar;   // mbarrier: the chunk's records have landed (LH_RECORD_BULK)
 };
 constexpr int kVertOutside = INT_MIN, kVertNonFinite = INT_MIN + 1;   // |snapped| <= 2^29, so neither can be a coordinate
 constexpr int kMaxOcclusionBlocks = 16;    // early-out reads at most 16 blocks of 8x4 pixels (512 keys)
@@ -115,6 +124,11 @@ __device__ __forceinline__ void mbar_wait(void* bar, uint32_t parity) {
         "LH_MBAR_DONE:\n"
         "}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
 }
+// 16 bytes global -> shared, asynchronously (cp.async: the data bypasses the register file and L1)
+__device__ __forceinline__ void async_copy16(void* dst, const void* src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void async_copy_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 // dst, src and bytes are multiples of 16
 __device__ __forceinline__ void bulk_copy_g2s(void* dst, const void* src, uint32_t bytes, void* bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)), "l"(src),
@@ -626,13 +640,14 @@ struct RasterCounters {
     uint32_t tris_done = 0, skipped_occluded = 0, skipped_empty = 0;
 };
 
-// One queued meshlet by one warp.  rec: its record; T, micro, index: its staged instance transform, micro-indices and
-// vertex indices (shared memory; micro / index point at the meshlet's first byte inside the staged 16-byte-aligned
-// ranges); first_keys: the lane's stored key under the first 8x4 block of the bound, prefetched a chunk ago;
+// One queued meshlet by one warp.  rec: its record (shared memory); T, micro_s, index_s: its instance transform,
+// micro-indices and vertex indices staged in shared memory (LH_STAGE_STREAMS; micro_s / index_s point at the meshlet's
+// first byte inside the staged 16-byte-aligned ranges), otherwise fetched through the record's pointers;
+// first_keys: the lane's stored key under the first 8x4 block of the bound, prefetched with the chunk;
 // M: the view's matrix (main view: the kernel parameter, i.e. constant-bank operands; cascade: shared memory).
 template <bool SHADOW, bool ALPHA>
 __device__ __forceinline__ void raster_one_meshlet(const FrameParams& P, const Target<SHADOW>& tg, WarpScratch& sv, const RasterRecord& rec,
-                                                   const float* T, const uint8_t* micro, const uint8_t* index, uint32_t first_keys, const float* M,
+                                                   const float* T, const uint8_t* micro_s, const uint8_t* index_s, uint32_t first_keys, const float* M,
                                                    bool affine, RasterCounters& cnt) {
     const uint32_t lane = threadIdx.x & 31;
     const int W = (int)tg.width, H = (int)tg.height;
@@ -669,15 +684,18 @@ __device__ __forceinline__ void raster_one_meshlet(const FrameParams& P, const T
     bool special = false;                          // some vertex is behind the near plane, non-finite or of negative depth
     {
         const uint16_t* positions = rec.positions;
-        // the instance transform from shared memory: live for this phase only
+        // the instance transform: live for this phase only
         float Tl[16];
 #pragma unroll
         for (int k = 0; k < 4; k++) {
-            const float4 c = *(const float4*)(T + 4 * k);
+            const float4 c = kStageStreams ? *(const float4*)(T + 4 * k) : __ldg((const float4*)rec.instance + k);
             Tl[4 * k] = c.x; Tl[4 * k + 1] = c.y; Tl[4 * k + 2] = c.z; Tl[4 * k + 3] = c.w;
         }
+        const uint8_t* index_g = rec.indices;
         for (uint32_t v = lane; v < nv; v += 32) {
-            const uint32_t idx = wide ? *(const uint32_t*)(index + 4 * v) : (uint32_t)*(const uint16_t*)(index + 2 * v);
+            uint32_t idx;
+            if (kStageStreams) idx = wide ? *(const uint32_t*)(index_s + 4 * v) : (uint32_t)*(const uint16_t*)(index_s + 2 * v);
+            else idx = wide ? __ldg((const uint32_t*)index_g + v) : (uint32_t)__ldg((const uint16_t*)index_g + v);
             const uint16_t* p = positions + 3 * (size_t)idx;
             const float px = (float)__ldg(p), py = (float)__ldg(p + 1), pz = (float)__ldg(p + 2);
             const V4 world = mat4_mul(Tl, px, py, pz, 1.0f);
@@ -748,6 +766,8 @@ __device__ __forceinline__ void raster_one_meshlet(const FrameParams& P, const T
     // cull modes: pipelines.cpp:10-25,255-315
     const int cull = alpha ? CULL_NONE : (SHADOW ? CULL_FRONT : CULL_BACK);
     const uint32_t lo_base = (P.slot_offset + rec.local) << LH_VIS_TRI_BITS;
+    const uint8_t* micro_g = rec.micro;
+    auto micro = [&](uint32_t k) -> uint32_t { return kStageStreams ? (uint32_t)micro_s[k] : (uint32_t)__ldg(micro_g + k); };
 
     // ---- (2) triangle cull phase ----
     uint32_t n_surv = 0;
@@ -756,7 +776,7 @@ __device__ __forceinline__ void raster_one_meshlet(const FrameParams& P, const T
         const uint32_t t = t0 + lane;
         bool keep = false;
         if (t < tri_count) {
-            const uint32_t i0 = micro[3 * t], i1 = micro[3 * t + 1], i2 = micro[3 * t + 2];
+            const uint32_t i0 = micro(3 * t), i1 = micro(3 * t + 1), i2 = micro(3 * t + 2);
             if (max(i0, max(i1, i2)) < nv) {
                 const uint32_t lo = lo_base | t;
                 // facing test and routing of a triangle whose pixel rectangle [px0,px1] x [py0,py1] is not empty
@@ -836,7 +856,7 @@ __device__ __forceinline__ void raster_one_meshlet(const FrameParams& P, const T
     for (uint32_t s = lane; s < n_surv; s += 32) {
         const uint32_t t = sv.surv[s];
         const uint32_t lo = lo_base | t;
-        uint32_t ia = micro[3 * t], ib = micro[3 * t + 1], ic = micro[3 * t + 2];
+        uint32_t ia = micro(3 * t), ib = micro(3 * t + 1), ic = micro(3 * t + 2);
         int ax = sv.sx[ia], ay = sv.sy[ia], bx = sv.sx[ib], by = sv.sy[ib], cx = sv.sx[ic], cy = sv.sy[ic];
         const int minx = min(ax, min(bx, cx)), maxx = max(ax, max(bx, cx));
         const int miny = min(ay, min(by, cy)), maxy = max(ay, max(by, cy));
@@ -866,7 +886,8 @@ __device__ __forceinline__ void raster_one_meshlet(const FrameParams& P, const T
             const uint32_t ids[3] = {ia, ib, ic};
             SnapVert* out[3] = {&A, &B, &C};
             for (int q = 0; q < 3; q++) {
-                const uint32_t idx = wide ? *(const uint32_t*)(index + 4 * ids[q]) : (uint32_t)*(const uint16_t*)(index + 2 * ids[q]);
+                const uint8_t* index_g = rec.indices;
+                const uint32_t idx = wide ? __ldg((const uint32_t*)index_g + ids[q]) : (uint32_t)__ldg((const uint16_t*)index_g + ids[q]);
                 out[q]->w = sv.w[ids[q]];
                 out[q]->u = padd(pmul((float)__ldg(uvs + 2 * (size_t)idx), tex_scale[0]), tex_offset[0]);
                 out[q]->v = padd(pmul((float)__ldg(uvs + 2 * (size_t)idx + 1), tex_scale[1]), tex_offset[1]);
@@ -892,11 +913,11 @@ __device__ __forceinline__ void raster_one_meshlet(const FrameParams& P, const T
     }
 }
 
-// One warp per queued meshlet.  The front end is a software pipeline of bulk-asynchronous copies, three chunks deep:
-// while chunk i is rasterised, the micro-indices, vertex indices and instance transforms of chunk i + 1 are landing in
-// shared memory (their addresses came with that chunk's records, which landed during chunk i - 1), the records of
-// chunk i + 2 are landing, and the ticket of chunk i + 3 is on its way back from L2.  Nothing in the loop waits on a
-// dependent global load except the vertex positions (gathered through the staged indices).
+// One warp per queued meshlet.  A warp takes up to kChunk queue entries per ticket (one when the band is small, so that
+// every warp gets work and a heavy near meshlet does not serialise its neighbours).  The front end costs three round
+// trips per CHUNK, none of them a pointer chase: the ticket (taken one chunk ahead, so it is already there), the
+// chunk's records (what the selection's lanes left: pointers, counts, bound), then -- issued together -- the stored
+// keys under each bound and the asynchronous copies of the chunk's micro-indices, vertex indices and transforms.
 template <bool SHADOW>
 __global__ void __launch_bounds__(kWarpsPerCta * 32, LH_RASTER_MIN_CTAS) raster_meshlets_kernel(const __grid_constant__ FrameParams P, uint32_t cascade, uint32_t band) {
     __shared__ WarpScratch scratch_all[kWarpsPerCta];
@@ -910,9 +931,8 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, LH_RASTER_MIN_CTAS) raster_
         P.pass->band_mark[band + 1] = band_end;
         if (P.flags & LH_CONFIG_PASS_TIMINGS) atomicAdd(&P.state->queued[SHADOW ? 1u + cascade : 0u], band_end - band_first);
     }
-    if (lane == 0) {
-        for (int s = 0; s < kRecSlots; s++) mbar_init(&sv.rec_bar[s], 1);
-        for (int s = 0; s < kAuxSlots; s++) mbar_init(&sv.aux_bar[s], kChunk);
+    if (kRecordBulk && lane == 0) {
+        mbar_init(&sv.rec_bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     // The main view multiplies by the kernel parameter itself (constant-bank operands, no registers); a cascade's
@@ -931,95 +951,83 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, LH_RASTER_MIN_CTAS) raster_
     const RasterRecord* records = (const RasterRecord*)P.raster_records;
     RasterCounters cnt;
 
-    // kChunk entries per ticket; one when the band is small, so that every warp gets work and a heavy near meshlet does
-    // not serialise its neighbours
     const uint32_t band_count = band_end - band_first;
     const uint32_t chunk = max(1u, min((uint32_t)kChunk, band_count / (gridDim.x * kWarpsPerCta * 8u)));
-    // lane 0 holds a ticket from the moment it is taken; everybody learns it (one shuffle) when it is first needed
-    auto take_ticket = [&]() -> uint32_t { return lane == 0 ? band_first + atomicAdd(&P.pass->band_ticket[band], chunk) : 0u; };
-    auto entries = [&](uint32_t first) -> uint32_t { return first < band_end ? min(chunk, band_end - first) : 0u; };
-    auto issue_records = [&](uint32_t slot, uint32_t first, uint32_t n) {
-        if (lane == 0 && n) {
-            mbar_arrive_expect_tx(&sv.rec_bar[slot], n * (uint32_t)sizeof(RasterRecord));
-            bulk_copy_g2s(&sv.rec[slot][0], records + first, n * (uint32_t)sizeof(RasterRecord), &sv.rec_bar[slot]);
-        }
-    };
-    // lane j < n stages entry j's streams: the 16-byte-aligned ranges around its micro-indices and vertex indices, and
-    // the instance transform; every lane prefetches the stored keys under the first 8x4 block of each bound
-    auto issue_streams = [&](uint32_t aux, uint32_t slot, uint32_t n, uint32_t* first_keys) {
-        if (lane < (uint32_t)kChunk) {
-            if (lane < n) {
-                const RasterRecord& r = sv.rec[slot][lane];
-                const uint32_t cf = r.counts_flags;
-                const uint32_t tris = min(cf & 0xFFu, (uint32_t)LH_MAX_MESHLET_TRIANGLES), verts = min((cf >> 8) & 0xFFu, (uint32_t)LH_MAX_MESHLET_UNIQUE_VERTICES);
-                const uintptr_t m = (uintptr_t)r.micro, x = (uintptr_t)r.indices;
-                const uint32_t m_bytes = tris ? (uint32_t)(((m & 15u) + 3u * tris + 15u) & ~15u) : 0u;
-                const uint32_t x_bytes = verts ? (uint32_t)(((x & 15u) + (((cf >> 16) & LH_MESH_INFO_FLAGS_32_BIT_INDICES) ? 4u : 2u) * verts + 15u) & ~15u) : 0u;
-                mbar_arrive_expect_tx(&sv.aux_bar[aux], m_bytes + x_bytes + 64u);
-                bulk_copy_g2s(&sv.T[aux][lane][0], r.instance, 64u, &sv.aux_bar[aux]);
-                if (m_bytes) bulk_copy_g2s(&sv.micro[aux][lane][0], (const void*)(m & ~(uintptr_t)15), m_bytes, &sv.aux_bar[aux]);
-                if (x_bytes) bulk_copy_g2s(&sv.index[aux][lane][0], (const void*)(x & ~(uintptr_t)15), x_bytes, &sv.aux_bar[aux]);
-            } else {
-                mbar_arrive(&sv.aux_bar[aux]);
+    // lane 0 holds the NEXT ticket (relative to band_first) from the moment it is requested; nothing reads it before the
+    // following iteration, so the atomic's round trip overlaps the current chunk
+    uint32_t next_ticket = 0;
+    if (lane == 0) next_ticket = atomicAdd(&P.pass->band_ticket[band], chunk);
+    for (uint32_t iteration = 0;; iteration++) {
+        const uint32_t ticket = band_first + __shfl_sync(0xFFFFFFFFu, next_ticket, 0);
+        if (ticket >= band_end) break;
+        if (lane == 0) next_ticket = atomicAdd(&P.pass->band_ticket[band], chunk);
+        const uint32_t n = min(chunk, band_end - ticket);
+        // ---- the chunk's records ----
+        uint32_t my_rx = kUntestable, my_ry = 0;
+        if (kRecordBulk) {
+            if (lane == 0) {
+                mbar_arrive_expect_tx(&sv.rec_bar, n * (uint32_t)sizeof(RasterRecord));
+                bulk_copy_g2s(&sv.rec[0], records + ticket, n * (uint32_t)sizeof(RasterRecord), &sv.rec_bar);
             }
+            mbar_wait(&sv.rec_bar, iteration & 1u);
+            if (lane < n) {
+                my_rx = sv.rec[lane].rect_x;
+                my_ry = sv.rec[lane].rect_y;
+            }
+        } else {
+            if (lane < n) {
+                const uint4* src = (const uint4*)(records + ticket + lane);
+                const uint4 a = __ldg(src), b = __ldg(src + 1), c = __ldg(src + 2), d = __ldg(src + 3);
+                uint4* dst = (uint4*)&sv.rec[lane];
+                dst[0] = a; dst[1] = b; dst[2] = c; dst[3] = d;
+                my_rx = d.x;
+                my_ry = d.y;
+            }
+            __syncwarp();
         }
+        // ---- the stored keys under the first 8x4 block of every bound, and the chunk's streams, all in flight together ----
+        uint32_t first_keys[kChunk];
 #pragma unroll
         for (int j = 0; j < kChunk; j++) {
             first_keys[j] = 0;
-            if ((uint32_t)j < n) {
-                const uint32_t rx = sv.rec[slot][j].rect_x, ry = sv.rec[slot][j].rect_y;
-                const int x = (int)(rx & 0xFFFFu) + (int)(lane & 7), y = (int)(ry & 0xFFFFu) + (int)(lane >> 3);
-                if (rx != kUntestable && x <= (int)(rx >> 16) && y <= (int)(ry >> 16)) {
-                    const size_t at = (size_t)y * W + x;
-                    first_keys[j] = SHADOW ? __ldcg(tg.layer + at) : __ldcg((const uint32_t*)tg.vis + 2 * at + 1);
-                }
+            const uint32_t rx = __shfl_sync(0xFFFFFFFFu, my_rx, j), ry = __shfl_sync(0xFFFFFFFFu, my_ry, j);
+            const int x = (int)(rx & 0xFFFFu) + (int)(lane & 7), y = (int)(ry & 0xFFFFu) + (int)(lane >> 3);
+            if (rx != kUntestable && x <= (int)(rx >> 16) && y <= (int)(ry >> 16)) {
+                const size_t at = (size_t)y * W + x;
+                first_keys[j] = SHADOW ? __ldcg(tg.layer + at) : __ldcg((const uint32_t*)tg.vis + 2 * at + 1);
             }
         }
-    };
-
-    // ---- prologue: chunk 0's records and streams, chunk 1's records, chunk 2's ticket ----
-    uint32_t t_cur = __shfl_sync(0xFFFFFFFFu, take_ticket(), 0);
-    uint32_t n_cur = entries(t_cur);
-    issue_records(0, t_cur, n_cur);
-    uint32_t t_next = __shfl_sync(0xFFFFFFFFu, take_ticket(), 0);
-    uint32_t n_next = entries(t_next);
-    uint32_t keys_cur[kChunk], keys_next[kChunk];
-    if (n_cur) {
-        mbar_wait(&sv.rec_bar[0], 0);
-        issue_streams(0, 0, n_cur, keys_cur);
-    }
-    issue_records(1, t_next, n_next);
-    uint32_t t_after = take_ticket();   // lane 0 only, until it is needed
-
-    for (uint32_t i = 0; n_cur != 0; i++) {
-        const uint32_t slot = i % kRecSlots, aux = i % kAuxSlots;
-        // ---- advance the pipeline: chunk i + 1's streams, chunk i + 2's records, chunk i + 3's ticket ----
-        if (n_next) {
-            mbar_wait(&sv.rec_bar[(i + 1) % kRecSlots], ((i + 1) / kRecSlots) & 1u);
-            issue_streams((i + 1) % kAuxSlots, (i + 1) % kRecSlots, n_next, keys_next);
-        }
-        const uint32_t t_after_all = __shfl_sync(0xFFFFFFFFu, t_after, 0);
-        const uint32_t n_after = entries(t_after_all);
-        issue_records((i + 2) % kRecSlots, t_after_all, n_after);
-        t_after = take_ticket();
-        // ---- chunk i ----
-        mbar_wait(&sv.aux_bar[aux], (i / kAuxSlots) & 1u);
+        if (kStageStreams) {
 #pragma unroll
-        for (int j = 0; j < kChunk; j++) {
-            if ((uint32_t)j >= n_cur) break;
-            const RasterRecord& rec = sv.rec[slot][j];
-            const uint8_t* micro = &sv.micro[aux][j][0] + ((uintptr_t)rec.micro & 15u);
-            const uint8_t* index = &sv.index[aux][j][0] + ((uintptr_t)rec.indices & 15u);
-            if ((rec.counts_flags >> 16) & LH_MESH_INFO_FLAGS_ALPHA_CLIP)
-                raster_one_meshlet<SHADOW, true>(P, tg, sv, rec, &sv.T[aux][j][0], micro, index, keys_cur[j], M, affine, cnt);
-            else
-                raster_one_meshlet<SHADOW, false>(P, tg, sv, rec, &sv.T[aux][j][0], micro, index, keys_cur[j], M, affine, cnt);
+            for (int j = 0; j < kChunk; j++) {
+                if ((uint32_t)j >= n) break;
+                const RasterRecord& r = sv.rec[j];
+                const uint32_t cf = r.counts_flags;
+                const uint32_t tris = min(cf & 0xFFu, (uint32_t)LH_MAX_MESHLET_TRIANGLES), verts = min((cf >> 8) & 0xFFu, (uint32_t)LH_MAX_MESHLET_UNIQUE_VERTICES);
+                const uintptr_t m = (uintptr_t)r.micro, x = (uintptr_t)r.indices;
+                const uint32_t m_bytes = (uint32_t)(m & 15u) + 3u * tris;                                                    // <= 387: pieces 0..24
+                const uint32_t x_bytes = (uint32_t)(x & 15u) + (((cf >> 16) & LH_MESH_INFO_FLAGS_32_BIT_INDICES) ? 4u : 2u) * verts;   // <= 271: pieces 0..16
+                // lanes 0..24: the micro-indices; lanes 28..31: the instance transform; then lanes 0..16: the vertex indices
+                if (lane * 16u < m_bytes) async_copy16(&sv.micro[kStageStreams ? j : 0][lane * 16u], (const uint8_t*)(m & ~(uintptr_t)15) + lane * 16u);
+                else if (lane >= 28u) async_copy16(&sv.T[kStageStreams ? j : 0][(lane - 28u) * 4u], (const uint8_t*)r.instance + (lane - 28u) * 16u);
+                if (lane * 16u < x_bytes) async_copy16(&sv.index[kStageStreams ? j : 0][lane * 16u], (const uint8_t*)(x & ~(uintptr_t)15) + lane * 16u);
+            }
+            async_copy_wait_all();
             __syncwarp();
         }
-        n_cur = n_next;
-        n_next = n_after;
 #pragma unroll
-        for (int j = 0; j < kChunk; j++) keys_cur[j] = keys_next[j];
+        for (int j = 0; j < kChunk; j++) {
+            if ((uint32_t)j >= n) break;
+            const RasterRecord& rec = sv.rec[j];
+            const int js = kStageStreams ? j : 0;
+            const uint8_t* micro = &sv.micro[js][0] + ((uintptr_t)rec.micro & 15u);
+            const uint8_t* index = &sv.index[js][0] + ((uintptr_t)rec.indices & 15u);
+            if ((rec.counts_flags >> 16) & LH_MESH_INFO_FLAGS_ALPHA_CLIP)
+                raster_one_meshlet<SHADOW, true>(P, tg, sv, rec, &sv.T[js][0], micro, index, first_keys[j], M, affine, cnt);
+            else
+                raster_one_meshlet<SHADOW, false>(P, tg, sv, rec, &sv.T[js][0], micro, index, first_keys[j], M, affine, cnt);
+            __syncwarp();
+        }
     }
     if (P.flags & LH_CONFIG_PASS_TIMINGS) {
         const uint32_t tris_done = __reduce_add_sync(0xFFFFFFFFu, cnt.tris_done);

@@ -20,6 +20,9 @@
 
 #include "lh_scene.h"
 #include "math.hpp"
+#ifdef LH_HAVE_MESHOPTIMIZER
+#include <meshoptimizer.h>
+#endif
 
 using namespace lh::host;
 
@@ -35,6 +38,7 @@ struct Mesh {
     std::vector<uint32_t> idx32;
     std::vector<uint8_t> micro;
     std::vector<LhMeshlet> meshlets;
+    std::vector<uint32_t> triangles;  // the triangle list the meshlets were built from (3 vertex indices each)
     uint64_t num_triangles = 0;
     LhMeshInfo info{};
     float dq_scale[3] = {1, 1, 1};
@@ -243,12 +247,71 @@ void meshlet_bounds(const uint32_t* verts, const uint8_t* tris, uint32_t tri_cou
     out->cone_cutoff = sqrtf(1 - mindp * mindp);
 }
 
+#ifdef LH_HAVE_MESHOPTIMIZER
+// The reference's build_meshlets (src/resources/meshlets.cpp:3-140): meshopt_buildMeshlets of the vendored
+// meshoptimizer v0.20 with 64 vertices / 124 triangles / cone weight 0.25, then the same packing into Meshlet records,
+// vertex indices and 4-byte-padded micro-index runs.  The library is compiled from where the reference vendors it
+// (Makefile: external/meshoptimizer/src/clusterizer.cpp); tests compare the result byte for byte with the reference's
+// own function (oracle/_ref/libref_sceneprep.so) and with tests/golden/torus_*_ref.npz.
+bool build_meshlets_meshopt(Mesh& mesh, const std::vector<uint32_t>& tris, const std::vector<float>& raw_positions, size_t num_vertices) {
+    if (tris.empty()) return true;
+    const size_t max_vertices = LH_MAX_MESHLET_UNIQUE_VERTICES, max_triangles = LH_MAX_MESHLET_TRIANGLES;
+    const float cone_weight = 0.25f;
+    const size_t max_meshlets = meshopt_buildMeshletsBound(tris.size(), max_vertices, max_triangles);
+    std::vector<meshopt_Meshlet> meshlets(max_meshlets);
+    std::vector<unsigned int> vertex_indices(max_meshlets * max_vertices);
+    std::vector<unsigned char> micro(max_meshlets * max_triangles * 3);
+    const size_t count = meshopt_buildMeshlets(meshlets.data(), vertex_indices.data(), micro.data(), tris.data(), tris.size(), raw_positions.data(),
+                                               num_vertices, sizeof(float) * 3, max_vertices, max_triangles, cone_weight);
+    if (count == 0) return true;
+    const meshopt_Meshlet& last = meshlets[count - 1];
+    vertex_indices.resize(last.vertex_offset + last.vertex_count);
+    micro.resize(last.triangle_offset + ((last.triangle_count * 3 + 3) & ~3u));
+    mesh.meshlets.resize(count);
+    for (size_t i = 0; i < count; i++) {
+        const meshopt_Meshlet& m = meshlets[i];
+        LhMeshlet out{};
+        meshlet_bounds(&vertex_indices[m.vertex_offset], &micro[m.triangle_offset], m.triangle_count, raw_positions.data(), &out);
+        out.triangle_offset = m.triangle_offset;
+        out.index_offset = m.vertex_offset;
+        out.triangle_count = (uint8_t)m.triangle_count;
+        out.index_count = (uint8_t)m.vertex_count;
+        mesh.meshlets[i] = out;
+    }
+    mesh.micro.assign(micro.begin(), micro.end());
+    mesh.wide_indices = num_vertices > 65536;
+    if (mesh.wide_indices) {
+        mesh.idx32.assign(vertex_indices.begin(), vertex_indices.end());
+    } else {
+        mesh.idx16.resize(vertex_indices.size());
+        for (size_t i = 0; i < vertex_indices.size(); i++) mesh.idx16[i] = (uint16_t)vertex_indices[i];
+    }
+    return true;
+}
+#endif
+
+bool use_meshoptimizer() {
+#ifdef LH_HAVE_MESHOPTIMIZER
+    const char* e = getenv("LH_MESHLET_BUILDER");   // "greedy": the built-in fallback even where meshoptimizer is linked
+    return !(e && strcmp(e, "greedy") == 0);
+#else
+    return false;
+#endif
+}
+
+// Fallback where the reference's vendored meshoptimizer is not available at build time.
 // Greedy meshlet fill: walk the triangle list in order, start a new meshlet
 // whenever adding the triangle would exceed 64 unique vertices or 124
 // triangles.  Output = Meshlet[] + vertex-index buffer + micro-indices with
 // each meshlet's run padded to 4 bytes, as the reference packs them.
 void build_meshlets(Mesh& mesh, const std::vector<uint32_t>& tris, const std::vector<float>& raw_positions,
                     size_t num_vertices) {
+#ifdef LH_HAVE_MESHOPTIMIZER
+    if (use_meshoptimizer()) {
+        build_meshlets_meshopt(mesh, tris, raw_positions, num_vertices);
+        return;
+    }
+#endif
     std::vector<int16_t> local(num_vertices, -1);
     std::vector<uint32_t> vertex_indices;  // concatenated per-meshlet vertex lists
     std::vector<uint32_t> cur_verts;
@@ -369,6 +432,7 @@ int lh_scene_add_mesh(LhScene* scene, const LhMeshDesc* desc) {
     }
     mesh->num_triangles = fm.tris.size() / 3;
     build_meshlets(*mesh, fm.tris, raw, nv);
+    mesh->triangles = fm.tris;
     if (mesh->meshlets.size() > 65535) return -2;  // 16-bit meshlet index cap (mesh_loading.cpp:710-713)
 
     LhMeshInfo& info = mesh->info;
@@ -419,6 +483,7 @@ int lh_scene_add_mesh_indexed(LhScene* scene, const LhIndexedMesh* d) {
     }
     mesh->num_triangles = tris.size() / 3;
     build_meshlets(*mesh, tris, raw, nv);
+    mesh->triangles = tris;
     if (d->index_bytes == 4 && !mesh->wide_indices) {   // the index width follows the accessor (mesh_loading.cpp:455-462)
         mesh->idx32.assign(mesh->idx16.begin(), mesh->idx16.end());
         mesh->idx16.clear();
@@ -893,6 +958,15 @@ void lh_binding_destroy(LhBinding* b) {
         for (uint64_t a : b->allocations) b->free_fn(b->user, a);
     delete b;
 }
+
+uint64_t lh_scene_mesh_triangles(const LhScene* scene, int id, uint32_t* out) {
+    if (!scene || id < 0 || id >= (int)scene->meshes.size()) return 0;
+    const Mesh& m = *scene->meshes[id];
+    if (out) memcpy(out, m.triangles.data(), m.triangles.size() * sizeof(uint32_t));
+    return m.triangles.size();
+}
+
+int lh_host_has_meshoptimizer(void) { return use_meshoptimizer() ? 1 : 0; }
 
 void lh_compute_bounding_sphere(float result[4], const float* points, uint64_t count) {
     bounding_sphere(result, points, (size_t)count);

@@ -125,6 +125,15 @@ class Scene:
             raise IndexError(mesh)
         return v
 
+    def mesh_triangles(self, mesh):
+        """The triangle list (uint32 vertex indices, 3 per triangle) the mesh's meshlets were built from."""
+        self.lib.lh_scene_mesh_triangles.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+        self.lib.lh_scene_mesh_triangles.restype = C.c_uint64
+        n = self.lib.lh_scene_mesh_triangles(self.handle, mesh, None)
+        out = np.zeros(n, np.uint32)
+        self.lib.lh_scene_mesh_triangles(self.handle, mesh, out.ctypes.data)
+        return out
+
     def mesh_arrays(self, mesh):
         """numpy copies of one mesh's streams."""
         v = self.mesh_view(mesh)
