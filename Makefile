@@ -64,7 +64,7 @@ oracle/liblh_oracle.so: $(ORACLE_SRCS) $(ORACLE_HDRS)
 REF_GLM := $(REF)/external/VulkanMemoryAllocator-Hpp/Vulkan-Hpp/glm
 REF_MESHOPT := $(REF)/external/meshoptimizer/src
 ref:
-	@if [ -d $(REF)/src ]; then $(MAKE) --no-print-directory oracle/_ref/libref_sceneprep.so oracle/_ref/libref_shaders.so; \
+	@if [ -d $(REF)/src ]; then $(MAKE) --no-print-directory oracle/_ref/libref_sceneprep.so oracle/_ref/libref_shaders.so oracle/_ref/tony_mc_mapface.dds; \
 	 else echo "no $(REF): keeping prebuilt oracle/_ref"; fi
 
 oracle/_ref/libref_sceneprep.so: oracle/ref_shim/ref_exports.cpp oracle/ref_shim/ref_pch.h
@@ -92,6 +92,12 @@ oracle/_ref/libref_shaders.so: oracle/ref_shim/ref_shaders.cpp oracle/ref_shim/g
 	$(CXX) -O2 -std=gnu++20 -fPIC -fvisibility=hidden -ffp-contract=off -w -shared -o $@ \
 	    -Ioracle/ref_shim -Ioracle/_ref -Ioracle -Iinclude -I$(REF)/src -I$(REF_GLM) oracle/ref_shim/ref_shaders.cpp \
 	    -Loracle -llh_oracle -Wl,-rpath,'$$ORIGIN/..' $(LDFLAGS_SO)
+
+# the reference's display LUT as a build output (git-ignored; travels to the GPU box with the prebuilt libraries): the
+# GPU test of the display transform runs the REAL table through lh_set_display_lut
+oracle/_ref/tony_mc_mapface.dds: $(REF)/external/tony-mc-mapface/shader/tony_mc_mapface.dds
+	@mkdir -p oracle/_ref
+	cp $< $@
 
 clean:
 	rm -f $(LIBDIR)/*.so oracle/*.so oracle/_ref/*.so lighthugger_b200/bin/lh_frame_loop

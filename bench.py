@@ -50,6 +50,57 @@ def measured_peak():
         return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+class NvmlSampler:
+    """SM clock and throttle reasons sampled in-process through NVML every 10 ms DURING the timed region (the timed
+    region of this bench is tens of milliseconds: nvidia-smi's 100 ms loop would see next to nothing of it)."""
+
+    def __init__(self, device):
+        self.device = device
+        self.ok = False
+        self.sm, self.reasons, self.max_mhz = [], set(), None
+        self._stop = threading.Event()
+        self._thread = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(device)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+            self.ok = True
+        except Exception:
+            self.ok = False
+
+    def _run(self):
+        nv = self.nv
+        names = {"hw_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwSlowdown", 0x8),
+                 "hw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40),
+                 "sw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20),
+                 "sw_power_cap": getattr(nv, "nvmlClocksThrottleReasonSwPowerCap", 0x4)}
+        while not self._stop.is_set():
+            try:
+                self.sm.append(float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+                bits = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
+                for n, b in names.items():
+                    if bits & b:
+                        self.reasons.add(n)
+            except Exception:
+                pass
+            self._stop.wait(0.010)
+
+    def start(self):
+        if self.ok:
+            self._thread = threading.Thread(target=self._run, daemon=True)
+            self._thread.start()
+
+    def stop(self):
+        if not self.ok:
+            return None
+        self._stop.set()
+        self._thread.join(timeout=2)
+        return {"sm_mhz": float(np.median(self.sm)) if self.sm else None, "sm_max_mhz": self.max_mhz, "samples": len(self.sm),
+                "reasons": sorted(self.reasons), "how": "NVML, 10 ms period, in-process"}
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
@@ -233,6 +284,28 @@ def run_ours(args):
         ctx.frame_begin(u)
         ctx.render_frame()
 
+    # ---- sort-last load balancing (untimed): the stripe bounds follow the ranks' measured pass times ----
+    balance_log = None
+    if world > 1 and args.partition == "stripes" and args.balance > 0:
+        bal = sortlast.StripeBalancer(world)
+        shadow_striped = args.shadow_split == "instances"
+        bal.apply(ctx, rank, views=(0, 1) if shadow_striped else (0,))
+        balance_log = []
+        for _ in range(args.balance):
+            ctx.flush_l2()
+            frame_resident()
+            ctx.sync()
+            t = ctx.timings()
+            mine = torch.tensor([t["cull_meshlets"] + t["visbuffer"], t["shadowmaps"]], device="cuda", dtype=torch.float64)
+            allc = [torch.zeros_like(mine) for _ in range(world)]
+            dist.all_gather(allc, mine)
+            costs = [[float(c[v]) for c in allc] for v in range(2)]
+            balance_log.append([round(bal.imbalance(costs[0]), 3), round(bal.imbalance(costs[1]), 3)])
+            bal.update(0, costs[0])
+            if shadow_striped:
+                bal.update(1, costs[1])
+            bal.apply(ctx, rank, views=(0, 1) if shadow_striped else (0,))
+
     # ---- warm-up (>= 3) ----
     warm = max(3, args.warmup)
     for _ in range(warm):
@@ -243,7 +316,9 @@ def run_ours(args):
     launches_before = ctx.launch_count()
 
     # ---- timed: device-resident frames, CUDA events on the context stream, L2 flushed between frames ----
-    sampler = ClockSampler(local_rank)
+    sampler = NvmlSampler(local_rank)
+    if not sampler.ok:
+        sampler = ClockSampler(local_rank)
     barrier()
     sampler.start()
     frame_ms, pass_ms = [], []
@@ -265,6 +340,16 @@ def run_ours(args):
         total_ms = float(t.item())
     ms_per_step = total_ms / args.steps
     value = 1e3 / ms_per_step
+    # per-rank medians of every pass (min / max over ranks name the limiter of the scaling curve)
+    my_med = {k: float(np.median([p[k] for p in pass_ms])) for k in pass_ms[0]}
+    rank_spread = None
+    if dist:
+        keys = sorted(my_med)
+        mine = torch.tensor([my_med[k] for k in keys], device="cuda", dtype=torch.float64)
+        allm = [torch.zeros_like(mine) for _ in range(world)]
+        dist.all_gather(allm, mine)
+        m = torch.stack(allm).cpu().numpy()
+        rank_spread = {k: {"min": round(float(m[:, i].min()), 4), "max": round(float(m[:, i].max()), 4)} for i, k in enumerate(keys) if m[:, i].max() > 0.002}
 
     # ---- e2e: the public host call, host buffers in, stats out, copies inside the timed region ----
     for _ in range(2):
@@ -282,6 +367,14 @@ def run_ours(args):
     e2e_value = args.steps / e2e_s
     h2d = C.sizeof(S.LhUniforms) + n * C.sizeof(S.LhInstance)
     d2h = C.sizeof(S.LhFrameStats)
+
+    # ---- one untimed frame with the rasteriser's sample counter on (one 8-byte reduction per covered sample) ----
+    flags = ctx.cfg.flags
+    ctx.set_config_flags(flags | S.LH_CONFIG_COUNT_SAMPLES)
+    frame_resident()
+    ctx.sync()
+    samples = [int(x) for x in ctx.stats().emitted_samples]
+    ctx.set_config_flags(flags)
 
     if rank != 0:
         ctx.close()
@@ -310,8 +403,8 @@ def run_ours(args):
         # the depth bounds folded in (the depth pass is then an 8-byte all-reduce)
         "composite": 8 * px_here * (n_gpus + 1) if peer else (2 * 8 * px * (n_gpus - 1) // n_gpus if n_gpus > 1 else 0),
         "depth_reduction": 0 if peer else 8 * px,
-        # the shadow phase of the resolve (what is left on the critical path): 40 B of material results in, 8 B colour out
-        "render_geometry": (40 + 8) * px_here,
+        # 8 B visibility word in + 8 B RGBA16F out per pixel (over the part of the pass on the critical path)
+        "render_geometry": 16 * px_here,
         # raster geometry fetch per rasterised meshlet: 56 + 3 tri + 2 idx + 6 pos per vertex + 64 B of instance transform
         "raster_meshlets_kernel": rasterised * (56 + 3 * avg_tris + (2 + 6) * 64 + 64),
     }
@@ -321,24 +414,51 @@ def run_ours(args):
         if ms > 0 and b > 0:
             passes[k] = {"ms": round(ms, 4), "alg_bytes": int(b), "gbs": round(b / ms / 1e6, 1), "frac": round(b / ms / 1e6 / peak, 4)}
     kernel_share = {k: round(v / med["frame"], 4) for k, v in med.items() if k not in ("frame", "raster_meshlets_kernel_launches") and med["frame"] > 0}
-    dom = "raster_meshlets_kernel"
-    n_launch = max(1, int(round(med.get("raster_meshlets_kernel_launches", 1))))
-    traffic = None
-    try:   # per-launch DRAM bytes of the same kernel from the committed `ncu --set full` capture (profiles/)
-        with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
-            traffic = json.load(f).get("raster_meshlets_kernel<main view>", {}).get("dram_bytes_per_launch")
+    # ---- roofline of the dominant kernel (the rasteriser is bound by L2 atomics / instruction issue, not HBM) ----
+    # raster_meshlets_kernel<cascades> is >= half of the GPU's work (the four cascades run on four streams; its time base
+    # is the shadowmaps span, which also holds the cascades' cull / selection launches, so the fraction is a lower bound).
+    # Issue roofline: warp instructions of the kernel per frame (ncu smsp__inst_executed.sum of the same command,
+    # profiles/raster_ceilings.json) over that span, against 148 SMs x 4 schedulers x SM clock.  Atomic roofline: the
+    # reductions counted live (one per depth-tested sample) over the live kernel time, against the measured ceiling of
+    # tools/atomic_probe.cu on the same GPU type (profiles/r2a_atomic_probe.txt).
+    ceil = {}
+    try:
+        with open(os.path.join(ROOT, "profiles", "raster_ceilings.json")) as f:
+            ceil = json.load(f)
     except Exception:
         pass
+    n_launch = max(1, int(round(med.get("raster_meshlets_kernel_launches", 1))))
+    main_ms = med.get("raster_meshlets_kernel", 0.0)
+    shadow_ms = med.get("shadowmaps", 0.0)
+    sm_mhz = (clocks or {}).get("sm_mhz") or (clocks or {}).get("sm_max_mhz") or 1965.0
+    issue_peak = 148 * 4 * sm_mhz / 1e3   # G warp instructions / s
+    inst = ceil.get("raster_meshlets_kernel_warp_instructions_per_frame", {}) if (args.workload == "c2" and n_gpus == 1) else {}
+    atomic_peak = ceil.get("l2_atomic_greductions_per_s", {}).get("8k_265MB_8x4_block_local" if px * 8 > 100e6 else "4k_66MB_8x4_block_local")
+    traffic = None
+    try:   # per-launch DRAM bytes of the same kernel from the committed ncu capture (profiles/)
+        with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
+            traffic = json.load(f).get("raster_meshlets_kernel<cascades>", {}).get("dram_bytes_per_launch")
+    except Exception:
+        pass
+    cascade_inst = inst.get("cascades")
+    achieved_issue = cascade_inst / shadow_ms / 1e6 if (cascade_inst and shadow_ms > 0) else None
+    atom_main = samples[0] / main_ms / 1e6 if main_ms > 0 else None
+    atom_casc = sum(samples[1:]) / shadow_ms / 1e6 if shadow_ms > 0 else None
     roofline = {
-        "bound": "hbm", "kernel": "raster_meshlets_kernel<main view> (one warp per meshlet; one launch per depth band)",
-        "launches_per_step": n_launch,
-        "avg_launch_ms": round(med.get(dom, 0.0) / n_launch, 4),
-        "alg_bytes_per_launch": int(alg[dom] / n_launch),
-        "achieved": passes.get(dom, {}).get("gbs"), "peak": peak, "unit": "GB/s", "frac": passes.get(dom, {}).get("frac"),
-        "traffic": traffic, "peak_source": peak_src,
-        "note": ("dominant kernel by time (the cascades run the same kernel on side streams); it is instruction-issue / L2-latency "
-                 "bound, not HBM bound: its working set (mesh data, 66 MB key buffer) lives in L2 (see DESIGN.md); the HBM-bound "
-                 "passes are under 'passes'"),
+        "bound": "issue", "kernel": "raster_meshlets_kernel<cascades> (one warp per meshlet; 24 launches on 4 streams)",
+        "launches_per_step": 24, "avg_launch_ms": round(shadow_ms / 24, 4),
+        "achieved": round(achieved_issue, 1) if achieved_issue else None, "peak": round(issue_peak, 1), "unit": "G warp-instructions/s",
+        "frac": round(achieved_issue / issue_peak, 4) if achieved_issue else None,
+        "traffic": traffic, "peak_source": "148 SMs x 4 warp schedulers x measured SM clock; instruction count from profiles/raster_ceilings.json (ncu, same command)",
+        "l2_atomic": {
+            "kernel": "raster_meshlets_kernel<main view>", "launches_per_step": n_launch, "kernel_ms": round(main_ms, 4),
+            "reductions_per_step": samples[0], "achieved": round(atom_main, 2) if atom_main else None, "peak": atomic_peak,
+            "unit": "G reductions/s", "frac": round(atom_main / atomic_peak, 4) if (atom_main and atomic_peak) else None,
+            "cascades": {"reductions_per_step": sum(samples[1:]), "achieved": round(atom_casc, 2) if atom_casc else None,
+                         "frac": round(atom_casc / atomic_peak, 4) if (atom_casc and atomic_peak) else None},
+            "peak_source": "tools/atomic_probe.cu, 64-bit min reductions into a key buffer of this footprint, 8x4-block-local (profiles/r2a_atomic_probe.txt)"},
+        "note": ("the rasteriser's working set lives in L2 (DRAM traffic per launch is a few MB): its ceilings are instruction issue and "
+                 "L2 reductions, not HBM; the HBM-bound passes (culls, depth reduction, resolve) are under 'passes' against the measured copy peak"),
     }
     cpu = None
     if n_gpus == 1 and not args.no_cpu_baseline:
@@ -352,20 +472,22 @@ def run_ours(args):
                    "candidate_meshlets": scene.total_meshlets, "l2": "flushed between timed frames (256 MB write)",
                    "parallelism": (f"sort-last x{n_gpus}: instances split by {args.partition}, {args.exchange} exchange, shadows split by {args.shadow_split}"
                                    if n_gpus > 1 else "single GPU"), "texture_format": "BC7_SRGB",
-                   "texture_size": args.tex_size},
+                   "texture_size": args.tex_size, "texture_sets": scene.num_texture_sets},
         "culled_mtri_per_s": scene.total_triangles / (ms_per_step / 1e3) / 1e6,
         "frame": {"visible_instances": stats.num_visible_instances, "candidate_meshlets": stats.num_candidate_meshlets,
                   "rasterised_meshlets": survivors, "deferred_triangle_tiles": stats.num_large_triangles,
                   "rasterised_triangles_nonempty": int(stats.rasterized_triangles),
                   "meshlets_skipped_no_sample": list(stats.meshlets_skipped_no_sample),
                   "meshlets_skipped_occluded": list(stats.meshlets_skipped_occluded),
-                  "meshlets_queued": list(stats.meshlets_queued),
+                  "meshlets_queued": list(stats.meshlets_queued), "emitted_samples": samples,
                   "shadow_rasterised_meshlets": [int(a) + int(b) for a, b in zip(stats.shadow_opaque, stats.shadow_alpha_clip)]},
         "pass_ms": {k: round(v, 4) for k, v in med.items()},
         "pass_notes": ("render_geometry is the resolve's shadow phase (critical path); its material phase (resolve_kernel<1>) runs on a "
                        "low-priority stream beside the depth and shadow passes; shadowmaps is the span of the four cascades on four "
                        "concurrent streams; raster_meshlets_kernel sums the main view's launches of that kernel"),
         "pass_share": kernel_share,
+        "pass_ms_over_ranks": rank_spread,
+        "stripe_balance": ({"iterations": args.balance, "imbalance_main_shadow_per_iteration": balance_log} if balance_log is not None else None),
         "passes": passes,
         "roofline": roofline,
         "cpu_baseline": cpu,
@@ -389,12 +511,13 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
-    ap.add_argument("--tex-size", type=int, default=256)
+    ap.add_argument("--tex-size", type=int, default=1024, help="SURVEY 8d: 1024^2 BC7 textures with full mip chains")
     ap.add_argument("--cpu-budget", type=float, default=15.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"], help="multi-GPU: peer-memory kernels or whole-buffer NCCL")
     ap.add_argument("--shadow-split", default="instances", choices=["instances", "cascades"])
     ap.add_argument("--partition", default="stripes", choices=["stripes", "range"], help="multi-GPU: how instances are shared out")
+    ap.add_argument("--balance", type=int, default=8, help="multi-GPU, stripes: untimed frames that move the stripe bounds towards equal per-rank pass times (0: equal-width interleaved stripes)")
     ap.add_argument("--stripes-per-rank", type=int, default=0, help="multi-GPU: interleaved screen stripes per GPU (0: sortlast.STRIPES_PER_RANK)")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -190,6 +190,11 @@ LH_HOST_API int lh_scene_add_mesh_indexed(LhScene* scene, const LhIndexedMesh* m
 /* an instance with the node's matrix as it is (column-major; the quantisation is already part of a glTF node's
  * scale / translation): Instance(transform, mesh_info) of src/main.cpp:433-440 */
 LH_HOST_API int lh_scene_add_instance_matrix(LhScene* scene, int mesh, const float transform[16]);
+/* a material variant of `mesh`: its own MeshInfo (texture indices, colour factor; NULL keeps the factor) over the same
+ * vertex / index / meshlet buffers; returns the new mesh id */
+LH_HOST_API int lh_scene_add_mesh_variant(LhScene* scene, int mesh, uint16_t base_color_texture_index,
+                                          uint16_t metallic_roughness_texture_index, uint16_t normal_texture_index,
+                                          const float base_color_factor[3]);
 
 /* ---- the reference's meshlet cache (src/resources/fs_cache.h:3-25, src/resources/mesh_loading.cpp:602-649) ----
  * Three raw blobs per primitive under <dir>/<std::hash of "<name> meshlets" | "<name> indices" | "<name> micro indices">:

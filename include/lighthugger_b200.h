@@ -46,7 +46,8 @@ enum {
 
 enum {
     LH_CONFIG_WRITE_DRAW_COMMANDS = 1u << 0,  /* keep materialising DrawIndirectCommand[] (default on) */
-    LH_CONFIG_PASS_TIMINGS = 1u << 1          /* record a CUDA event pair around every pass */
+    LH_CONFIG_PASS_TIMINGS = 1u << 1,         /* record a CUDA event pair around every pass */
+    LH_CONFIG_COUNT_SAMPLES = 1u << 2         /* count the depth-tested samples the rasteriser writes (LhFrameStats.emitted_samples) */
 };
 
 typedef struct LhContext LhContext;
@@ -97,6 +98,7 @@ typedef struct LhFrameStats {
     uint32_t meshlets_skipped_occluded[5];  /* every key already stored in the bound is nearer */
     uint32_t meshlets_queued[5];            /* meshlets the band selection handed to the raster kernel */
     uint32_t _pad1;
+    uint64_t emitted_samples[5];            /* 64-/32-bit min reductions issued, [0] main view, [1..4] cascades (LH_CONFIG_COUNT_SAMPLES) */
 } LhFrameStats;
 
 enum {
@@ -119,6 +121,8 @@ enum {
     LH_PASS_SHADOWMAPS,
     LH_PASS_RENDER_GEOMETRY,
     LH_PASS_DISPLAY_TRANSFORM,
+    LH_PASS_SHADOW_EXCHANGE,   /* sort-last: merging the ranks' shadow layers (new) */
+    LH_PASS_FRAME_BARRIER,     /* sort-last: every rank has delivered its rows of the frame (new) */
     LH_PASS_COUNT
 };
 
@@ -187,6 +191,10 @@ LH_API int lh_set_instance_range(LhContext* ctx, uint32_t first, uint32_t count)
  * itself (an index range hands every GPU a sparse copy of the whole scene whose hidden layers all get rasterised);
  * interleaving several stripes per GPU evens the load.  stripes == 0 turns it off (default). */
 LH_API int lh_set_instance_stripes(LhContext* ctx, int view, uint32_t stripes, uint32_t index, uint32_t count);
+/* The same with stripes of unequal width: bounds[0 .. stripes] ascend from 0 to 1 across the view (the outer two are
+ * taken as open-ended); every context of the group must be given the same bounds.  A host that measures each GPU's
+ * pass times can move the bounds from frame to frame to even the load (lighthugger_b200/sortlast.py does). */
+LH_API int lh_set_instance_stripe_bounds(LhContext* ctx, int view, const float* bounds, uint32_t stripes, uint32_t index, uint32_t count);
 /* cascades this context renders in lh_render_frame (bit c = cascade c; default 0xF).
  * "One cascade per GPU" = mask 1 << rank; the layers are merged by lh_shadow_exchange. */
 LH_API int lh_set_shadow_cascade_mask(LhContext* ctx, uint32_t mask);
@@ -222,6 +230,8 @@ LH_API int lh_render_frame_host(LhContext* ctx, const LhUniforms* uniforms,
 
 /* ---- readback (new; needed for parity and bench) ---- */
 LH_API int lh_get_frame_stats(LhContext* ctx, LhFrameStats* out);   /* synchronises */
+/* replaces LhConfig.flags for the frames that follow (e.g. to count samples on one untimed frame) */
+LH_API int lh_set_config_flags(LhContext* ctx, uint32_t flags);
 LH_API int lh_get_target(LhContext* ctx, int target, void* dst, uint64_t bytes);
 LH_API int lh_get_timings(LhContext* ctx, LhPassTimes* out);
 LH_API int lh_get_launch_count(LhContext* ctx, uint64_t* kernels_launched);   /* kernels this context has launched so far */

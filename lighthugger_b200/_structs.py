@@ -78,10 +78,11 @@ for _t, _n in ((LhMeshInfo, 104), (LhMiscStorage, 792), (LhUniforms, 560), (LhDr
 
 # ---- include/lighthugger_b200.h ----
 LH_PASS_NAMES = ["reset", "cull_instances", "cull_meshlets", "visbuffer", "composite", "depth_reduction", "shadow_matrices",
-                 "cull_instances_shadows", "shadowmaps", "render_geometry", "display_transform"]
+                 "cull_instances_shadows", "shadowmaps", "render_geometry", "display_transform", "shadow_exchange", "frame_barrier"]
 LH_PASS_COUNT = len(LH_PASS_NAMES)
 LH_CONFIG_WRITE_DRAW_COMMANDS = 1
 LH_CONFIG_PASS_TIMINGS = 2
+LH_CONFIG_COUNT_SAMPLES = 4
 LH_TARGET_VIS64, LH_TARGET_DEPTH, LH_TARGET_SCENE_RGBA16F, LH_TARGET_SHADOW, LH_TARGET_DISPLAY_BGRA8 = range(5)
 LH_TEXTURE_RGBA8_SRGB, LH_TEXTURE_RGBA8_UNORM, LH_TEXTURE_BC7_SRGB, LH_TEXTURE_BC1_SRGB = range(4)
 LH_ERR_CAPACITY = -4
@@ -116,7 +117,7 @@ class LhFrameStats(C.Structure):
         ("shadow_candidate_meshlets", u32 * 4), ("shadow_opaque", u32 * 4), ("shadow_alpha_clip", u32 * 4),
         ("num_large_triangles", u32), ("overflow", u32), ("rasterized_triangles", u64),
         ("meshlets_skipped_no_sample", u32 * 5), ("meshlets_skipped_occluded", u32 * 5),
-        ("meshlets_queued", u32 * 5), ("_pad1", u32),
+        ("meshlets_queued", u32 * 5), ("_pad1", u32), ("emitted_samples", C.c_uint64 * 5),
     ]
 
 

@@ -54,7 +54,9 @@ FrameParams make_params(LhContext* ctx, int cascade, int set, bool internal_list
         p.stripes[v] = ctx->stripes[v];
         p.stripe_index[v] = ctx->stripe_index[v];
         p.stripe_count[v] = ctx->stripe_count[v];
+        for (uint32_t s = 0; s <= kMaxStripes; s++) p.stripe_bounds[v][s] = ctx->stripe_bounds[v][s];
     }
+    p.small_max_area = ctx->tune.small_max_area;
     p.shadowmap_size = ctx->cfg.shadowmap_size;
     p.flags = ctx->cfg.flags;
     p.max_large = ctx->cfg.max_large_triangles;
@@ -116,7 +118,7 @@ namespace {
 const char* const kPassZone[LH_PASS_COUNT] = {
     "reset buffers", "cull instances", "cull meshlets and write draw calls", "visbuffer rendering", "composite (sort-last)",
     "depth reduction", "generate shadow matrices", "cull instances for shadows", "shadowmap rasterization", "render geometry",
-    "display transform"};
+    "display transform", "shadow exchange (sort-last)", "frame barrier (sort-last)"};
 
 struct PassScope {
     LhContext* ctx;
@@ -129,6 +131,10 @@ struct PassScope {
         if (ctx->cfg.flags & LH_CONFIG_PASS_TIMINGS) {
             cudaEventRecord(ctx->pass_stop[pass], ctx->stream);
             ctx->pass_recorded[pass] = true;
+            if (pass != LH_PASS_DISPLAY_TRANSFORM) {
+                if (ctx->first_pass < 0) ctx->first_pass = pass;
+                ctx->last_pass = pass;
+            }
         }
         nvtxRangePop();
     }
@@ -297,8 +303,9 @@ int lh_context_create(const LhConfig* cfg, LhContext** out) {
         sscanf(t, "%f,%f,%f,%f,%f,%f,%f", &f[0], &f[1], &f[2], &f[3], &f[4], &f[5], &f[6]);
     }
     if (const char* t = getenv("LH_TUNE")) {
-        unsigned v[7] = {ctx->tune.main_bands, ctx->tune.shadow_bands, ctx->tune.main_grid, ctx->tune.shadow_grid, ctx->tune.resolve_low_priority, ctx->tune.select_grid, ctx->tune.resolve_split};
-        sscanf(t, "%u,%u,%u,%u,%u,%u,%u", &v[0], &v[1], &v[2], &v[3], &v[4], &v[5], &v[6]);
+        unsigned v[8] = {ctx->tune.main_bands, ctx->tune.shadow_bands, ctx->tune.main_grid, ctx->tune.shadow_grid, ctx->tune.resolve_low_priority, ctx->tune.select_grid, ctx->tune.resolve_split, ctx->tune.small_max_area};
+        sscanf(t, "%u,%u,%u,%u,%u,%u,%u,%u", &v[0], &v[1], &v[2], &v[3], &v[4], &v[5], &v[6], &v[7]);
+        ctx->tune.small_max_area = v[7] < 1 ? 1 : (v[7] > 1024 ? 1024 : v[7]);
         ctx->tune.resolve_low_priority = v[4] != 0;
         ctx->tune.resolve_split = v[6] != 0;
         auto clamp = [](unsigned x, unsigned lo, unsigned hi) { return x < lo ? lo : (x > hi ? hi : x); };
@@ -629,10 +636,23 @@ int lh_set_shadow_instance_range(LhContext* ctx, uint32_t first, uint32_t count)
 }
 
 int lh_set_instance_stripes(LhContext* ctx, int view, uint32_t stripes, uint32_t index, uint32_t count) {
-    if (!ctx || view < 0 || view > 1 || (stripes && (count == 0 || index >= count))) return LH_ERR_INVALID_ARGUMENT;
+    if (!ctx || view < 0 || view > 1 || stripes > kMaxStripes || (stripes && (count == 0 || index >= count))) return LH_ERR_INVALID_ARGUMENT;
     ctx->stripes[view] = stripes;
     ctx->stripe_index[view] = index;
     ctx->stripe_count[view] = count ? count : 1;
+    for (uint32_t s = 0; s <= kMaxStripes; s++) ctx->stripe_bounds[view][s] = stripes ? (s < stripes ? (float)s / (float)stripes : 1.0f) : 0.0f;
+    return LH_OK;
+}
+
+int lh_set_instance_stripe_bounds(LhContext* ctx, int view, const float* bounds, uint32_t stripes, uint32_t index, uint32_t count) {
+    if (!ctx || !bounds || view < 0 || view > 1 || stripes == 0 || stripes > kMaxStripes || count == 0 || index >= count) return LH_ERR_INVALID_ARGUMENT;
+    for (uint32_t s = 0; s < stripes; s++)
+        if (!(bounds[s] <= bounds[s + 1])) return fail(ctx, LH_ERR_INVALID_ARGUMENT, "stripe bounds must ascend");
+    ctx->stripes[view] = stripes;
+    ctx->stripe_index[view] = index;
+    ctx->stripe_count[view] = count;
+    // the outer bounds are open: every centre belongs to some stripe
+    for (uint32_t s = 0; s <= kMaxStripes; s++) ctx->stripe_bounds[view][s] = s == 0 ? 0.0f : (s < stripes ? bounds[s] : 1.0f);
     return LH_OK;
 }
 
@@ -652,6 +672,7 @@ int lh_frame_begin(LhContext* ctx, const LhUniforms* u) {
     ctx->uniforms = *u;
     ctx->have_uniforms = true;
     for (int i = 0; i < LH_PASS_COUNT; i++) ctx->pass_recorded[i] = false;
+    ctx->first_pass = ctx->last_pass = -1;
     ctx->raster_bands_recorded = 0;
     if (int rc = ensure_peer_maps(ctx)) return rc;
     return ensure_instance_tiles(ctx, u->num_instances);
@@ -804,7 +825,10 @@ int lh_render_frame(LhContext* ctx) {
         for (int i = 0; i < n_others; i++) LH_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->join_events[i], 0));
         if ((rc = check_launch(ctx, "shadow cascades"))) return rc;
     }
-    if ((rc = lh_shadow_exchange(ctx))) return rc;
+    if (ctx->nccl_comm && ctx->nranks > 1) {
+        PassScope scope(ctx, LH_PASS_SHADOW_EXCHANGE);
+        if ((rc = lh_shadow_exchange(ctx))) return rc;
+    }
     {
         PassScope scope(ctx, LH_PASS_RENDER_GEOMETRY);   // what is left of the resolve on the critical path
         if (split) LH_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->material_done, 0));
@@ -812,7 +836,10 @@ int lh_render_frame(LhContext* ctx) {
         if ((rc = check_launch(ctx, "resolve"))) return rc;
     }
     // rank 0's frame is complete, and every table a peer reads may be rewritten, once all ranks have resolved their rows
-    if (peer_exchange(ctx)) return frame_barrier(ctx);
+    if (peer_exchange(ctx)) {
+        PassScope scope(ctx, LH_PASS_FRAME_BARRIER);
+        return frame_barrier(ctx);
+    }
     return LH_OK;
 }
 
@@ -901,21 +928,23 @@ int lh_get_timings(LhContext* ctx, LhPassTimes* out) {
     if (!(ctx->cfg.flags & LH_CONFIG_PASS_TIMINGS)) return fail(ctx, LH_ERR_NOT_READY, "context was created without LH_CONFIG_PASS_TIMINGS");
     LH_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     memset(out, 0, sizeof(*out));
-    int first = -1, last = -1;
-    for (int i = 0; i < LH_PASS_COUNT; i++) {
-        if (!ctx->pass_recorded[i]) continue;
-        cudaEventElapsedTime(&out->ms[i], ctx->pass_start[i], ctx->pass_stop[i]);
-        if (i == LH_PASS_DISPLAY_TRANSFORM) continue;
-        if (first < 0) first = i;
-        last = i;
-    }
-    if (first >= 0) cudaEventElapsedTime(&out->frame_ms, ctx->pass_start[first], ctx->pass_stop[last]);
+    for (int i = 0; i < LH_PASS_COUNT; i++)
+        if (ctx->pass_recorded[i]) cudaEventElapsedTime(&out->ms[i], ctx->pass_start[i], ctx->pass_stop[i]);
+    // the frame: first pass recorded to last pass recorded, in time order (the display transform is timed separately:
+    // SURVEY 8d, the frame is steps 1-11)
+    if (ctx->first_pass >= 0) cudaEventElapsedTime(&out->frame_ms, ctx->pass_start[ctx->first_pass], ctx->pass_stop[ctx->last_pass]);
     out->raster_meshlets_kernel_launches = ctx->raster_bands_recorded;
     for (uint32_t i = 0; i < ctx->raster_bands_recorded; i++) {   // sum over the main view's launches of the kernel
         float ms = 0.0f;
         cudaEventElapsedTime(&ms, ctx->raster_band_a[i], ctx->raster_band_b[i]);
         out->raster_meshlets_kernel_ms += ms;
     }
+    return LH_OK;
+}
+
+int lh_set_config_flags(LhContext* ctx, uint32_t flags) {
+    if (!ctx) return LH_ERR_INVALID_ARGUMENT;
+    ctx->cfg.flags = flags;
     return LH_OK;
 }
 

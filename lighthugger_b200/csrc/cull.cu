@@ -141,22 +141,23 @@ __device__ __forceinline__ bool cull_sphere_shadows(const LhMiscStorage* misc, V
 // Sort-last ownership by screen stripes (new; lh_set_instance_stripes).  A pure function of (instance, camera), evaluated
 // identically by every rank, so the ranks' lists partition the single-GPU list.  Main view: stripe of the centre's
 // ndc x under initial_view (the culling camera); cascade: stripe of its light-space x over [-R, R].
-__device__ __forceinline__ uint32_t stripe_of(float t01, uint32_t stripes) {
-    const float s = pmul(t01, (float)stripes);
-    if (!(s > 0.0f)) return 0u;   // also NaN
-    return min((uint32_t)s, stripes - 1u);
+// the stripe whose [bounds[s], bounds[s + 1]) holds t01; the outer stripes are open-ended, NaN goes to stripe 0
+__device__ __forceinline__ uint32_t stripe_of(float t01, uint32_t stripes, const float* bounds) {
+    uint32_t s = 0;
+    while (s + 1 < stripes && t01 >= bounds[s + 1]) s++;
+    return s;
 }
 __device__ __forceinline__ bool owned_main(const FrameParams& P, V4 ws) {
     if (P.stripes[0] == 0) return true;
     const V4 v = mat4_mul(&P.u.initial_view.m[0][0], ws.x, ws.y, ws.z, 1.0f);
     const float ndc = pdiv(pmul(P.u.perspective.m[0][0], v.x), fmaxf(-v.z, LH_NEAR_PLANE));
-    return stripe_of(padd(pmul(ndc, 0.5f), 0.5f), P.stripes[0]) % P.stripe_count[0] == P.stripe_index[0];
+    return stripe_of(padd(pmul(ndc, 0.5f), 0.5f), P.stripes[0], P.stripe_bounds[0]) % P.stripe_count[0] == P.stripe_index[0];
 }
 __device__ __forceinline__ bool owned_shadow(const FrameParams& P, const LhMiscStorage* misc, V4 ws, uint32_t cascade) {
     if (P.stripes[1] == 0) return true;
     const V4 v = mat4_mul(&misc->shadow_view_matrices[cascade].m[0][0], ws.x, ws.y, ws.z, 1.0f);
     const float t = padd(pmul(pdiv(v.x, misc->shadow_sphere_radii[cascade]), 0.5f), 0.5f);
-    return stripe_of(t, P.stripes[1]) % P.stripe_count[1] == P.stripe_index[1];
+    return stripe_of(t, P.stripes[1], P.stripe_bounds[1]) % P.stripe_count[1] == P.stripe_index[1];
 }
 
 // ---- K1: reset_buffers_a + reset_counters ----
@@ -177,7 +178,10 @@ __global__ void reset_kernel(const __grid_constant__ FrameParams P) {
     s->main_large_count = 0;
     s->main_visible = s->main_candidates = s->main_opaque = s->main_alpha_clip = 0;
     s->rasterized_triangles = 0ull;
-    for (int c = 0; c < 5; c++) s->skipped_empty[c] = s->skipped_occluded[c] = s->queued[c] = 0;
+    for (int c = 0; c < 5; c++) {
+        s->skipped_empty[c] = s->skipped_occluded[c] = s->queued[c] = 0;
+        s->samples[c] = 0ull;
+    }
     for (int c = 0; c < 4; c++) {
         s->shadow_opaque[c] = 0;
         s->shadow_alpha_clip[c] = 0;

@@ -206,6 +206,7 @@ __global__ void gather_stats_kernel(const __grid_constant__ FrameParams P, LhFra
         s.meshlets_skipped_no_sample[c] = st->skipped_empty[c];
         s.meshlets_skipped_occluded[c] = st->skipped_occluded[c];
         s.meshlets_queued[c] = st->queued[c];
+        s.emitted_samples[c] = st->samples[c];
     }
     *out = s;
 }

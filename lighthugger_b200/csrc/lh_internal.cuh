@@ -73,7 +73,8 @@ struct FrameState {
     uint32_t shadow_candidates[4];
     uint32_t done[4];              // instance cull: CTAs finished per sector (self-cleaning of the tile states)
     unsigned long long rasterized_triangles;
-    uint32_t skipped_empty[5], skipped_occluded[5], queued[5];   // meshlets dropped by the rasteriser's early-outs: [0] main view, [1..4] cascades (stats)
+    uint32_t skipped_empty[5], skipped_occluded[5], queued[5];
+    unsigned long long samples[5];      // reductions issued by the rasteriser (LH_CONFIG_COUNT_SAMPLES): [0] main view, [1..4] cascades   // meshlets dropped by the rasteriser's early-outs: [0] main view, [1..4] cascades (stats)
 };
 
 // Work counters of one view (the main view or one cascade) through meshlet cull and rasterisation.  Each view that
@@ -95,6 +96,7 @@ struct PassState {
     uint32_t cta_done;                 // CTAs of the running raster / deferred launch that have finished (self-cleaning)
 };
 
+constexpr uint32_t kMaxStripes = 32;          // sort-last ownership stripes per view (lh_set_instance_stripes / _stripe_bounds)
 constexpr uint32_t kMeshletTile = 1024;        // candidate meshlets per scan tile
 constexpr uint32_t kInstanceTile = 256;        // instances per scan tile
 constexpr uint64_t kMaxMeshletTiles = (1ull << 32) / kMeshletTile;  // lo32 of the prefix counter bounds the candidates
@@ -108,10 +110,12 @@ struct FrameParams {
     // sort-last ownership by screen stripes (lh_set_instance_stripes): stripes == 0 means off; otherwise an instance
     // belongs to the context whose index equals (stripe of its projected centre) % count.  [0] main view, [1] cascades
     uint32_t stripes[2], stripe_index[2], stripe_count[2];
+    float stripe_bounds[2][kMaxStripes + 1]; // stripe s holds the centres with bounds[s] <= t < bounds[s + 1], t in [0, 1] across the view
     uint32_t shadowmap_size;
     uint32_t flags;
     uint32_t max_large;
     uint32_t num_bands;                      // depth bands of the raster pass being launched (raster.cu)
+    uint32_t small_max_area;                 // a lane finishes triangles of at most this many pixel tests itself (raster.cu)
     float band_fractions[7];                 // cumulative meshlet-count fractions at which its bands end; [0] == 0: built-in table
     FrameState* state;
     unsigned long long* instance_tiles;      // [4][tiles] decoupled-lookback states
@@ -158,6 +162,7 @@ struct LhContext {
     uint32_t instance_first = 0, instance_count = 0xFFFFFFFFu;
     bool shadow_range_set = false;
     uint32_t stripes[2] = {0, 0}, stripe_index[2] = {0, 0}, stripe_count[2] = {1, 1};
+    float stripe_bounds[2][33] = {};   // kMaxStripes + 1
     uint32_t shadow_instance_first = 0, shadow_instance_count = 0xFFFFFFFFu;
     uint32_t cascade_mask = 0xF;
 
@@ -214,6 +219,7 @@ struct LhContext {
     // timing
     cudaEvent_t pass_start[LH_PASS_COUNT] = {}, pass_stop[LH_PASS_COUNT] = {};
     bool pass_recorded[LH_PASS_COUNT] = {};
+    int first_pass = -1, last_pass = -1;   // of the current frame, in the order they were recorded
     cudaEvent_t timer_a = nullptr, timer_b = nullptr;
     cudaEvent_t raster_band_a[8] = {}, raster_band_b[8] = {};   // around each main-view raster_meshlets_kernel launch
     uint32_t raster_bands_recorded = 0;
@@ -241,10 +247,10 @@ struct LhContext {
     uint32_t row0 = 0, row1 = 0;           // screen rows this rank composites and resolves
     int num_sms = 148;
     // launch shapes of the rasteriser; defaults measured on B200 at BASELINE config 2.  Developer overrides:
-    // LH_TUNE="main_bands,shadow_bands,main_grid,shadow_grid,resolve_low_priority,select_grid,resolve_split" in the environment at context creation.
+    // LH_TUNE="main_bands,shadow_bands,main_grid,shadow_grid,resolve_low_priority,select_grid,resolve_split,small_max_area" in the environment at context creation.
     struct Tuning {
         float main_fractions[7] = {0, 0, 0, 0, 0, 0, 0};   // LH_TUNE_FRACTIONS="f0,f1,..." (main view)
-        uint32_t main_bands = 4, shadow_bands = 6, main_grid = 16, shadow_grid = 3, resolve_low_priority = 1, select_grid = 16, resolve_split = 1;
+        uint32_t main_bands = 4, shadow_bands = 6, main_grid = 16, shadow_grid = 3, resolve_low_priority = 1, select_grid = 16, resolve_split = 1, small_max_area = 128;
     } tune;
 
     std::vector<void*> buffers;

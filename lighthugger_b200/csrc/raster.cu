@@ -100,6 +100,14 @@ struct alignas(16) WarpScratch {
     unsigned long long rec_bar;   // mbarrier: the chunk's records have landed (LH_RECORD_BULK)
 };
 constexpr int kVertOutside = INT_MIN, kVertNonFinite = INT_MIN + 1;   // |snapped| <= 2^29, so neither can be a coordinate
+#ifndef LH_SELECT_EXACT_PIXELS
+#define LH_SELECT_EXACT_PIXELS 16
+#endif
+constexpr int kSelectExactPixels = LH_SELECT_EXACT_PIXELS;   // selection tests rectangles of at most this many pixels against the stored values themselves (0: hierarchical Z only)
+#ifndef LH_FEW_SAMPLES_PATH
+#define LH_FEW_SAMPLES_PATH 0
+#endif
+constexpr bool kFewSamplesPath = LH_FEW_SAMPLES_PATH != 0;   // meshlets touching at most 2x2 samples skip the per-triangle rectangle / compaction machinery
 constexpr int kMaxOcclusionBlocks = 16;    // early-out reads at most 16 blocks of 8x4 pixels (512 keys)
 
 // ---- bulk-asynchronous copies global -> shared, completion counted in bytes on an mbarrier ----
@@ -174,8 +182,11 @@ struct Target {
     unsigned long long* vis;
     uint32_t* layer;
     uint32_t width, height;
+    bool count;                 // LH_CONFIG_COUNT_SAMPLES
+    mutable uint32_t samples;   // reductions this thread has issued (counted only then)
     // depth test + write of one covered sample
     __device__ __forceinline__ void emit(int x, int y, float z, uint32_t lo) const {
+        if (count) samples++;
         if (SHADOW) {
             z = padd(z, 0.0f);                      // canonicalise -0
             if (!(z >= 0.0f && z < 1.0f)) return;   // 0 <= z <= w clip; LESS against the 1.0 clear
@@ -590,12 +601,23 @@ __global__ void __launch_bounds__(256) raster_select_kernel(const __grid_constan
         if (keep) mb = __ldg((const uint4*)(bounds + k));
         if (keep && band != 0 && mb.x != kUntestable) {
             const int px0 = (int)(mb.x & 0xFFFFu), px1 = (int)(mb.x >> 16), py0 = (int)(mb.y & 0xFFFFu), py1 = (int)(mb.y >> 16);
-            const bool fine = ((px1 >> kHizShift0) - (px0 >> kHizShift0) + 1) * ((py1 >> kHizShift0) - (py0 >> kHizShift0) + 1) <= kMaxHizTiles;
-            const int shift = fine ? kHizShift0 : kHizShift1, TW = fine ? TW0 : TW1;
-            const uint32_t* level = fine ? level0 : level1;
             uint32_t worst = 0;   // main view: largest stored key high word; cascade: largest stored depth
-            for (int ty = py0 >> shift; ty <= (py1 >> shift); ty++)
-                for (int tx = px0 >> shift; tx <= (px1 >> shift); tx++) worst = max(worst, __ldcg(level + (size_t)ty * TW + tx));
+            if ((px1 - px0 + 1) * (py1 - py0 + 1) <= kSelectExactPixels) {
+                // a rectangle of a few pixels (most meshlets of a far cascade): the stored values themselves, which is
+                // what the raster kernel's own re-test would read -- with one LANE per meshlet instead of one warp
+                const uint32_t* layer = SHADOW ? P.shadow + (size_t)cascade * P.shadowmap_size * P.shadowmap_size : nullptr;
+                for (int y = py0; y <= py1; y++)
+                    for (int x = px0; x <= px1; x++) {
+                        const size_t at = (size_t)y * W + x;
+                        worst = max(worst, SHADOW ? __ldcg(layer + at) : __ldcg((const uint32_t*)P.vis + 2 * at + 1));
+                    }
+            } else {
+                const bool fine = ((px1 >> kHizShift0) - (px0 >> kHizShift0) + 1) * ((py1 >> kHizShift0) - (py0 >> kHizShift0) + 1) <= kMaxHizTiles;
+                const int shift = fine ? kHizShift0 : kHizShift1, TW = fine ? TW0 : TW1;
+                const uint32_t* level = fine ? level0 : level1;
+                for (int ty = py0 >> shift; ty <= (py1 >> shift); ty++)
+                    for (int tx = px0 >> shift; tx <= (px1 >> shift); tx++) worst = max(worst, __ldcg(level + (size_t)ty * TW + tx));
+            }
             if (SHADOW ? mb.z >= worst : worst < mb.z) {
                 keep = false;
                 occluded++;
@@ -692,12 +714,25 @@ __device__ __forceinline__ void raster_one_meshlet(const FrameParams& P, const T
             Tl[4 * k] = c.x; Tl[4 * k + 1] = c.y; Tl[4 * k + 2] = c.z; Tl[4 * k + 3] = c.w;
         }
         const uint8_t* index_g = rec.indices;
-        for (uint32_t v = lane; v < nv; v += 32) {
-            uint32_t idx;
-            if (kStageStreams) idx = wide ? *(const uint32_t*)(index_s + 4 * v) : (uint32_t)*(const uint16_t*)(index_s + 2 * v);
-            else idx = wide ? __ldg((const uint32_t*)index_g + v) : (uint32_t)__ldg((const uint16_t*)index_g + v);
-            const uint16_t* p = positions + 3 * (size_t)idx;
-            const float px = (float)__ldg(p), py = (float)__ldg(p + 1), pz = (float)__ldg(p + 2);
+        // A meshlet has at most 64 vertices: two per lane.  Both vertex indices, then all six position loads, are issued
+        // before anything is used, so the phase pays the index and the position round trip once, not once per vertex.
+        auto load_index = [&](uint32_t v) -> uint32_t {
+            if (kStageStreams) return wide ? *(const uint32_t*)(index_s + 4 * v) : (uint32_t)*(const uint16_t*)(index_s + 2 * v);
+            return wide ? __ldg((const uint32_t*)index_g + v) : (uint32_t)__ldg((const uint16_t*)index_g + v);
+        };
+        const uint32_t v0 = lane, v1 = lane + 32u;
+        const bool has0 = v0 < nv, has1 = v1 < nv;
+        const uint32_t idx0 = has0 ? load_index(v0) : 0u, idx1 = has1 ? load_index(v1) : 0u;
+        const uint16_t* p0 = positions + 3 * (size_t)idx0;
+        const uint16_t* p1 = positions + 3 * (size_t)idx1;
+        uint16_t q[6] = {0, 0, 0, 0, 0, 0};
+        if (has0) { q[0] = __ldg(p0); q[1] = __ldg(p0 + 1); q[2] = __ldg(p0 + 2); }
+        if (has1) { q[3] = __ldg(p1); q[4] = __ldg(p1 + 1); q[5] = __ldg(p1 + 2); }
+#pragma unroll
+        for (int k = 0; k < 2; k++) {
+            if (!(k ? has1 : has0)) continue;
+            const uint32_t v = k ? v1 : v0;
+            const float px = (float)q[3 * k], py = (float)q[3 * k + 1], pz = (float)q[3 * k + 2];
             const V4 world = mat4_mul(Tl, px, py, pz, 1.0f);
             V4 clip;
             if (SHADOW && affine) {
@@ -735,11 +770,12 @@ __device__ __forceinline__ void raster_one_meshlet(const FrameParams& P, const T
     // ---- (1b) the same two early-outs with the exact vertex bounds: every triangle lies inside the vertices'
     // rectangle, and (screen-linear depth) no fragment is nearer than the nearest vertex ----
     const bool any_special = __any_sync(0xFFFFFFFFu, special);
+    int bx0 = 0, bx1 = INT_MAX, by0 = 0, by1 = INT_MAX;   // pixels whose centres lie inside the vertices' rectangle
     if (!any_special) {
         vminx = __reduce_min_sync(0xFFFFFFFFu, vminx); vmaxx = __reduce_max_sync(0xFFFFFFFFu, vmaxx);
         vminy = __reduce_min_sync(0xFFFFFFFFu, vminy); vmaxy = __reduce_max_sync(0xFFFFFFFFu, vmaxy);
-        const int bx0 = max(0, (vminx - 128 + 255) >> 8), bx1 = min(W - 1, (vmaxx - 128) >> 8);
-        const int by0 = max(0, (vminy - 128 + 255) >> 8), by1 = min(H - 1, (vmaxy - 128) >> 8);
+        bx0 = max(0, (vminx - 128 + 255) >> 8); bx1 = min(W - 1, (vmaxx - 128) >> 8);
+        by0 = max(0, (vminy - 128 + 255) >> 8); by1 = min(H - 1, (vmaxy - 128) >> 8);
         if (bx0 > bx1 || by0 > by1) {   // no pixel centre inside
             cnt.skipped_empty++;
             return;
@@ -769,6 +805,62 @@ __device__ __forceinline__ void raster_one_meshlet(const FrameParams& P, const T
     const uint8_t* micro_g = rec.micro;
     auto micro = [&](uint32_t k) -> uint32_t { return kStageStreams ? (uint32_t)micro_s[k] : (uint32_t)__ldg(micro_g + k); };
 
+    // ---- (2') a meshlet that can touch at most 2x2 samples -- most meshlets of a far cascade or of distant instances:
+    // every triangle tests those samples directly (same integer edge functions, same top-left rule, same depth
+    // expression as below), with no per-triangle rectangle, no compaction and no second pass over the survivors ----
+    if (kFewSamplesPath && !ALPHA && !any_special && bx1 - bx0 <= 1 && by1 - by0 <= 1) {
+        const int ccx = bx0 * 256 + 128, ccy = by0 * 256 + 128;
+        const int nx = bx1 - bx0, ny = by1 - by0;   // 0 or 1 more sample per axis
+        for (uint32_t t = lane; t < tri_count; t += 32) {
+            const uint32_t ia = micro(3 * t);
+            uint32_t ib = micro(3 * t + 1), ic = micro(3 * t + 2);
+            if (max(ia, max(ib, ic)) >= nv) continue;
+            const int ax = sv.sx[ia], ay = sv.sy[ia];
+            int bx = sv.sx[ib], by = sv.sy[ib], cx = sv.sx[ic], cy = sv.sy[ic];
+            // the vertices span fewer than three pixels: every product below is far inside 32 bits
+            int A2 = (bx - ax) * (cy - ay) - (by - ay) * (cx - ax);
+            const bool front = A2 < 0;
+            if (A2 == 0 || (cull == CULL_BACK && !front) || (cull == CULL_FRONT && front)) continue;
+            if (front) {
+                int s0 = bx; bx = cx; cx = s0;
+                s0 = by; by = cy; cy = s0;
+                const uint32_t si = ib; ib = ic; ic = si;
+                A2 = -A2;
+            }
+            const int e0x = cx - bx, e0y = cy - by, e1x = ax - cx, e1y = ay - cy, e2x = bx - ax, e2y = by - ay;
+            const int bias0 = top_left(e0x, e0y) ? 0 : -1, bias1 = top_left(e1x, e1y) ? 0 : -1, bias2 = top_left(e2x, e2y) ? 0 : -1;
+            int w0_row = e0x * (ccy - by) - e0y * (ccx - bx);
+            int w1_row = e1x * (ccy - cy) - e1y * (ccx - cx);
+            int w2_row = e2x * (ccy - ay) - e2y * (ccx - ax);
+            bool any = false;
+            float az = 0.0f, dz1 = 0.0f, dz2 = 0.0f, inv_area = 0.0f;
+            for (int dy = 0; dy <= ny; dy++) {
+                int w0 = w0_row, w1 = w1_row, w2 = w2_row;
+                for (int dx = 0; dx <= nx; dx++) {
+                    if (((w0 + bias0) | (w1 + bias1) | (w2 + bias2)) >= 0) {
+                        if (!any) {
+                            any = true;
+                            az = sv.z[ia];
+                            dz1 = psub(sv.z[ib], az);
+                            dz2 = psub(sv.z[ic], az);
+                            inv_area = pdiv(1.0f, (float)A2);
+                            cnt.tris_done++;
+                        }
+                        const float z = padd(az, pmul(padd(pmul((float)w1, dz1), pmul((float)w2, dz2)), inv_area));
+                        tg.emit(bx0 + dx, by0 + dy, z, lo_base | t);
+                    }
+                    w0 -= e0y * 256;
+                    w1 -= e1y * 256;
+                    w2 -= e2y * 256;
+                }
+                w0_row += e0x * 256;
+                w1_row += e1x * 256;
+                w2_row += e2x * 256;
+            }
+        }
+        return;
+    }
+
     // ---- (2) triangle cull phase ----
     uint32_t n_surv = 0;
     const uint32_t screen_max = (uint32_t)(W - 1) | ((uint32_t)(H - 1) << 16);
@@ -793,7 +885,7 @@ __device__ __forceinline__ void raster_one_meshlet(const FrameParams& P, const T
                     const bool front = A2 < 0;
                     if (A2 == 0 || (cull == CULL_BACK && !front) || (cull == CULL_FRONT && front)) return;
                     const int spanx = px1 - px0 + 1, spany = py1 - py0 + 1;
-                    if (small_extent && spanx <= kSmallMaxSpan && spany <= kSmallMaxSpan && spanx * spany <= kSmallMaxArea) {
+                    if (small_extent && spanx <= kSmallMaxSpan && spany <= kSmallMaxSpan && spanx * spany <= (int)P.small_max_area) {
                         keep = true;
                     } else {
                         // large footprint: one queue entry per 128x32 screen tile the bounding box touches
@@ -945,6 +1037,8 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, LH_RASTER_MIN_CTAS) raster_
     tg.layer = SHADOW ? P.shadow + (size_t)cascade * P.shadowmap_size * P.shadowmap_size : nullptr;
     tg.width = SHADOW ? P.shadowmap_size : P.u.window_size[0];
     tg.height = SHADOW ? P.shadowmap_size : P.u.window_size[1];
+    tg.count = (P.flags & LH_CONFIG_COUNT_SAMPLES) != 0;
+    tg.samples = 0;
     const int W = (int)tg.width;
     const float* M = SHADOW ? cascade_matrix : &P.u.combined_perspective_view.m[0][0];
     const bool affine = SHADOW && cascade_matrix[3] == 0.0f && cascade_matrix[7] == 0.0f && cascade_matrix[11] == 0.0f && cascade_matrix[15] == 1.0f;
@@ -1038,6 +1132,10 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, LH_RASTER_MIN_CTAS) raster_
             if (cnt.skipped_empty) atomicAdd(&P.state->skipped_empty[pass], cnt.skipped_empty);
         }
     }
+    if (tg.count) {
+        const uint32_t n = __reduce_add_sync(0xFFFFFFFFu, tg.samples);
+        if (lane == 0 && n) atomicAdd(&P.state->samples[SHADOW ? 1u + cascade : 0u], (unsigned long long)n);
+    }
     publish_queue_end(&P.pass->cta_done, &P.pass->large_count, &P.pass->drain_end[band + 1], P.max_large);
 }
 
@@ -1074,6 +1172,8 @@ __global__ void __launch_bounds__(kDeferredWarps * 32) raster_deferred_kernel(co
     tg.layer = SHADOW ? P.shadow + (size_t)cascade * P.shadowmap_size * P.shadowmap_size : nullptr;
     tg.width = SHADOW ? P.shadowmap_size : P.u.window_size[0];
     tg.height = SHADOW ? P.shadowmap_size : P.u.window_size[1];
+    tg.count = (P.flags & LH_CONFIG_COUNT_SAMPLES) != 0;
+    tg.samples = 0;
     const float* M = SHADOW ? &((const LhMiscStorage*)P.u.misc_storage)->shadow_matrices[cascade].m[0][0] : &P.u.combined_perspective_view.m[0][0];
 
     for (uint32_t base = range_begin + (blockIdx.x * kDeferredWarps + warp) * 32; base < range_end; base += gridDim.x * kDeferredWarps * 32) {
@@ -1180,6 +1280,10 @@ __global__ void __launch_bounds__(kDeferredWarps * 32) raster_deferred_kernel(co
             }
         }
         __syncwarp();
+    }
+    if (tg.count) {
+        const uint32_t n = __reduce_add_sync(0xFFFFFFFFu, tg.samples);
+        if (lane == 0 && n) atomicAdd(&P.state->samples[SHADOW ? 1u + cascade : 0u], (unsigned long long)n);
     }
     if (round == 0) publish_queue_end(&P.pass->cta_done_deferred, &P.pass->split_count, &P.pass->split_end[drain + 1], P.max_large);
 }

@@ -51,24 +51,30 @@ struct Bary {
     F3 lambda, ddx, ddy;
 };
 
-// CalcFullBary, vbuffer.glsl:11-63
+// CalcFullBary, vbuffer.glsl:11-63.  Everything up to the barycentrics themselves is PINNED arithmetic (the reference's
+// operation order with IEEE operations, lh_internal.cuh): the barycentrics give the world position, the world position
+// gives the shadow coordinate, and the shadow lookup COMPARES it with stored depths -- without a depth bias for opaque
+// meshes -- so a last-bit difference would flip comparisons on every surface that grazes its own shadow-map texels.
+// With this part bit-identical to the oracle (which is bit-identical to the reference's GLSL compiled on the host), the
+// shadow term only differs by the rounding of the filter weights.  The derivatives that follow feed texture footprints
+// only and use fused / fast arithmetic.
 __device__ Bary calc_full_bary(float4 p0, float4 p1, float4 p2, float ndc_x, float ndc_y, float win_w, float win_h) {
     Bary r;
-    F3 invw{1.0f / p0.w, 1.0f / p1.w, 1.0f / p2.w};
-    float n0x = p0.x * invw.x, n0y = p0.y * invw.x;
-    float n1x = p1.x * invw.y, n1y = p1.y * invw.y;
-    float n2x = p2.x * invw.z, n2y = p2.y * invw.z;
-    float inv_det = 1.0f / ((n2x - n1x) * (n0y - n1y) - (n0x - n1x) * (n2y - n1y));
-    r.ddx = F3{(n1y - n2y) * inv_det * invw.x, (n2y - n0y) * inv_det * invw.y, (n0y - n1y) * inv_det * invw.z};
-    r.ddy = F3{(n2x - n1x) * inv_det * invw.x, (n0x - n2x) * inv_det * invw.y, (n1x - n0x) * inv_det * invw.z};
-    float ddx_sum = r.ddx.x + r.ddx.y + r.ddx.z;
-    float ddy_sum = r.ddy.x + r.ddy.y + r.ddy.z;
-    float dvx = ndc_x - n0x, dvy = ndc_y - n0y;
-    float interp_inv_w = invw.x + dvx * ddx_sum + dvy * ddy_sum;
-    float interp_w = 1.0f / interp_inv_w;
-    r.lambda.x = interp_w * (invw.x + dvx * r.ddx.x + dvy * r.ddy.x);
-    r.lambda.y = interp_w * (0.0f + dvx * r.ddx.y + dvy * r.ddy.y);
-    r.lambda.z = interp_w * (0.0f + dvx * r.ddx.z + dvy * r.ddy.z);
+    F3 invw{pdiv(1.0f, p0.w), pdiv(1.0f, p1.w), pdiv(1.0f, p2.w)};
+    float n0x = pmul(p0.x, invw.x), n0y = pmul(p0.y, invw.x);
+    float n1x = pmul(p1.x, invw.y), n1y = pmul(p1.y, invw.y);
+    float n2x = pmul(p2.x, invw.z), n2y = pmul(p2.y, invw.z);
+    float inv_det = pdiv(1.0f, psub(pmul(psub(n2x, n1x), psub(n0y, n1y)), pmul(psub(n0x, n1x), psub(n2y, n1y))));
+    r.ddx = F3{pmul(pmul(psub(n1y, n2y), inv_det), invw.x), pmul(pmul(psub(n2y, n0y), inv_det), invw.y), pmul(pmul(psub(n0y, n1y), inv_det), invw.z)};
+    r.ddy = F3{pmul(pmul(psub(n2x, n1x), inv_det), invw.x), pmul(pmul(psub(n0x, n2x), inv_det), invw.y), pmul(pmul(psub(n1x, n0x), inv_det), invw.z)};
+    float ddx_sum = padd(padd(r.ddx.x, r.ddx.y), r.ddx.z);
+    float ddy_sum = padd(padd(r.ddy.x, r.ddy.y), r.ddy.z);
+    float dvx = psub(ndc_x, n0x), dvy = psub(ndc_y, n0y);
+    float interp_inv_w = padd(padd(invw.x, pmul(dvx, ddx_sum)), pmul(dvy, ddy_sum));
+    float interp_w = pdiv(1.0f, interp_inv_w);
+    r.lambda.x = pmul(interp_w, padd(padd(invw.x, pmul(dvx, r.ddx.x)), pmul(dvy, r.ddy.x)));
+    r.lambda.y = pmul(interp_w, padd(padd(0.0f, pmul(dvx, r.ddx.y)), pmul(dvy, r.ddy.y)));
+    r.lambda.z = pmul(interp_w, padd(padd(0.0f, pmul(dvx, r.ddx.z)), pmul(dvy, r.ddy.z)));
     float sx = 2.0f / win_w, sy = -2.0f / win_h;  // the y derivative is flipped (vbuffer.glsl:50-51)
     r.ddx = r.ddx * sx;
     r.ddy = r.ddy * sy;
@@ -86,6 +92,11 @@ struct Interp {
 __device__ __forceinline__ Interp interp1(const Bary& b, float v0, float v1, float v2) {
     F3 m{v0, v1, v2};
     return Interp{dot(m, b.lambda), dot(m, b.ddx), dot(m, b.ddy)};
+}
+// ... with the value in pinned arithmetic (the world position)
+__device__ __forceinline__ Interp interp1_pinned(const Bary& b, float v0, float v1, float v2) {
+    F3 m{v0, v1, v2};
+    return Interp{padd(padd(pmul(v0, b.lambda.x), pmul(v1, b.lambda.y)), pmul(v2, b.lambda.z)), dot(m, b.ddx), dot(m, b.ddy)};
 }
 
 // pbr.glsl:3-96
@@ -255,12 +266,14 @@ __global__ void __launch_bounds__(256) resolve_kernel(const __grid_constant__ Fr
     const uint32_t y = P.resolve_y0 + blockIdx.y * 8 + (warp >> 2) * 4 + (lane >> 3);
     if (x >= W || y >= min(H, P.resolve_y1)) return;
     const size_t pixel = (size_t)y * W + x;
-    const float ndc_x = (float)x / (float)W * 2.0f - 1.0f;  // pixel corner, render_geometry.comp:82-84
-    const float ndc_y = (float)y / (float)H * 2.0f - 1.0f;
+    const float ndc_x = psub(pmul(pdiv((float)x, (float)W), 2.0f), 1.0f);  // pixel corner, render_geometry.comp:82-84
+    const float ndc_y = psub(pmul(pdiv((float)y, (float)H), 2.0f), 1.0f);
     float4* tmp0 = (float4*)P.resolve_tmp;
     float4* tmp1 = tmp0 + (size_t)W * H;
     float2* tmp2 = (float2*)(tmp1 + (size_t)W * H);
     F3 world, sun, ambient;
+    F3 dbg_base{0, 0, 0}, dbg_normal{0, 0, 0};
+    float2 dbg_rm = make_float2(0, 0), dbg_uv = make_float2(0, 0);
     bool alpha;
     if (PHASE != 2) {
     const unsigned long long key = P.vis[pixel];
@@ -311,18 +324,19 @@ __global__ void __launch_bounds__(256) resolve_kernel(const __grid_constant__ Fr
         const uint32_t vi = index_offset + __ldg(micro + k);
         const uint32_t idx = wide ? __ldg((const uint32_t*)indices + vi) : (uint32_t)__ldg((const uint16_t*)indices + vi);
         const uint16_t* p = positions + 3 * (size_t)idx;
-        float4 w = mul4(T, (float)__ldg(p), (float)__ldg(p + 1), (float)__ldg(p + 2), 1.0f);
+        const V4 w = mat4_mul(T, (float)__ldg(p), (float)__ldg(p + 1), (float)__ldg(p + 2), 1.0f);   // pinned, like the raster pass
         pos[k] = F3{w.x, w.y, w.z};
-        clip[k] = mul4(&P.u.combined_perspective_view.m[0][0], w.x, w.y, w.z, 1.0f);
+        const V4 c = mat4_mul(&P.u.combined_perspective_view.m[0][0], w.x, w.y, w.z, 1.0f);
+        clip[k] = make_float4(c.x, c.y, c.z, c.w);
         const int8_t* n = normals + 3 * (size_t)idx;
         nrm[k] = normalize(F3{(float)__ldg(n), (float)__ldg(n + 1), (float)__ldg(n + 2)});
         tu[k] = (float)__ldg(uvs + 2 * (size_t)idx) * ts0;
         tv[k] = (float)__ldg(uvs + 2 * (size_t)idx + 1) * ts1;
     }
     const Bary bary = calc_full_bary(clip[0], clip[1], clip[2], ndc_x, ndc_y, (float)W, (float)H);
-    const Interp wx = interp1(bary, pos[0].x, pos[1].x, pos[2].x);
-    const Interp wy = interp1(bary, pos[0].y, pos[1].y, pos[2].y);
-    const Interp wz = interp1(bary, pos[0].z, pos[1].z, pos[2].z);
+    const Interp wx = interp1_pinned(bary, pos[0].x, pos[1].x, pos[2].x);
+    const Interp wy = interp1_pinned(bary, pos[0].y, pos[1].y, pos[2].y);
+    const Interp wz = interp1_pinned(bary, pos[0].z, pos[1].z, pos[2].z);
     world = F3{wx.value, wy.value, wz.value};
     const Interp iu = interp1(bary, tu[0], tu[1], tu[2]), iv = interp1(bary, tv[0], tv[1], tv[2]);
     const float u = iu.value + __ldg(&mi->texture_offset[0]), v = iv.value + __ldg(&mi->texture_offset[1]);
@@ -379,6 +393,9 @@ __global__ void __launch_bounds__(256) resolve_kernel(const __grid_constant__ Fr
         float invmax = 1.0f / sqrtf(fmaxf(dot(t3, t3), dot(b3, b3)));
         normal = normalize(t3 * (invmax * mn.x) + b3 * (invmax * mn.y) + normal * mn.z);
     }
+    if (PHASE == 0) {
+        dbg_base = base; dbg_normal = normal; dbg_rm = make_float2(roughness, metallic); dbg_uv = make_float2(u, v);
+    }
     const float amb = 0.025f + 0.025f * normal.y;  // SH with sh[0] = sh[2] = 0.025 (:40-57)
     sun = brdf(view_vec, F3{P.u.sun_dir[0], P.u.sun_dir[1], P.u.sun_dir[2]}, normal, roughness, metallic, base, alpha);
     const float adm = __fmul_rn(amb, 1.0f - metallic);
@@ -404,27 +421,41 @@ __global__ void __launch_bounds__(256) resolve_kernel(const __grid_constant__ Fr
     uint32_t cascade;
     float4 sc = make_float4(0, 0, 0, 0);
     for (cascade = 0; cascade < 4; cascade++) {
-        sc = mul4(&misc->uv_space_shadow_matrices[cascade].m[0][0], world.x, world.y, world.z, 1.0f);
-        if (fabsf(sc.x - 0.5f) < 0.5f && fabsf(sc.y - 0.5f) < 0.5f) break;
+        const V4 c = mat4_mul(&misc->uv_space_shadow_matrices[cascade].m[0][0], world.x, world.y, world.z, 1.0f);   // pinned
+        sc = make_float4(c.x, c.y, c.z, c.w);
+        if (fabsf(psub(sc.x, 0.5f)) < 0.5f && fabsf(psub(sc.y, 0.5f)) < 0.5f) break;
     }
     const float bias = alpha ? 0.000002f : 0.0f;
-    const float inv_w = 1.0f / sc.w;
-    sc.x *= inv_w; sc.y *= inv_w; sc.z *= inv_w;
+    if (sc.w != 1.0f) {   // x / 1.0f == x exactly: an orthographic cascade skips the three IEEE divisions
+        sc.x = pdiv(sc.x, sc.w); sc.y = pdiv(sc.y, sc.w); sc.z = pdiv(sc.z, sc.w);
+    }
     const int sn = (int)P.shadowmap_size;
     const uint32_t* layer = P.shadow + (size_t)min(cascade, 3u) * sn * sn;
     float shadow_sum = 0.0f;
     if (sn == 1024) {
-        shadow_sum = pcf3x3_texel_spaced(layer, sn, sc.x, sc.y, sc.z - bias);
+        shadow_sum = pcf3x3_texel_spaced(layer, sn, sc.x, sc.y, psub(sc.z, bias));
     } else {
 #pragma unroll
         for (int ox = -1; ox <= 1; ox++)
 #pragma unroll
             for (int oy = -1; oy <= 1; oy++)
-                shadow_sum += sample_shadow(layer, sn, sc.x + (float)ox / 1024.0f, sc.y + (float)oy / 1024.0f, sc.z - bias);
+                shadow_sum += sample_shadow(layer, sn, padd(sc.x, (float)ox / 1024.0f), padd(sc.y, (float)oy / 1024.0f), psub(sc.z, bias));
     }
     shadow_sum *= (1.0f / 9.0f);
     if (sc.z > 1.0f) shadow_sum = 1.0f;
 
+    if (PHASE == 0 && P.u.debug >= 100) {
+        // attribution aid (not part of the reference's debug views, which are not reproduced): one input of the pass
+        // instead of the colour (tools/resolve_diag.py compares it with the checker's).  Only the single-launch pass (lh_resolve) supports it.
+        F3 t = world;
+        if (P.u.debug == 100) t = F3{shadow_sum, shadow_sum, shadow_sum};
+        else if (P.u.debug == 101) t = dbg_base;
+        else if (P.u.debug == 102) t = dbg_normal;
+        else if (P.u.debug == 103) t = F3{dbg_rm.x, dbg_rm.y, (float)cascade * 0.25f};
+        else if (P.u.debug == 105) t = F3{dbg_uv.x, dbg_uv.y, 0.0f};
+        store_rgba16f(P.scene, P.scene_remote, pixel, t.x, t.y, t.z, 1.0f);
+        return;
+    }
     const float sun_intensity = __fmul_rn(kPi, shadow_sum);
     store_rgba16f(P.scene, P.scene_remote, pixel, __fmaf_rn(sun.x, sun_intensity, ambient.x), __fmaf_rn(sun.y, sun_intensity, ambient.y),
                   __fmaf_rn(sun.z, sun_intensity, ambient.z), 1.0f);

@@ -44,6 +44,7 @@ struct Mesh {
     float dq_scale[3] = {1, 1, 1};
     float dq_offset[3] = {0, 0, 0};
     bool wide_indices = false;
+    int shares_geometry_of = -1;      // >= 0: a material variant of that mesh: own MeshInfo, the other mesh's stream buffers
 };
 
 struct InstanceRecord {
@@ -507,6 +508,24 @@ int lh_scene_add_mesh_indexed(LhScene* scene, const LhIndexedMesh* d) {
     return (int)scene->meshes.size() - 1;
 }
 
+// A material variant: a second MeshInfo (own texture indices / colour factor) over the SAME vertex, index and meshlet
+// buffers -- in the reference every glTF primitive has its own MeshInfo buffer (mesh_loading.cpp:699-708), and
+// primitives that differ only in material are exactly this.
+int lh_scene_add_mesh_variant(LhScene* scene, int mesh, uint16_t base_color, uint16_t metallic_roughness, uint16_t normal,
+                              const float base_color_factor[3]) {
+    if (!scene || mesh < 0 || mesh >= (int)scene->meshes.size()) return -1;
+    const Mesh& src = *scene->meshes[mesh];
+    auto v = std::make_unique<Mesh>(src);
+    v->shares_geometry_of = src.shares_geometry_of >= 0 ? src.shares_geometry_of : mesh;
+    v->info.base_color_texture_index = base_color;
+    v->info.metallic_roughness_texture_index = metallic_roughness;
+    v->info.normal_texture_index = normal;
+    if (base_color_factor)
+        for (int a = 0; a < 3; a++) v->info.base_color_factor[a] = base_color_factor[a];
+    scene->meshes.push_back(std::move(v));
+    return (int)scene->meshes.size() - 1;
+}
+
 int lh_scene_add_instance_matrix(LhScene* scene, int mesh, const float transform[16]) {
     if (!scene || !transform || mesh < 0 || mesh >= (int)scene->meshes.size()) return -1;
     LhMat4 m;
@@ -831,7 +850,10 @@ int lh_scene_build_preset(LhScene* scene, int preset, uint32_t instance_count, u
         extent *= std::cbrt((float)instance_count / (float)count);
         count = instance_count;
     }
-    uint32_t n_sets = (uint32_t)std::min<size_t>(16, meshes.size());
+    // 16 base-colour + 16 metallic-roughness + 16 normal maps.  A preset with fewer than 16 meshes gets
+    // material variants (same geometry buffers, own MeshInfo and texture set) up to 16; the unit-test preset keeps one.
+    const uint32_t n_variants = (preset == LH_PRESET_TINY || meshes.size() >= 16) ? 1u : (uint32_t)(16 / meshes.size());
+    uint32_t n_sets = (uint32_t)std::min<size_t>(16, meshes.size() * n_variants);
     out->num_texture_sets = n_sets;
     std::vector<int32_t> opaque_ids, alpha_ids;
     for (size_t k = 0; k < meshes.size(); k++) {
@@ -851,6 +873,12 @@ int lh_scene_build_preset(LhScene* scene, int preset, uint32_t instance_count, u
         int id = lh_scene_add_mesh(scene, &d);
         if (id < 0) return id;
         (meshes[k].alpha ? alpha_ids : opaque_ids).push_back(id);
+        for (uint32_t v = 1; v < n_variants; v++) {
+            const uint32_t vset = (uint32_t)((k + v * meshes.size()) % n_sets);
+            int vid = lh_scene_add_mesh_variant(scene, id, (uint16_t)vset, (uint16_t)(n_sets + vset), (uint16_t)(2 * n_sets + vset), nullptr);
+            if (vid < 0) return vid;
+            (meshes[k].alpha ? alpha_ids : opaque_ids).push_back(vid);
+        }
     }
     // mesh id per instance: every 20th is foliage when the preset has any
     std::vector<int32_t> ids(alpha_ids.empty() ? opaque_ids.size() : 20 * opaque_ids.size());
@@ -918,9 +946,20 @@ int lh_scene_bind(const LhScene* scene, const LhCapacities* caps, LhAllocFn allo
         lh_binding_destroy(raw);
         return rc ? rc : -1;
     };
+    std::vector<LhMeshInfo> bound_infos;
     for (auto& mp : scene->meshes) {
         const Mesh& m = *mp;
         LhMeshInfo info = m.info;
+        if (m.shares_geometry_of >= 0) {   // a material variant: the original's stream addresses, its own MeshInfo buffer
+            const LhMeshInfo& g = bound_infos[(size_t)m.shares_geometry_of];
+            info.positions = g.positions; info.indices = g.indices; info.normals = g.normals; info.uvs = g.uvs;
+            info.micro_indices = g.micro_indices; info.meshlets = g.meshlets;
+            uint64_t info_addr = 0;
+            if (!put(&info, sizeof(info), &info_addr)) return fail();
+            b->mesh_info_addresses.push_back(info_addr);
+            bound_infos.push_back(info);
+            continue;
+        }
         if (!put(m.positions.data(), m.positions.size() * 2, &info.positions)) return fail();
         if (m.wide_indices) {
             if (!put(m.idx32.data(), m.idx32.size() * 4, &info.indices)) return fail();
@@ -934,6 +973,7 @@ int lh_scene_bind(const LhScene* scene, const LhCapacities* caps, LhAllocFn allo
         uint64_t info_addr = 0;
         if (!put(&info, sizeof(info), &info_addr)) return fail();  // one buffer per mesh (mesh_loading.cpp:699-708)
         b->mesh_info_addresses.push_back(info_addr);
+        bound_infos.push_back(info);
     }
     b->instances.resize(scene->instances.size());
     if (!b->instances.empty()) lh_scene_build_instances(scene, b->mesh_info_addresses.data(), b->instances.data());

@@ -18,9 +18,9 @@ EXPORTS = [
     "lh_skybox_create", "lh_targets_resize", "lh_set_instance_range", "lh_frame_begin", "lh_reset", "lh_cull_instances",
     "lh_cull_meshlets", "lh_raster_visbuffer", "lh_composite", "lh_reduce_depth", "lh_generate_shadow_matrices",
     "lh_cull_instances_shadows", "lh_shadow_cascade", "lh_resolve", "lh_display_transform", "lh_render_frame",
-    "lh_frame_sync", "lh_render_frame_host", "lh_get_frame_stats", "lh_get_target", "lh_get_timings",
+    "lh_frame_sync", "lh_render_frame_host", "lh_get_frame_stats", "lh_set_config_flags", "lh_get_target", "lh_get_timings",
     "lh_get_target_address", "lh_get_launch_count", "lh_timer_start", "lh_timer_stop", "lh_flush_l2", "lh_comm_unique_id", "lh_comm_init",
-    "lh_comm_destroy", "lh_comm_info", "lh_comm_set_exchange", "lh_comm_remap", "lh_comm_rows", "lh_set_shadow_instance_range", "lh_set_instance_stripes", "lh_set_display_lut", "lh_set_shadow_cascade_mask", "lh_shadow_exchange",
+    "lh_comm_destroy", "lh_comm_info", "lh_comm_set_exchange", "lh_comm_remap", "lh_comm_rows", "lh_set_shadow_instance_range", "lh_set_instance_stripes", "lh_set_instance_stripe_bounds", "lh_set_display_lut", "lh_set_shadow_cascade_mask", "lh_shadow_exchange",
 ]
 
 
@@ -66,6 +66,8 @@ def cuda_lib():
         lib.lh_comm_remap.argtypes = [vp]
         if hasattr(lib, "lh_set_instance_stripes") or not os.environ.get("LH_CUDA_LIB"):   # an older A/B build may lack it
             lib.lh_set_instance_stripes.argtypes = [vp, C.c_int, u32, u32, u32]
+        if hasattr(lib, "lh_set_instance_stripe_bounds"):
+            lib.lh_set_instance_stripe_bounds.argtypes = [vp, C.c_int, C.POINTER(C.c_float), u32, u32, u32]
         lib.lh_comm_rows.argtypes = [vp, C.POINTER(u32), C.POINTER(u32)]
         lib.lh_frame_begin.argtypes = [vp, C.POINTER(S.LhUniforms)]
         for name in ("lh_reset", "lh_cull_instances", "lh_cull_meshlets", "lh_raster_visbuffer", "lh_composite",
@@ -76,6 +78,7 @@ def cuda_lib():
         lib.lh_shadow_cascade.argtypes = [vp, u32]
         lib.lh_render_frame_host.argtypes = [vp, C.POINTER(S.LhUniforms), vp, u32, C.POINTER(S.LhFrameStats)]
         lib.lh_get_frame_stats.argtypes = [vp, C.POINTER(S.LhFrameStats)]
+        lib.lh_set_config_flags.argtypes = [vp, C.c_uint32]
         lib.lh_get_target.argtypes = [vp, C.c_int, vp, u64]
         lib.lh_get_timings.argtypes = [vp, C.POINTER(S.LhPassTimes)]
         lib.lh_get_target_address.argtypes = [vp, C.c_int, C.POINTER(u64)]
@@ -179,6 +182,10 @@ class Context:
     def set_shadow_instance_range(self, first, count):
         self._check(self.lib.lh_set_shadow_instance_range(self.handle, first, count))
 
+    def set_instance_stripe_bounds(self, view, bounds, index, count):
+        arr = (C.c_float * len(bounds))(*[float(b) for b in bounds])
+        self._check(self.lib.lh_set_instance_stripe_bounds(self.handle, view, arr, len(bounds) - 1, index, count))
+
     def set_instance_stripes(self, view, stripes, index=0, count=1):
         self._check(self.lib.lh_set_instance_stripes(self.handle, view, stripes, index, count))
 
@@ -230,6 +237,10 @@ class Context:
         ptr, n = self.host_instances() if upload_instances else (None, 0)
         self._check(self.lib.lh_render_frame_host(self.handle, C.byref(u), ptr, n, C.byref(stats)))
         return stats
+
+    def set_config_flags(self, flags):
+        self._check(self.lib.lh_set_config_flags(self.handle, flags))
+        self.cfg.flags = flags
 
     # ---- readback ----
     def stats(self):

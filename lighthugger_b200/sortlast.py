@@ -92,6 +92,52 @@ def apply(ctx, num_instances, rank, world, split="instances", partition="stripes
     ctx.set_instance_stripes(1, sstripes, sindex, smembers)
 
 
+class StripeBalancer:
+    """Load balancing of the stripe partition from measured pass times (frame-to-frame coherence: the bounds found on one
+    frame are used for the next).  One contiguous stripe per rank and view; every rank runs the same update on the same
+    gathered costs, so all ranks hold identical bounds (which lh_set_instance_stripe_bounds requires).
+
+    update(view, costs): costs[r] is what rank r measured for the view's passes with the current bounds.  The cost is
+    taken as uniformly spread inside each stripe; the new bounds cut the cumulative cost into equal parts, and the move
+    towards them is damped (the measured times also hold per-pass fixed costs that do not move with the bounds)."""
+
+    def __init__(self, world, damping=0.6, min_width=0.005):
+        self.world = world
+        self.damping = damping
+        self.min_width = min_width
+        self.bounds = [[i / world for i in range(world + 1)] for _ in range(2)]
+
+    def update(self, view, costs):
+        b, n = self.bounds[view], self.world
+        costs = [max(float(c), 1e-9) for c in costs]
+        target = sum(costs) / n
+        ideal = [0.0]
+        r, acc = 0, 0.0
+        for k in range(1, n):
+            need = k * target
+            while r < n - 1 and acc + costs[r] < need:
+                acc += costs[r]
+                r += 1
+            ideal.append(b[r] + (b[r + 1] - b[r]) * min(1.0, max(0.0, (need - acc) / costs[r])))
+        ideal.append(1.0)
+        new = [bo + self.damping * (nw - bo) for bo, nw in zip(b, ideal)]
+        new[0], new[-1] = 0.0, 1.0
+        for k in range(1, n):                      # ascending, no stripe thinner than min_width
+            new[k] = max(new[k], new[k - 1] + self.min_width)
+        for k in range(n - 1, 0, -1):
+            new[k] = min(new[k], new[k + 1] - self.min_width)
+        self.bounds[view] = new
+        return new
+
+    def imbalance(self, costs):
+        """max / mean of the measured costs (1.0 = perfectly even)"""
+        return max(costs) / (sum(costs) / len(costs)) if costs else 1.0
+
+    def apply(self, ctx, rank, views=(0, 1)):
+        for v in views:
+            ctx.set_instance_stripe_bounds(v, self.bounds[v], rank, self.world)
+
+
 def row_range(height, rank, world):
     """Screen rows [y0, y1) a rank composites and resolves (what lh_comm_init derives): even-sized slices."""
     per = ((height + world - 1) // world + 1) & ~1

@@ -79,6 +79,13 @@ int lho_cull_instances_shadows(const LhUniforms* u, const LhoConfig* cfg);
 int lho_shadow_cascade(const LhUniforms* u, const LhoConfig* cfg, uint32_t cascade, float* shadow);
 /* render_geometry main (render_geometry.comp:70-266); out = width*height RGBA32F (the device stores RGBA16F) */
 int lho_resolve(const LhUniforms* u, const LhoConfig* cfg, const uint64_t* vis, const float* shadow, float* out_rgba32f);
+/* one input of the lighting resolve instead of the colour (100 shadow term, 101 base colour, 102 normal, 103 roughness /
+ * metallic / cascade, 104 world position, 105 uv): attribution of differences, not part of the reference */
+int lho_resolve_debug(const LhUniforms* u, const LhoConfig* cfg, const uint64_t* vis, const float* shadow, int debug_term, float* out_rgba32f);
+/* display_transform (display_transform.comp:5-81, debug overlay off): scene RGBA32F + LUT (size^3 RGB32F) -> the
+ * sRGB-encoded RGBA32F value stored to the UNORM swapchain image */
+int lho_display_transform(const LhUniforms* u, const LhoConfig* cfg, const float* scene_rgba32f, const float* lut_rgb32f, uint32_t lut_size,
+                          float* out_rgba32f);
 /* steps 1-11 of rendering.cpp (reset ... resolve); out_rgba32f may be NULL to skip the resolve */
 int lho_render_frame(const LhUniforms* u, const LhoConfig* cfg, uint64_t* vis, float* shadow, float* out_rgba32f);
 

@@ -88,6 +88,7 @@ void sample_texture_lod(const LhoTexture& t, float u, float v, float lod, float 
 void sample_texture_grad(const LhoTexture& t, const float uv[2], const float dx[2], const float dy[2], float out[4]);
 void sample_skybox(const LhoConfig* cfg, V3 d, float out[3]);
 float sample_shadow(const float* layer, uint32_t n, float u, float v, float ref);
+void sample_lut(const float* lut_rgb, uint32_t n, const float uvw[3], float out[3]);   // display_transform_lut + clamp_sampler
 
 struct AlphaTest {
     bool enabled;

@@ -155,6 +155,28 @@ float sample_shadow(const float* layer, uint32_t n, float u, float v, float ref)
     return top + wy * (bot - top);
 }
 
+// textureLod(sampler3D(display_transform_lut, clamp_sampler), uvw, 0): trilinear, clamp to edge, 8-bit sub-texel weights
+void sample_lut(const float* lut, uint32_t n, const float uvw[3], float out[3]) {
+    float f[3];
+    int i0[3], i1[3];
+    for (int a = 0; a < 3; a++) {
+        float x = snap_subtexel(uvw[a] * (float)n - 0.5f), fl = floorf(x);
+        f[a] = x - fl;
+        int i = (int)fl;
+        i0[a] = std::min(std::max(i, 0), (int)n - 1);
+        i1[a] = std::min(std::max(i + 1, 0), (int)n - 1);
+    }
+    for (int c = 0; c < 3; c++) {
+        auto at = [&](int x, int y, int z) { return lut[(((uint64_t)z * n + y) * n + x) * 3 + c]; };
+        float x00 = at(i0[0], i0[1], i0[2]) + f[0] * (at(i1[0], i0[1], i0[2]) - at(i0[0], i0[1], i0[2]));
+        float x10 = at(i0[0], i1[1], i0[2]) + f[0] * (at(i1[0], i1[1], i0[2]) - at(i0[0], i1[1], i0[2]));
+        float x01 = at(i0[0], i0[1], i1[2]) + f[0] * (at(i1[0], i0[1], i1[2]) - at(i0[0], i0[1], i1[2]));
+        float x11 = at(i0[0], i1[1], i1[2]) + f[0] * (at(i1[0], i1[1], i1[2]) - at(i0[0], i1[1], i1[2]));
+        float y0 = x00 + f[1] * (x10 - x00), y1 = x01 + f[1] * (x11 - x01);
+        out[c] = y0 + f[2] * (y1 - y0);
+    }
+}
+
 struct Bary {
     V3 lambda, ddx, ddy;
 };
@@ -249,8 +271,11 @@ static void brdf(V3 v, V3 l, V3 n, float perceptual_roughness, float metallic, c
     }
 }
 
+// debug_term (not part of the reference): 0 = the lit colour; 100 shadow term, 101 base colour, 102 shading normal,
+// 103 (roughness, metallic, cascade / 4), 104 world position, 105 uv -- written instead of the colour, so that a
+// difference between two implementations of the pass can be attributed to one of its inputs
 static void resolve_pixel(const LhUniforms* u, const LhoConfig* cfg, const uint64_t* vis, const float* shadow, uint32_t x,
-                          uint32_t y, float out[4]) {
+                          uint32_t y, float out[4], int debug_term = 0) {
     const uint32_t W = u->window_size[0], H = u->window_size[1];
     float ndc_x = (float)x / (float)W * 2.0f - 1.0f;  // pixel corner, render_geometry.comp:82-84
     float ndc_y = (float)y / (float)H * 2.0f - 1.0f;
@@ -376,11 +401,51 @@ static void resolve_pixel(const LhUniforms* u, const LhoConfig* cfg, const uint6
     brdf(view_vec, V3{u->sun_dir[0], u->sun_dir[1], u->sun_dir[2]}, normal, roughness, metallic, base, alpha, sun);
     float sun_intensity = kPi * shadow_sum;
     for (int c = 0; c < 3; c++) out[c] = sun[c] * sun_intensity + amb * ((1.0f - metallic) * base[c]);
+    if (debug_term == 100) out[0] = out[1] = out[2] = shadow_sum;
+    else if (debug_term == 101) { out[0] = base[0]; out[1] = base[1]; out[2] = base[2]; }
+    else if (debug_term == 102) { out[0] = normal.x; out[1] = normal.y; out[2] = normal.z; }
+    else if (debug_term == 103) { out[0] = roughness; out[1] = metallic; out[2] = (float)cascade * 0.25f; }
+    else if (debug_term == 104) { out[0] = world.x; out[1] = world.y; out[2] = world.z; }
+    else if (debug_term == 105) { out[0] = uv[0]; out[1] = uv[1]; out[2] = 0.0f; }
 }
 
 }  // namespace lho
 
 using namespace lho;
+
+// display_transform.comp:5-81 (without the shadow-map debug overlay): tony_mc_mapface through the 48^3 LUT, then the
+// sRGB transfer function; `out` is what the reference stores to its swapchain image (RGBA32F before the UNORM conversion)
+extern "C" int lho_display_transform(const LhUniforms* u, const LhoConfig* cfg, const float* scene_rgba32f, const float* lut_rgb32f,
+                                     uint32_t lut_size, float* out_rgba32f) {
+    const uint32_t W = u->window_size[0], H = u->window_size[1];
+    parallel_for(H, thread_count(cfg), [&](uint64_t b, uint64_t e) {
+        for (uint64_t i = b * W; i < e * W; i++) {
+            const float* s = scene_rgba32f + 4 * i;
+            float uvw[3], mapped[3];
+            const float dims = 48.0f;   // LUT_DIMS is a constant of the shader, whatever the bound table's size
+            for (int c = 0; c < 3; c++) {
+                float encoded = s[c] / (s[c] + 1.0f);                                  // :7
+                uvw[c] = encoded * ((dims - 1.0f) / dims) + 0.5f / dims;               // :11
+            }
+            sample_lut(lut_rgb32f, lut_size, uvw, mapped);
+            for (int c = 0; c < 3; c++) {
+                float v = mapped[c];
+                out_rgba32f[4 * i + c] = v <= 0.003130f ? v * 12.92f : 1.055f * powf(v, 1.0f / 2.4f) - 0.055f;   // :19-25
+            }
+            out_rgba32f[4 * i + 3] = 1.0f;
+        }
+    });
+    return 0;
+}
+
+extern "C" int lho_resolve_debug(const LhUniforms* u, const LhoConfig* cfg, const uint64_t* vis, const float* shadow, int debug_term, float* out) {
+    const uint32_t W = u->window_size[0], H = u->window_size[1];
+    parallel_for(H, thread_count(cfg), [&](uint64_t b, uint64_t e) {
+        for (uint64_t y = b; y < e; y++)
+            for (uint32_t x = 0; x < W; x++) resolve_pixel(u, cfg, vis, shadow, x, (uint32_t)y, out + ((uint64_t)y * W + x) * 4, debug_term);
+    });
+    return 0;
+}
 
 extern "C" int lho_resolve(const LhUniforms* u, const LhoConfig* cfg, const uint64_t* vis, const float* shadow, float* out) {
     const uint32_t W = u->window_size[0], H = u->window_size[1];

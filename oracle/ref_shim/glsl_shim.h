@@ -255,28 +255,9 @@ inline vec4 textureLod(sampler2DArray, vec3 c, float) {   // display_transform's
 }
 // textureLod(display_transform_lut + clamp_sampler): trilinear, clamp to edge
 inline vec4 textureLod(sampler3D, vec3 uvw, float) {
-    const int n = (int)shim_frame.lut_size;
-    const float* L = shim_frame.lut;
-    float f[3];
-    int i0[3], i1[3];
-    for (int a = 0; a < 3; a++) {
-        const float x = uvw[a] * (float)n - 0.5f, fl = std::floor(x);
-        f[a] = x - fl;
-        const int i = (int)fl;
-        i0[a] = i < 0 ? 0 : (i > n - 1 ? n - 1 : i);
-        i1[a] = i + 1 < 0 ? 0 : (i + 1 > n - 1 ? n - 1 : i + 1);
-    }
-    vec3 r(0.0f);
-    for (int c = 0; c < 3; c++) {
-        auto at = [&](int x, int y, int z) { return L[(((size_t)z * n + y) * n + x) * 3 + c]; };
-        const float x00 = at(i0[0], i0[1], i0[2]) + f[0] * (at(i1[0], i0[1], i0[2]) - at(i0[0], i0[1], i0[2]));
-        const float x10 = at(i0[0], i1[1], i0[2]) + f[0] * (at(i1[0], i1[1], i0[2]) - at(i0[0], i1[1], i0[2]));
-        const float x01 = at(i0[0], i0[1], i1[2]) + f[0] * (at(i1[0], i0[1], i1[2]) - at(i0[0], i0[1], i1[2]));
-        const float x11 = at(i0[0], i1[1], i1[2]) + f[0] * (at(i1[0], i1[1], i1[2]) - at(i0[0], i1[1], i1[2]));
-        const float y0 = x00 + f[1] * (x10 - x00), y1 = x01 + f[1] * (x11 - x01);
-        r[c] = y0 + f[2] * (y1 - y0);
-    }
-    return vec4(r, 1.0f);
+    float out[3];
+    lho::sample_lut(shim_frame.lut, shim_frame.lut_size, &uvw.x, out);
+    return vec4(out[0], out[1], out[2], 1.0f);
 }
 inline void imageStore(image2D img, ivec2 c, vec4 v) {
     float* dst = (img.id == 0 ? shim_frame.scene_out : shim_frame.swapchain_out) + ((size_t)c.y * shim_frame.width + c.x) * 4;

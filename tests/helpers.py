@@ -57,22 +57,37 @@ class Textures:
     def __init__(self, scene, size=TEX_SIZE, bc7=True):
         self.size = size
         self.bc7 = bc7
-        self.entries = []  # (device_bytes, levels, decoded_rgba8_chain)
-        for rgba, levels, _ in scene.texture_table(size):
+        self.entries = []  # [device_bytes, levels, decoded_rgba8_chain or None (decoded on first use by the oracle)]
+        self._blocks = []
+        def encode(entry):
+            rgba, levels, _ = entry
+            blocks, off = [], 0
+            for l in range(levels):
+                s = max(1, size >> l)
+                level = rgba[off:off + s * s * 4]
+                off += s * s * 4
+                blocks.append(scene.bc7_encode(np.ascontiguousarray(level), s, s))
+            return blocks
+
+        table = scene.texture_table(size)
+        if bc7:
+            # the encoder is C (the GIL is released inside ctypes calls): one texture per host thread
+            from concurrent.futures import ThreadPoolExecutor
+            with ThreadPoolExecutor(max_workers=min(32, (os.cpu_count() or 1))) as pool:
+                encoded = list(pool.map(encode, table))
+        for k, (rgba, levels, _) in enumerate(table):
             if bc7:
-                blocks, decoded, off = [], [], 0
-                for l in range(levels):
-                    s = max(1, size >> l)
-                    level = rgba[off:off + s * s * 4]
-                    off += s * s * 4
-                    b = scene.bc7_encode(np.ascontiguousarray(level), s, s)
-                    blocks.append(b)
-                    decoded.append(bc7_decode_mode6(b, s, s).reshape(-1))
-                self.entries.append((np.concatenate(blocks), levels, np.ascontiguousarray(np.concatenate(decoded))))
+                self._blocks.append(encoded[k])
+                self.entries.append([np.concatenate(encoded[k]), levels, None])
             else:
-                self.entries.append((rgba, levels, rgba))
+                self._blocks.append(None)
+                self.entries.append([rgba, levels, rgba])
 
     def oracle_table(self):
+        for e, blocks in zip(self.entries, self._blocks):
+            if e[2] is None:
+                e[2] = np.ascontiguousarray(np.concatenate([bc7_decode_mode6(b, max(1, self.size >> l), max(1, self.size >> l)).reshape(-1)
+                                                            for l, b in enumerate(blocks)]))
         return [(dec, levels, self.size, True) for (_, levels, dec) in self.entries]
 
     def upload(self, ctx):
@@ -165,3 +180,44 @@ def compare_color(ctx, o, frac_tol=COLOR_FRAC_TOL, tight=COLOR_TIGHT, loose=COLO
     assert bad <= frac_tol, f"{bad:.4%} of pixels differ by more than {tight * 255:.0f}/255 (max {d.max() * 255:.2f}/255)"
     assert d.max() <= loose, f"maximum error {d.max() * 255:.2f}/255 exceeds {loose * 255:.0f}/255"
     return bad, float(d.max())
+
+
+REAL_LUT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle", "_ref", "tony_mc_mapface.dds")
+
+
+def real_display_lut():
+    """The reference's own Tony McMapface table (48^3 RGB9E5 DDS) decoded to float RGB by the host library, or None.
+    The file is a build output of `make ref` (oracle/_ref/, git-ignored, shipped to the GPU box with the prebuilt
+    libraries); it is never committed."""
+    if not os.path.exists(REAL_LUT):
+        return None
+    from lighthugger_b200 import image_files as IF
+    info, payload = IF.decode(open(REAL_LUT, "rb").read())
+    assert (info.format, info.dimension, info.width, info.height, info.depth) == (IF.LH_PIXEL_RGB9E5, 3, 48, 48, 48)
+    return np.ascontiguousarray(IF.rgb9e5_to_float(payload[:info.levels_info[0].bytes].view(np.uint32)).reshape(-1))
+
+
+def classify_vis_mismatches(got, want, width, height):
+    """visibility ids may differ from the oracle's only on EDGE or TIE pixels.  Returns the number of
+    mismatching pixels that are neither:
+      tie   the two keys carry the same depth bits (the reference's own tie order is schedule-dependent);
+      edge  the surface one side shows at the pixel is what the other side shows on an adjacent pixel (3x3
+            neighbourhood) -- the two sides disagree about where the boundary between two neighbouring surfaces runs
+            (the alpha test samples a texture: the cut-out contour moves by a fraction of a pixel), not about what is there."""
+    got = np.asarray(got, np.uint64).reshape(height, width)
+    want = np.asarray(want, np.uint64).reshape(height, width)
+    ys, xs = np.nonzero(got != want)
+    # the surface a key belongs to: its meshlet slot (bits 7..31 of the low word); the cleared background is a surface too
+    surface = lambda k: (k & np.uint64(0xFFFFFFFF)) >> np.uint64(S.LH_VIS_TRI_BITS)
+    sg, sw = surface(got), surface(want)
+    unexplained = 0
+    for y, x in zip(ys, xs):
+        g, w = got[y, x], want[y, x]
+        if (g >> np.uint64(32)) == (w >> np.uint64(32)):
+            continue                                     # tie: equal depth bits
+        y0, y1, x0, x1 = max(0, y - 1), min(height, y + 2), max(0, x - 1), min(width, x + 2)
+        # edge: the surface each side shows here is one the OTHER side shows on this pixel or next to it
+        if (sw[y0:y1, x0:x1] == sg[y, x]).any() and (sg[y0:y1, x0:x1] == sw[y, x]).any():
+            continue
+        unexplained += 1
+    return unexplained

@@ -44,6 +44,8 @@ def oracle_lib():
         lib.lho_shadow_cascade.argtypes = [U, K, C.c_uint32, vp]
         lib.lho_resolve.argtypes = [U, K, vp, vp, vp]
         lib.lho_render_frame.argtypes = [U, K, vp, vp, vp]
+        lib.lho_display_transform.argtypes = [U, K, vp, vp, C.c_uint32, vp]
+        lib.lho_resolve_debug.argtypes = [U, K, vp, vp, C.c_int, vp]
         lib.lho_composite_min.argtypes = [vp, vp, C.c_uint64]
         lib.lho_composite_min.restype = None
         lib.lho_pinned_powf.argtypes = [C.c_float, C.c_float]
@@ -108,6 +110,20 @@ class Oracle:
     def resolve(self):
         self.color = np.zeros(self.width * self.height * 4, np.float32)
         return self._call("lho_resolve", self.vis.ctypes.data, self.shadow.ctypes.data, self.color.ctypes.data)
+
+    def resolve_debug(self, term):
+        out = np.zeros(self.width * self.height * 4, np.float32)
+        self._call("lho_resolve_debug", self.vis.ctypes.data, self.shadow.ctypes.data, term, out.ctypes.data)
+        return out.reshape(-1, 4)
+
+    def display_transform(self, scene_rgba32f, lut_rgb32f, lut_size=48):
+        """display_transform.comp on a scene-referred RGBA32F image: the sRGB-encoded RGBA32F the reference stores."""
+        scene = np.ascontiguousarray(scene_rgba32f, np.float32).reshape(-1)
+        lut = np.ascontiguousarray(lut_rgb32f, np.float32).reshape(-1)
+        out = np.zeros(self.width * self.height * 4, np.float32)
+        assert scene.size == out.size and lut.size == 3 * lut_size ** 3
+        self._call("lho_display_transform", scene.ctypes.data, lut.ctypes.data, lut_size, out.ctypes.data)
+        return out.reshape(-1, 4)
 
     def render_frame(self, resolve=True):
         """Steps 1-11 of rendering.cpp, pass by pass (so the main view's draw counts can be noted before the cascades

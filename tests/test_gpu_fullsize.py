@@ -10,7 +10,7 @@ import pytest
 from lighthugger_b200 import _structs as S
 from lighthugger_b200 import sortlast
 from lighthugger_b200.scene import Scene
-from helpers import Textures, compare_color, make_context, make_oracle, rotated_scene
+from helpers import Textures, classify_vis_mismatches, compare_color, make_context, make_oracle, rotated_scene
 
 pytestmark = pytest.mark.gpu
 
@@ -45,6 +45,7 @@ def assert_frame_bit_exact(o, ctx, st, alpha_clip=False):
     sh_g, sh_o = ctx.target(S.LH_TARGET_SHADOW).view(np.uint32), o.shadow.view(np.uint32)
     if alpha_clip:   # the alpha test samples a texture inside the raster: 0.1 % of covered pixels
         assert mismatch <= 0.001 * covered, f"{mismatch} / {covered} pixels differ"
+        assert classify_vis_mismatches(got, o.vis, o.width, o.height) == 0   # all of them edge or tie pixels
         assert np.count_nonzero(sh_g != sh_o) <= 0.001 * np.count_nonzero(sh_o != 0x3F800000)
     else:
         assert mismatch == 0, f"{mismatch} of {covered} covered pixels differ"

@@ -9,7 +9,7 @@ import pytest
 
 from lighthugger_b200 import _structs as S
 from lighthugger_b200.scene import Scene
-from helpers import Textures, compare_color, display, make_context, make_oracle, vis_fields
+from helpers import Textures, classify_vis_mismatches, compare_color, display, make_context, make_oracle, vis_fields
 
 pytestmark = pytest.mark.gpu
 
@@ -54,6 +54,8 @@ def test_alpha_clip_geometry_mixed_scene():
     covered = np.count_nonzero(o.vis != S.LH_VIS_CLEAR)
     mismatch = np.count_nonzero(got != o.vis)
     assert mismatch <= 0.001 * covered, f"{mismatch} / {covered} pixels differ (alpha-test texture filtering)"
+    # ... and every one of them is an edge or a tie pixel
+    assert classify_vis_mismatches(got, o.vis, sc.width, sc.height) == 0
     sh_g, sh_o = ctx.target(S.LH_TARGET_SHADOW).view(np.uint32), o.shadow.view(np.uint32)
     assert np.count_nonzero(sh_g != sh_o) <= 0.001 * np.count_nonzero(sh_o != 0x3F800000)
     ctx.close()
@@ -154,3 +156,31 @@ def test_gltf_scene_renders_like_the_directly_built_scene(tmp_path):
     assert np.array_equal(frames[0][0], frames[1][0]) and np.array_equal(frames[0][1], frames[1][1])
     depth, _, _ = vis_fields(frames[0][0])
     assert np.count_nonzero(depth) > 0.02 * depth.size
+
+
+def test_display_transform_with_the_reference_lut_matches_the_oracle():
+    """the REAL Tony McMapface table (the reference's own DDS, read through the DDS parser and
+    lh_set_display_lut) on a lit frame: B8G8R8A8 output within 1/255 of the oracle's display_transform.comp restatement,
+    which is itself bit-identical to the reference's shader (tests/test_ref_shaders.py)."""
+    from helpers import REAL_LUT, real_display_lut
+    from lighthugger_b200 import image_files as IF
+    lut = real_display_lut()
+    if lut is None:
+        pytest.skip("oracle/_ref/tony_mc_mapface.dds not present (built by `make ref` where /root/reference exists)")
+    sc = Scene.preset("c1", width=960, height=540)
+    tex = Textures(sc, 64)
+    sky = sc.make_skybox(16)
+    ctx = make_context(sc, textures=tex, skybox=sky)
+    assert IF.upload(ctx, open(REAL_LUT, "rb").read()) == ("lut", 48)
+    ctx.render_frame_host(ctx.uniforms())
+    ctx.display_transform(); ctx.sync()
+    scene = ctx.target(S.LH_TARGET_SCENE_RGBA16F).astype(np.float32).reshape(-1, 4)
+    bgra = ctx.target(S.LH_TARGET_DISPLAY_BGRA8).reshape(-1, 4).astype(np.int32)
+    o = make_oracle(sc, textures=tex, skybox=sky)
+    want = np.rint(np.clip(o.display_transform(scene, lut)[:, :3], 0, 1) * 255).astype(np.int32)   # the UNORM store
+    diff = np.abs(want[:, ::-1] - bgra[:, :3])
+    assert (bgra[:, 3] == 255).all()
+    assert diff.max() <= 1, f"max difference {diff.max()}/255 on {np.count_nonzero(diff > 1)} pixels"
+    assert np.count_nonzero(diff) <= 0.05 * diff.size   # and almost all pixels identical
+    assert len(np.unique(bgra[:, :3])) > 100            # a real image, not a constant
+    ctx.close()

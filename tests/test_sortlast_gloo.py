@@ -137,3 +137,23 @@ def test_plan_tiles_instances_and_cascades():
         for h in (1, 2, 1080, 2160, 4320, 37):
             rows = [sortlast.row_range(h, r, world) for r in range(world)]
             assert rows[0][0] == 0 and rows[-1][1] == h and all(rows[r][1] == rows[r + 1][0] for r in range(world - 1))
+
+
+def test_stripe_balancer_converges_on_a_skewed_cost_field():
+    """The balancer sees only per-rank costs; with a cost density that is 8x higher on the left of the view the bounds
+    must move until every rank's cost is within a few percent of the mean, and stay ascending inside [0, 1]."""
+    from lighthugger_b200.sortlast import StripeBalancer
+    import math
+    density = lambda t: 8.0 if t < 0.25 else 1.0          # cost per unit width
+    def cost(a, b, fixed=0.05):
+        n = 2000
+        return fixed + sum(density(a + (b - a) * (i + 0.5) / n) for i in range(n)) * (b - a) / n
+    for world in (2, 4, 8):
+        bal = StripeBalancer(world)
+        for _ in range(12):
+            c = [cost(bal.bounds[0][r], bal.bounds[0][r + 1]) for r in range(world)]
+            bal.update(0, c)
+        b = bal.bounds[0]
+        assert b[0] == 0.0 and b[-1] == 1.0 and all(b[k] < b[k + 1] for k in range(world))
+        c = [cost(b[r], b[r + 1]) for r in range(world)]
+        assert bal.imbalance(c) < 1.08, (world, c)
