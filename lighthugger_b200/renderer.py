@@ -192,6 +192,11 @@ class Context:
     def comm_set_exchange(self, mode):
         self._check(self.lib.lh_comm_set_exchange(self.handle, mode))
 
+    def resize(self, width, height):
+        """lh_targets_resize (sort-last ranks call it together: it is collective under LH_EXCHANGE_PEER)."""
+        self._check(self.lib.lh_targets_resize(self.handle, width, height))
+        self.width, self.height = width, height
+
     def comm_remap(self):
         """Collective: drop every peer mapping (call on all ranks before moving the MeshletReference buffer)."""
         self._check(self.lib.lh_comm_remap(self.handle))

@@ -50,70 +50,95 @@ def main():
     n = sc.num_instances
     W, H = sc.width, sc.height
 
-    want = None
+    W2, H2 = (W * 3 // 4) & ~1, (H * 5 // 8) & ~1     # the size the resize case switches to
+    want = want_resized = None
     if rank == 0:
-        one = make_context(sc, textures=tex, skybox=sky, device=local_rank)
-        one.render_frame_host(one.uniforms())
-        st = one.stats()
-        table = one.meshlet_references(0, one.caps.max_opaque_draws + st.num_alpha_clip)
-        d, triples = decode(one.target(S.LH_TARGET_VIS64), [table], one.caps.max_opaque_draws + one.caps.max_alpha_clip_draws)
-        want = dict(depth=d, triples=triples, misc=bytes(one.misc()), shadow=one.target(S.LH_TARGET_SHADOW).view(np.uint32).copy(),
-                    color=one.target(S.LH_TARGET_SCENE_RGBA16F).view(np.uint16).copy())
-        one.close()
+        def single_gpu(width, height):
+            one = make_context(sc, textures=tex, skybox=sky, device=local_rank, width=width, height=height)
+            one.render_frame_host(one.uniforms())
+            st = one.stats()
+            table = one.meshlet_references(0, one.caps.max_opaque_draws + st.num_alpha_clip)
+            d, triples = decode(one.target(S.LH_TARGET_VIS64), [table], one.caps.max_opaque_draws + one.caps.max_alpha_clip_draws)
+            w = dict(depth=d, triples=triples, misc=bytes(one.misc()), shadow=one.target(S.LH_TARGET_SHADOW).view(np.uint32).copy(),
+                     color=one.target(S.LH_TARGET_SCENE_RGBA16F).view(np.uint16).copy())
+            one.close()
+            return w
+        want = single_gpu(W, H)
+        want_resized = single_gpu(W2, H2)
 
     failures = []
+
+    def check(ctx, tag, want, W, H, exchange, caps, per_rank):
+        """gathers every rank's part of the frame on rank 0 and compares it with the single-GPU frame `want`"""
+        y0, y1 = ctx.comm_rows()
+        assert (y0, y1) == (sortlast.row_range(H, rank, world) if exchange == S.LH_EXCHANGE_PEER else (0, H))
+        st = ctx.stats()
+        mine = dict(rows=(y0, y1), vis=ctx.target(S.LH_TARGET_VIS64)[y0 * W:y1 * W].copy(),
+                    table=ctx.meshlet_references(0, caps.max_opaque_draws + st.num_alpha_clip), misc=bytes(ctx.misc()),
+                    shadow=ctx.target(S.LH_TARGET_SHADOW).view(np.uint32).copy(),
+                    color=ctx.target(S.LH_TARGET_SCENE_RGBA16F).view(np.uint16).copy())
+        parts = [None] * world
+        dist.all_gather_object(parts, mine)
+        if rank != 0:
+            return
+        tables = [p["table"] for p in parts]
+        if exchange == S.LH_EXCHANGE_PEER:
+            vis = np.concatenate([p["vis"] for p in parts])
+        else:
+            vis = parts[0]["vis"]
+            if any(not np.array_equal(p["vis"], vis) for p in parts):
+                failures.append(f"{tag}: ranks hold different composites")
+        d, triples = decode(vis, tables, per_rank)
+        if not np.array_equal(d, want["depth"]):
+            failures.append(f"{tag}: depth bits differ on {(d != want['depth']).sum()} pixels")
+        if not np.array_equal(triples, want["triples"]):
+            failures.append(f"{tag}: (instance, meshlet, triangle) differ on {(triples != want['triples']).any(1).sum()} pixels")
+        for r, p in enumerate(parts):
+            if p["misc"] != want["misc"]:
+                failures.append(f"{tag}: MiscStorage of rank {r} differs")
+            if not np.array_equal(p["shadow"], want["shadow"]):
+                failures.append(f"{tag}: shadow layers of rank {r} differ on {(p['shadow'] != want['shadow']).sum()} texels")
+        # rank 0 holds the whole lit frame in both modes
+        if not np.array_equal(parts[0]["color"], want["color"]):
+            bad = (parts[0]["color"] != want["color"]).reshape(-1, 4).any(1)
+            failures.append(f"{tag}: lit colour differs on {bad.sum()} pixels (rows {np.unique(np.nonzero(bad)[0] // W)[:8]})")
+        print(f"[mgpu] {tag}: checked {vis.size} pixels, {int((d != 0).sum())} covered", flush=True)
+
     for exchange, ename, split, partition in ((S.LH_EXCHANGE_PEER, "peer", "instances", "stripes"),
                                               (S.LH_EXCHANGE_PEER, "peer", "cascades", "stripes"),
                                               (S.LH_EXCHANGE_PEER, "peer", "instances", "range"),
                                               (S.LH_EXCHANGE_NCCL, "nccl", "cascades", "range"),
-                                              (S.LH_EXCHANGE_NCCL, "nccl", "instances", "stripes")):
-        if True:
-            caps = sortlast.capacities(sc, world, split)
-            per_rank = caps.max_opaque_draws + caps.max_alpha_clip_draws
-            ctx = make_context(sc, textures=tex, skybox=sky, caps=caps, device=local_rank)
-            ids = [ctx.comm_unique_id() if rank == 0 else None]
-            dist.broadcast_object_list(ids, src=0)
-            ctx.comm_init(rank, world, ids[0])
-            ctx.comm_set_exchange(exchange)
+                                              (S.LH_EXCHANGE_NCCL, "nccl", "instances", "stripes"),
+                                              # stripes of unequal width (what the load balancer produces), then a collective
+                                              # resize of every rank's targets and a frame at the new size
+                                              (S.LH_EXCHANGE_PEER, "peer", "instances", "bounds")):
+        caps = sortlast.capacities(sc, world, split)
+        per_rank = caps.max_opaque_draws + caps.max_alpha_clip_draws
+        ctx = make_context(sc, textures=tex, skybox=sky, caps=caps, device=local_rank)
+        ids = [ctx.comm_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(ids, src=0)
+        ctx.comm_init(rank, world, ids[0])
+        ctx.comm_set_exchange(exchange)
+        if partition == "bounds":
+            sortlast.apply(ctx, n, rank, world, split, "stripes")
+            bal = sortlast.StripeBalancer(world)
+            bal.update(0, [1.0 + 3.0 * r for r in range(world)])      # pretend the right-hand ranks were slower
+            bal.update(1, [4.0 - 3.0 * r / max(1, world - 1) for r in range(world)])
+            bal.apply(ctx, rank)
+        else:
             sortlast.apply(ctx, n, rank, world, split, partition)
+        u = ctx.uniforms()
+        for _ in range(2):   # the second frame reuses the peer mappings and every self-cleaning counter
+            ctx.render_frame_host(u)
+        check(ctx, f"{ename}/{split}/{partition}", want, W, H, exchange, caps, per_rank)
+        if partition == "bounds":
+            ctx.resize(W2, H2)          # collective: unmap -> barrier -> reallocate; the row slices follow the new height
             u = ctx.uniforms()
-            for _ in range(2):   # the second frame reuses the peer mappings and every self-cleaning counter
+            for _ in range(2):
                 ctx.render_frame_host(u)
-            y0, y1 = ctx.comm_rows()
-            assert (y0, y1) == (sortlast.row_range(H, rank, world) if exchange == S.LH_EXCHANGE_PEER else (0, H))
-            st = ctx.stats()
-            mine = dict(rows=(y0, y1), vis=ctx.target(S.LH_TARGET_VIS64)[y0 * W:y1 * W].copy(),
-                        table=ctx.meshlet_references(0, caps.max_opaque_draws + st.num_alpha_clip), misc=bytes(ctx.misc()),
-                        shadow=ctx.target(S.LH_TARGET_SHADOW).view(np.uint32).copy(),
-                        color=ctx.target(S.LH_TARGET_SCENE_RGBA16F).view(np.uint16).copy())
-            parts = [None] * world
-            dist.all_gather_object(parts, mine)
-            if rank == 0:
-                tag = f"{ename}/{split}/{partition}"
-                tables = [p["table"] for p in parts]
-                if exchange == S.LH_EXCHANGE_PEER:
-                    vis = np.concatenate([p["vis"] for p in parts])
-                else:
-                    vis = parts[0]["vis"]
-                    if any(not np.array_equal(p["vis"], vis) for p in parts):
-                        failures.append(f"{tag}: ranks hold different composites")
-                d, triples = decode(vis, tables, per_rank)
-                if not np.array_equal(d, want["depth"]):
-                    failures.append(f"{tag}: depth bits differ on {(d != want['depth']).sum()} pixels")
-                if not np.array_equal(triples, want["triples"]):
-                    failures.append(f"{tag}: (instance, meshlet, triangle) differ on {(triples != want['triples']).any(1).sum()} pixels")
-                for r, p in enumerate(parts):
-                    if p["misc"] != want["misc"]:
-                        failures.append(f"{tag}: MiscStorage of rank {r} differs")
-                    if not np.array_equal(p["shadow"], want["shadow"]):
-                        failures.append(f"{tag}: shadow layers of rank {r} differ on {(p['shadow'] != want['shadow']).sum()} texels")
-                # rank 0 holds the whole lit frame in both modes
-                if not np.array_equal(parts[0]["color"], want["color"]):
-                    bad = (parts[0]["color"] != want["color"]).reshape(-1, 4).any(1)
-                    failures.append(f"{tag}: lit colour differs on {bad.sum()} pixels (rows {np.unique(np.nonzero(bad)[0] // W)[:8]})")
-                print(f"[mgpu] {tag}: checked {vis.size} pixels, {int((d != 0).sum())} covered", flush=True)
-            ctx.close()
-            dist.barrier()
+            check(ctx, f"{ename}/{split}/{partition} after resize to {W2}x{H2}", want_resized, W2, H2, exchange, caps, per_rank)
+        ctx.close()
+        dist.barrier()
     ok = [not failures]
     dist.broadcast_object_list(ok, src=0)
     if rank == 0:
