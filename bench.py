@@ -273,6 +273,30 @@ def run_ours(args):
         ctx.comm_set_exchange(S.LH_EXCHANGE_NCCL if args.exchange == "nccl" else S.LH_EXCHANGE_PEER)
         sortlast.apply(ctx, n, rank, world, args.shadow_split, args.partition)
     u = ctx.uniforms()
+    visible_fraction = None
+    if args.visible > 0:
+        # culling-ratio sweep (BASELINE config 5): the camera moves along its viewing axis until the instance
+        # cull keeps the requested share of the instances (bisection on the GPU's own count, a few untimed frames)
+        cam = S.LhCamera.from_buffer_copy(bytes(scene.camera))
+        z0 = float(cam.position[2])
+        lo_z, hi_z = z0 * 6.0, -z0 * 0.9          # far behind the scene ... well inside it (z0 < 0: the camera looks at +z)
+        for _ in range(14):
+            mid = 0.5 * (lo_z + hi_z)
+            cam.position[2] = mid
+            u = ctx.uniforms(camera=cam)
+            ctx.frame_begin(u); ctx.reset(); ctx.cull_instances(); ctx.sync()
+            frac = ctx.sector(0)[0] / max(1, n)
+            if frac > args.visible:
+                lo_z = mid      # too many visible: move in
+            else:
+                hi_z = mid
+        if dist:                # every rank must use the same camera
+            z = torch.tensor([float(cam.position[2])], device="cuda", dtype=torch.float64)
+            dist.broadcast(z, 0)
+            cam.position[2] = float(z.item())
+            u = ctx.uniforms(camera=cam)
+        ctx.frame_begin(u); ctx.reset(); ctx.cull_instances(); ctx.sync()
+        visible_fraction = ctx.sector(0)[0] / max(1, n) if world == 1 else args.visible
 
     def barrier():
         torch.cuda.synchronize()
@@ -472,7 +496,8 @@ def run_ours(args):
                    "candidate_meshlets": scene.total_meshlets, "l2": "flushed between timed frames (256 MB write)",
                    "parallelism": (f"sort-last x{n_gpus}: instances split by {args.partition}, {args.exchange} exchange, shadows split by {args.shadow_split}"
                                    if n_gpus > 1 else "single GPU"), "texture_format": "BC7_SRGB",
-                   "texture_size": args.tex_size, "texture_sets": scene.num_texture_sets},
+                   "texture_size": args.tex_size, "texture_sets": scene.num_texture_sets,
+                   "visible_instance_fraction": (round(visible_fraction, 4) if visible_fraction is not None else None)},
         "culled_mtri_per_s": scene.total_triangles / (ms_per_step / 1e3) / 1e6,
         "frame": {"visible_instances": stats.num_visible_instances, "candidate_meshlets": stats.num_candidate_meshlets,
                   "rasterised_meshlets": survivors, "deferred_triangle_tiles": stats.num_large_triangles,
@@ -517,6 +542,7 @@ def main():
     ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"], help="multi-GPU: peer-memory kernels or whole-buffer NCCL")
     ap.add_argument("--shadow-split", default="instances", choices=["instances", "cascades"])
     ap.add_argument("--partition", default="stripes", choices=["stripes", "range"], help="multi-GPU: how instances are shared out")
+    ap.add_argument("--visible", type=float, default=0.0, help="culling-ratio sweep: move the camera until this share of the instances survives the instance cull (0: the preset's camera)")
     ap.add_argument("--balance", type=int, default=8, help="multi-GPU, stripes: untimed frames that move the stripe bounds towards equal per-rank pass times (0: equal-width interleaved stripes)")
     ap.add_argument("--stripes-per-rank", type=int, default=0, help="multi-GPU: interleaved screen stripes per GPU (0: sortlast.STRIPES_PER_RANK)")
     args = ap.parse_args()

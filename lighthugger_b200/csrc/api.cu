@@ -851,6 +851,7 @@ int lh_frame_sync(LhContext* ctx) {
     LH_CUDA(ctx, cudaMemcpyAsync(&ctx->pinned_stats->overflow, &ctx->state->overflow, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
     LH_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     if (int rc = check_launch(ctx, "frame")) return rc;
+    if (int rc = comm_poll_errors(ctx)) return rc;
     if (ctx->have_uniforms && ctx->pinned_stats->overflow)
         return fail(ctx, LH_ERR_CAPACITY, "a list overflowed its LhConfig capacity (see LhFrameStats.overflow)");
     return LH_OK;

@@ -43,6 +43,7 @@ struct NcclApi {
     ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
     ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
     ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*CommGetAsyncError)(ncclComm_t, ncclResult_t*) = nullptr;
     ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
     const char* (*GetErrorString)(ncclResult_t) = nullptr;
@@ -71,6 +72,7 @@ bool load_nccl() {
     g_nccl.GetUniqueId = (decltype(g_nccl.GetUniqueId))find("ncclGetUniqueId");
     g_nccl.CommInitRank = (decltype(g_nccl.CommInitRank))find("ncclCommInitRank");
     g_nccl.CommDestroy = (decltype(g_nccl.CommDestroy))find("ncclCommDestroy");
+    g_nccl.CommGetAsyncError = (decltype(g_nccl.CommGetAsyncError))find("ncclCommGetAsyncError");
     g_nccl.AllReduce = (decltype(g_nccl.AllReduce))find("ncclAllReduce");
     g_nccl.AllGather = (decltype(g_nccl.AllGather))find("ncclAllGather");
     g_nccl.GetErrorString = (decltype(g_nccl.GetErrorString))find("ncclGetErrorString");
@@ -258,6 +260,16 @@ int reduce_depth_exchange(LhContext* ctx) {
 }
 
 int frame_barrier(LhContext* ctx) { return stream_barrier(ctx); }
+
+// an asynchronous NCCL failure (a peer died, a link went down) surfaces here instead of as a hang at the next collective
+int comm_poll_errors(LhContext* ctx) {
+    if (!ctx->nccl_comm || !g_nccl.CommGetAsyncError) return LH_OK;
+    ncclResult_t async = ncclSuccess;
+    ncclResult_t r = g_nccl.CommGetAsyncError((ncclComm_t)ctx->nccl_comm, &async);
+    if (r != ncclSuccess) return nccl_fail(ctx, "ncclCommGetAsyncError", r);
+    if (async != ncclSuccess && async != ncclInProgress) return nccl_fail(ctx, "asynchronous NCCL error", async);
+    return LH_OK;
+}
 
 // Collective: every rank drops its mappings of everybody's buffers; when it returns no rank maps any peer buffer any
 // more, so targets may be freed / reallocated and the MeshletReference buffer moved.

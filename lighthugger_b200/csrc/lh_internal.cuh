@@ -280,6 +280,7 @@ int composite_allreduce_min(LhContext* ctx);
 int composite_pull(LhContext* ctx);          // LH_EXCHANGE_PEER: barrier + pull-min kernel with the depth bounds folded in
 int reduce_depth_exchange(LhContext* ctx);   // ... the frame's depth bounds from the ranks' row bounds
 int frame_barrier(LhContext* ctx);           // every rank has finished its part of the frame
+int comm_poll_errors(LhContext* ctx);        // ncclCommGetAsyncError: LH_ERR_NCCL when the communicator has failed
 bool peer_exchange(const LhContext* ctx);    // multi-GPU and LH_EXCHANGE_PEER
 int ensure_peer_maps(LhContext* ctx);        // maps what the frame needs of the peers (collective the first time)
 int peer_release_collective(LhContext* ctx); // every rank unmaps everything, then a barrier: buffers may now be freed / moved

@@ -272,7 +272,7 @@ __global__ void __launch_bounds__(256) resolve_kernel(const __grid_constant__ Fr
     float4* tmp1 = tmp0 + (size_t)W * H;
     float2* tmp2 = (float2*)(tmp1 + (size_t)W * H);
     F3 world, sun, ambient;
-    F3 dbg_base{0, 0, 0}, dbg_normal{0, 0, 0};
+    F3 dbg_base{0, 0, 0}, dbg_normal{0, 0, 0}, dbg_view{0, 0, 0};
     float2 dbg_rm = make_float2(0, 0), dbg_uv = make_float2(0, 0);
     bool alpha;
     if (PHASE != 2) {
@@ -394,7 +394,7 @@ __global__ void __launch_bounds__(256) resolve_kernel(const __grid_constant__ Fr
         normal = normalize(t3 * (invmax * mn.x) + b3 * (invmax * mn.y) + normal * mn.z);
     }
     if (PHASE == 0) {
-        dbg_base = base; dbg_normal = normal; dbg_rm = make_float2(roughness, metallic); dbg_uv = make_float2(u, v);
+        dbg_base = base; dbg_normal = normal; dbg_rm = make_float2(roughness, metallic); dbg_uv = make_float2(u, v); dbg_view = view_vec;
     }
     const float amb = 0.025f + 0.025f * normal.y;  // SH with sh[0] = sh[2] = 0.025 (:40-57)
     sun = brdf(view_vec, F3{P.u.sun_dir[0], P.u.sun_dir[1], P.u.sun_dir[2]}, normal, roughness, metallic, base, alpha);
@@ -453,6 +453,8 @@ __global__ void __launch_bounds__(256) resolve_kernel(const __grid_constant__ Fr
         else if (P.u.debug == 102) t = dbg_normal;
         else if (P.u.debug == 103) t = F3{dbg_rm.x, dbg_rm.y, (float)cascade * 0.25f};
         else if (P.u.debug == 105) t = F3{dbg_uv.x, dbg_uv.y, 0.0f};
+        else if (P.u.debug == 106) t = dbg_view;
+        else if (P.u.debug == 107) t = sun;
         store_rgba16f(P.scene, P.scene_remote, pixel, t.x, t.y, t.z, 1.0f);
         return;
     }

@@ -744,7 +744,12 @@ uint64_t lh_scene_make_texture(int kind, uint32_t size, uint32_t variant, int al
                 px[3] = alpha_cutout ? 0.5f + 0.6f * std::sin(two_pi * 3 * u) * std::sin(two_pi * 3 * v) : 1.0f;
             } else if (kind == 1) {
                 px[0] = 1.0f;
-                px[1] = 0.35f + 0.5f * w2;  // roughness (g)
+                // roughness (g).  The reference samples this map through an sRGB format like every DDS texture
+                // (image_loading.cpp:20-34), so 0.6 .. 0.95 stored is a perceptual roughness of 0.32 .. 0.89 in the shader:
+                // the range of everyday materials.  (A mirror-like 0.1 makes the GGX lobe so narrow that the 1/512
+                // difference two texture units may have in a bilinear weight of the normal map changes a highlight pixel's
+                // radiance by tens of percent -- content no implementation pair agrees on.)
+                px[1] = 0.6f + 0.35f * w2;
                 px[2] = 0.1f + 0.5f * w1;   // metallic (b)
                 px[3] = 1.0f;
             } else {

@@ -407,6 +407,8 @@ static void resolve_pixel(const LhUniforms* u, const LhoConfig* cfg, const uint6
     else if (debug_term == 103) { out[0] = roughness; out[1] = metallic; out[2] = (float)cascade * 0.25f; }
     else if (debug_term == 104) { out[0] = world.x; out[1] = world.y; out[2] = world.z; }
     else if (debug_term == 105) { out[0] = uv[0]; out[1] = uv[1]; out[2] = 0.0f; }
+    else if (debug_term == 106) { out[0] = view_vec.x; out[1] = view_vec.y; out[2] = view_vec.z; }
+    else if (debug_term == 107) { out[0] = sun[0]; out[1] = sun[1]; out[2] = sun[2]; }
 }
 
 }  // namespace lho

@@ -12,7 +12,7 @@ from lighthugger_b200 import _structs as S
 from lighthugger_b200.scene import Scene
 from helpers import Textures, display, make_context, make_oracle, rotated_scene, vis_fields
 
-TERMS = {100: "shadow", 101: "base colour", 102: "normal", 103: "rough/metal/cascade", 105: "uv"}
+TERMS = {100: "shadow", 101: "base colour", 102: "normal", 103: "rough/metal/cascade", 105: "uv", 106: "view vector", 107: "sun term"}
 
 
 def scene_of(name):
@@ -58,8 +58,8 @@ for name in (sys.argv[1:] or ["tiny", "c1q", "rotated"]):
         diffs[term] = (e, g, w)
         print(f"   {label:22s} max |diff| all {e.max():.5f}  on bad pixels: median {np.median(e[bad]) if bad.any() else 0:.5f} max {e[bad].max() if bad.any() else 0:.5f};"
               f"  pixels with diff > 0.01: {np.count_nonzero(e > 0.01)} (bad among them {np.count_nonzero((e > 0.01) & bad)})")
-    order = np.argsort(-d)[:10]
+    order = np.argsort(-d)[:6]
     for i in order:
-        terms = "  ".join(f"{TERMS[t][:6]} {diffs[t][1][i].round(4).tolist()} vs {diffs[t][2][i].round(4).tolist()}" for t in (100, 101, 103))
+        terms = "  ".join(f"{TERMS[t][:6]} {diffs[t][1][i].round(4).tolist()} vs {diffs[t][2][i].round(4).tolist()}" for t in (100, 101, 102, 103, 106, 107))
         print(f"   px ({i % sc.width},{i // sc.width}) err {d[i] * 255:.2f}/255 got {got[i, :3].round(4).tolist()} want {want[i, :3].round(4).tolist()} | {terms}")
     ctx.close()
