@@ -22,14 +22,22 @@ NVCCFLAGS := -gencode arch=compute_100a,code=sm_100a -O3 -std=c++20 -lineinfo \
 LDFLAGS_SO := -Wl,--exclude-libs,ALL
 CXXFLAGS := -O2 -std=c++20 -fPIC -fvisibility=hidden -ffp-contract=off -Iinclude -Wall -Wextra -Wno-unused-parameter
 
-all: cuda host oracle ref examples
+all: cuda host oracle ref examples probes
 
 cuda: $(LIBDIR)/liblighthugger_b200.so
 host: $(LIBDIR)/liblh_host.so
 oracle: oracle/liblh_oracle.so
 examples: lighthugger_b200/bin/lh_frame_loop
+# hardware probes (texture-unit filter arithmetic, L2 atomic ceilings): run on the GPU box, fitted offline (tools/*.py)
+PROBES := build/texvalue_probe build/texsrgb_probe build/texfilter_probe build/atomic_probe
+probes: $(PROBES)
+build/%_probe: tools/%_probe.cu
+	@mkdir -p build
+	$(NVCC) -gencode arch=compute_100a,code=sm_100a -O3 -o $@ $<
 
 CUDA_OBJS := $(patsubst lighthugger_b200/csrc/%.cu,build/%.o,$(CUDA_SRCS))
+# the lighting resolve keeps the reference shader's operation order with IEEE operations only (see resolve.cu)
+build/resolve.o: NVCCFLAGS += -fmad=false
 build/%.o: lighthugger_b200/csrc/%.cu $(CUDA_HDRS)
 	@mkdir -p build
 	$(NVCC) $(NVCCFLAGS) -c -o $@ $<

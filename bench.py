@@ -264,6 +264,12 @@ def run_ours(args):
     (first, count), _ = sortlast.main_plan(n, rank, world, args.partition)
     end = first + count
     caps = sortlast.capacities(scene, world, args.shadow_split)
+    emulate = None
+    if args.emulate_rank and world == 1:
+        # profiling aid: one GPU does the local work of rank R of N (stripe partition, no exchange), so that a launch list
+        # of a single rank of a large world can be captured on one device; not a bench value
+        emulate = tuple(int(x) for x in args.emulate_rank.split("/"))
+        caps = sortlast.capacities(scene, emulate[1], args.shadow_split)
     ctx = make_context(scene, textures=tex, skybox=sky, caps=caps, flags=S.LH_CONFIG_WRITE_DRAW_COMMANDS | S.LH_CONFIG_PASS_TIMINGS,
                        device=local_rank)
     if world > 1:
@@ -272,6 +278,8 @@ def run_ours(args):
         ctx.comm_init(rank, world, ids[0])
         ctx.comm_set_exchange(S.LH_EXCHANGE_NCCL if args.exchange == "nccl" else S.LH_EXCHANGE_PEER)
         sortlast.apply(ctx, n, rank, world, args.shadow_split, args.partition)
+    if emulate:
+        sortlast.apply(ctx, n, emulate[0], emulate[1], args.shadow_split, args.partition)
     u = ctx.uniforms()
     visible_fraction = None
     if args.visible > 0:
@@ -497,7 +505,8 @@ def run_ours(args):
                    "parallelism": (f"sort-last x{n_gpus}: instances split by {args.partition}, {args.exchange} exchange, shadows split by {args.shadow_split}"
                                    if n_gpus > 1 else "single GPU"), "texture_format": "BC7_SRGB",
                    "texture_size": args.tex_size, "texture_sets": scene.num_texture_sets,
-                   "visible_instance_fraction": (round(visible_fraction, 4) if visible_fraction is not None else None)},
+                   "visible_instance_fraction": (round(visible_fraction, 4) if visible_fraction is not None else None),
+                   **({"emulated_rank": args.emulate_rank, "note": "profiling aid: one rank's local work, NOT a bench value"} if emulate else {})},
         "culled_mtri_per_s": scene.total_triangles / (ms_per_step / 1e3) / 1e6,
         "frame": {"visible_instances": stats.num_visible_instances, "candidate_meshlets": stats.num_candidate_meshlets,
                   "rasterised_meshlets": survivors, "deferred_triangle_tiles": stats.num_large_triangles,
@@ -544,6 +553,7 @@ def main():
     ap.add_argument("--partition", default="stripes", choices=["stripes", "range"], help="multi-GPU: how instances are shared out")
     ap.add_argument("--visible", type=float, default=0.0, help="culling-ratio sweep: move the camera until this share of the instances survives the instance cull (0: the preset's camera)")
     ap.add_argument("--balance", type=int, default=8, help="multi-GPU, stripes: untimed frames that move the stripe bounds towards equal per-rank pass times (0: equal-width interleaved stripes)")
+    ap.add_argument("--emulate-rank", default="", help="profiling aid, one GPU: do the local work of rank R of N, given as R/N (no exchange)")
     ap.add_argument("--stripes-per-rank", type=int, default=0, help="multi-GPU: interleaved screen stripes per GPU (0: sortlast.STRIPES_PER_RANK)")
     args = ap.parse_args()
     if args.impl == "reference":

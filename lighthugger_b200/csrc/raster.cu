@@ -63,7 +63,7 @@ struct alignas(16) RasterRecord {
 static_assert(sizeof(RasterRecord) == 64, "records are moved in 16-byte units");
 
 #ifndef LH_CHUNK
-#define LH_CHUNK 4
+#define LH_CHUNK 2
 #endif
 constexpr int kChunk = LH_CHUNK;   // queue entries a warp takes per ticket
 // LH_STAGE_STREAMS: the chunk's micro-indices, vertex indices and instance transforms are copied to shared memory

@@ -20,8 +20,11 @@
 // has no sampler for, is done by hand from the u32 depth layers.  Output is
 // written as one 8-byte RGBA16F store per pixel.
 //
-// This pass is floating-point and tolerance-checked (tests/test_resolve.py);
-// it may use fused multiply-adds and fast reciprocals.
+// This pass is floating point, and REPRODUCIBLE: the file is compiled with -fmad=false (Makefile), divisions and
+// square roots are IEEE, and every expression keeps the operation order of the reference's shader as restated by the
+// checker (which models the texture unit's filter bit for bit), so the RGBA16F colour of a covered pixel is meant to
+// be bit-identical to the checker's -- the pass has several discontinuous choices (shadow compares, anisotropic probe
+// count, the BRDF where N.V is clamped) on which a last-bit difference would otherwise become a visible one.
 #include <cuda_fp16.h>
 
 #include "lh_internal.cuh"
@@ -42,11 +45,6 @@ __device__ __forceinline__ F3 normalize(F3 a) {
     float inv = 1.0f / sqrtf(dot(a, a));
     return a * inv;
 }
-__device__ __forceinline__ float4 mul4(const float* m, float x, float y, float z, float w) {
-    return make_float4(m[0] * x + m[4] * y + m[8] * z + m[12] * w, m[1] * x + m[5] * y + m[9] * z + m[13] * w,
-                       m[2] * x + m[6] * y + m[10] * z + m[14] * w, m[3] * x + m[7] * y + m[11] * z + m[15] * w);
-}
-
 struct Bary {
     F3 lambda, ddx, ddy;
 };
@@ -56,8 +54,7 @@ struct Bary {
 // gives the shadow coordinate, and the shadow lookup COMPARES it with stored depths -- without a depth bias for opaque
 // meshes -- so a last-bit difference would flip comparisons on every surface that grazes its own shadow-map texels.
 // With this part bit-identical to the oracle (which is bit-identical to the reference's GLSL compiled on the host), the
-// shadow term only differs by the rounding of the filter weights.  The derivatives that follow feed texture footprints
-// only and use fused / fast arithmetic.
+// shadow term only differs by the rounding of the filter weights.
 __device__ Bary calc_full_bary(float4 p0, float4 p1, float4 p2, float ndc_x, float ndc_y, float win_w, float win_h) {
     Bary r;
     F3 invw{pdiv(1.0f, p0.w), pdiv(1.0f, p1.w), pdiv(1.0f, p2.w)};
@@ -75,14 +72,17 @@ __device__ Bary calc_full_bary(float4 p0, float4 p1, float4 p2, float ndc_x, flo
     r.lambda.x = pmul(interp_w, padd(padd(invw.x, pmul(dvx, r.ddx.x)), pmul(dvy, r.ddy.x)));
     r.lambda.y = pmul(interp_w, padd(padd(0.0f, pmul(dvx, r.ddx.y)), pmul(dvy, r.ddy.y)));
     r.lambda.z = pmul(interp_w, padd(padd(0.0f, pmul(dvx, r.ddx.z)), pmul(dvy, r.ddy.z)));
-    float sx = 2.0f / win_w, sy = -2.0f / win_h;  // the y derivative is flipped (vbuffer.glsl:50-51)
-    r.ddx = r.ddx * sx;
-    r.ddy = r.ddy * sy;
-    ddx_sum *= sx;
-    ddy_sum *= sy;
-    float iw_ddx = 1.0f / (interp_inv_w + ddx_sum), iw_ddy = 1.0f / (interp_inv_w + ddy_sum);
-    r.ddx = (r.lambda * interp_inv_w + r.ddx) * iw_ddx - r.lambda;
-    r.ddy = (r.lambda * interp_inv_w + r.ddy) * iw_ddy - r.lambda;
+    // The derivatives decide the anisotropic footprint (probe count, major axis: discontinuous choices), so they are
+    // pinned as well.
+    float sx = pdiv(2.0f, win_w), sy = -pdiv(2.0f, win_h);  // the y derivative is flipped (vbuffer.glsl:50-51)
+    r.ddx = F3{pmul(r.ddx.x, sx), pmul(r.ddx.y, sx), pmul(r.ddx.z, sx)};
+    r.ddy = F3{pmul(r.ddy.x, sy), pmul(r.ddy.y, sy), pmul(r.ddy.z, sy)};
+    ddx_sum = pmul(ddx_sum, sx);
+    ddy_sum = pmul(ddy_sum, sy);
+    const float iw_ddx = pdiv(1.0f, padd(interp_inv_w, ddx_sum)), iw_ddy = pdiv(1.0f, padd(interp_inv_w, ddy_sum));
+    auto perspective = [&](float lambda, float d, float iw) { return psub(pmul(iw, padd(pmul(lambda, interp_inv_w), d)), lambda); };
+    r.ddx = F3{perspective(r.lambda.x, r.ddx.x, iw_ddx), perspective(r.lambda.y, r.ddx.y, iw_ddx), perspective(r.lambda.z, r.ddx.z, iw_ddx)};
+    r.ddy = F3{perspective(r.lambda.x, r.ddy.x, iw_ddy), perspective(r.lambda.y, r.ddy.y, iw_ddy), perspective(r.lambda.z, r.ddy.z, iw_ddy)};
     return r;
 }
 
@@ -94,54 +94,83 @@ __device__ __forceinline__ Interp interp1(const Bary& b, float v0, float v1, flo
     return Interp{dot(m, b.lambda), dot(m, b.ddx), dot(m, b.ddy)};
 }
 // ... with the value in pinned arithmetic (the world position)
+__device__ __forceinline__ float dot_pinned(float v0, float v1, float v2, F3 w) { return padd(padd(pmul(v0, w.x), pmul(v1, w.y)), pmul(v2, w.z)); }
 __device__ __forceinline__ Interp interp1_pinned(const Bary& b, float v0, float v1, float v2) {
     F3 m{v0, v1, v2};
-    return Interp{padd(padd(pmul(v0, b.lambda.x), pmul(v1, b.lambda.y)), pmul(v2, b.lambda.z)), dot(m, b.ddx), dot(m, b.ddy)};
+    return Interp{dot_pinned(v0, v1, v2, b.lambda), dot(m, b.ddx), dot(m, b.ddy)};
+}
+// ... with value and derivatives pinned (the texture coordinate: its derivatives lay out the footprint)
+__device__ __forceinline__ Interp interp1_all_pinned(const Bary& b, float v0, float v1, float v2) {
+    return Interp{dot_pinned(v0, v1, v2, b.lambda), dot_pinned(v0, v1, v2, b.ddx), dot_pinned(v0, v1, v2, b.ddy)};
 }
 
-// pbr.glsl:3-96
+// pbr.glsl:3-96, in the checker's operation order (no contraction in this file)
 constexpr float kPi = 3.14159265358979323846f;
-__device__ __forceinline__ float pow5(float x) {
+__device__ __forceinline__ float pow5(float x) {   // pow(x, 5.0): implementation-defined in GLSL, pinned as ((x*x)*(x*x))*x
     float x2 = x * x;
     return x2 * x2 * x;
 }
+__device__ __forceinline__ float f_schlick1(float u, float f0, float f90) { return f0 + (f90 - f0) * pow5(1.0f - u); }
 __device__ __forceinline__ float fd_burley(float nov, float nol, float loh, float roughness) {
     float f90 = 0.5f + 2.0f * roughness * loh * loh;
-    float ls = 1.0f + (f90 - 1.0f) * pow5(1.0f - nol), vs = 1.0f + (f90 - 1.0f) * pow5(1.0f - nov);
-    return ls * vs * (1.0f / kPi);
+    return f_schlick1(nol, 1.0f, f90) * f_schlick1(nov, 1.0f, f90) * (1.0f / kPi);
 }
 __device__ __forceinline__ float clampf(float x, float lo, float hi) { return fminf(fmaxf(x, lo), hi); }
 
 __device__ F3 brdf(F3 v, F3 l, F3 n, float perceptual_roughness, float metallic, F3 base, bool thin_walled) {
-    F3 h = normalize(v + l);
-    F3 diffuse = base * (1.0f - metallic);
-    const float refl = 0.04f;  // reflectance_for_ior(1.5) = ((1.5-1)/(1.5+1))^2
-    F3 f0 = F3{refl * (1.0f - metallic) + base.x * metallic, refl * (1.0f - metallic) + base.y * metallic,
-               refl * (1.0f - metallic) + base.z * metallic};
+    F3 h = normalize(F3{v.x + l.x, v.y + l.y, v.z + l.z});
+    const float refl = ((1.5f - 1.0f) / (1.5f + 1.0f)) * ((1.5f - 1.0f) / (1.5f + 1.0f));   // reflectance_for_ior(1.5)
+    const float* bp = &base.x;
+    float diffuse[3], f0[3];
+#pragma unroll
+    for (int c = 0; c < 3; c++) {
+        diffuse[c] = (1.0f - metallic) * bp[c];
+        f0[c] = refl * (1.0f - metallic) + bp[c] * metallic;
+    }
     float nov = clampf(dot(n, v), 1e-5f, 1.0f), nol = clampf(dot(n, l), 0.0f, 1.0f);
     float noh = clampf(dot(n, h), 0.0f, 1.0f), loh = clampf(dot(l, h), 0.0f, 1.0f);
     float roughness = perceptual_roughness * perceptual_roughness;
     float a2 = roughness * roughness;
     float f = (noh * a2 - noh) * noh + 1.0f;
     float D = a2 / (kPi * f * f);
-    float ggxl = nov * sqrtf((-nol * a2 + nol) * nol + a2), ggxv = nol * sqrtf((-nov * a2 + nov) * nov + a2);
+    float ggxl = nov * sqrtf((-nol * a2 + nol) * nol + a2);
+    float ggxv = nol * sqrtf((-nov * a2 + nov) * nov + a2);
     float V = 0.5f / (ggxv + ggxl);
     float p5 = pow5(1.0f - loh);
     float burley = fd_burley(nov, nol, loh, roughness);
-    float rev_nov = clampf(-dot(n, v), 1e-5f, 1.0f), rev_nol = clampf(-dot(n, l), 0.0f, 1.0f);
-    float rev = thin_walled ? fd_burley(rev_nov, rev_nol, loh, roughness) * rev_nol : 0.0f;
-    float dv = D * V;
+    F3 nn{-n.x, -n.y, -n.z};
+    float rev_nov = clampf(dot(nn, v), 1e-5f, 1.0f), rev_nol = clampf(dot(nn, l), 0.0f, 1.0f);
+    float rev_burley = thin_walled ? fd_burley(rev_nov, rev_nol, loh, roughness) : 0.0f;
     F3 out;
     float* o = &out.x;
-    const float* f0p = &f0.x;
-    const float* dp = &diffuse.x;
+#pragma unroll
     for (int c = 0; c < 3; c++) {
-        float F = f0p[c] + (1.0f - f0p[c]) * p5;
-        float irr = fmaxf((dp[c] * burley + dv * F) * nol, 0.0f);
-        irr += dp[c] * rev;
+        float F = f0[c] + (1.0f - f0[c]) * p5;
+        float fr = (D * V) * F;
+        float fd = diffuse[c] * burley;
+        float irr = fmaxf((fd + fr) * nol, 0.0f);
+        if (thin_walled) irr += diffuse[c] * rev_burley * rev_nol;
         o[c] = isnan(irr) ? 0.0f : irr;
     }
     return out;
+}
+
+// log2 of a positive normal float by a fixed sequence of IEEE single operations (the checker runs the same sequence):
+// the level of detail decides the blend of two mip levels, and libm / the SFU would each round it their own way
+__device__ __forceinline__ float pinned_log2f(float x) {
+    uint32_t bits = __float_as_uint(x);
+    int e = (int)(bits >> 23) - 127;
+    float m = __uint_as_float((bits & 0x007FFFFFu) | 0x3F800000u);   // [1, 2)
+    if (m > 1.41421354f) {
+        m = m * 0.5f;
+        e += 1;
+    }
+    const float s = (m - 1.0f) / (m + 1.0f), s2 = s * s;
+    float q = 0.142857149f;            // 2 * atanh(s) = 2 s (1 + s^2/3 + s^4/5 + s^6/7), |s| < 0.1716
+    q = q * s2 + 0.2f;
+    q = q * s2 + 0.333333343f;
+    q = q * s2 + 1.0f;
+    return (float)e + (2.0f * s * q) * 1.44269502f;
 }
 
 // sampler2DArrayShadow + compare LESS + linear (src/main.cpp:569-581), by hand
@@ -161,26 +190,48 @@ __device__ __forceinline__ float sample_shadow(const uint32_t* layer, int n, flo
     return top + wy * (bot - top);
 }
 
-// The 3x3 PCF of render_geometry.comp:200-226 when the tap spacing (1/1024) is exactly one texel: the nine bilinear
-// compare taps share their fractional weights and touch a 4x4 texel neighbourhood, each texel with the summed weight
-// (1-w, 1, 1, w) per axis -- 16 loads instead of 36.  Returns the sum over the nine taps.
+// The 3x3 PCF of render_geometry.comp:200-226 when the tap spacing (1/1024) is one texel: the nine bilinear compare taps
+// touch a 4x4 texel neighbourhood, which is loaded and compared ONCE (16 loads instead of 36, one bit per texel); every
+// tap then computes its own texel position and weights exactly as sample_shadow does and picks its four compare
+// results out of the bit mask (a tap whose texels fall outside the neighbourhood -- possible only through the rounding
+// of u + k/1024 -- takes the direct path), so the sum is bit-identical to nine sample_shadow calls.
 __device__ __forceinline__ float pcf3x3_texel_spaced(const uint32_t* layer, int n, float u, float v, float ref) {
-    float x = u * (float)n - 0.5f, y = v * (float)n - 0.5f;
-    if (!(isfinite(x) && isfinite(y))) return 0.0f;
-    float fx = floorf(x), fy = floorf(y);
-    const float wx = x - fx, wy = y - fy;
-    fx = fminf(fmaxf(fx, -3.0f), (float)n + 2.0f);
-    fy = fminf(fmaxf(fy, -3.0f), (float)n + 2.0f);
+    const float x = u * (float)n - 0.5f, y = v * (float)n - 0.5f;
+    if (!(isfinite(x) && isfinite(y))) return 0.0f;   // then every tap is 0
+    const float fx = fminf(fmaxf(floorf(x), -3.0f), (float)n + 2.0f), fy = fminf(fmaxf(floorf(y), -3.0f), (float)n + 2.0f);
     const int bx = (int)fx - 1, by = (int)fy - 1;
-    const float wcol[4] = {1.0f - wx, 1.0f, 1.0f, wx}, wrow[4] = {1.0f - wy, 1.0f, 1.0f, wy};
-    float sum = 0.0f;
+    uint32_t mask = 0;
 #pragma unroll
     for (int r = 0; r < 4; r++) {
         const uint32_t* row = layer + (size_t)min(max(by + r, 0), n - 1) * n;
-        float acc = 0.0f;
 #pragma unroll
-        for (int c = 0; c < 4; c++) acc += ref < __uint_as_float(__ldg(row + min(max(bx + c, 0), n - 1))) ? wcol[c] : 0.0f;
-        sum += wrow[r] * acc;
+        for (int c = 0; c < 4; c++)
+            if (ref < __uint_as_float(__ldg(row + min(max(bx + c, 0), n - 1)))) mask |= 1u << (4 * r + c);
+    }
+    float sum = 0.0f;
+#pragma unroll
+    for (int ox = -1; ox <= 1; ox++) {
+        const float tu = u + (float)ox / 1024.0f;
+        const float tx = tu * (float)n - 0.5f;
+        const float tfx = floorf(tx), wx = tx - tfx;
+        const int ix = (int)fminf(fmaxf(tfx, -2.0f), (float)n + 1.0f) - bx;
+#pragma unroll
+        for (int oy = -1; oy <= 1; oy++) {
+            const float tv = v + (float)oy / 1024.0f;
+            const float ty = tv * (float)n - 0.5f;
+            const float tfy = floorf(ty), wy = ty - tfy;
+            const int iy = (int)fminf(fmaxf(tfy, -2.0f), (float)n + 1.0f) - by;
+            float tap;
+            if ((unsigned)ix <= 2u && (unsigned)iy <= 2u && isfinite(tx) && isfinite(ty)) {
+                const uint32_t m = mask >> (4 * iy + ix);
+                const float c00 = (float)(m & 1u), c10 = (float)((m >> 1) & 1u), c01 = (float)((m >> 4) & 1u), c11 = (float)((m >> 5) & 1u);
+                const float top = c00 + wx * (c10 - c00), bot = c01 + wx * (c11 - c01);
+                tap = top + wy * (bot - top);
+            } else {
+                tap = sample_shadow(layer, n, tu, tv, ref);
+            }
+            sum += tap;
+        }
     }
     return sum;
 }
@@ -194,7 +245,9 @@ __device__ __forceinline__ float4 sample_trilinear(cudaTextureObject_t t, float 
     float4 a = tex2DLod<float4>(t, u, v, l0);
     if (f > 0.0f && l0 + 1.0f <= max_level) {
         const float4 b = tex2DLod<float4>(t, u, v, l0 + 1.0f);
-        a.x += f * (b.x - a.x); a.y += f * (b.y - a.y); a.z += f * (b.z - a.z); a.w += f * (b.w - a.w);
+        // pinned (no contraction): the oracle models the texture unit bit for bit, so the blend of two fetches should not differ either
+        a.x = padd(a.x, pmul(f, psub(b.x, a.x))); a.y = padd(a.y, pmul(f, psub(b.y, a.y)));
+        a.z = padd(a.z, pmul(f, psub(b.z, a.z))); a.w = padd(a.w, pmul(f, psub(b.w, a.w)));
     }
     return a;
 }
@@ -209,16 +262,16 @@ __device__ __forceinline__ Footprint texture_footprint(uint4 dims, float2 ddx, f
     Footprint f;
     const float w = (float)dims.x, h = (float)dims.y;
     f.max_level = (float)(dims.z - 1u);
-    const float ax0 = ddx.x * w, ax1 = ddx.y * h, ay0 = ddy.x * w, ay1 = ddy.y * h;
-    const float px = sqrtf(ax0 * ax0 + ax1 * ax1), py = sqrtf(ay0 * ay0 + ay1 * ay1);
+    const float ax0 = pmul(ddx.x, w), ax1 = pmul(ddx.y, h), ay0 = pmul(ddy.x, w), ay1 = pmul(ddy.y, h);
+    const float px = __fsqrt_rn(padd(pmul(ax0, ax0), pmul(ax1, ax1))), py = __fsqrt_rn(padd(pmul(ay0, ay0), pmul(ay1, ay1)));
     const float pmax = fmaxf(px, py), pmin = fminf(px, py);
     f.probes = 0;
     f.lod = 0.0f;
     f.major = make_float2(0.0f, 0.0f);
     if (!(pmax > 0.0f) || !isfinite(pmax)) return f;
-    float n = pmin > 0.0f ? fminf(ceilf(pmax / pmin), 16.0f) : 16.0f;
+    float n = pmin > 0.0f ? fminf(ceilf(pdiv(pmax, pmin)), 16.0f) : 16.0f;
     if (pmax <= 1.0f) n = 1.0f;  // magnification: a single bilinear probe
-    f.lod = log2f(pmax / n);
+    f.lod = pinned_log2f(pdiv(pmax, n));
     f.probes = (int)n;
     f.major = px >= py ? ddx : ddy;
     return f;
@@ -227,12 +280,12 @@ __device__ float4 sample_texture_footprint(cudaTextureObject_t t, const Footprin
     if (f.probes == 0) return sample_trilinear(t, u, v, 0.0f, f.max_level);
     float4 acc = make_float4(0, 0, 0, 0);
     for (int i = 0; i < f.probes; i++) {
-        const float o = ((float)i + 0.5f) / (float)f.probes - 0.5f;
-        const float4 s = sample_trilinear(t, u + o * f.major.x, v + o * f.major.y, f.lod, f.max_level);
-        acc.x += s.x; acc.y += s.y; acc.z += s.z; acc.w += s.w;
+        const float o = psub(pdiv((float)i + 0.5f, (float)f.probes), 0.5f);
+        const float4 s = sample_trilinear(t, padd(u, pmul(o, f.major.x)), padd(v, pmul(o, f.major.y)), f.lod, f.max_level);
+        acc.x = padd(acc.x, s.x); acc.y = padd(acc.y, s.y); acc.z = padd(acc.z, s.z); acc.w = padd(acc.w, s.w);
     }
-    const float inv = 1.0f / (float)f.probes;
-    return make_float4(acc.x * inv, acc.y * inv, acc.z * inv, acc.w * inv);
+    const float inv = pdiv(1.0f, (float)f.probes);
+    return make_float4(pmul(acc.x, inv), pmul(acc.y, inv), pmul(acc.z, inv), pmul(acc.w, inv));
 }
 
 // scene_remote: rank 0's target in peer memory (sort-last ranks != 0 deliver their rows there; a warp row is 64 B)
@@ -272,15 +325,15 @@ __global__ void __launch_bounds__(256) resolve_kernel(const __grid_constant__ Fr
     float4* tmp1 = tmp0 + (size_t)W * H;
     float2* tmp2 = (float2*)(tmp1 + (size_t)W * H);
     F3 world, sun, ambient;
-    F3 dbg_base{0, 0, 0}, dbg_normal{0, 0, 0}, dbg_view{0, 0, 0};
+    F3 dbg_base{0, 0, 0}, dbg_normal{0, 0, 0}, dbg_view{0, 0, 0}, dbg_fp{0, 0, 0};
     float2 dbg_rm = make_float2(0, 0), dbg_uv = make_float2(0, 0);
     bool alpha;
     if (PHASE != 2) {
     const unsigned long long key = P.vis[pixel];
     if (lh_vis_depth_bits(key) == 0u) {  // depth == 0: sky (:86-101)
-        float4 un = mul4(&P.u.perspective_inverse.m[0][0], ndc_x, ndc_y, 0.0f, 1.0f);
+        const V4 un = mat4_mul(&P.u.perspective_inverse.m[0][0], ndc_x, ndc_y, 0.0f, 1.0f);
         F3 local = normalize(F3{un.x, un.y, un.z});
-        float4 ray = mul4(&P.u.view_inverse.m[0][0], local.x, local.y, local.z, 0.0f);
+        const V4 ray = mat4_mul(&P.u.view_inverse.m[0][0], local.x, local.y, local.z, 0.0f);
         float4 s = P.sky ? texCubemapLod<float4>(P.sky, ray.x, ray.y, ray.z, 0.0f) : make_float4(0, 0, 0, 0);
         store_rgba16f(P.scene, P.scene_remote, pixel, s.x * 8.0f, s.y * 8.0f, s.z * 8.0f, 1.0f);
         if (PHASE == 1) tmp2[pixel] = make_float2(0.0f, -1.0f);   // nothing left to do for this pixel
@@ -338,7 +391,7 @@ __global__ void __launch_bounds__(256) resolve_kernel(const __grid_constant__ Fr
     const Interp wy = interp1_pinned(bary, pos[0].y, pos[1].y, pos[2].y);
     const Interp wz = interp1_pinned(bary, pos[0].z, pos[1].z, pos[2].z);
     world = F3{wx.value, wy.value, wz.value};
-    const Interp iu = interp1(bary, tu[0], tu[1], tu[2]), iv = interp1(bary, tv[0], tv[1], tv[2]);
+    const Interp iu = interp1_all_pinned(bary, tu[0], tu[1], tu[2]), iv = interp1_all_pinned(bary, tv[0], tv[1], tv[2]);
     const float u = iu.value + __ldg(&mi->texture_offset[0]), v = iv.value + __ldg(&mi->texture_offset[1]);
     const float2 duv_dx = make_float2(iu.dx, iv.dx), duv_dy = make_float2(iu.dy, iv.dy);
 
@@ -384,22 +437,24 @@ __global__ void __launch_bounds__(256) resolve_kernel(const __grid_constant__ Fr
     if (t_nrm != LH_UNUSED_TEXTURE_INDEX && t_nrm < LH_MAX_TEXTURES && P.textures[t_nrm]) {
         footprint_for(t_nrm);
         float4 s = sample_texture_footprint(P.textures[t_nrm], fp, u, v);
-        F3 mn{s.x * (255.0f / 127.0f) - 128.0f / 127.0f, s.y * (255.0f / 127.0f) - 128.0f / 127.0f, s.z * (255.0f / 127.0f) - 128.0f / 127.0f};
+        F3 mn{s.x * 255.0f / 127.0f - 128.0f / 127.0f, s.y * 255.0f / 127.0f - 128.0f / 127.0f, s.z * 255.0f / 127.0f - 128.0f / 127.0f};
         // compute_cotangent_frame (:25-38)
         F3 pdx{wx.dx, wy.dx, wz.dx}, pdy{wx.dy, wy.dy, wz.dy};
         F3 dpy_perp = cross(pdy, normal), dpx_perp = cross(normal, pdx);
         F3 t3 = dpy_perp * duv_dx.x + dpx_perp * duv_dy.x;
         F3 b3 = dpy_perp * duv_dx.y + dpx_perp * duv_dy.y;
         float invmax = 1.0f / sqrtf(fmaxf(dot(t3, t3), dot(b3, b3)));
-        normal = normalize(t3 * (invmax * mn.x) + b3 * (invmax * mn.y) + normal * mn.z);
+        normal = normalize(F3{(t3.x * invmax) * mn.x + (b3.x * invmax) * mn.y + normal.x * mn.z,
+                              (t3.y * invmax) * mn.x + (b3.y * invmax) * mn.y + normal.y * mn.z,
+                              (t3.z * invmax) * mn.x + (b3.z * invmax) * mn.y + normal.z * mn.z});
     }
     if (PHASE == 0) {
         dbg_base = base; dbg_normal = normal; dbg_rm = make_float2(roughness, metallic); dbg_uv = make_float2(u, v); dbg_view = view_vec;
+        dbg_fp = F3{(float)fp.probes, fp.lod, 0.0f};
     }
     const float amb = 0.025f + 0.025f * normal.y;  // SH with sh[0] = sh[2] = 0.025 (:40-57)
     sun = brdf(view_vec, F3{P.u.sun_dir[0], P.u.sun_dir[1], P.u.sun_dir[2]}, normal, roughness, metallic, base, alpha);
-    const float adm = __fmul_rn(amb, 1.0f - metallic);
-    ambient = F3{__fmul_rn(adm, base.x), __fmul_rn(adm, base.y), __fmul_rn(adm, base.z)};
+    ambient = F3{amb * ((1.0f - metallic) * base.x), amb * ((1.0f - metallic) * base.y), amb * ((1.0f - metallic) * base.z)};
     if (PHASE == 1) {
         tmp0[pixel] = make_float4(sun.x, sun.y, sun.z, world.x);
         tmp1[pixel] = make_float4(ambient.x, ambient.y, ambient.z, world.y);
@@ -441,7 +496,7 @@ __global__ void __launch_bounds__(256) resolve_kernel(const __grid_constant__ Fr
             for (int oy = -1; oy <= 1; oy++)
                 shadow_sum += sample_shadow(layer, sn, padd(sc.x, (float)ox / 1024.0f), padd(sc.y, (float)oy / 1024.0f), psub(sc.z, bias));
     }
-    shadow_sum *= (1.0f / 9.0f);
+    shadow_sum /= 9.0f;
     if (sc.z > 1.0f) shadow_sum = 1.0f;
 
     if (PHASE == 0 && P.u.debug >= 100) {
@@ -455,12 +510,13 @@ __global__ void __launch_bounds__(256) resolve_kernel(const __grid_constant__ Fr
         else if (P.u.debug == 105) t = F3{dbg_uv.x, dbg_uv.y, 0.0f};
         else if (P.u.debug == 106) t = dbg_view;
         else if (P.u.debug == 107) t = sun;
+        else if (P.u.debug == 108) t = dbg_fp;
         store_rgba16f(P.scene, P.scene_remote, pixel, t.x, t.y, t.z, 1.0f);
         return;
     }
-    const float sun_intensity = __fmul_rn(kPi, shadow_sum);
-    store_rgba16f(P.scene, P.scene_remote, pixel, __fmaf_rn(sun.x, sun_intensity, ambient.x), __fmaf_rn(sun.y, sun_intensity, ambient.y),
-                  __fmaf_rn(sun.z, sun_intensity, ambient.z), 1.0f);
+    const float sun_intensity = kPi * shadow_sum;
+    store_rgba16f(P.scene, P.scene_remote, pixel, sun.x * sun_intensity + ambient.x, sun.y * sun_intensity + ambient.y,
+                  sun.z * sun_intensity + ambient.z, 1.0f);
 }
 
 // display_transform.comp:37-81: Tony McMapface LUT (48^3) + sRGB OETF -> BGRA8

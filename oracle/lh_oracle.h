@@ -82,6 +82,14 @@ int lho_resolve(const LhUniforms* u, const LhoConfig* cfg, const uint64_t* vis, 
 /* one input of the lighting resolve instead of the colour (100 shadow term, 101 base colour, 102 normal, 103 roughness /
  * metallic / cascade, 104 world position, 105 uv): attribution of differences, not part of the reference */
 int lho_resolve_debug(const LhUniforms* u, const LhoConfig* cfg, const uint64_t* vis, const float* shadow, int debug_term, float* out_rgba32f);
+/* the texture unit's bilinear filter (level 0 of an RGBA8 texture, repeat addressing) at `count` positions: replayed
+ * against dumps of the real texture unit (tests/golden/texture_unit_*.bin) */
+void lho_test_sample_bilinear(const uint8_t* rgba8, uint32_t width, uint32_t height, uint32_t srgb, uint64_t count, const float* uv,
+                              float* out_rgba);
+/* the lit colour of `count` listed pixels (y * width + x) with `bias` added to the rgb of every material texture sample:
+ * the conditioning of the reference's own result at those pixels (not part of the reference) */
+int lho_resolve_pixels(const LhUniforms* u, const LhoConfig* cfg, const uint64_t* vis, const float* shadow, uint64_t count,
+                       const uint32_t* pixels, const float bias[3], float* out_rgba32f);
 /* display_transform (display_transform.comp:5-81, debug overlay off): scene RGBA32F + LUT (size^3 RGB32F) -> the
  * sRGB-encoded RGBA32F value stored to the UNORM swapchain image */
 int lho_display_transform(const LhUniforms* u, const LhoConfig* cfg, const float* scene_rgba32f, const float* lut_rgb32f, uint32_t lut_size,

@@ -55,6 +55,11 @@ inline vec3 operator*(vec3 const& a, int b) { return a * (float)b; }
 inline vec2 operator*(vec2 const& a, int b) { return a * (float)b; }
 inline vec2 operator/(vec2 const& a, uvec2 const& b) { return a / vec2(b); }
 inline float pow(int a, float b) { return std::pow((float)a, b); }
+// pow(x, 5.0) as pinned by the oracle and the CUDA pass (GLSL leaves pow's precision to the implementation)
+inline float shim_pow5(float x) {
+    float x2 = x * x;
+    return x2 * x2 * x;
+}
 inline float clamp(float x, float lo, float hi) { return min(max(x, lo), hi); }
 }  // namespace glm
 

@@ -46,6 +46,7 @@ def oracle_lib():
         lib.lho_render_frame.argtypes = [U, K, vp, vp, vp]
         lib.lho_display_transform.argtypes = [U, K, vp, vp, C.c_uint32, vp]
         lib.lho_resolve_debug.argtypes = [U, K, vp, vp, C.c_int, vp]
+        lib.lho_resolve_pixels.argtypes = [U, K, vp, vp, C.c_uint64, vp, vp, vp]
         lib.lho_composite_min.argtypes = [vp, vp, C.c_uint64]
         lib.lho_composite_min.restype = None
         lib.lho_pinned_powf.argtypes = [C.c_float, C.c_float]
@@ -115,6 +116,14 @@ class Oracle:
         out = np.zeros(self.width * self.height * 4, np.float32)
         self._call("lho_resolve_debug", self.vis.ctypes.data, self.shadow.ctypes.data, term, out.ctypes.data)
         return out.reshape(-1, 4)
+
+    def resolve_pixels(self, pixels, bias=(0.0, 0.0, 0.0)):
+        """The lit colour of the listed pixels with `bias` added to every material texture sample (conditioning probe)."""
+        px = np.ascontiguousarray(pixels, np.uint32)
+        b = np.asarray(bias, np.float32)
+        out = np.zeros((len(px), 4), np.float32)
+        self._call("lho_resolve_pixels", self.vis.ctypes.data, self.shadow.ctypes.data, len(px), px.ctypes.data, b.ctypes.data, out.ctypes.data)
+        return out
 
     def display_transform(self, scene_rgba32f, lut_rgb32f, lut_size=48):
         """display_transform.comp on a scene-referred RGBA32F image: the sRGB-encoded RGBA32F the reference stores."""

@@ -205,6 +205,20 @@ def test_resolve_is_finite_and_sky_where_empty():
     assert (depth == 0).any() and (depth != 0).any()
 
 
+def test_resolve_pixels_repeats_the_frame_and_finds_the_brdf_discontinuity():
+    """lho_resolve_pixels with a zero bias is the resolve itself; with the texture samples moved by one 8-bit code the
+    colour moves a little almost everywhere and a lot on the few pixels where pbr.glsl is discontinuous (helpers.compare_color)."""
+    from helpers import TEXTURE_UNIT_PRECISION, Textures, display
+    sc = Scene.preset("c1", width=240, height=135)
+    o = make_oracle(sc, textures=Textures(sc, 32), skybox=sc.make_skybox(8))
+    o.render_frame(resolve=True)
+    every = np.arange(sc.width * sc.height, dtype=np.uint32)
+    assert np.array_equal(o.resolve_pixels(every), o.color.reshape(-1, 4))
+    e = TEXTURE_UNIT_PRECISION
+    moved = np.abs(display(o.resolve_pixels(every, (e, -e, e))[:, :3]) - display(o.color.reshape(-1, 4)[:, :3])).max(axis=1)
+    assert np.median(moved) < 1 / 255 and np.quantile(moved, 0.99) < 4 / 255
+
+
 def test_oracle_frame_is_clean_under_address_and_ub_sanitizers(tmp_path):
     # the oracle is the checker of every parity test: one whole frame of it (all passes, textures, skybox) runs here in
     # a build with -fsanitize=address,undefined (SURVEY.md 5: "host -fsanitize=address,undefined for the oracle")

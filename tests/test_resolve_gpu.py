@@ -53,6 +53,11 @@ def test_alpha_clip_geometry_mixed_scene():
     got = ctx.target(S.LH_TARGET_VIS64)
     covered = np.count_nonzero(o.vis != S.LH_VIS_CLEAR)
     mismatch = np.count_nonzero(got != o.vis)
+    import helpers
+    if helpers.COLOR_LOG:
+        with open(helpers.COLOR_LOG, "a") as f:
+            f.write('{"test": "alpha_clip_vis", "covered": %d, "mismatch": %d, "shadow_mismatch": %d}\n' % (
+                covered, mismatch, np.count_nonzero(ctx.target(S.LH_TARGET_SHADOW).view(np.uint32) != o.shadow.view(np.uint32))))
     assert mismatch <= 0.001 * covered, f"{mismatch} / {covered} pixels differ (alpha-test texture filtering)"
     # ... and every one of them is an edge or a tie pixel
     assert classify_vis_mismatches(got, o.vis, sc.width, sc.height) == 0

@@ -1,0 +1,120 @@
+"""The oracle's texture filter against dumps of the real thing.
+
+textureGrad leaves the filter arithmetic to the implementation, so "what the reference computes" for a material sample
+is what the GPU's texture unit computes.  tests/golden/texture_unit_*.bin are outputs of a B200's texture unit
+(tools/texvalue_probe.cu, tools/texsrgb_probe.cu, run through gpurun; the generating sources are committed): RGBA8
+textures of random bytes sampled at random positions, all 257 weights between chosen texel pairs, and a grid of 2D
+weights inside chosen 2x2 cells, as UNORM and as sRGB.  The oracle's model (oracle/lh_oracle_resolve.cpp,
+sample_bilinear_level) must reproduce every one of those 49,152 fetches BIT FOR BIT; the GPU test at the end re-runs the
+probes' fetches on the device at hand, so a texture unit that filters differently is noticed."""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+from oracle_api import oracle_lib
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+W = 64
+PAIRS = [(0, 255), (255, 0), (188, 21), (21, 188), (74, 255), (255, 74), (128, 255), (0, 128), (64, 192), (192, 64), (250, 15),
+         (100, 101), (254, 255), (1, 0), (17, 255), (119, 250), (0, 1), (0, 16), (16, 32), (32, 64), (64, 128), (200, 40),
+         (40, 200), (10, 240), (240, 10), (128, 129), (90, 180), (180, 90), (5, 250), (250, 5), (60, 61), (255, 254)]
+CELLS = [(0, 255, 255, 0), (255, 0, 0, 255), (246, 239, 139, 84), (10, 200, 90, 250), (255, 255, 0, 0), (0, 0, 255, 255),
+         (128, 64, 32, 16), (200, 40, 120, 250)]
+
+
+def model(tex_rgba8, srgb, uv):
+    lib = oracle_lib()
+    lib.lho_test_sample_bilinear.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint64, C.c_void_p, C.c_void_p]
+    lib.lho_test_sample_bilinear.restype = None
+    tex = np.ascontiguousarray(tex_rgba8, np.uint8)
+    uv = np.ascontiguousarray(uv, np.float32)
+    out = np.zeros((len(uv), 4), np.float32)
+    lib.lho_test_sample_bilinear(tex.ctypes.data, W, W, int(srgb), len(uv), uv.ctypes.data, out.ctypes.data)
+    return out
+
+
+def pair_texture():
+    tex = np.zeros((W, W, 4), np.uint8)
+    for x in range(W):
+        tex[:, x, :] = PAIRS[x // 2][x & 1]
+    return tex
+
+
+def pair_uv():
+    return np.array([((2 * i + 0.5 + k / 256.0) / W, 8.5 / W) for i in range(32) for k in range(257)], np.float32)
+
+
+def cell_texture():
+    tex = np.zeros((W, W, 4), np.uint8)
+    for i, cell in enumerate(CELLS):
+        for j, value in enumerate(cell):
+            tex[8 + j // 2, 4 * i + (j & 1), :] = value
+    return tex
+
+
+def cell_uv():
+    return np.array([((4 * i + 0.5 + kx / 256.0) / W, (8.5 + ky / 256.0) / W) for i in range(8) for ky in range(0, 257, 8)
+                     for kx in range(0, 257, 8)], np.float32)
+
+
+@pytest.mark.parametrize("name", ["unorm", "srgb"])
+def test_random_texture_fetches_are_reproduced_bit_for_bit(name):
+    raw = open(os.path.join(GOLDEN, f"texture_unit_{name}.bin"), "rb").read()
+    tex = np.frombuffer(raw[:W * W * 4], np.uint8).reshape(W, W, 4)
+    rec = np.frombuffer(raw[W * W * 4:], np.float32).reshape(-1, 6)
+    got = model(tex, name == "srgb", rec[:, :2])
+    assert len(rec) == 16384
+    assert np.array_equal(got.view(np.uint32), np.ascontiguousarray(rec[:, 2:]).view(np.uint32))
+
+
+def test_every_weight_between_two_texels():
+    # [mode][pair][k] -> (rgb value, alpha value); mode 0 UNORM, mode 1 sRGB (whose alpha stays linear)
+    want = np.frombuffer(open(os.path.join(GOLDEN, "texture_unit_srgb_1d.bin"), "rb").read(), np.float32).reshape(2, 32 * 257, 2)
+    for srgb in (0, 1):
+        got = model(pair_texture(), srgb, pair_uv())
+        assert np.array_equal(got[:, 0].view(np.uint32), np.ascontiguousarray(want[srgb, :, 0]).view(np.uint32))
+        assert np.array_equal(got[:, 3].view(np.uint32), np.ascontiguousarray(want[srgb, :, 1]).view(np.uint32))
+
+
+def test_weight_grid_inside_a_cell():
+    want = np.frombuffer(open(os.path.join(GOLDEN, "texture_unit_srgb_2d.bin"), "rb").read(), np.float32).reshape(2, 8 * 33 * 33, 2)
+    for srgb in (0, 1):
+        got = model(cell_texture(), srgb, cell_uv())
+        assert np.array_equal(got[:, 0].view(np.uint32), np.ascontiguousarray(want[srgb, :, 0]).view(np.uint32))
+        assert np.array_equal(got[:, 3].view(np.uint32), np.ascontiguousarray(want[srgb, :, 1]).view(np.uint32))
+
+
+def test_srgb_decode_table_is_the_point_sampled_one():
+    tab = np.frombuffer(open(os.path.join(GOLDEN, "texture_unit_srgb_table.bin"), "rb").read(), np.float32).reshape(256, 2)
+    tex = np.zeros((W, W, 4), np.uint8)
+    codes = np.arange(256, dtype=np.uint8)
+    tex.reshape(-1, 4)[:256, :] = codes[:, None]
+    uv = np.array([((c % W + 0.5) / W, (c // W + 0.5) / W) for c in range(256)], np.float32)   # texel centres: one weight of 256
+    got = model(tex, 1, uv)
+    assert np.array_equal(got[:, 0], tab[:, 0]) and np.array_equal(got[:, 3], tab[:, 1])
+    # ... and it is the sRGB transfer function to 8 significant bits
+    c = codes / 255.0
+    exact = np.where(c <= 0.04045, c / 12.92, ((c + 0.055) / 1.055) ** 2.4)
+    assert np.abs(tab[:, 0] - exact).max() < 2.0 ** -8
+
+
+@pytest.mark.gpu
+def test_this_gpus_texture_unit_still_filters_like_the_model():
+    """Re-runs a slice of the probes on the device at hand (through torch-free CUDA: the product library's own texture
+    path): a random sRGB texture sampled through lh's texture objects must match the model bit for bit."""
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    probe = os.path.join(root, "build", "texvalue_probe")
+    if not os.path.exists(probe):
+        pytest.skip("build/texvalue_probe is not built (make probes)")
+    out = os.path.join(root, "gpurun_out", "texture_unit_check")
+    os.makedirs(out, exist_ok=True)
+    subprocess.run([probe, out], check=True, timeout=120)
+    for name in ("unorm", "srgb"):
+        raw = open(os.path.join(out, f"texvalue_{name}.bin"), "rb").read()
+        tex = np.frombuffer(raw[:W * W * 4], np.uint8).reshape(W, W, 4)
+        rec = np.frombuffer(raw[W * W * 4:], np.float32).reshape(-1, 6)
+        got = model(tex, name == "srgb", rec[:, :2])
+        assert np.array_equal(got.view(np.uint32), np.ascontiguousarray(rec[:, 2:]).view(np.uint32)), name

@@ -12,7 +12,7 @@ from lighthugger_b200 import _structs as S
 from lighthugger_b200.scene import Scene
 from helpers import Textures, display, make_context, make_oracle, rotated_scene, vis_fields
 
-TERMS = {100: "shadow", 101: "base colour", 102: "normal", 103: "rough/metal/cascade", 105: "uv", 106: "view vector", 107: "sun term"}
+TERMS = {100: "shadow", 101: "base colour", 102: "normal", 103: "rough/metal/cascade", 105: "uv", 106: "view vector", 107: "sun term", 108: "footprint (probes, lod)"}
 
 
 def scene_of(name):
@@ -56,7 +56,8 @@ for name in (sys.argv[1:] or ["tiny", "c1q", "rotated"]):
         e = np.abs(g - w).max(axis=1)
         e[~cov] = 0
         diffs[term] = (e, g, w)
-        print(f"   {label:22s} max |diff| all {e.max():.5f}  on bad pixels: median {np.median(e[bad]) if bad.any() else 0:.5f} max {e[bad].max() if bad.any() else 0:.5f};"
+        q = np.quantile(e[cov], [0.5, 0.9, 0.99, 0.999]) if cov.any() else [0] * 4
+        print(f"   {label:22s} q50/q90/q99/q99.9 {q[0]:.5f} {q[1]:.5f} {q[2]:.5f} {q[3]:.5f}  max |diff| all {e.max():.5f}  on bad pixels: median {np.median(e[bad]) if bad.any() else 0:.5f} max {e[bad].max() if bad.any() else 0:.5f};"
               f"  pixels with diff > 0.01: {np.count_nonzero(e > 0.01)} (bad among them {np.count_nonzero((e > 0.01) & bad)})")
     order = np.argsort(-d)[:6]
     for i in order:
