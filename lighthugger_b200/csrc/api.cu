@@ -68,6 +68,7 @@ FrameParams make_params(LhContext* ctx, int cascade, int set, bool internal_list
     p.large_queue = sc.large_queue;
     p.meshlet_bounds = sc.meshlet_bounds;
     p.raster_records = sc.raster_records;
+    p.first_wave_ctas = (uint32_t)ctx->num_sms * 4u;   // LH_RASTER_MIN_CTAS
     p.depth_keys = sc.depth_keys;
     p.depth_hist = sc.depth_hist;
     p.hiz = sc.hiz;
@@ -309,6 +310,7 @@ int lh_context_create(const LhConfig* cfg, LhContext** out) {
         ctx->tune.resolve_low_priority = v[4] != 0;
         ctx->tune.resolve_split = v[6] != 0;
         auto clamp = [](unsigned x, unsigned lo, unsigned hi) { return x < lo ? lo : (x > hi ? hi : x); };
+        ctx->tune.from_environment = true;
         ctx->tune.main_bands = clamp(v[0], 2, 8);
         ctx->tune.shadow_bands = clamp(v[1], 2, 8);
         ctx->tune.main_grid = clamp(v[2], 1, 64);

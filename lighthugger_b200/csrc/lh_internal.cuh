@@ -128,6 +128,7 @@ struct FrameParams {
     uint32_t* large_queue;
     void* meshlet_bounds;                    // 16 B per surviving meshlet of the current raster pass (raster.cu MeshletBound)
     void* raster_records;                    // 64 B per meshlet selected for rasterisation, band after band (raster.cu RasterRecord)
+    uint32_t first_wave_ctas;                // CTAs of the raster kernel that are resident together when it has the GPU to itself
     uint32_t* depth_keys;                    // the bounds' depth keys on their own (4 B per meshlet): what band selection scans
     uint32_t* depth_hist;                    // 8192 bins of the depth-key histogram (self-cleaning)
     uint32_t* hiz;                           // two hierarchical-Z levels of the current raster target: farthest stored value per 4x4- and per 16x16-pixel tile
@@ -251,6 +252,7 @@ struct LhContext {
     struct Tuning {
         float main_fractions[7] = {0, 0, 0, 0, 0, 0, 0};   // LH_TUNE_FRACTIONS="f0,f1,..." (main view)
         uint32_t main_bands = 4, shadow_bands = 6, main_grid = 16, shadow_grid = 3, resolve_low_priority = 1, select_grid = 16, resolve_split = 1, small_max_area = 128;
+        bool from_environment = false;     // LH_TUNE was given: no automatic choices
     } tune;
 
     std::vector<void*> buffers;

@@ -104,6 +104,14 @@ constexpr int kVertOutside = INT_MIN, kVertNonFinite = INT_MIN + 1;   // |snappe
 #define LH_SELECT_EXACT_PIXELS 16
 #endif
 constexpr int kSelectExactPixels = LH_SELECT_EXACT_PIXELS;   // selection tests rectangles of at most this many pixels against the stored values themselves (0: hierarchical Z only)
+#ifndef LH_SELECT_CTA_CLAIM
+#define LH_SELECT_CTA_CLAIM 0
+#endif
+constexpr bool kSelectCtaClaim = LH_SELECT_CTA_CLAIM != 0;   // the selection claims queue space once per CTA and iteration instead of once per warp (measured: -1.5 % at C2, the two barriers cost more than the atomics)
+#ifndef LH_STATIC_FIRST
+#define LH_STATIC_FIRST 1
+#endif
+constexpr bool kStaticFirst = LH_STATIC_FIRST != 0;          // first-wave CTAs of the raster kernel take their first chunk without a ticket
 #ifndef LH_FEW_SAMPLES_PATH
 #define LH_FEW_SAMPLES_PATH 0
 #endif
@@ -591,7 +599,13 @@ __global__ void __launch_bounds__(256) raster_select_kernel(const __grid_constan
     const MeshletBound* bounds = (const MeshletBound*)P.meshlet_bounds;
     uint32_t occluded = 0;
     const uint32_t stride = gridDim.x * blockDim.x;
-    for (uint32_t base = blockIdx.x * blockDim.x + (threadIdx.x & ~31u); base < total; base += stride) {
+    // queue space is claimed once per CTA and iteration (eight warps' survivors in one atomic): the queue counter is a
+    // single address, and one atomic per warp made it the bottleneck of the long cascade lists
+    __shared__ uint32_t warp_keep[2][8], cta_at[2];
+    const uint32_t warp = threadIdx.x >> 5;
+    uint32_t iteration = 0;
+    for (uint32_t cta_base = blockIdx.x * blockDim.x; cta_base < total; cta_base += stride, iteration ^= 1u) {
+        const uint32_t base = cta_base + (threadIdx.x & ~31u);
         // bounds and keys sit at the meshlets' list indices: the opaque draws from 0, the alpha-clip draws from max_opaque
         const uint32_t k = base + lane < n_opaque ? base + lane : P.max_opaque + (base + lane - n_opaque);
         // the scan reads the 4-byte keys only; the 16-byte bound is fetched for the band's own meshlets
@@ -624,7 +638,22 @@ __global__ void __launch_bounds__(256) raster_select_kernel(const __grid_constan
             }
         }
         const uint32_t ballot = __ballot_sync(0xFFFFFFFFu, keep);
-        if (ballot) {
+        if (kSelectCtaClaim) {
+            if (lane == 0) warp_keep[iteration][warp] = (uint32_t)__popc(ballot);
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                uint32_t sum = 0;
+#pragma unroll
+                for (int w = 0; w < 8; w++) sum += warp_keep[iteration][w];
+                cta_at[iteration] = sum ? atomicAdd(&P.pass->queue_count, sum) : 0u;
+            }
+            __syncthreads();
+            if (keep) {
+                uint32_t at = cta_at[iteration] + (uint32_t)__popc(ballot & ((1u << lane) - 1u));
+                for (uint32_t w = 0; w < warp; w++) at += warp_keep[iteration][w];
+                make_record(P, k, mb, (RasterRecord*)P.raster_records + at);
+            }
+        } else if (ballot) {
             uint32_t at = 0;
             if (lane == 0) at = atomicAdd(&P.pass->queue_count, (uint32_t)__popc(ballot));
             at = __shfl_sync(0xFFFFFFFFu, at, 0);
@@ -1047,14 +1076,30 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, LH_RASTER_MIN_CTAS) raster_
 
     const uint32_t band_count = band_end - band_first;
     const uint32_t chunk = max(1u, min((uint32_t)kChunk, band_count / (gridDim.x * kWarpsPerCta * 8u)));
+    // The CTAs of the first wave -- resident together when the launch has the GPU to itself -- take their FIRST chunk
+    // statically (their warp index); the rest of the band is handed out by tickets, and a CTA of a later wave looks at
+    // the counter once (one load per CTA) before any of its warps asks it for work.  A short band -- a rank's share on
+    // eight GPUs, the near cascades -- then costs no atomic at all instead of one per warp of the grid on a single
+    // address, and a long one saves a round trip per first-wave warp.
     // lane 0 holds the NEXT ticket (relative to band_first) from the moment it is requested; nothing reads it before the
-    // following iteration, so the atomic's round trip overlaps the current chunk
-    uint32_t next_ticket = 0;
-    if (lane == 0) next_ticket = atomicAdd(&P.pass->band_ticket[band], chunk);
+    // following iteration, so the atomic's round trip overlaps the current chunk.
+    const uint32_t first_wave = kStaticFirst ? min(gridDim.x, P.first_wave_ctas) : 0u;
+    const uint32_t static_end = min(band_count, first_wave * kWarpsPerCta * chunk);   // entries [0, static_end) are assigned statically
+    uint32_t next_ticket;
+    if (blockIdx.x < first_wave) {
+        next_ticket = (blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5)) * chunk;
+        if (next_ticket >= static_end) next_ticket = band_count;   // nothing static left for this warp: the band is short
+    } else {
+        __shared__ uint32_t taken;
+        if (threadIdx.x == 0) taken = __ldcg(&P.pass->band_ticket[band]);
+        __syncthreads();
+        next_ticket = band_count;
+        if (static_end + taken < band_count && lane == 0) next_ticket = static_end + atomicAdd(&P.pass->band_ticket[band], chunk);
+    }
     for (uint32_t iteration = 0;; iteration++) {
         const uint32_t ticket = band_first + __shfl_sync(0xFFFFFFFFu, next_ticket, 0);
         if (ticket >= band_end) break;
-        if (lane == 0) next_ticket = atomicAdd(&P.pass->band_ticket[band], chunk);
+        if (lane == 0) next_ticket = static_end < band_count ? static_end + atomicAdd(&P.pass->band_ticket[band], chunk) : band_count;
         const uint32_t n = min(chunk, band_end - ticket);
         // ---- the chunk's records ----
         uint32_t my_rx = kUntestable, my_ry = 0;
@@ -1298,7 +1343,12 @@ void launch_raster(LhContext* ctx, const FrameParams& params, int cascade, cudaS
     if (!stream) stream = ctx->stream;
     // The main view runs alone: many small CTAs even out its heavy near meshlets.  The cascades run side by side on
     // four streams: grids of about one wave each let their kernels share the SMs instead of queueing behind one another.
-    const uint32_t bands = cascade < 0 ? ctx->tune.main_bands : ctx->tune.shadow_bands;
+    // Every band costs a hierarchical-Z rebuild, a selection and a raster launch in a dependent chain.  A rank's share of
+    // the lists shrinks with the world size while those launches do not, so fewer bands pay off on many GPUs (measured
+    // at C2 on 8 x B200: 4/6 bands 568, 3/4 594, 2/3 599, 2/2 576 frames/s; on 2 x B200 4/6 wins).  LH_TUNE overrides.
+    uint32_t bands = cascade < 0 ? ctx->tune.main_bands : ctx->tune.shadow_bands;
+    if (!ctx->tune.from_environment && ctx->nranks >= 4)
+        bands = ctx->nranks >= 8 ? (cascade < 0 ? 2u : 3u) : (cascade < 0 ? 3u : 4u);
     const uint32_t grid = (uint32_t)ctx->num_sms * (cascade < 0 ? ctx->tune.main_grid : ctx->tune.shadow_grid);
     const uint32_t select_grid = (uint32_t)ctx->num_sms * ctx->tune.select_grid;
     const uint32_t deferred_grid = (uint32_t)ctx->num_sms * (cascade < 0 ? 8u : ctx->tune.shadow_grid);

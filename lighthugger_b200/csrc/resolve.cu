@@ -191,15 +191,35 @@ __device__ __forceinline__ float sample_shadow(const uint32_t* layer, int n, flo
 }
 
 // The 3x3 PCF of render_geometry.comp:200-226 when the tap spacing (1/1024) is one texel: the nine bilinear compare taps
-// touch a 4x4 texel neighbourhood, which is loaded and compared ONCE (16 loads instead of 36, one bit per texel); every
-// tap then computes its own texel position and weights exactly as sample_shadow does and picks its four compare
-// results out of the bit mask (a tap whose texels fall outside the neighbourhood -- possible only through the rounding
-// of u + k/1024 -- takes the direct path), so the sum is bit-identical to nine sample_shadow calls.
+// touch a 4x4 texel neighbourhood, which is loaded and compared ONCE (16 loads instead of 36, one bit per texel).  Every
+// tap keeps its own texel position and weights, computed exactly as sample_shadow computes them (u + k/1024 rounds, so
+// the three fractions along an axis differ in their last bits), and the sum runs in sample_shadow's order, so the
+// result is bit-identical to nine sample_shadow calls.  Common case: tap k along an axis starts at texel floor + k, so
+// row r of tap column k lerps the mask bits (r, k + 1) and (r, k + 2) -- twelve x-lerps shared by the nine taps.  A tap
+// whose floor lands elsewhere (possible only through that rounding) sends the pixel down the literal path.
 __device__ __forceinline__ float pcf3x3_texel_spaced(const uint32_t* layer, int n, float u, float v, float ref) {
     const float x = u * (float)n - 0.5f, y = v * (float)n - 0.5f;
     if (!(isfinite(x) && isfinite(y))) return 0.0f;   // then every tap is 0
     const float fx = fminf(fmaxf(floorf(x), -3.0f), (float)n + 2.0f), fy = fminf(fmaxf(floorf(y), -3.0f), (float)n + 2.0f);
     const int bx = (int)fx - 1, by = (int)fy - 1;
+    float wx[3], wy[3];
+    bool regular = true;
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+        const float tx = (u + (float)(k - 1) / 1024.0f) * (float)n - 0.5f, ty = (v + (float)(k - 1) / 1024.0f) * (float)n - 0.5f;
+        const float tfx = floorf(tx), tfy = floorf(ty);
+        wx[k] = tx - tfx;
+        wy[k] = ty - tfy;
+        // tfx == fx + (k - 1) also rules out a non-finite tap and the clamps of sample_shadow (fx is inside them by 1)
+        regular = regular && tfx == fx + (float)(k - 1) && tfy == fy + (float)(k - 1);
+    }
+    regular = regular && fx >= -1.0f && fx <= (float)n && fy >= -1.0f && fy <= (float)n;   // so that fx +- 1 stays inside sample_shadow's clamp [-2, n + 1]
+    if (!regular) {
+        float sum = 0.0f;
+        for (int ox = -1; ox <= 1; ox++)
+            for (int oy = -1; oy <= 1; oy++) sum += sample_shadow(layer, n, u + (float)ox / 1024.0f, v + (float)oy / 1024.0f, ref);
+        return sum;
+    }
     uint32_t mask = 0;
 #pragma unroll
     for (int r = 0; r < 4; r++) {
@@ -208,31 +228,25 @@ __device__ __forceinline__ float pcf3x3_texel_spaced(const uint32_t* layer, int 
         for (int c = 0; c < 4; c++)
             if (ref < __uint_as_float(__ldg(row + min(max(bx + c, 0), n - 1)))) mask |= 1u << (4 * r + c);
     }
-    float sum = 0.0f;
+    // c + w * (d - c) with c, d in {0, 1} is one of 0, 1, w, 1 - w -- each exactly what the expression rounds to
+    float lerp_x[3][4];
 #pragma unroll
-    for (int ox = -1; ox <= 1; ox++) {
-        const float tu = u + (float)ox / 1024.0f;
-        const float tx = tu * (float)n - 0.5f;
-        const float tfx = floorf(tx), wx = tx - tfx;
-        const int ix = (int)fminf(fmaxf(tfx, -2.0f), (float)n + 1.0f) - bx;
+    for (int k = 0; k < 3; k++) {
+        const float w = wx[k], omw = 1.0f - w;
 #pragma unroll
-        for (int oy = -1; oy <= 1; oy++) {
-            const float tv = v + (float)oy / 1024.0f;
-            const float ty = tv * (float)n - 0.5f;
-            const float tfy = floorf(ty), wy = ty - tfy;
-            const int iy = (int)fminf(fmaxf(tfy, -2.0f), (float)n + 1.0f) - by;
-            float tap;
-            if ((unsigned)ix <= 2u && (unsigned)iy <= 2u && isfinite(tx) && isfinite(ty)) {
-                const uint32_t m = mask >> (4 * iy + ix);
-                const float c00 = (float)(m & 1u), c10 = (float)((m >> 1) & 1u), c01 = (float)((m >> 4) & 1u), c11 = (float)((m >> 5) & 1u);
-                const float top = c00 + wx * (c10 - c00), bot = c01 + wx * (c11 - c01);
-                tap = top + wy * (bot - top);
-            } else {
-                tap = sample_shadow(layer, n, tu, tv, ref);
-            }
-            sum += tap;
+        for (int r = 0; r < 4; r++) {
+            const bool c = (mask >> (4 * r + k)) & 1u, d = (mask >> (4 * r + k + 1)) & 1u;
+            lerp_x[k][r] = c ? (d ? 1.0f : omw) : (d ? w : 0.0f);
         }
     }
+    float sum = 0.0f;
+#pragma unroll
+    for (int kx = 0; kx < 3; kx++)
+#pragma unroll
+        for (int ky = 0; ky < 3; ky++) {
+            const float top = lerp_x[kx][ky], bot = lerp_x[kx][ky + 1];
+            sum += top + wy[ky] * (bot - top);
+        }
     return sum;
 }
 
@@ -310,9 +324,20 @@ __device__ __forceinline__ unsigned long long owner_load(const LhMeshletReferenc
 //          are finished here;
 // PHASE 2 (shadow): cascade selection, 3x3 PCF, combination, RGBA16F store.
 // The combination is written with explicit roundings so that all phases produce the same bits.
+#ifndef LH_RESOLVE_MIN_CTAS
+#define LH_RESOLVE_MIN_CTAS 4   // 64 registers, 48 bytes of spills, 32 warps per SM: the pass waits on dependent loads (measured: 0.90 -> 0.74 ms against 3 CTAs at 79 registers)
+#endif
 template <int PHASE>
-__global__ void __launch_bounds__(256) resolve_kernel(const __grid_constant__ FrameParams P) {
+__global__ void __launch_bounds__(256, LH_RESOLVE_MIN_CTAS) resolve_kernel(const __grid_constant__ FrameParams P) {
     const uint32_t W = P.u.window_size[0], H = P.u.window_size[1];
+    // the four cascade matrices are produced on the device (MiscStorage): staged once per CTA instead of 16 loads per
+    // thread and cascade
+    __shared__ float cascade_matrix[4][16];
+    if (PHASE != 1) {
+        const LhMiscStorage* misc = (const LhMiscStorage*)P.u.misc_storage;
+        if (threadIdx.x < 64) cascade_matrix[threadIdx.x >> 4][threadIdx.x & 15] = (&misc->uv_space_shadow_matrices[threadIdx.x >> 4].m[0][0])[threadIdx.x & 15];
+        __syncthreads();
+    }
     // 32x8 pixels per CTA, one 8x4 block per warp
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint32_t x = blockIdx.x * 32 + (warp & 3) * 8 + (lane & 7);
@@ -340,33 +365,40 @@ __global__ void __launch_bounds__(256) resolve_kernel(const __grid_constant__ Fr
         return;
     }
     const uint32_t slot = lh_vis_slot(key), tri = lh_vis_tri(key);
-    // sort-last: the slot is global (rank * slots_per_rank + local) and the reference lives in the owning rank's table
-    const LhMeshletReference* ref_at = P.resolve_refs + slot;
-    if (P.peer_refs) {
-        const uint32_t owner = slot / P.slots_per_rank;
-        ref_at = P.peer_refs[owner] + (slot - owner * P.slots_per_rank);
+    const LhInstance* inst;
+    const LhMeshInfo* mi;
+    const uint8_t* micro;
+    const uint8_t* first_index;   // byte address of the meshlet's first vertex index
+    uint32_t flags;
+    {
+        // sort-last: the slot is global (rank * slots_per_rank + local) and the reference lives in the owning rank's table
+        const LhMeshletReference* ref_at = P.resolve_refs + slot;
+        if (P.peer_refs) {
+            const uint32_t owner = slot / P.slots_per_rank;
+            ref_at = P.peer_refs[owner] + (slot - owner * P.slots_per_rank);
+        }
+        const unsigned long long ref = owner_load(ref_at);
+        inst = (const LhInstance*)P.u.instances + (uint32_t)ref;
+        const uint32_t meshlet_index = (uint32_t)(ref >> 32) & 0xFFFFu;
+        mi = (const LhMeshInfo*)__ldg((const unsigned long long*)&inst->mesh_info_address);
+        const LhMeshlet* m = (const LhMeshlet*)__ldg((const unsigned long long*)&mi->meshlets) + meshlet_index;
+        flags = __ldg(&mi->flags);
+        micro = (const uint8_t*)__ldg((const unsigned long long*)&mi->micro_indices) + __ldg(&m->triangle_offset);
+        first_index = (const uint8_t*)__ldg((const unsigned long long*)&mi->indices) +
+                      (size_t)__ldg(&m->index_offset) * ((flags & LH_MESH_INFO_FLAGS_32_BIT_INDICES) ? 4u : 2u);
     }
-    const unsigned long long ref = owner_load(ref_at);
-    const LhInstance* inst = (const LhInstance*)P.u.instances + (uint32_t)ref;
-    const uint32_t meshlet_index = (uint32_t)(ref >> 32) & 0xFFFFu;
+    micro += 3 * tri;
     float T[16];
 #pragma unroll
     for (int k = 0; k < 4; k++) {
         float4 c = __ldg((const float4*)&inst->transform + k);
         T[4 * k] = c.x; T[4 * k + 1] = c.y; T[4 * k + 2] = c.z; T[4 * k + 3] = c.w;
     }
-    const LhMeshInfo* mi = (const LhMeshInfo*)__ldg((const unsigned long long*)&inst->mesh_info_address);
     const uint16_t* positions = (const uint16_t*)__ldg((const unsigned long long*)&mi->positions);
-    const void* indices = (const void*)__ldg((const unsigned long long*)&mi->indices);
     const int8_t* normals = (const int8_t*)__ldg((const unsigned long long*)&mi->normals);
     const uint16_t* uvs = (const uint16_t*)__ldg((const unsigned long long*)&mi->uvs);
-    const uint8_t* micro = (const uint8_t*)__ldg((const unsigned long long*)&mi->micro_indices);
-    const LhMeshlet* m = (const LhMeshlet*)__ldg((const unsigned long long*)&mi->meshlets) + meshlet_index;
-    const uint32_t flags = __ldg(&mi->flags);
     const bool wide = (flags & LH_MESH_INFO_FLAGS_32_BIT_INDICES) != 0;
     alpha = (flags & LH_MESH_INFO_FLAGS_ALPHA_CLIP) != 0;
-    const uint32_t index_offset = __ldg(&m->index_offset);
-    micro += __ldg(&m->triangle_offset) + 3 * tri;
 
     F3 pos[3], nrm[3];
     float4 clip[3];
@@ -374,8 +406,8 @@ __global__ void __launch_bounds__(256) resolve_kernel(const __grid_constant__ Fr
     const float ts0 = __ldg(&mi->texture_scale[0]), ts1 = __ldg(&mi->texture_scale[1]);
 #pragma unroll
     for (int k = 0; k < 3; k++) {
-        const uint32_t vi = index_offset + __ldg(micro + k);
-        const uint32_t idx = wide ? __ldg((const uint32_t*)indices + vi) : (uint32_t)__ldg((const uint16_t*)indices + vi);
+        const uint32_t vi = __ldg(micro + k);
+        const uint32_t idx = wide ? __ldg((const uint32_t*)first_index + vi) : (uint32_t)__ldg((const uint16_t*)first_index + vi);
         const uint16_t* p = positions + 3 * (size_t)idx;
         const V4 w = mat4_mul(T, (float)__ldg(p), (float)__ldg(p + 1), (float)__ldg(p + 2), 1.0f);   // pinned, like the raster pass
         pos[k] = F3{w.x, w.y, w.z};
@@ -472,11 +504,10 @@ __global__ void __launch_bounds__(256) resolve_kernel(const __grid_constant__ Fr
     }
 
     // cascade selection (:183-196) and 3x3 PCF (:200-226)
-    const LhMiscStorage* misc = (const LhMiscStorage*)P.u.misc_storage;
     uint32_t cascade;
     float4 sc = make_float4(0, 0, 0, 0);
     for (cascade = 0; cascade < 4; cascade++) {
-        const V4 c = mat4_mul(&misc->uv_space_shadow_matrices[cascade].m[0][0], world.x, world.y, world.z, 1.0f);   // pinned
+        const V4 c = mat4_mul(cascade_matrix[cascade], world.x, world.y, world.z, 1.0f);   // pinned
         sc = make_float4(c.x, c.y, c.z, c.w);
         if (fabsf(psub(sc.x, 0.5f)) < 0.5f && fabsf(psub(sc.y, 0.5f)) < 0.5f) break;
     }

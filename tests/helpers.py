@@ -164,16 +164,20 @@ def display(c):
 
 
 # SURVEY 8c asks for |delta| <= 2/255 per channel after the display transfer on >= 99.9 % of pixels and <= 8/255 on the
-# rest.  With the oracle modelling the texture unit bit for bit (tests/test_texture_unit.py) and the resolve's
-# discontinuous choices (barycentrics, derivatives, anisotropic footprint, shadow coordinates) in pinned arithmetic, the
-# CUDA frame is far closer than that: what is left is the RGBA16F store and the last bits of the BRDF arithmetic.  The
-# bound used here is therefore 16x tighter on both counts:  <= 0.125/255 on >= 99.9 % of the pixels (the RGBA16F
-# quantisation alone is up to 0.06/255 in the dark), <= 2/255 on the rest --
+# rest.  With the oracle modelling the texture unit bit for bit (tests/test_texture_unit.py) and the resolve compiled
+# without contraction in the reference shader's operation order, the CUDA frame is far closer than that:
+#   * covered pixels: the stored RGBA16F colour is BIT-IDENTICAL to the oracle's colour rounded to half precision, on
+#     all but COLOR_INEXACT_FRAC of them (measured on B200: 0 of 8,293,873 at C2 / 3840x2160, 5 of 7,925,799 at C4);
+#   * sky pixels go through the texture unit's cube-map filter of a float texture, which the oracle models with fp32
+#     lerps and 8-bit weights only, and differ in the last half-precision bit on about 1 % of the sky;
+#   * every pixel: <= 0.125/255 after the display transfer on >= 99.9 % of the pixels and <= 2/255 on the rest (16x tighter
+#     than SURVEY 8c on both counts; the RGBA16F quantisation alone is 0.023/255, which is what is measured) --
 # except where the reference's own shader is discontinuous.  pbr.glsl clamps N.V to 1e-5 on shading normals that face
 # away from the camera; there the visibility term 0.5 / (ggxv + ggxl) grows like 1 / N.L, the specular term times N.L
 # jumps from 0 (N.L <= 0) to D * F * 0.5 / alpha (N.L > 0), and the last bit of the normal decides the pixel.  Such a
 # pixel is accepted when the oracle itself, with every texture sample moved by CONDITIONING_STEP (a quarter of the
 # smallest 8-bit texel step), spans the CUDA result; at most COLOR_HARD_FRAC of the pixels may need that.
+COLOR_INEXACT_FRAC = 1e-5
 COLOR_FRAC_TOL, COLOR_TIGHT, COLOR_LOOSE = 0.001, 0.125 / 255, 2 / 255
 COLOR_HARD_FRAC, CONDITIONING_STEP = 1e-5, 0.001
 TEXTURE_UNIT_PRECISION = 0.004   # what an fp32 bilinear model of the filter is off by (tools/texvalue_fit.py): used by the CPU tests only
@@ -195,6 +199,9 @@ def compare_color(ctx, o, frac_tol=COLOR_FRAC_TOL, tight=COLOR_TIGHT, loose=COLO
     # bit-exactness of the stored half floats (the oracle's fp32 colour rounded to nearest even, as the device store does)
     same = (ctx.target(S.LH_TARGET_SCENE_RGBA16F).reshape(-1, 4)[:, :3].view(np.uint16) == want[:, :3].astype(np.float16).view(np.uint16)).all(axis=1)
     covered = vis_fields(o.vis.reshape(-1))[0] != 0
+    if ignore is not None and len(ignore):
+        same[ignore] = True
+    inexact = int(np.count_nonzero(covered & ~same))
     if COLOR_LOG:
         import inspect, json
         with open(COLOR_LOG, "a") as f:
@@ -204,6 +211,7 @@ def compare_color(ctx, o, frac_tol=COLOR_FRAC_TOL, tight=COLOR_TIGHT, loose=COLO
                                 "covered": int(covered.sum()), "covered_not_bit_exact": int(np.count_nonzero(covered & ~same)),
                                 "sky_not_bit_exact": int(np.count_nonzero(~covered & ~same))}) + "\n")
     assert bad <= frac_tol, f"{bad:.4%} of pixels differ by more than {tight * 255:.3f}/255 (max {d.max() * 255:.2f}/255)"
+    assert inexact <= max(2, int(COLOR_INEXACT_FRAC * covered.sum())), f"{inexact} of {covered.sum()} covered pixels are not bit-identical in RGBA16F"
     hard = np.flatnonzero(d > loose).astype(np.uint32)
     if len(hard):
         assert len(hard) <= max(1, int(COLOR_HARD_FRAC * len(d))), f"{len(hard)} pixels exceed {loose * 255:.0f}/255 (max {d.max() * 255:.2f}/255)"

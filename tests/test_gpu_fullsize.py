@@ -43,6 +43,11 @@ def assert_frame_bit_exact(o, ctx, st, alpha_clip=False):
     covered = np.count_nonzero(o.vis != S.LH_VIS_CLEAR)
     mismatch = np.count_nonzero(got != o.vis)
     sh_g, sh_o = ctx.target(S.LH_TARGET_SHADOW).view(np.uint32), o.shadow.view(np.uint32)
+    import helpers
+    if helpers.COLOR_LOG:
+        with open(helpers.COLOR_LOG, "a") as f:
+            f.write('{"test": "fullsize_vis", "alpha_clip": %d, "covered": %d, "mismatch": %d, "shadow_mismatch": %d}\n' % (
+                int(alpha_clip), covered, mismatch, np.count_nonzero(sh_g != sh_o)))
     if alpha_clip:   # the alpha test samples a texture inside the raster: 0.1 % of covered pixels
         assert mismatch <= 0.001 * covered, f"{mismatch} / {covered} pixels differ"
         assert classify_vis_mismatches(got, o.vis, o.width, o.height) == 0   # all of them edge or tie pixels
