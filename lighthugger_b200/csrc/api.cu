@@ -169,7 +169,9 @@ int alloc_targets(LhContext* ctx, uint32_t w, uint32_t h) {
     ctx->depth_plane = nullptr;
     uint64_t px = (uint64_t)w * h;
     if (px == 0) return fail(ctx, LH_ERR_INVALID_ARGUMENT, "zero-sized render target");
-    LH_CUDA(ctx, cudaMalloc(&ctx->vis, px * 8 + 16));
+    // + one byte per 64x16-pixel tile behind the keys: "this rank drew something here" (sort-last composite, comm.cu)
+    const size_t flag_bytes = (size_t)((w + 63) / 64) * ((h + 15) / 16);
+    LH_CUDA(ctx, cudaMalloc(&ctx->vis, px * 8 + 16 + flag_bytes));
     LH_CUDA(ctx, cudaMalloc(&ctx->scene, px * 8));
     LH_CUDA(ctx, cudaMalloc(&ctx->display, px * 4));
     LH_CUDA(ctx, cudaMalloc(&ctx->depth_plane, px * 4));
@@ -180,7 +182,7 @@ int alloc_targets(LhContext* ctx, uint32_t w, uint32_t h) {
         ctx->scratch[0].hiz = nullptr;
         LH_CUDA(ctx, cudaMalloc(&ctx->scratch[0].hiz, (main_tiles > shadow_tiles ? main_tiles : shadow_tiles) * 4));
     }
-    LH_CUDA(ctx, cudaMemset(ctx->vis, 0xFF, px * 8 + 16));
+    LH_CUDA(ctx, cudaMemset(ctx->vis, 0xFF, px * 8 + 16 + flag_bytes));
     LH_CUDA(ctx, cudaMemset(ctx->scene, 0, px * 8));
     LH_CUDA(ctx, cudaMemset(ctx->display, 0, px * 4));
     ctx->cfg.width = w;

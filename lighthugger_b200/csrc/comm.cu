@@ -174,26 +174,79 @@ __global__ void depth_pair_store_kernel(const __grid_constant__ FrameParams P) {
     }
 }
 
-// The sort-last composite of this rank's rows: min over every rank's keys, read through peer memory.  Two pixels per
-// 128-bit load; the loads of all ranks are issued before the first min so that up to nranks NVLink round trips overlap.
+// The sort-last composite of this rank's rows: min over every rank's keys, read through peer memory.
+//
+// A rank draws the instances of its screen stripe, so most of its key buffer is still clear when the frame is
+// composited, and pulling every rank's copy of every row would move mostly all-ones words over NVLink (58 of 66 MB per
+// rank on 8 GPUs).  Each rank therefore first marks which 64x16-pixel tiles of its own buffer hold anything
+// (tile_flags_kernel: one streaming pass over its L2-resident keys, one byte per tile behind the keys, so the flags are
+// peer-mapped with them); the composite then works tile by tile, asks every rank's flag, and reads only the ranks that
+// drew there.  A tile nobody drew in is skipped outright; a tile only this rank drew in needs no store.  Two pixels per
+// 128-bit load; the loads of all flagged ranks are issued before the first min so the NVLink round trips overlap.
 constexpr int kMaxRanks = 16;
-__global__ void __launch_bounds__(256) composite_pull_kernel(const __grid_constant__ FrameParams P, uint64_t first_pair, uint64_t pairs) {
+constexpr uint32_t kFlagTileW = 64, kFlagTileH = 16;
+
+__device__ __forceinline__ const uint8_t* tile_flags_of(const unsigned long long* vis, uint64_t pixels) { return (const uint8_t*)(vis + pixels) + 16; }
+
+__global__ void __launch_bounds__(256) tile_flags_kernel(const __grid_constant__ FrameParams P) {
+    const uint32_t W = P.u.window_size[0], H = P.u.window_size[1];
+    const uint32_t tiles_x = (W + kFlagTileW - 1) / kFlagTileW, tiles = tiles_x * ((H + kFlagTileH - 1) / kFlagTileH);
+    const uint32_t tile = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (tile >= tiles) return;
+    const uint32_t x = (tile % tiles_x) * kFlagTileW + 2 * lane, y0 = (tile / tiles_x) * kFlagTileH;
+    bool any = false;
+    if (x < W) {
+#pragma unroll 4
+        for (uint32_t r = 0; r < kFlagTileH; r++) {
+            if (y0 + r >= H) break;
+            const unsigned long long* at = P.vis + (size_t)(y0 + r) * W + x;
+            if (x + 1 < W) {
+                const ulonglong2 v = __ldcg((const ulonglong2*)at);
+                any = any || (v.x & v.y) != ~0ull;
+            } else {
+                any = any || __ldcg(at) != ~0ull;
+            }
+        }
+    }
+    any = __any_sync(0xFFFFFFFFu, any);
+    if (lane == 0) ((uint8_t*)tile_flags_of(P.vis, (uint64_t)W * H))[tile] = any ? 1 : 0;
+}
+
+// one CTA per tile that touches the rank's rows [row0, row1)
+__global__ void __launch_bounds__(256) composite_pull_kernel(const __grid_constant__ FrameParams P, uint32_t row0, uint32_t row1) {
     const uint32_t n = P.nranks, self = P.rank;
+    const uint32_t W = P.u.window_size[0], H = P.u.window_size[1];
+    const uint64_t pixels = (uint64_t)W * H;
+    const uint32_t tiles_x = (W + kFlagTileW - 1) / kFlagTileW;
+    const uint32_t tx = blockIdx.x % tiles_x, ty = row0 / kFlagTileH + blockIdx.x / tiles_x, tile = ty * tiles_x + tx;
+    __shared__ uint32_t drew;
+    if (threadIdx.x < 32) {
+        const bool flag = threadIdx.x < n && __ldcg(tile_flags_of(P.peer_vis[threadIdx.x], pixels) + tile) != 0;
+        const uint32_t mask = __ballot_sync(0xFFFFFFFFu, flag);
+        if (threadIdx.x == 0) drew = mask;
+    }
+    __syncthreads();
+    const uint32_t mask = drew;
+    if (mask == 0) return;   // clear on every rank: sky, which moves neither depth bound
     uint32_t mn = 0xFFFFFFFFu, inv_mx = 0xFFFFFFFFu;
-    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
-    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < pairs; i += stride) {
+#pragma unroll
+    for (uint32_t j = 0; j < kFlagTileW * kFlagTileH / 2 / 256; j++) {
+        const uint32_t item = threadIdx.x + 256 * j;
+        const uint32_t x = tx * kFlagTileW + 2 * (item % (kFlagTileW / 2)), y = ty * kFlagTileH + item / (kFlagTileW / 2);
+        if (x >= W || y < row0 || y >= row1) continue;   // W is even (checked by the caller): a pair never straddles a row
+        const uint64_t pair = ((uint64_t)y * W + x) / 2;
         ulonglong2 v[kMaxRanks];
 #pragma unroll
         for (uint32_t q = 0; q < (uint32_t)kMaxRanks; q++)
-            if (q < n) v[q] = __ldcg((const ulonglong2*)P.peer_vis[q] + first_pair + i);
-        ulonglong2 best = v[0];
+            if ((mask >> q) & 1u) v[q] = __ldcg((const ulonglong2*)P.peer_vis[q] + pair);
+        ulonglong2 best = make_ulonglong2(~0ull, ~0ull);
 #pragma unroll
-        for (uint32_t q = 1; q < (uint32_t)kMaxRanks; q++)
-            if (q < n) {
+        for (uint32_t q = 0; q < (uint32_t)kMaxRanks; q++)
+            if ((mask >> q) & 1u) {
                 best.x = min(best.x, v[q].x);
                 best.y = min(best.y, v[q].y);
             }
-        ((ulonglong2*)P.peer_vis[self])[first_pair + i] = best;
+        if (mask != (1u << self)) ((ulonglong2*)P.peer_vis[self])[pair] = best;
         const uint32_t d0 = ~(uint32_t)(best.x >> 32), d1 = ~(uint32_t)(best.y >> 32);
         if (d0) mn = min(mn, d0);                 // min_if_not_zero, read_depth.glsl:3-7
         if (d1) mn = min(mn, d1);
@@ -240,14 +293,15 @@ int composite_pull(LhContext* ctx) {
     if (ctx->nranks > kMaxRanks) return fail(ctx, LH_ERR_UNSUPPORTED, "LH_EXCHANGE_PEER supports at most 16 ranks");
     FrameParams p = make_params(ctx);
     depth_pair_init_kernel<<<1, 32, 0, ctx->stream>>>(ctx->comm_scratch); ctx->launches++;
-    if (int rc = stream_barrier(ctx)) return rc;   // every rank has rasterised its instances
-    const uint64_t W = ctx->cfg.width;
-    const uint64_t first = (uint64_t)ctx->row0 * W, count = (uint64_t)(ctx->row1 - ctx->row0) * W;
-    // row slices hold an even number of rows (lh_comm_init), so they are whole 16-byte key pairs unless both the
-    // width and the last slice's height are odd
-    if ((first | count) & 1ull) return fail(ctx, LH_ERR_UNSUPPORTED, "LH_EXCHANGE_PEER needs an even number of pixels per row slice");
-    if (count) {
-        composite_pull_kernel<<<ctx->num_sms * 8, 256, 0, ctx->stream>>>(p, first / 2, count / 2); ctx->launches++;
+    const uint32_t W = ctx->cfg.width, H = ctx->cfg.height;
+    // the keys are read as 16-byte pairs that must not straddle rows, and row slices hold an even number of rows
+    if (W & 1u) return fail(ctx, LH_ERR_UNSUPPORTED, "LH_EXCHANGE_PEER needs an even frame width");
+    const uint32_t tiles_x = (W + kFlagTileW - 1) / kFlagTileW, tiles = tiles_x * ((H + kFlagTileH - 1) / kFlagTileH);
+    tile_flags_kernel<<<(tiles + 7) / 8, 256, 0, ctx->stream>>>(p); ctx->launches++;
+    if (int rc = stream_barrier(ctx)) return rc;   // every rank has rasterised its instances and flagged its tiles
+    if (ctx->row1 > ctx->row0) {
+        const uint32_t tile_rows = (ctx->row1 - 1) / kFlagTileH - ctx->row0 / kFlagTileH + 1;
+        composite_pull_kernel<<<tiles_x * tile_rows, 256, 0, ctx->stream>>>(p, ctx->row0, ctx->row1); ctx->launches++;
     }
     return LH_OK;
 }
