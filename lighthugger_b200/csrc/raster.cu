@@ -31,7 +31,10 @@ namespace lh {
 
 namespace {
 
-constexpr int kWarpsPerCta = 8;
+#ifndef LH_WARPS_PER_CTA
+#define LH_WARPS_PER_CTA 8
+#endif
+constexpr int kWarpsPerCta = LH_WARPS_PER_CTA;
 constexpr uint32_t kTileW = 128, kTileH = 32;   // deferred-triangle screen tile
 constexpr uint32_t kWholeTriangle = 0xFFFFFFFFu;
 constexpr int kSmallMaxSpan = 32;               // small path: pixel bbox < 32 on each axis ...
@@ -112,6 +115,9 @@ constexpr bool kSelectCtaClaim = LH_SELECT_CTA_CLAIM != 0;   // the selection cl
 #define LH_STATIC_FIRST 1
 #endif
 constexpr bool kStaticFirst = LH_STATIC_FIRST != 0;          // first-wave CTAs of the raster kernel take their first chunk without a ticket
+#ifndef LH_LANE_PINNED
+#define LH_LANE_PINNED 1
+#endif
 #ifndef LH_FEW_SAMPLES_PATH
 #define LH_FEW_SAMPLES_PATH 0
 #endif
@@ -699,8 +705,7 @@ struct RasterCounters {
 template <bool SHADOW, bool ALPHA>
 __device__ __forceinline__ void raster_one_meshlet(const FrameParams& P, const Target<SHADOW>& tg, WarpScratch& sv, const RasterRecord& rec,
                                                    const float* T, const uint8_t* micro_s, const uint8_t* index_s, uint32_t first_keys, const float* M,
-                                                   bool affine, RasterCounters& cnt) {
-    const uint32_t lane = threadIdx.x & 31;
+                                                   bool affine, RasterCounters& cnt, uint32_t lane) {
     const int W = (int)tg.width, H = (int)tg.height;
     // ---- (0) re-test against the keys stored since the selection (the band's own meshlets occlude one another) ----
     {
@@ -1043,7 +1048,15 @@ template <bool SHADOW>
 __global__ void __launch_bounds__(kWarpsPerCta * 32, LH_RASTER_MIN_CTAS) raster_meshlets_kernel(const __grid_constant__ FrameParams P, uint32_t cascade, uint32_t band) {
     __shared__ WarpScratch scratch_all[kWarpsPerCta];
     __shared__ float cascade_matrix[16];
+#if LH_LANE_PINNED
+    // read once through an opaque instruction: under the 64-register cap the compiler otherwise re-reads the special
+    // register (S2R) and rebuilds the warp's shared-memory base all over the chunk loop
+    uint32_t lane, warp;
+    asm volatile("mov.u32 %0, %%laneid;" : "=r"(lane));
+    asm volatile("shr.u32 %0, %1, 5;" : "=r"(warp) : "r"(threadIdx.x));
+#else
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#endif
     WarpScratch& sv = scratch_all[warp];
     // band b owns the queue entries appended by its selection: [band_mark[b], queue_count); nothing appends while
     // this kernel runs, and the mark it leaves for band b + 1 is read by that band's launch only
@@ -1162,9 +1175,9 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, LH_RASTER_MIN_CTAS) raster_
             const uint8_t* micro = &sv.micro[js][0] + ((uintptr_t)rec.micro & 15u);
             const uint8_t* index = &sv.index[js][0] + ((uintptr_t)rec.indices & 15u);
             if ((rec.counts_flags >> 16) & LH_MESH_INFO_FLAGS_ALPHA_CLIP)
-                raster_one_meshlet<SHADOW, true>(P, tg, sv, rec, &sv.T[js][0], micro, index, first_keys[j], M, affine, cnt);
+                raster_one_meshlet<SHADOW, true>(P, tg, sv, rec, &sv.T[js][0], micro, index, first_keys[j], M, affine, cnt, lane);
             else
-                raster_one_meshlet<SHADOW, false>(P, tg, sv, rec, &sv.T[js][0], micro, index, first_keys[j], M, affine, cnt);
+                raster_one_meshlet<SHADOW, false>(P, tg, sv, rec, &sv.T[js][0], micro, index, first_keys[j], M, affine, cnt, lane);
             __syncwarp();
         }
     }
