@@ -339,7 +339,7 @@ __global__ void __launch_bounds__(256) cull_meshlets_kernel(const __grid_constan
     __shared__ uint4 staged_bound[kMeshletTile];
     __shared__ BoundView bview;
     __shared__ WindowInstance win[kWindowMax];
-    __shared__ uint32_t warp_counts[2][8];
+    __shared__ uint32_t warp_counts[2][8];   // per class, the eight warps' survivor counts of the current tile
     __shared__ uint32_t window[2];
     __shared__ uint32_t tile_ticket;
     __shared__ unsigned long long tile_exclusive;
@@ -417,9 +417,13 @@ __global__ void __launch_bounds__(256) cull_meshlets_kernel(const __grid_constan
         }
         __syncthreads();
 
-        uint32_t base_count[2] = {0, 0};
-        for (uint32_t round = 0; round < kMeshletTile / 256; round++) {
-            const uint32_t g = g0 + round * 256 + tid;
+        // Each warp owns a contiguous eighth of the tile (128 candidates, four rounds of 32) and stages its survivors in
+        // its own eighth of the staging arrays -- opaque from the front, alpha-clip from the back -- so the rounds need no
+        // CTA barrier; warps are in candidate order, so the lists stay in ascending candidate order.
+        constexpr uint32_t kPerWarp = kMeshletTile / 8;
+        uint32_t base_count[2] = {0, 0};   // this warp's survivors so far, per class
+        for (uint32_t round = 0; round < kPerWarp / 32; round++) {
+            const uint32_t g = g0 + warp * kPerWarp + round * 32 + lane;
             uint32_t cls = 2;  // 0 opaque survivor, 1 alpha-clip survivor, 2 culled
             Survivor sv{0, 0};
             uint4 bound = make_uint4(0u, 0u, 0u, 0u);
@@ -504,53 +508,53 @@ __global__ void __launch_bounds__(256) cull_meshlets_kernel(const __grid_constan
                 }
             }
             // stable ranks inside the round, per class
-            uint32_t b0 = __ballot_sync(0xFFFFFFFFu, cls == 0), b1 = __ballot_sync(0xFFFFFFFFu, cls == 1);
-            if (lane == 0) {
-                warp_counts[0][warp] = __popc(b0);
-                warp_counts[1][warp] = __popc(b1);
-            }
-            __syncthreads();
-            uint32_t before[2] = {0, 0}, round_total[2] = {0, 0};
-            for (uint32_t w = 0; w < 8; w++) {
-                uint32_t c0 = warp_counts[0][w], c1 = warp_counts[1][w];
-                if (w < warp) {
-                    before[0] += c0;
-                    before[1] += c1;
-                }
-                round_total[0] += c0;
-                round_total[1] += c1;
-            }
+            const uint32_t b0 = __ballot_sync(0xFFFFFFFFu, cls == 0), b1 = __ballot_sync(0xFFFFFFFFu, cls == 1);
             if (cls < 2) {
-                uint32_t rank = base_count[cls] + before[cls] + __popc((cls ? b1 : b0) & ((1u << lane) - 1u));
-                const uint32_t at = cls ? kMeshletTile - 1u - rank : rank;
+                const uint32_t rank = (cls ? base_count[1] : base_count[0]) + __popc((cls ? b1 : b0) & ((1u << lane) - 1u));
+                const uint32_t at = warp * kPerWarp + (cls ? kPerWarp - 1u - rank : rank);
                 staged[at] = sv;
                 staged_bound[at] = bound;
             }
-            base_count[0] += round_total[0];
-            base_count[1] += round_total[1];
-            __syncthreads();
+            base_count[0] += __popc(b0);
+            base_count[1] += __popc(b1);
+        }
+        if (lane == 0) {
+            warp_counts[0][warp] = base_count[0];
+            warp_counts[1][warp] = base_count[1];
+        }
+        __syncthreads();
+        uint32_t before[2] = {0, 0}, tile_count[2] = {0, 0};   // survivors of the earlier warps / of the whole tile
+#pragma unroll
+        for (uint32_t w = 0; w < 8; w++) {
+            const uint32_t c0 = warp_counts[0][w], c1 = warp_counts[1][w];
+            if (w < warp) {
+                before[0] += c0;
+                before[1] += c1;
+            }
+            tile_count[0] += c0;
+            tile_count[1] += c1;
         }
         // tile aggregate -> exclusive prefix over all earlier tiles
         if (warp == 0) {
-            unsigned long long aggregate = ((unsigned long long)base_count[0] << 31) | base_count[1];
+            unsigned long long aggregate = ((unsigned long long)tile_count[0] << 31) | tile_count[1];
             unsigned long long ex = lookback(P.meshlet_tiles, tile, aggregate, 0ull);
             if (lane == 0) tile_exclusive = ex;
         }
         __syncthreads();
         const unsigned long long ex = tile_exclusive;
         const uint32_t ex_count[2] = {(uint32_t)(ex >> 31), (uint32_t)(ex & 0x7FFFFFFFu)};
-        // coalesced write-out of the compacted lists
+        // write-out of the compacted lists: every warp moves its own staged survivors, coalesced
 #pragma unroll
         for (uint32_t cls = 0; cls < 2; cls++) {
             const uint32_t cap = cls ? P.max_alpha : P.max_opaque;
             const uint32_t first_draw = cls ? P.max_opaque : 0u;  // ALPHA_CLIP_DRAWS_OFFSET
-            for (uint32_t k = tid; k < base_count[cls]; k += 256) {
-                uint32_t n = ex_count[cls] + k;
+            for (uint32_t k = lane; k < base_count[cls]; k += 32) {
+                uint32_t n = ex_count[cls] + before[cls] + k;
                 if (n >= cap) {
                     atomicOr(&st->overflow, cls ? (uint32_t)LH_OVERFLOW_ALPHA_CLIP : (uint32_t)LH_OVERFLOW_OPAQUE);
                     continue;
                 }
-                const uint32_t at = cls ? kMeshletTile - 1u - k : k;
+                const uint32_t at = warp * kPerWarp + (cls ? kPerWarp - 1u - k : k);
                 Survivor s = staged[at];
                 uint32_t draw_index = first_draw + n, slot = draw_index + P.pass_slot_base;
                 const uint4 bound = staged_bound[at];
@@ -566,7 +570,7 @@ __global__ void __launch_bounds__(256) cull_meshlets_kernel(const __grid_constan
             }
         }
         if (tile == num_tiles - 1 && tid == 0) {
-            uint32_t n0 = ex_count[0] + base_count[0], n1 = ex_count[1] + base_count[1];
+            uint32_t n0 = ex_count[0] + tile_count[0], n1 = ex_count[1] + tile_count[1];
             draw[0] = n0;
             draw[1] = n1;
             if (SHADOWS) {
