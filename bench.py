@@ -320,6 +320,8 @@ def run_ours(args):
     balance_log = None
     if world > 1 and args.partition == "stripes" and args.balance > 0:
         bal = sortlast.StripeBalancer(world)
+        # ... and the row slices the ranks composite and resolve follow their measured composite + resolve times
+        rows = sortlast.RowBalancer(scene.height, world) if args.exchange == "peer" and not args.equal_rows else None
         shadow_striped = args.shadow_split == "instances"
         bal.apply(ctx, rank, views=(0, 1) if shadow_striped else (0,))
         balance_log = []
@@ -328,15 +330,18 @@ def run_ours(args):
             frame_resident()
             ctx.sync()
             t = ctx.timings()
-            mine = torch.tensor([t["cull_meshlets"] + t["visbuffer"], t["shadowmaps"]], device="cuda", dtype=torch.float64)
+            mine = torch.tensor([t["cull_meshlets"] + t["visbuffer"], t["shadowmaps"], t["composite"] + t["render_geometry"]], device="cuda", dtype=torch.float64)
             allc = [torch.zeros_like(mine) for _ in range(world)]
             dist.all_gather(allc, mine)
-            costs = [[float(c[v]) for c in allc] for v in range(2)]
-            balance_log.append([round(bal.imbalance(costs[0]), 3), round(bal.imbalance(costs[1]), 3)])
+            costs = [[float(c[v]) for c in allc] for v in range(3)]
+            balance_log.append([round(bal.imbalance(costs[0]), 3), round(bal.imbalance(costs[1]), 3), round(bal.imbalance(costs[2]), 3)])
             bal.update(0, costs[0])
             if shadow_striped:
                 bal.update(1, costs[1])
             bal.apply(ctx, rank, views=(0, 1) if shadow_striped else (0,))
+            if rows:
+                rows.update(costs[2])
+                rows.apply(ctx, rank)
 
     # ---- warm-up (>= 3) ----
     warm = max(3, args.warmup)
@@ -553,6 +558,7 @@ def main():
     ap.add_argument("--partition", default="stripes", choices=["stripes", "range"], help="multi-GPU: how instances are shared out")
     ap.add_argument("--visible", type=float, default=0.0, help="culling-ratio sweep: move the camera until this share of the instances survives the instance cull (0: the preset's camera)")
     ap.add_argument("--balance", type=int, default=8, help="multi-GPU, stripes: untimed frames that move the stripe bounds towards equal per-rank pass times (0: equal-width interleaved stripes)")
+    ap.add_argument("--equal-rows", action="store_true", help="multi-GPU: keep the even row slices (no row balancing)")
     ap.add_argument("--emulate-rank", default="", help="profiling aid, one GPU: do the local work of rank R of N, given as R/N (no exchange)")
     ap.add_argument("--stripes-per-rank", type=int, default=0, help="multi-GPU: interleaved screen stripes per GPU (0: sortlast.STRIPES_PER_RANK)")
     args = ap.parse_args()

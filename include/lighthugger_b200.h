@@ -264,6 +264,10 @@ LH_API int lh_comm_set_exchange(LhContext* ctx, int mode);
  * same internally (ranks resize together); the next lh_frame_begin maps the current buffers again. */
 LH_API int lh_comm_remap(LhContext* ctx);
 LH_API int lh_comm_rows(LhContext* ctx, uint32_t* y0, uint32_t* y1);   /* rows this rank composites and resolves */
+/* Replaces the rank's even share of the screen rows (lh_comm_init / lh_targets_resize restore it): rows of sky resolve
+ * in a fraction of the time of rows of geometry, so a host may move the boundaries towards equal measured pass times
+ * (sortlast.RowBalancer).  The ranks' slices must tile [0, height) between them; the library cannot check that. */
+LH_API int lh_comm_set_rows(LhContext* ctx, uint32_t y0, uint32_t y1);
 
 #ifdef __cplusplus
 }

@@ -416,6 +416,15 @@ int lh_comm_rows(LhContext* ctx, uint32_t* y0, uint32_t* y1) {
     return LH_OK;
 }
 
+int lh_comm_set_rows(LhContext* ctx, uint32_t y0, uint32_t y1) {
+    if (!ctx) return LH_ERR_INVALID_ARGUMENT;
+    if (!ctx->nccl_comm) return fail(ctx, LH_ERR_NOT_READY, "lh_comm_set_rows before lh_comm_init");
+    if (y0 > y1 || y1 > ctx->cfg.height) return fail(ctx, LH_ERR_INVALID_ARGUMENT, "lh_comm_set_rows: need y0 <= y1 <= height");
+    ctx->row0 = y0;
+    ctx->row1 = y1;
+    return LH_OK;
+}
+
 int lh_comm_destroy(LhContext* ctx) {
     if (!ctx) return LH_ERR_INVALID_ARGUMENT;
     if (ctx->nccl_comm && g_nccl.CommDestroy) {

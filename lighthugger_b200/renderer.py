@@ -20,7 +20,7 @@ EXPORTS = [
     "lh_cull_instances_shadows", "lh_shadow_cascade", "lh_resolve", "lh_display_transform", "lh_render_frame",
     "lh_frame_sync", "lh_render_frame_host", "lh_get_frame_stats", "lh_set_config_flags", "lh_get_target", "lh_get_timings",
     "lh_get_target_address", "lh_get_launch_count", "lh_timer_start", "lh_timer_stop", "lh_flush_l2", "lh_comm_unique_id", "lh_comm_init",
-    "lh_comm_destroy", "lh_comm_info", "lh_comm_set_exchange", "lh_comm_remap", "lh_comm_rows", "lh_set_shadow_instance_range", "lh_set_instance_stripes", "lh_set_instance_stripe_bounds", "lh_set_display_lut", "lh_set_shadow_cascade_mask", "lh_shadow_exchange",
+    "lh_comm_destroy", "lh_comm_info", "lh_comm_set_exchange", "lh_comm_remap", "lh_comm_rows", "lh_comm_set_rows", "lh_set_shadow_instance_range", "lh_set_instance_stripes", "lh_set_instance_stripe_bounds", "lh_set_display_lut", "lh_set_shadow_cascade_mask", "lh_shadow_exchange",
 ]
 
 
@@ -69,6 +69,7 @@ def cuda_lib():
         if hasattr(lib, "lh_set_instance_stripe_bounds"):
             lib.lh_set_instance_stripe_bounds.argtypes = [vp, C.c_int, C.POINTER(C.c_float), u32, u32, u32]
         lib.lh_comm_rows.argtypes = [vp, C.POINTER(u32), C.POINTER(u32)]
+        lib.lh_comm_set_rows.argtypes = [vp, u32, u32]
         lib.lh_frame_begin.argtypes = [vp, C.POINTER(S.LhUniforms)]
         for name in ("lh_reset", "lh_cull_instances", "lh_cull_meshlets", "lh_raster_visbuffer", "lh_composite",
                      "lh_reduce_depth", "lh_generate_shadow_matrices", "lh_cull_instances_shadows", "lh_resolve",
@@ -200,6 +201,9 @@ class Context:
     def comm_remap(self):
         """Collective: drop every peer mapping (call on all ranks before moving the MeshletReference buffer)."""
         self._check(self.lib.lh_comm_remap(self.handle))
+
+    def comm_set_rows(self, y0, y1):
+        self._check(self.lib.lh_comm_set_rows(self.handle, int(y0), int(y1)))
 
     def comm_rows(self):
         y0, y1 = C.c_uint32(0), C.c_uint32(0)

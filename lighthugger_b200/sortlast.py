@@ -138,6 +138,42 @@ class StripeBalancer:
             ctx.set_instance_stripe_bounds(v, self.bounds[v], rank, self.world)
 
 
+class RowBalancer:
+    """Load balancing of the row slices the ranks composite and resolve (lh_comm_set_rows), from measured pass times: a
+    slice of sky resolves in a fraction of the time of a slice of geometry, and the frame's closing barrier waits for the
+    slowest rank.  Same rule as StripeBalancer: the cost is taken as uniform inside a slice, the new boundaries cut the
+    cumulative cost into equal parts, the move is damped; every rank runs the same update on the same gathered costs."""
+
+    def __init__(self, height, world, damping=0.6, min_rows=8):
+        self.height, self.world, self.damping, self.min_rows = height, world, damping, min_rows
+        self.bounds = [row_range(height, r, world)[0] for r in range(world)] + [height]
+
+    def update(self, costs):
+        b, n = [float(x) for x in self.bounds], self.world
+        costs = [max(float(c), 1e-9) for c in costs]
+        target = sum(costs) / n
+        ideal = [0.0]
+        r, acc = 0, 0.0
+        for k in range(1, n):
+            need = k * target
+            while r < n - 1 and acc + costs[r] < need:
+                acc += costs[r]
+                r += 1
+            ideal.append(b[r] + (b[r + 1] - b[r]) * min(1.0, max(0.0, (need - acc) / costs[r])))
+        ideal.append(float(self.height))
+        new = [int(round(bo + self.damping * (nw - bo))) for bo, nw in zip(b, ideal)]
+        new[0], new[-1] = 0, self.height
+        for k in range(1, n):
+            new[k] = max(new[k], new[k - 1] + self.min_rows)
+        for k in range(n - 1, 0, -1):
+            new[k] = min(new[k], new[k + 1] - self.min_rows)
+        self.bounds = new
+        return new
+
+    def apply(self, ctx, rank):
+        ctx.comm_set_rows(self.bounds[rank], self.bounds[rank + 1])
+
+
 def row_range(height, rank, world):
     """Screen rows [y0, y1) a rank composites and resolves (what lh_comm_init derives): even-sized slices."""
     per = ((height + world - 1) // world + 1) & ~1

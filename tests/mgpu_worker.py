@@ -125,6 +125,11 @@ def main():
             bal.update(0, [1.0 + 3.0 * r for r in range(world)])      # pretend the right-hand ranks were slower
             bal.update(1, [4.0 - 3.0 * r / max(1, world - 1) for r in range(world)])
             bal.apply(ctx, rank)
+            # ... and row slices of unequal height (lh_comm_set_rows; the balancer's rule on made-up costs)
+            rows = sortlast.RowBalancer(H, world, min_rows=2)
+            rows.update([1.0 + 2.0 * r for r in range(world)])
+            rows.apply(ctx, rank)
+            assert ctx.comm_rows() == (rows.bounds[rank], rows.bounds[rank + 1])
         else:
             sortlast.apply(ctx, n, rank, world, split, partition)
         u = ctx.uniforms()

@@ -157,3 +157,21 @@ def test_stripe_balancer_converges_on_a_skewed_cost_field():
         assert b[0] == 0.0 and b[-1] == 1.0 and all(b[k] < b[k + 1] for k in range(world))
         c = [cost(b[r], b[r + 1]) for r in range(world)]
         assert bal.imbalance(c) < 1.08, (world, c)
+
+
+def test_row_balancer_moves_rows_away_from_the_expensive_slices():
+    """Rows of sky cost a fraction of rows of geometry: the slices must keep tiling [0, height) with integer bounds and
+    end up with nearly equal costs."""
+    from lighthugger_b200.sortlast import RowBalancer, row_range
+    height = 2160
+    per_row = lambda y: 0.1 if y < 700 else 1.0            # the top third of the frame is sky
+    cost = lambda a, b: 5.0 + sum(per_row(y) for y in range(a, b))
+    for world in (2, 4, 8):
+        bal = RowBalancer(height, world)
+        assert bal.bounds == [row_range(height, r, world)[0] for r in range(world)] + [height]
+        for _ in range(12):
+            bal.update([cost(bal.bounds[r], bal.bounds[r + 1]) for r in range(world)])
+        b = bal.bounds
+        assert b[0] == 0 and b[-1] == height and all(isinstance(x, int) for x in b) and all(b[k] + 8 <= b[k + 1] for k in range(world))
+        c = [cost(b[r], b[r + 1]) for r in range(world)]
+        assert max(c) / (sum(c) / world) < 1.1, (world, b, c)
