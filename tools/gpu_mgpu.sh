@@ -23,7 +23,10 @@ except Exception as e:
 PY
 }
 ENVX="" run balanced
+ENVX="" run equal_rows --equal-rows
+if [ "$3" != "quick" ]; then
 ENVX="" run equal --balance 0
+fi
 if [ "$4" = "more" ]; then
 ENVX="LH_TUNE=3,4,16,3,1,16,1,128" run bands34
 ENVX="LH_TUNE=4,6,16,3,1,16,1,32" run area32
