@@ -320,7 +320,7 @@ def run_ours(args):
     balance_log = None
     if world > 1 and args.partition == "stripes" and args.balance > 0:
         bal = sortlast.StripeBalancer(world)
-        # ... and the row slices the ranks composite and resolve follow their measured composite + resolve times
+        # ... and the row slices the ranks composite and resolve follow their measured resolve times
         rows = sortlast.RowBalancer(scene.height, world) if args.exchange == "peer" and not args.equal_rows else None
         shadow_striped = args.shadow_split == "instances"
         bal.apply(ctx, rank, views=(0, 1) if shadow_striped else (0,))
@@ -330,7 +330,8 @@ def run_ours(args):
             frame_resident()
             ctx.sync()
             t = ctx.timings()
-            mine = torch.tensor([t["cull_meshlets"] + t["visbuffer"], t["shadowmaps"], t["composite"] + t["render_geometry"]], device="cuda", dtype=torch.float64)
+            # (the composite's time includes its barrier, i.e. the other ranks' raster imbalance: the rows follow the resolve alone)
+            mine = torch.tensor([t["cull_meshlets"] + t["visbuffer"], t["shadowmaps"], t["render_geometry"]], device="cuda", dtype=torch.float64)
             allc = [torch.zeros_like(mine) for _ in range(world)]
             dist.all_gather(allc, mine)
             costs = [[float(c[v]) for c in allc] for v in range(3)]
