@@ -249,9 +249,10 @@ LH_API int lh_comm_init(LhContext* ctx, int rank, int nranks, const void* id128)
 LH_API int lh_comm_destroy(LhContext* ctx);
 LH_API int lh_comm_info(LhContext* ctx, int* rank, int* nranks);
 /* How the exchange steps move data.  LH_EXCHANGE_PEER (default when every rank can map its peers' buffers through
- * CUDA IPC over NVLink): each rank owns the screen rows [y0, y1) of lh_comm_rows; lh_composite is ONE kernel that
- * pulls those rows of every peer's key buffer through peer memory, takes the uint64 min and folds the depth min/max
- * in; the resolve reads the winners' MeshletReference from the owning rank's table through peer memory and stores
+ * CUDA IPC over NVLink): each rank owns the screen rows [y0, y1) of lh_comm_rows; every rank flags the 64x16-pixel tiles
+ * of its key buffer it drew into, and lh_composite is ONE kernel that pulls the rank's rows of the peers that drew
+ * there through peer memory, takes the uint64 min and folds the depth min/max in (the frame width must be even: keys
+ * move as 16-byte pairs; LH_ERR_UNSUPPORTED otherwise); the resolve reads the winners' MeshletReference from the owning rank's table through peer memory and stores
  * its rows of lit colour into rank 0's frame.  LH_EXCHANGE_NCCL: ncclAllReduce(uint64, min) of whole buffers and an
  * all-gather of the reference tables; every rank then holds and resolves the whole frame.
  * LH_EXCHANGE_PEER maps whole allocations: LhUniforms.meshlet_references must be an address lh_buffer_alloc returned
