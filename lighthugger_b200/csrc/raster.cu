@@ -38,10 +38,7 @@ constexpr int kWarpsPerCta = LH_WARPS_PER_CTA;
 constexpr uint32_t kTileW = 128, kTileH = 32;   // deferred-triangle screen tile
 constexpr uint32_t kWholeTriangle = 0xFFFFFFFFu;
 constexpr int kSmallMaxSpan = 32;               // small path: pixel bbox < 32 on each axis ...
-#ifndef LH_SMALL_MAX_AREA
-#define LH_SMALL_MAX_AREA 128
-#endif
-constexpr int kSmallMaxArea = LH_SMALL_MAX_AREA;   // ... and at most this many pixel tests (swept on B200: 16..1024)
+// ... and at most FrameParams::small_max_area pixel tests (LhContext::Tuning, default 128; swept on B200: 16..1024)
 constexpr int kSmallMaxExtent = 1 << 14;        // ... and sub-pixel extent < 2^14 (32-bit edge functions stay exact)
 
 enum { CULL_NONE = 0, CULL_BACK = 1, CULL_FRONT = 2 };
@@ -131,9 +128,6 @@ __device__ __forceinline__ void mbar_init(void* bar, uint32_t arrivals) {
 }
 __device__ __forceinline__ void mbar_arrive_expect_tx(void* bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(void* bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ void mbar_wait(void* bar, uint32_t parity) {
     asm volatile(
