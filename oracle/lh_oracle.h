@@ -86,6 +86,9 @@ int lho_resolve_debug(const LhUniforms* u, const LhoConfig* cfg, const uint64_t*
  * against dumps of the real texture unit (tests/golden/texture_unit_*.bin) */
 void lho_test_sample_bilinear(const uint8_t* rgba8, uint32_t width, uint32_t height, uint32_t srgb, uint64_t count, const float* uv,
                               float* out_rgba);
+/* textureLod(level 0) with repeat addressing at arbitrary coordinates (wraps into [0, 1) first, then filters) */
+void lho_test_sample_lod0(const uint8_t* rgba8, uint32_t width, uint32_t height, uint32_t srgb, uint64_t count, const float* uv,
+                          float* out_rgba);
 /* the lit colour of `count` listed pixels (y * width + x) with `bias` added to the rgb of every material texture sample:
  * the conditioning of the reference's own result at those pixels (not part of the reference) */
 int lho_resolve_pixels(const LhUniforms* u, const LhoConfig* cfg, const uint64_t* vis, const float* shadow, uint64_t count,

@@ -547,6 +547,20 @@ extern "C" void lho_test_sample_bilinear(const uint8_t* rgba8, uint32_t width, u
     for (uint64_t i = 0; i < count; i++) sample_bilinear_level(t, uv[2 * i], uv[2 * i + 1], 0, out_rgba + 4 * i);
 }
 
+// ... and textureLod(level 0) as the resolve and the alpha test call it: the coordinate is wrapped into [0, 1) first, which
+// is what the texture unit does too (tools/texwrap_probe.cu: 65,536 of 65,536 fetches of a 48 x 80 texture at u, v in
+// [-4, 4) bit-identical with the wrap, 99.8 % without)
+extern "C" void lho_test_sample_lod0(const uint8_t* rgba8, uint32_t width, uint32_t height, uint32_t srgb, uint64_t count,
+                                     const float* uv, float* out_rgba) {
+    LhoTexture t{};
+    t.rgba8 = rgba8;
+    t.width = width;
+    t.height = height;
+    t.mip_levels = 1;
+    t.srgb = srgb;
+    for (uint64_t i = 0; i < count; i++) sample_texture_lod(t, uv[2 * i], uv[2 * i + 1], 0.0f, out_rgba + 4 * i);
+}
+
 // The lit colour of the listed pixels (index = y * width + x) with `bias` added to the rgb of every material texture
 // sample: how far does the reference's own result move when its texture samples move by the precision of a texture
 // unit?  (tests/helpers.py compare_color: the BRDF is discontinuous where N.V is clamped and N.L crosses zero.)

@@ -5,7 +5,7 @@ is what the GPU's texture unit computes.  tests/golden/texture_unit_*.bin are ou
 (tools/texvalue_probe.cu, tools/texsrgb_probe.cu, run through gpurun; the generating sources are committed): RGBA8
 textures of random bytes sampled at random positions, all 257 weights between chosen texel pairs, and a grid of 2D
 weights inside chosen 2x2 cells, as UNORM and as sRGB.  The oracle's model (oracle/lh_oracle_resolve.cpp,
-sample_bilinear_level) must reproduce every one of those 49,152 fetches BIT FOR BIT; the GPU test at the end re-runs the
+sample_bilinear_level) must reproduce every one of those 65,536 fetches BIT FOR BIT; the GPU test at the end re-runs the
 probes' fetches on the device at hand, so a texture unit that filters differently is noticed."""
 import ctypes as C
 import os
@@ -67,6 +67,25 @@ def test_random_texture_fetches_are_reproduced_bit_for_bit(name):
     got = model(tex, name == "srgb", rec[:, :2])
     assert len(rec) == 16384
     assert np.array_equal(got.view(np.uint32), np.ascontiguousarray(rec[:, 2:]).view(np.uint32))
+
+
+@pytest.mark.parametrize("name", ["unorm", "srgb"])
+def test_sides_that_are_not_powers_of_two_and_coordinates_outside_the_unit_square(name):
+    """tools/texwrap_probe.cu: a 48 x 80 texture, u and v in [-4, 4), repeat addressing.  The texture unit wraps the
+    coordinate into [0, 1) before it scales it (feeding the model the raw coordinate matches 99.8 % only), which is what
+    the oracle's textureLod does."""
+    lib = oracle_lib()
+    lib.lho_test_sample_lod0.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint64, C.c_void_p, C.c_void_p]
+    lib.lho_test_sample_lod0.restype = None
+    w, h = 48, 80
+    raw = open(os.path.join(GOLDEN, f"texture_unit_wrap_{name}.bin"), "rb").read()
+    tex = np.frombuffer(raw[:w * h * 4], np.uint8).copy()
+    rec = np.frombuffer(raw[w * h * 4:], np.float32).reshape(-1, 6)
+    uv = np.ascontiguousarray(rec[:, :2])
+    assert len(rec) == 8192 and uv.min() < -3.9 and uv.max() > 3.9
+    out = np.zeros((len(uv), 4), np.float32)
+    lib.lho_test_sample_lod0(tex.ctypes.data, w, h, int(name == "srgb"), len(uv), uv.ctypes.data, out.ctypes.data)
+    assert np.array_equal(out.view(np.uint32), np.ascontiguousarray(rec[:, 2:]).view(np.uint32))
 
 
 def test_every_weight_between_two_texels():
