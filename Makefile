@@ -29,7 +29,7 @@ host: $(LIBDIR)/liblh_host.so
 oracle: oracle/liblh_oracle.so
 examples: lighthugger_b200/bin/lh_frame_loop
 # hardware probes (texture-unit filter arithmetic, L2 atomic ceilings): run on the GPU box, fitted offline (tools/*.py)
-PROBES := build/texwrap_probe build/texvalue_probe build/texsrgb_probe build/texfilter_probe build/atomic_probe
+PROBES := build/texfloat_probe build/texwrap_probe build/texvalue_probe build/texsrgb_probe build/texfilter_probe build/atomic_probe
 probes: $(PROBES)
 build/%_probe: tools/%_probe.cu
 	@mkdir -p build
