@@ -62,6 +62,45 @@ __device__ __forceinline__ V3 cross3(V3 a, V3 b) {
     return V3{psub(pmul(a.y, b.z), pmul(b.y, a.z)), psub(pmul(a.z, b.x), pmul(b.z, a.x)), psub(pmul(a.x, b.y), pmul(b.x, a.y))};
 }
 
+// pow(x, p) for x > 0 by a fixed sequence of IEEE double operations (no libm),
+// the same sequence the CPU checker uses (the reference's GLSL pow is
+// implementation-defined).
+__device__ inline float pinned_powf(float xf, float pf) {
+    if (!(xf > 0.0f)) return xf == 0.0f ? 0.0f : __int_as_float(0x7FC00000);
+    double x = (double)xf;
+    unsigned long long bits = (unsigned long long)__double_as_longlong(x);
+    int e = (int)((bits >> 52) & 0x7FF) - 1023;
+    bits = (bits & 0x000FFFFFFFFFFFFFull) | 0x3FF0000000000000ull;
+    double m = __longlong_as_double((long long)bits);
+    if (m > 1.4142135623730951) {
+        m = __dmul_rn(m, 0.5);
+        e += 1;
+    }
+    double s = __ddiv_rn(__dsub_rn(m, 1.0), __dadd_rn(m, 1.0));
+    double s2 = __dmul_rn(s, s);
+    double term = s, acc = 0.0;
+    for (int k = 1; k <= 25; k += 2) {
+        acc = __dadd_rn(acc, __ddiv_rn(term, (double)k));
+        term = __dmul_rn(term, s2);
+    }
+    const double ln2 = 0.6931471805599453;
+    double lnx = __dadd_rn(__dmul_rn((double)e, ln2), __dmul_rn(2.0, acc));
+    double y = __dmul_rn((double)pf, lnx);
+    double kf = floor(__dadd_rn(__ddiv_rn(y, ln2), 0.5));
+    double r = __dsub_rn(y, __dmul_rn(kf, ln2));
+    double et = 1.0, ex = 1.0;
+    for (int k = 1; k <= 18; k++) {
+        et = __ddiv_rn(__dmul_rn(et, r), (double)k);
+        ex = __dadd_rn(ex, et);
+    }
+    int ki = (int)kf;
+    if (ki > 1000) return __int_as_float(0x7F800000);
+    if (ki < -1000) return 0.0f;
+    double p2 = __longlong_as_double((long long)((unsigned long long)(ki + 1023) << 52));
+    return (float)__dmul_rn(ex, p2);
+}
+
+
 // ---- device-side scratch that lives across passes of one frame -------------
 struct FrameState {
     uint32_t overflow;             // LH_OVERFLOW_* bits

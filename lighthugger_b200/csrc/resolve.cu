@@ -551,7 +551,8 @@ __global__ void __launch_bounds__(256, LH_RESOLVE_MIN_CTAS) resolve_kernel(const
 }
 
 // display_transform.comp:37-81: Tony McMapface LUT (48^3) + sRGB OETF -> BGRA8
-__device__ __forceinline__ float srgb_oetf(float v) { return v <= 0.003130f ? 12.92f * v : 1.055f * __powf(v, 1.0f / 2.4f) - 0.055f; }
+// pow is implementation-defined in GLSL: pinned as the fixed IEEE sequence the checker uses (lh_internal.cuh)
+__device__ __forceinline__ float srgb_oetf(float v) { return v <= 0.003130f ? 12.92f * v : 1.055f * pinned_powf(v, 1.0f / 2.4f) - 0.055f; }
 
 __global__ void __launch_bounds__(256) display_transform_kernel(const __grid_constant__ FrameParams P) {
     const uint32_t W = P.u.window_size[0], H = P.u.window_size[1];

@@ -86,6 +86,8 @@ int lho_resolve_debug(const LhUniforms* u, const LhoConfig* cfg, const uint64_t*
  * against dumps of the real texture unit (tests/golden/texture_unit_*.bin) */
 void lho_test_sample_bilinear(const uint8_t* rgba8, uint32_t width, uint32_t height, uint32_t srgb, uint64_t count, const float* uv,
                               float* out_rgba);
+/* textureLod(sampler3D, uvw, 0) of a size^3 RGB32F table with clamp addressing at `count` positions */
+void lho_test_sample_lut(const float* lut_rgb32f, uint32_t size, uint64_t count, const float* uvw, float* out_rgb);
 /* textureLod(samplerCube, direction, 0) of a size x size RGBA32F cube map at `count` directions (out: rgb) */
 void lho_test_sample_cube(const float* faces_rgba32f, uint32_t size, uint64_t count, const float* xyz, float* out_rgb);
 /* textureLod(level 0) with repeat addressing at arbitrary coordinates (wraps into [0, 1) first, then filters) */

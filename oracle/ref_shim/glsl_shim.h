@@ -55,6 +55,14 @@ inline vec3 operator*(vec3 const& a, int b) { return a * (float)b; }
 inline vec2 operator*(vec2 const& a, int b) { return a * (float)b; }
 inline vec2 operator/(vec2 const& a, uvec2 const& b) { return a / vec2(b); }
 inline float pow(int a, float b) { return std::pow((float)a, b); }
+// pow(x, p) as pinned by the oracle and the CUDA pass: applied per component (the display transform calls it on a vec3)
+inline float shim_pinned_pow(float x, float p) { return lho_pinned_powf(x, p); }
+template <typename V>
+inline V shim_pinned_pow(const V& x, float p) {
+    V r = x;
+    for (int i = 0; i < (int)x.length(); i++) r[i] = lho_pinned_powf(x[i], p);
+    return r;
+}
 // pow(x, 5.0) as pinned by the oracle and the CUDA pass (GLSL leaves pow's precision to the implementation)
 inline float shim_pow5(float x) {
     float x2 = x * x;

@@ -164,8 +164,9 @@ def test_gltf_scene_renders_like_the_directly_built_scene(tmp_path):
 
 def test_display_transform_with_the_reference_lut_matches_the_oracle():
     """the REAL Tony McMapface table (the reference's own DDS, read through the DDS parser and
-    lh_set_display_lut) on a lit frame: B8G8R8A8 output within 1/255 of the oracle's display_transform.comp restatement,
-    which is itself bit-identical to the reference's shader (tests/test_ref_shaders.py)."""
+    lh_set_display_lut) on a lit frame: B8G8R8A8 output within 1/255 of the oracle's display_transform.comp restatement on
+    every byte and identical on 99.9 % of them; the restatement is itself bit-identical to the reference's shader
+    (tests/test_ref_shaders.py)."""
     from helpers import REAL_LUT, real_display_lut
     from lighthugger_b200 import image_files as IF
     lut = real_display_lut()
@@ -183,8 +184,14 @@ def test_display_transform_with_the_reference_lut_matches_the_oracle():
     o = make_oracle(sc, textures=tex, skybox=sky)
     want = np.rint(np.clip(o.display_transform(scene, lut)[:, :3], 0, 1) * 255).astype(np.int32)   # the UNORM store
     diff = np.abs(want[:, ::-1] - bgra[:, :3])
+    import helpers
+    if helpers.COLOR_LOG:
+        with open(helpers.COLOR_LOG, "a") as f:
+            f.write('{"test": "display_transform_real_lut", "pixels": %d, "bytes_differing": %d, "max": %d}\n' % (len(diff), np.count_nonzero(diff), diff.max()))
     assert (bgra[:, 3] == 255).all()
     assert diff.max() <= 1, f"max difference {diff.max()}/255 on {np.count_nonzero(diff > 1)} pixels"
-    assert np.count_nonzero(diff) <= 0.05 * diff.size   # and almost all pixels identical
+    # the oracle models the unit's 3D float filter (99.86 % of fetches bit for bit) and both sides pin pow: measured on
+    # B200, 339 of 1,555,200 bytes differ, by 1
+    assert np.count_nonzero(diff) <= 0.001 * diff.size
     assert len(np.unique(bgra[:, :3])) > 100            # a real image, not a constant
     ctx.close()

@@ -108,6 +108,25 @@ def test_float_cube_map_filter():
     assert np.abs(out - rec[:, 3:6]).max() < 0.05       # a neighbouring 1/256 weight, not a different texel
 
 
+def test_float_3d_filter():
+    """tools/texfloat_probe.cu: a 12^3 RGBA32F texture (RGB kept) at random positions, clamp addressing: the display LUT's
+    filter.  Eight 8-bit weights, exact sum, one rounding; the fitted splitting rule reproduces all but 13 of these 8,192
+    fetches bit for bit, and those are off by one 1/256 weight."""
+    lib = oracle_lib()
+    lib.lho_test_sample_lut.argtypes = [C.c_void_p, C.c_uint32, C.c_uint64, C.c_void_p, C.c_void_p]
+    lib.lho_test_sample_lut.restype = None
+    size = 12
+    raw = np.frombuffer(open(os.path.join(GOLDEN, "texture_unit_3d_f32.bin"), "rb").read(), np.float32)
+    lut = raw[:size ** 3 * 3].copy()
+    rec = raw[size ** 3 * 3:].reshape(-1, 6)
+    uvw = np.ascontiguousarray(rec[:, :3])
+    out = np.zeros((len(rec), 3), np.float32)
+    lib.lho_test_sample_lut(lut.ctypes.data, size, len(rec), uvw.ctypes.data, out.ctypes.data)
+    same = (out.view(np.uint32) == np.ascontiguousarray(rec[:, 3:]).view(np.uint32)).all(axis=1)
+    assert len(rec) == 8192 and np.count_nonzero(~same) <= 13
+    assert np.abs(out - rec[:, 3:]).max() < 1.0 / 256
+
+
 def test_every_weight_between_two_texels():
     # [mode][pair][k] -> (rgb value, alpha value); mode 0 UNORM, mode 1 sRGB (whose alpha stays linear)
     want = np.frombuffer(open(os.path.join(GOLDEN, "texture_unit_srgb_1d.bin"), "rb").read(), np.float32).reshape(2, 32 * 257, 2)
