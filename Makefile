@@ -55,9 +55,17 @@ HOST_MESHOPT_FLAGS :=
 else
 HOST_MESHOPT_FLAGS := -DLH_HAVE_MESHOPTIMIZER -I$(REF)/external/meshoptimizer/src
 endif
+# Where the reference is absent (the GPU box) an existing library is KEPT whatever the timestamps say: it was built here
+# with the reference's meshoptimizer, and rebuilding it there would silently swap the meshlet builder (and with it the
+# benchmark scene) for the greedy fallback.
+ifeq ($(REF_MESHOPT_SRCS)$(wildcard $(LIBDIR)/liblh_host.so),$(LIBDIR)/liblh_host.so)
+$(LIBDIR)/liblh_host.so:
+	@true
+else
 $(LIBDIR)/liblh_host.so: $(HOST_SRCS) $(HOST_HDRS)
 	@mkdir -p $(LIBDIR)
 	$(CXX) $(CXXFLAGS) $(HOST_MESHOPT_FLAGS) -shared -o $@ $(HOST_SRCS) $(REF_MESHOPT_SRCS) $(LDFLAGS_SO) -ldl
+endif
 
 # a C++20 host on top of the two C ABIs, the counterpart of the reference's main() frame loop
 lighthugger_b200/bin/lh_frame_loop: examples/frame_loop.cpp $(LIBDIR)/liblighthugger_b200.so $(LIBDIR)/liblh_host.so $(HOST_HDRS)

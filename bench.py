@@ -238,6 +238,12 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+def meshlet_builder():
+    """Which meshlet builder the host library was built with (the reference's vendored meshoptimizer, or the greedy fallback)."""
+    from lighthugger_b200.scene import host_lib
+    return "meshoptimizer (reference's vendored copy)" if host_lib().lh_host_has_meshoptimizer() else "greedy fallback"
+
+
 # ---------------------------------------------------------------- our arm
 def run_ours(args):
     import torch
@@ -510,7 +516,7 @@ def run_ours(args):
                    "candidate_meshlets": scene.total_meshlets, "l2": "flushed between timed frames (256 MB write)",
                    "parallelism": (f"sort-last x{n_gpus}: instances split by {args.partition}, {args.exchange} exchange, shadows split by {args.shadow_split}"
                                    if n_gpus > 1 else "single GPU"), "texture_format": "BC7_SRGB",
-                   "texture_size": args.tex_size, "texture_sets": scene.num_texture_sets,
+                   "texture_size": args.tex_size, "texture_sets": scene.num_texture_sets, "meshlet_builder": meshlet_builder(),
                    "visible_instance_fraction": (round(visible_fraction, 4) if visible_fraction is not None else None),
                    **({"emulated_rank": args.emulate_rank, "note": "profiling aid: one rank's local work, NOT a bench value"} if emulate else {})},
         "culled_mtri_per_s": scene.total_triangles / (ms_per_step / 1e3) / 1e6,
